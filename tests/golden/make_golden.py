@@ -278,7 +278,11 @@ def make_ppo_golden(out_path):
 
     torch.manual_seed(11)
     data = {}
-    ac = ActorCritic(705, 219, 12, actor_hidden_dims=[512, 256, 128], critic_hidden_dims=[768, 256, 128],
+    # A reduced architecture keeps the fixture small; the arithmetic being pinned (ELU MLP,
+    # diag-Normal, GAE, clipped PPO loss, adaptive-KL lr, grad clip, Adam) is shape-independent.
+    # The full 705-512-256-128-12 actor is pinned by policy_example_kat.npz.
+    NA, NC = 60, 40
+    ac = ActorCritic(NA, NC, 12, actor_hidden_dims=[32, 24, 16], critic_hidden_dims=[48, 24, 16],
                      init_noise_std=1.0)
     with torch.no_grad():
         ac.std.copy_(0.6 + 0.8 * torch.rand(12))      # non-trivial sigma
@@ -287,8 +291,8 @@ def make_ppo_golden(out_path):
 
     # --- A1/A2: forward, sample statistics, log-prob, entropy
     M = 96
-    obs = torch.randn(M, 705).clamp(-18, 18)
-    cobs = torch.randn(M, 219).clamp(-18, 18)
+    obs = torch.randn(M, NA).clamp(-18, 18)
+    cobs = torch.randn(M, NC).clamp(-18, 18)
     acts = torch.randn(M, 12)
     with torch.no_grad():
         ac.update_distribution(obs)
@@ -301,7 +305,7 @@ def make_ppo_golden(out_path):
 
     # --- A5: GAE + advantage normalisation
     T, N = 24, 40
-    st = RolloutStorage(N, T, [705], [219], [12], "cpu")
+    st = RolloutStorage(N, T, [NA], [NC], [12], "cpu")
     st.rewards.copy_(torch.rand(T, N, 1))
     st.values.copy_(torch.randn(T, N, 1))
     st.dones.copy_((torch.rand(T, N, 1) < 0.08).byte())
@@ -316,10 +320,10 @@ def make_ppo_golden(out_path):
     alg = PPO(ac, num_learning_epochs=2, num_mini_batches=4, clip_param=0.2, gamma=0.994, lam=0.9,
               value_loss_coef=1.0, entropy_coef=0.001, learning_rate=1e-5, max_grad_norm=1.0,
               use_clipped_value_loss=True, schedule="adaptive", desired_kl=0.01, device="cpu")
-    alg.init_storage(N, T, [705], [219], [12])
+    alg.init_storage(N, T, [NA], [NC], [12])
     alg.actor_critic.train()
-    obs = torch.randn(N, 705).clamp(-18, 18)
-    cobs = torch.randn(N, 219).clamp(-18, 18)
+    obs = torch.randn(N, NA).clamp(-18, 18)
+    cobs = torch.randn(N, NC).clamp(-18, 18)
     with torch.inference_mode():
         for t in range(T):
             a = alg.act(obs, cobs)
@@ -327,8 +331,8 @@ def make_ppo_golden(out_path):
             dones = torch.rand(N) < 0.1
             infos = {"time_outs": dones & (torch.rand(N) < 0.5)}
             alg.process_env_step(rew, dones, infos)
-            obs = (0.7 * obs + 0.6 * torch.randn(N, 705)).clamp(-18, 18)
-            cobs = (0.7 * cobs + 0.6 * torch.randn(N, 219)).clamp(-18, 18)
+            obs = (0.7 * obs + 0.6 * torch.randn(N, NA)).clamp(-18, 18)
+            cobs = (0.7 * cobs + 0.6 * torch.randn(N, NC)).clamp(-18, 18)
         alg.compute_returns(cobs)
     s = alg.storage
     for k in ("observations", "privileged_observations", "actions", "rewards", "dones", "values",
@@ -359,7 +363,7 @@ def make_ppo_golden(out_path):
         torch.randperm = real_randperm
         torch.nn.utils.clip_grad_norm_ = real_clip
     data["upd.perm"] = perms[0]
-    data["upd.grads"] = np.stack(grads)                # (8, 926105) pre-clip gradients per optimizer step
+    data["upd.grads"] = np.stack(grads)                # (8, n_params) pre-clip gradients per optimizer step
     data["upd.lrs"] = np.array(lrs, np.float64)        # lr in force at each optimizer step
     data["upd.mean_value_loss"] = np.float64(mv)
     data["upd.mean_surrogate_loss"] = np.float64(ms)
@@ -367,9 +371,6 @@ def make_ppo_golden(out_path):
     for k, v in ac.state_dict().items():
         data["w1." + k] = v.numpy().copy()
     data["param_order"] = np.array([k for k, _ in ac.named_parameters()])
-    # keep the fixture small: only the first two and the last gradient
-    data["upd.grads"] = data["upd.grads"][[0, 1, 7]]
-    data["upd.grads_idx"] = np.array([0, 1, 7])
     np.savez_compressed(out_path, **data)
     print(f"wrote {out_path}: {os.path.getsize(out_path) / 1e6:.2f} MB")
 
