@@ -1,0 +1,232 @@
+// ActorCritic MLP forward / backward (algo/ppo/actor_critic.py:54-77, autograd in ppo.py:170-173).
+//
+// This file holds the exact-fp32 CUDA-core GEMM path: C(i,j) = sum_p A(i,p) * B(p,j) with arbitrary
+// element strides on both operands so that the three products of a Linear layer
+//     forward  Y  = X  W^T        (A = X  row-major,   B(p,j) = W[j][p])
+//     dgrad    dX = dZ W          (A = dZ row-major,   B(p,j) = W[p][j])
+//     wgrad    dW = dZ^T X        (A(i,p) = dZ[p][i],  B(p,j) = X[p][j], split-K over the batch)
+// share one kernel, with the bias+ELU and ELU' epilogues fused.  It is the bit-for-bit-fp32 reference
+// for the tcgen05 path (hg_gemm_tc.cu) and the fallback for shapes the tensor-core tiles do not cover
+// (K = 219 / 705 row pitches that TMA cannot address, N = 12 / 1 output layers).
+#include "hg_common.cuh"
+
+namespace {
+
+constexpr int BM = 128, BN = 128, BK = 8, TM = 8, TN = 8;
+constexpr int GEMM_THREADS = (BM / TM) * (BN / TN);   // 256
+
+enum Epilogue : int { EPI_NONE = 0, EPI_BIAS = 1, EPI_BIAS_ELU = 2, EPI_MUL_DELU = 3, EPI_ATOMIC = 4 };
+
+struct GemmArgs {
+    const float* A; const float* B; float* C;
+    const float* bias;      // (N) for EPI_BIAS*
+    const float* h;         // (M, ldh) post-ELU activations for EPI_MUL_DELU
+    int M, N, K;
+    int64_t sai, sap, sbp, sbj, ldc, ldh;
+    int k_chunk;            // split-K: p range per blockIdx.z
+};
+
+// A_IMAJ: A is contiguous along i (sai == 1); otherwise contiguous along p.
+// B_JMAJ: B is contiguous along j (sbj == 1); otherwise contiguous along p.
+template <int EPI, bool A_IMAJ, bool B_JMAJ>
+__global__ void __launch_bounds__(GEMM_THREADS, 2) gemm_kernel(GemmArgs g) {
+    __shared__ __align__(16) float As[2][BK][BM + 4];   // +4: conflict-free transposed stores
+    __shared__ __align__(16) float Bs[2][BK][BN + 4];
+    const int tid = threadIdx.x;
+    const int i0 = blockIdx.y * BM, j0 = blockIdx.x * BN;
+    const int p_begin = blockIdx.z * g.k_chunk;
+    const int p_end = min(g.K, p_begin + g.k_chunk);
+
+    // global->smem mapping: 4 elements per thread per operand
+    int a_i[4], a_p[4], b_j[4], b_p[4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        int idx = tid + r * GEMM_THREADS;               // 0..1023
+        if (A_IMAJ) { a_p[r] = idx / BM; a_i[r] = idx % BM; } else { a_i[r] = idx / BK; a_p[r] = idx % BK; }
+        if (B_JMAJ) { b_p[r] = idx / BN; b_j[r] = idx % BN; } else { b_j[r] = idx / BK; b_p[r] = idx % BK; }
+    }
+    float ra[4], rb[4];
+    auto fetch = [&](int p0) {
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            int i = i0 + a_i[r], p = p0 + a_p[r];
+            ra[r] = (i < g.M && p < p_end) ? __ldg(g.A + (int64_t)i * g.sai + (int64_t)p * g.sap) : 0.0f;
+            int j = j0 + b_j[r];
+            p = p0 + b_p[r];
+            rb[r] = (j < g.N && p < p_end) ? __ldg(g.B + (int64_t)p * g.sbp + (int64_t)j * g.sbj) : 0.0f;
+        }
+    };
+    auto stash = [&](int buf) {
+#pragma unroll
+        for (int r = 0; r < 4; ++r) { As[buf][a_p[r]][a_i[r]] = ra[r]; Bs[buf][b_p[r]][b_j[r]] = rb[r]; }
+    };
+
+    const int ty = tid / (BN / TN), tx = tid % (BN / TN);   // 16 x 16
+    float acc[TM][TN];
+#pragma unroll
+    for (int a = 0; a < TM; ++a)
+#pragma unroll
+        for (int b = 0; b < TN; ++b) acc[a][b] = 0.0f;
+
+    int buf = 0;
+    fetch(p_begin);
+    stash(0);
+    __syncthreads();
+    for (int p0 = p_begin; p0 < p_end; p0 += BK) {
+        const bool more = p0 + BK < p_end;
+        if (more) fetch(p0 + BK);
+#pragma unroll
+        for (int k = 0; k < BK; ++k) {
+            float4 a0 = *reinterpret_cast<const float4*>(&As[buf][k][ty * 4]);
+            float4 a1 = *reinterpret_cast<const float4*>(&As[buf][k][64 + ty * 4]);
+            float4 b0 = *reinterpret_cast<const float4*>(&Bs[buf][k][tx * 4]);
+            float4 b1 = *reinterpret_cast<const float4*>(&Bs[buf][k][64 + tx * 4]);
+            float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+            float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+            for (int a = 0; a < TM; ++a)
+#pragma unroll
+                for (int b = 0; b < TN; ++b) acc[a][b] = fmaf(av[a], bv[b], acc[a][b]);
+        }
+        if (more) {
+            stash(buf ^ 1);
+            __syncthreads();
+            buf ^= 1;
+        }
+    }
+
+#pragma unroll
+    for (int a = 0; a < TM; ++a) {
+        int i = i0 + (a < 4 ? ty * 4 + a : 64 + ty * 4 + (a - 4));
+        if (i >= g.M) continue;
+#pragma unroll
+        for (int b = 0; b < TN; ++b) {
+            int j = j0 + (b < 4 ? tx * 4 + b : 64 + tx * 4 + (b - 4));
+            if (j >= g.N) continue;
+            float v = acc[a][b];
+            float* dst = g.C + (int64_t)i * g.ldc + j;
+            if (EPI == EPI_BIAS || EPI == EPI_BIAS_ELU) v += g.bias[j];
+            if (EPI == EPI_BIAS_ELU) v = v > 0.0f ? v : expm1f(v);          // nn.ELU(alpha=1)
+            if (EPI == EPI_MUL_DELU) {                                       // ELU'(z) from h = ELU(z)
+                float h = g.h[(int64_t)i * g.ldh + j];
+                v *= (h > 0.0f) ? 1.0f : (h + 1.0f);
+            }
+            if (EPI == EPI_ATOMIC) atomicAdd(dst, v); else *dst = v;
+        }
+    }
+}
+
+template <int EPI>
+int32_t launch_gemm(const GemmArgs& g, int splits, cudaStream_t st) {
+    dim3 grid((g.N + BN - 1) / BN, (g.M + BM - 1) / BM, splits);
+    const bool a_imaj = (g.sai == 1 && g.sap != 1), b_jmaj = (g.sbj == 1);
+    if (a_imaj && b_jmaj) gemm_kernel<EPI, true, true><<<grid, GEMM_THREADS, 0, st>>>(g);
+    else if (a_imaj) gemm_kernel<EPI, true, false><<<grid, GEMM_THREADS, 0, st>>>(g);
+    else if (b_jmaj) gemm_kernel<EPI, false, true><<<grid, GEMM_THREADS, 0, st>>>(g);
+    else gemm_kernel<EPI, false, false><<<grid, GEMM_THREADS, 0, st>>>(g);
+    HG_LAUNCHED(1);
+    return hg_cuda_status("hg gemm");
+}
+
+// db[n] = sum_m dZ[m][n]
+__global__ void colsum_kernel(const float* __restrict__ dZ, float* __restrict__ db, int M, int N, int rows_per_block) {
+    int n = blockIdx.x * blockDim.x + threadIdx.x;
+    int m0 = blockIdx.y * rows_per_block, m1 = min(M, m0 + rows_per_block);
+    if (n >= N) return;
+    float s = 0.0f;
+    for (int m = m0; m < m1; ++m) s += dZ[(int64_t)m * N + n];
+    atomicAdd(db + n, s);
+}
+
+int32_t check_net(const HgMlpDesc* net) {
+    HG_REQUIRE(net);
+    if (net->n_layers < 1 || net->n_layers > HG_MAX_LAYERS) return hg_fail(HG_E_ARG, "HgMlpDesc: bad n_layers");
+    for (int l = 0; l <= net->n_layers; ++l)
+        if (net->dims[l] < 1) return hg_fail(HG_E_SIZE, "HgMlpDesc: bad layer width");
+    return 0;
+}
+
+}  // namespace
+
+extern "C" int32_t hg_mlp_forward(const HgMlpDesc* net, const float* params, const float* X, int64_t ldx,
+                                  float* hidden, float* out, int64_t M, void* stream) {
+    if (int32_t rc = check_net(net)) return rc;
+    HG_REQUIRE(params); HG_REQUIRE(X); HG_REQUIRE(out);
+    if (net->n_layers > 1) HG_REQUIRE(hidden);
+    if (M <= 0 || M > (1 << 28) || ldx < net->dims[0]) return hg_fail(HG_E_SIZE, "hg_mlp_forward: bad M/ldx");
+    cudaStream_t st = (cudaStream_t)stream;
+    const float* in = X;
+    int64_t ld_in = ldx;
+    float* h = hidden;
+    for (int l = 0; l < net->n_layers; ++l) {
+        const int K = net->dims[l], N = net->dims[l + 1];
+        const bool last = (l + 1 == net->n_layers);
+        GemmArgs g{};
+        g.A = in; g.sai = ld_in; g.sap = 1;
+        g.B = params + net->w_off[l]; g.sbp = 1; g.sbj = K;
+        g.C = last ? out : h; g.ldc = N;
+        g.bias = params + net->b_off[l];
+        g.M = (int)M; g.N = N; g.K = K; g.k_chunk = K;
+        int32_t rc = last ? launch_gemm<EPI_BIAS>(g, 1, st) : launch_gemm<EPI_BIAS_ELU>(g, 1, st);
+        if (rc) return rc;
+        in = h; ld_in = N;
+        h += M * N;
+    }
+    return 0;
+}
+
+extern "C" int32_t hg_mlp_backward(const HgMlpDesc* net, const float* params, const float* X, int64_t ldx,
+                                   const float* hidden, const float* dY, float* dhidden, float* grads,
+                                   int64_t M, void* stream) {
+    if (int32_t rc = check_net(net)) return rc;
+    HG_REQUIRE(params); HG_REQUIRE(X); HG_REQUIRE(dY); HG_REQUIRE(grads);
+    if (net->n_layers > 1) { HG_REQUIRE(hidden); HG_REQUIRE(dhidden); }
+    if (M <= 0 || M > (1 << 28) || ldx < net->dims[0]) return hg_fail(HG_E_SIZE, "hg_mlp_backward: bad M/ldx");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int L = net->n_layers;
+    // element offset of hidden layer l's output (l = 1..L-1) inside hidden / dhidden
+    int64_t off[HG_MAX_LAYERS + 1];
+    off[0] = 0; off[1] = 0;
+    for (int l = 1; l < L; ++l) off[l + 1] = off[l] + M * net->dims[l];
+    const float* dZ = dY;                                   // gradient w.r.t. layer l's pre-activation
+    for (int l = L - 1; l >= 0; --l) {
+        const int K = net->dims[l], N = net->dims[l + 1];
+        const float* in = (l == 0) ? X : hidden + off[l];
+        const int64_t ld_in = (l == 0) ? ldx : K;
+        float* dW = grads + net->w_off[l];
+        float* db = grads + net->b_off[l];
+        cudaMemsetAsync(dW, 0, sizeof(float) * (size_t)N * K, st);
+        cudaMemsetAsync(db, 0, sizeof(float) * (size_t)N, st);
+        {   // dW[n][k] = sum_m dZ[m][n] X[m][k]
+            GemmArgs g{};
+            g.A = dZ; g.sai = 1; g.sap = N;
+            g.B = in; g.sbp = ld_in; g.sbj = 1;
+            g.C = dW; g.ldc = K;
+            g.M = N; g.N = K; g.K = (int)M;
+            int tiles = ((N + BM - 1) / BM) * ((K + BN - 1) / BN);
+            int64_t want = (4 * HG_NUM_SMS + tiles - 1) / tiles, cap = (M + 255) / 256;
+            int splits = (int)(want < cap ? want : cap);
+            if (splits < 1) splits = 1;
+            g.k_chunk = (int)(((M + splits - 1) / splits + BK - 1) / BK * BK);
+            splits = (int)((M + g.k_chunk - 1) / g.k_chunk);
+            if (int32_t rc = launch_gemm<EPI_ATOMIC>(g, splits, st)) return rc;
+        }
+        {
+            int rows = 512;
+            dim3 grid((N + 127) / 128, (unsigned)((M + rows - 1) / rows));
+            colsum_kernel<<<grid, 128, 0, st>>>(dZ, db, (int)M, N, rows);
+            HG_LAUNCHED(1);
+        }
+        if (l > 0) {   // dZ_{l-1} = (dZ_l W_l) * ELU'(h_{l-1})
+            GemmArgs g{};
+            g.A = dZ; g.sai = N; g.sap = 1;
+            g.B = params + net->w_off[l]; g.sbp = K; g.sbj = 1;
+            g.C = dhidden + off[l]; g.ldc = K;
+            g.h = hidden + off[l]; g.ldh = K;
+            g.M = (int)M; g.N = K; g.K = N; g.k_chunk = N;
+            if (int32_t rc = launch_gemm<EPI_MUL_DELU>(g, 1, st)) return rc;
+            dZ = dhidden + off[l];
+        }
+    }
+    return hg_cuda_status("hg_mlp_backward");
+}

@@ -1,0 +1,151 @@
+"""ActorCritic with the reference's constructor, module tree and state-dict keys
+(reference algo/ppo/actor_critic.py:36-128), whose forward / backward run in libhg_b200.
+
+All parameters are views into ONE flat fp32 buffer (order == named_parameters(): std, actor.*,
+critic.*) so that the gradient all-reduce, the norm clip and Adam each touch a single range.
+`self.actor` / `self.critic` stay real nn.Sequential(Linear, ELU, ...) modules: checkpoints
+(`model_state_dict`) and export_policy_as_jit keep working unchanged.
+"""
+import torch
+import torch.nn as nn
+from torch.distributions import Normal
+
+from humanoid import _native as nat
+
+
+def _mlp(inp, hidden, out, activation):
+    dims = [inp] + list(hidden) + [out]
+    layers = []
+    for i in range(len(dims) - 1):
+        layers.append(nn.Linear(dims[i], dims[i + 1]))
+        if i < len(dims) - 2:
+            layers.append(activation)
+    return nn.Sequential(*layers), dims
+
+
+class ActorCritic(nn.Module):
+    def __init__(self, num_actor_obs, num_critic_obs, num_actions, actor_hidden_dims=[256, 256, 256],
+                 critic_hidden_dims=[256, 256, 256], init_noise_std=1.0, activation=nn.ELU(), **kwargs):
+        if kwargs:
+            print("ActorCritic.__init__ got unexpected arguments, which will be ignored: " + str(list(kwargs.keys())))
+        super().__init__()
+        if not (isinstance(activation, nn.ELU) and activation.alpha == 1.0):
+            raise nat.NativeError("the native MLP kernels implement ELU(alpha=1) only (XBotLCfgPPO default)")
+        self.actor, self._actor_dims = _mlp(num_actor_obs, actor_hidden_dims, num_actions, activation)
+        self.critic, self._critic_dims = _mlp(num_critic_obs, critic_hidden_dims, 1, activation)
+        print(f"Actor MLP: {self.actor}")
+        print(f"Critic MLP: {self.critic}")
+        self.std = nn.Parameter(init_noise_std * torch.ones(num_actions))
+        self.num_actions = num_actions
+        self.distribution = None
+        Normal.set_default_validate_args = False
+        self._flat = None
+        self._scratch = {}
+
+    # ------------------------------------------------------------------------------------------
+    # flat parameter buffer + native descriptors
+    # ------------------------------------------------------------------------------------------
+    def _flatten(self):
+        """(Re)alias every parameter into one contiguous buffer on its current device."""
+        params = list(self.parameters())
+        dev = params[0].device
+        if dev.type != "cuda":
+            raise nat.NativeError("ActorCritic must live on a CUDA device: no CPU fallback for the hot path")
+        n = sum(p.numel() for p in params)
+        flat = torch.empty(n, dtype=torch.float32, device=dev)
+        off = 0
+        self._offsets = {}
+        for name, p in self.named_parameters():
+            k = p.numel()
+            flat[off:off + k].copy_(p.data.reshape(-1))
+            p.data = flat[off:off + k].view(p.shape)
+            self._offsets[name] = off
+            off += k
+        self._flat = flat
+        self.num_params = n
+        self._desc = {}
+        for prefix, dims in (("actor", self._actor_dims), ("critic", self._critic_dims)):
+            d = nat.MlpDesc()
+            d.n_layers = len(dims) - 1
+            for i, w in enumerate(dims):
+                d.dims[i] = w
+            for l in range(d.n_layers):
+                d.w_off[l] = self._offsets[f"{prefix}.{2 * l}.weight"]
+                d.b_off[l] = self._offsets[f"{prefix}.{2 * l}.bias"]
+            self._desc[prefix] = d
+        self._scratch = {}
+
+    def flat_params(self):
+        first = next(self.parameters())
+        if self._flat is None or first.data_ptr() != self._flat.data_ptr() or self._flat.device != first.device:
+            self._flatten()
+        return self._flat
+
+    def hidden_width(self, which):
+        dims = self._actor_dims if which == "actor" else self._critic_dims
+        return sum(dims[1:-1])
+
+    def _hidden_scratch(self, which, M):
+        key = (which, M)
+        if key not in self._scratch:
+            self._scratch[key] = torch.empty(M * self.hidden_width(which), dtype=torch.float32, device=self._flat.device)
+        return self._scratch[key]
+
+    def native_forward(self, which, x, out, hidden=None):
+        """out (M, dims[-1]) <- MLP_which(x); returns the hidden-activation scratch."""
+        flat = self.flat_params()
+        M = x.shape[0]
+        assert x.is_contiguous() and x.dtype == torch.float32
+        if hidden is None:
+            hidden = self._hidden_scratch(which, M)
+        nat.check(nat.lib.hg_mlp_forward(self._desc[which], flat.data_ptr(), x.data_ptr(), x.shape[1],
+                                         hidden.data_ptr(), out.data_ptr(), M, nat.stream_ptr(flat.device.index)),
+                  "hg_mlp_forward")
+        return hidden
+
+    # ------------------------------------------------------------------------------------------
+    # reference API
+    # ------------------------------------------------------------------------------------------
+    def reset(self, dones=None):
+        pass
+
+    def forward(self):
+        raise NotImplementedError
+
+    @property
+    def action_mean(self):
+        return self.distribution.mean
+
+    @property
+    def action_std(self):
+        return self.distribution.stddev
+
+    @property
+    def entropy(self):
+        return self.distribution.entropy().sum(dim=-1)
+
+    def _actor_mean(self, observations):
+        obs = observations.to(torch.float32).contiguous()
+        mean = torch.empty(obs.shape[0], self.num_actions, dtype=torch.float32, device=obs.device)
+        self.native_forward("actor", obs, mean)
+        return mean
+
+    def update_distribution(self, observations):
+        mean = self._actor_mean(observations)
+        self.distribution = Normal(mean, mean * 0. + self.std.detach())
+
+    def act(self, observations, **kwargs):
+        self.update_distribution(observations)
+        return self.distribution.sample()
+
+    def get_actions_log_prob(self, actions):
+        return self.distribution.log_prob(actions).sum(dim=-1)
+
+    def act_inference(self, observations):
+        return self._actor_mean(observations)
+
+    def evaluate(self, critic_observations, **kwargs):
+        cobs = critic_observations.to(torch.float32).contiguous()
+        value = torch.empty(cobs.shape[0], 1, dtype=torch.float32, device=cobs.device)
+        self.native_forward("critic", cobs, value)
+        return value

@@ -1,0 +1,212 @@
+"""OnPolicyRunner: rollout + update loop, logging, checkpoints
+(reference algo/ppo/on_policy_runner.py:47-307; same checkpoint format and console/TensorBoard scalars).
+
+Differences that matter for speed only: episode bookkeeping stays on the device (no per-step .cpu()),
+and TensorBoard / wandb are optional imports."""
+import os
+import statistics
+import time
+from collections import deque
+from datetime import datetime
+
+import torch
+
+from .ppo import PPO
+from .actor_critic import ActorCritic
+from humanoid.algo.vec_env import VecEnv  # noqa: F401
+
+_CLASSES = {"PPO": PPO, "ActorCritic": ActorCritic}
+
+
+class OnPolicyRunner:
+    def __init__(self, env, train_cfg, log_dir=None, device="cpu"):
+        self.cfg = train_cfg["runner"]
+        self.alg_cfg = train_cfg["algorithm"]
+        self.policy_cfg = train_cfg["policy"]
+        self.all_cfg = train_cfg
+        self.wandb_run_name = (datetime.now().strftime("%b%d_%H-%M-%S") + "_" + train_cfg["runner"]["experiment_name"]
+                               + "_" + train_cfg["runner"]["run_name"])
+        self.device = device
+        self.env = env
+        num_critic_obs = self.env.num_privileged_obs if self.env.num_privileged_obs is not None else self.env.num_obs
+        actor_critic = _CLASSES[self.cfg["policy_class_name"]](
+            self.env.num_obs, num_critic_obs, self.env.num_actions, **self.policy_cfg).to(self.device)
+        self.alg = _CLASSES[self.cfg["algorithm_class_name"]](actor_critic, device=self.device, **self.alg_cfg)
+        self.num_steps_per_env = self.cfg["num_steps_per_env"]
+        self.save_interval = self.cfg["save_interval"]
+        self.alg.init_storage(self.env.num_envs, self.num_steps_per_env, [self.env.num_obs],
+                              [self.env.num_privileged_obs], [self.env.num_actions])
+        self.log_dir = log_dir
+        self.writer = None
+        self.tot_timesteps = 0
+        self.tot_time = 0
+        self.current_learning_iteration = 0
+        self.last_perf = {}
+        _, _ = self.env.reset()
+
+    # ------------------------------------------------------------------------------------------
+    def _init_writer(self):
+        try:
+            import wandb
+            wandb.init(project="XBot", sync_tensorboard=True, name=self.wandb_run_name, config=self.all_cfg,
+                       mode=os.environ.get("WANDB_MODE", "disabled"))
+        except Exception as e:      # no network in most deployments
+            print(f"wandb disabled: {e}")
+        from torch.utils.tensorboard import SummaryWriter
+        self.writer = SummaryWriter(log_dir=self.log_dir, flush_secs=10)
+
+    def rollout(self, obs, critic_obs, book=None):
+        """One collection phase: num_steps_per_env x (act, env.step, process_env_step) + compute_returns."""
+        env, alg = self.env, self.alg
+        for _ in range(self.num_steps_per_env):
+            actions = alg.act(obs, critic_obs)
+            obs, privileged_obs, rewards, dones, infos = env.step(actions)
+            critic_obs = privileged_obs if privileged_obs is not None else obs
+            alg.process_env_step(rewards, dones, infos)
+            if book is not None:
+                book.step(rewards, dones, infos)
+        alg.compute_returns(critic_obs)
+        return obs, critic_obs
+
+    def learn(self, num_learning_iterations, init_at_random_ep_len=False):
+        if self.log_dir is not None and self.writer is None:
+            self._init_writer()
+        if init_at_random_ep_len:
+            self.env.episode_length_buf = torch.randint_like(self.env.episode_length_buf, high=int(self.env.max_episode_length))
+        obs = self.env.get_observations()
+        privileged_obs = self.env.get_privileged_observations()
+        critic_obs = privileged_obs if privileged_obs is not None else obs
+        self.alg.actor_critic.train()
+        book = _EpisodeBook(self.env.num_envs, self.device) if self.log_dir is not None else None
+
+        tot_iter = self.current_learning_iteration + num_learning_iterations
+        for it in range(self.current_learning_iteration, tot_iter):
+            start = time.time()
+            with torch.inference_mode():
+                obs, critic_obs = self.rollout(obs, critic_obs, book)
+                torch.cuda.synchronize(self.device)
+                stop = time.time()
+                collection_time = stop - start
+                start = stop
+                mean_value_loss, mean_surrogate_loss = self.alg.update()
+            stop = time.time()
+            learn_time = stop - start
+            self.last_perf = dict(collection_time=collection_time, learn_time=learn_time,
+                                  fps=self.num_steps_per_env * self.env.num_envs / (collection_time + learn_time))
+            if self.log_dir is not None:
+                ep_infos = book.drain_infos()
+                rewbuffer, lenbuffer = book.rewbuffer, book.lenbuffer
+                self.log(locals())
+                if it % self.save_interval == 0:
+                    self.save(os.path.join(self.log_dir, "model_{}.pt".format(it)))
+        self.current_learning_iteration += num_learning_iterations
+        if self.log_dir is not None:
+            self.save(os.path.join(self.log_dir, "model_{}.pt".format(self.current_learning_iteration)))
+
+    # ------------------------------------------------------------------------------------------
+    def log(self, locs, width=80, pad=35):
+        self.tot_timesteps += self.num_steps_per_env * self.env.num_envs
+        iteration_time = locs["collection_time"] + locs["learn_time"]
+        self.tot_time += iteration_time
+        it = locs["it"]
+        ep_string = ""
+        for key, value in locs["ep_infos"].items():
+            self.writer.add_scalar("Episode/" + key, value, it)
+            ep_string += f"""{f'Mean episode {key}:':>{pad}} {value:.4f}\n"""
+        mean_std = self.alg.actor_critic.std.mean().item()
+        fps = int(self.num_steps_per_env * self.env.num_envs / iteration_time)
+        w = self.writer
+        w.add_scalar("Loss/value_function", locs["mean_value_loss"], it)
+        w.add_scalar("Loss/surrogate", locs["mean_surrogate_loss"], it)
+        w.add_scalar("Loss/learning_rate", self.alg.learning_rate, it)
+        w.add_scalar("Policy/mean_noise_std", mean_std, it)
+        w.add_scalar("Perf/total_fps", fps, it)
+        w.add_scalar("Perf/collection time", locs["collection_time"], it)
+        w.add_scalar("Perf/learning_time", locs["learn_time"], it)
+        have_eps = len(locs["rewbuffer"]) > 0
+        if have_eps:
+            mr, ml = statistics.mean(locs["rewbuffer"]), statistics.mean(locs["lenbuffer"])
+            w.add_scalar("Train/mean_reward", mr, it)
+            w.add_scalar("Train/mean_episode_length", ml, it)
+            w.add_scalar("Train/mean_reward/time", mr, self.tot_time)
+            w.add_scalar("Train/mean_episode_length/time", ml, self.tot_time)
+        head = f" \033[1m Learning iteration {it}/{self.current_learning_iteration + locs['num_learning_iterations']} \033[0m "
+        out = (f"""{'#' * width}\n{head.center(width, ' ')}\n\n"""
+               f"""{'Computation:':>{pad}} {fps:.0f} steps/s (collection: {locs['collection_time']:.3f}s, learning {locs['learn_time']:.3f}s)\n"""
+               f"""{'Value function loss:':>{pad}} {locs['mean_value_loss']:.4f}\n"""
+               f"""{'Surrogate loss:':>{pad}} {locs['mean_surrogate_loss']:.4f}\n"""
+               f"""{'Mean action noise std:':>{pad}} {mean_std:.2f}\n""")
+        if have_eps:
+            out += (f"""{'Mean reward:':>{pad}} {mr:.2f}\n"""
+                    f"""{'Mean episode length:':>{pad}} {ml:.2f}\n""")
+        out += ep_string
+        out += (f"""{'-' * width}\n"""
+                f"""{'Total timesteps:':>{pad}} {self.tot_timesteps}\n"""
+                f"""{'Iteration time:':>{pad}} {iteration_time:.2f}s\n"""
+                f"""{'Total time:':>{pad}} {self.tot_time:.2f}s\n"""
+                f"""{'ETA:':>{pad}} {self.tot_time / (it + 1) * (locs['num_learning_iterations'] - it):.1f}s\n""")
+        print(out)
+
+    def save(self, path, infos=None):
+        self.alg.sync_optimizer_container()
+        torch.save({"model_state_dict": self.alg.actor_critic.state_dict(),
+                    "optimizer_state_dict": self.alg.optimizer.state_dict(),
+                    "iter": self.current_learning_iteration, "infos": infos}, path)
+
+    def load(self, path, load_optimizer=True):
+        loaded = torch.load(path, map_location=self.device)
+        self.alg.actor_critic.load_state_dict(loaded["model_state_dict"])
+        if load_optimizer:
+            self.alg.optimizer.load_state_dict(loaded["optimizer_state_dict"])
+            self.alg.load_optimizer_container()
+        self.current_learning_iteration = loaded["iter"]
+        return loaded["infos"]
+
+    def get_inference_policy(self, device=None):
+        self.alg.actor_critic.eval()
+        if device is not None:
+            self.alg.actor_critic.to(device)
+        return self.alg.actor_critic.act_inference
+
+    def get_inference_critic(self, device=None):
+        self.alg.actor_critic.eval()
+        if device is not None:
+            self.alg.actor_critic.to(device)
+        return self.alg.actor_critic.evaluate
+
+
+class _EpisodeBook:
+    """Per-episode reward / length bookkeeping of on_policy_runner.py:140-154, kept on the device;
+    finished-episode statistics are read back once per iteration instead of once per step."""
+
+    def __init__(self, n, device):
+        self.cur_reward_sum = torch.zeros(n, dtype=torch.float, device=device)
+        self.cur_episode_length = torch.zeros(n, dtype=torch.float, device=device)
+        self.rewbuffer, self.lenbuffer = deque(maxlen=100), deque(maxlen=100)
+        self._done_rew, self._done_len, self._infos = [], [], []
+
+    def step(self, rewards, dones, infos):
+        if "episode" in infos:
+            self._infos.append(torch.stack(list(infos["episode"].values())).clone())
+            self._info_keys = list(infos["episode"].keys())
+        self.cur_reward_sum += rewards
+        self.cur_episode_length += 1
+        d = dones > 0
+        self._done_rew.append(torch.where(d, self.cur_reward_sum, torch.full_like(self.cur_reward_sum, float("nan"))))
+        self._done_len.append(torch.where(d, self.cur_episode_length, torch.full_like(self.cur_reward_sum, float("nan"))))
+        self.cur_reward_sum.masked_fill_(d, 0)
+        self.cur_episode_length.masked_fill_(d, 0)
+
+    def drain_infos(self):
+        if self._done_rew:
+            r = torch.stack(self._done_rew).flatten()
+            ln = torch.stack(self._done_len).flatten()
+            keep = ~torch.isnan(r)
+            self.rewbuffer.extend(r[keep].cpu().tolist())
+            self.lenbuffer.extend(ln[keep].cpu().tolist())
+        out = {}
+        if self._infos:
+            m = torch.stack(self._infos).mean(dim=0).cpu().tolist()
+            out = dict(zip(self._info_keys, m))
+        self._done_rew, self._done_len, self._infos = [], [], []
+        return out

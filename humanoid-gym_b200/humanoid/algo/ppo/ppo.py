@@ -1,0 +1,232 @@
+"""PPO with the reference's constructor and methods (reference algo/ppo/ppo.py:41-184); act /
+process_env_step / compute_returns / update are sequences of native launches with NO torch op and NO
+host synchronisation inside (the adaptive-KL learning rate and the Adam step count live in HBM).
+
+Env-sharded data parallelism: when torch.distributed is initialised, the flat
+gradient buffer -- whose tail carries [surrogate, value loss, entropy, KL] partial means -- is
+all-reduced (SUM) once per optimizer step; every mean already uses 1/B_global, so the summed buffer is
+exactly the single-process gradient of the G*B-sample minibatch and all ranks take the same lr decision.
+"""
+import torch
+import torch.distributed as dist
+import torch.optim as optim
+
+from humanoid import _native as nat
+from .actor_critic import ActorCritic
+from .rollout_storage import RolloutStorage
+
+_TAIL = 8   # [surrogate, value_loss, entropy, kl_mean, pad...]
+
+
+class PPO:
+    actor_critic: ActorCritic
+
+    def __init__(self, actor_critic, num_learning_epochs=1, num_mini_batches=1, clip_param=0.2, gamma=0.998, lam=0.95,
+                 value_loss_coef=1.0, entropy_coef=0.0, learning_rate=1e-3, max_grad_norm=1.0, use_clipped_value_loss=True,
+                 schedule="fixed", desired_kl=0.01, device="cpu"):
+        self.device = device
+        if torch.device(device).type != "cuda":
+            raise nat.NativeError(f"PPO(device={device!r}): the learning side runs on sm_100a only (no CPU fallback)")
+        self.desired_kl, self.schedule = desired_kl, schedule
+        self.actor_critic = actor_critic
+        self.actor_critic.to(self.device)
+        self.storage = None
+        self.optimizer = optim.Adam(self.actor_critic.parameters(), lr=learning_rate)   # checkpoint container only
+        self.transition = RolloutStorage.Transition()
+        self.clip_param, self.num_learning_epochs, self.num_mini_batches = clip_param, num_learning_epochs, num_mini_batches
+        self.value_loss_coef, self.entropy_coef = value_loss_coef, entropy_coef
+        self.gamma, self.lam, self.max_grad_norm = gamma, lam, max_grad_norm
+        self.use_clipped_value_loss = use_clipped_value_loss
+        self.global_advantage_norm = False      # True: one extra 3-double all-reduce per iteration (section 8e)
+
+        flat = self.actor_critic.flat_params()
+        n = self.actor_critic.num_params
+        dev = flat.device
+        self._dev_index = dev.index
+        self._grad = torch.zeros(n + _TAIL, dtype=torch.float32, device=dev)
+        self._scalars = self._grad[n:]
+        self._exp_avg = torch.zeros(n, dtype=torch.float32, device=dev)
+        self._exp_avg_sq = torch.zeros(n, dtype=torch.float32, device=dev)
+        self._sqnorm = torch.zeros(1, dtype=torch.float64, device=dev)
+        self._lr = torch.full((1,), learning_rate, dtype=torch.float64, device=dev)
+        self._adam_step = torch.zeros(1, dtype=torch.int32, device=dev)
+        self._loss_sums = torch.zeros(_TAIL, dtype=torch.float32, device=dev)
+        self._sample_step = 0
+        self._seed = (torch.initial_seed() * 0x9E3779B97F4A7C15 + 12345) % (1 << 64)
+        self._alias_grads_and_state()
+        self._mb_scratch = {}
+
+    # ------------------------------------------------------------------------------------------
+    def _alias_grads_and_state(self):
+        """p.grad and the torch Adam state become views of the flat buffers (checkpoint compatibility)."""
+        ac = self.actor_critic
+        for name, p in ac.named_parameters():
+            off, k = ac._offsets[name], p.numel()
+            p.grad = self._grad[off:off + k].view(p.shape)
+            self.optimizer.state[p] = dict(step=torch.tensor(0.0), exp_avg=self._exp_avg[off:off + k].view(p.shape),
+                                           exp_avg_sq=self._exp_avg_sq[off:off + k].view(p.shape))
+
+    def sync_optimizer_container(self):
+        """Refresh the torch.optim.Adam container from the device-resident lr / step (before save)."""
+        lr, step = float(self._lr.item()), float(self._adam_step.item())
+        for gparam in self.optimizer.param_groups:
+            gparam["lr"] = lr
+        for st in self.optimizer.state.values():
+            st["step"] = torch.tensor(step)
+
+    def load_optimizer_container(self):
+        """After optimizer.load_state_dict: pull exp_avg / exp_avg_sq / step / lr back into the flat buffers."""
+        ac = self.actor_critic
+        step = 0.0
+        for name, p in ac.named_parameters():
+            st = self.optimizer.state.get(p)
+            if not st:
+                continue
+            off, k = ac._offsets[name], p.numel()
+            self._exp_avg[off:off + k].copy_(st["exp_avg"].reshape(-1))
+            self._exp_avg_sq[off:off + k].copy_(st["exp_avg_sq"].reshape(-1))
+            step = float(st["step"])
+        self._adam_step.fill_(int(step))
+        self._lr.fill_(self.optimizer.param_groups[0]["lr"])
+        self._alias_grads_and_state()
+        self.sync_optimizer_container()
+
+    @property
+    def learning_rate(self):
+        return float(self._lr.item())
+
+    @learning_rate.setter
+    def learning_rate(self, v):
+        self._lr.fill_(float(v))
+
+    def init_storage(self, num_envs, num_transitions_per_env, actor_obs_shape, critic_obs_shape, action_shape):
+        self.storage = RolloutStorage(num_envs, num_transitions_per_env, actor_obs_shape, critic_obs_shape, action_shape, self.device)
+
+    def test_mode(self):
+        self.actor_critic.eval()
+
+    def train_mode(self):
+        self.actor_critic.train()
+
+    # ------------------------------------------------------------------------------------------
+    # rollout
+    # ------------------------------------------------------------------------------------------
+    def act(self, obs, critic_obs, eps=None):
+        """ppo.py:91-101.  Everything lands directly in slab t of the storage: actor mean -> mu[t],
+        value -> values[t], sampled actions / log-prob / sigma -> actions[t] / actions_log_prob[t] / sigma[t];
+        obs and critic obs are copied now, because env.step() overwrites the env's buffers in place."""
+        s, ac = self.storage, self.actor_critic
+        t = s.step
+        if t >= s.num_transitions_per_env:
+            raise AssertionError("Rollout buffer overflow")
+        st = nat.stream_ptr(self._dev_index)
+        ac.native_forward("actor", obs, s.mu[t])
+        ac.native_forward("critic", critic_obs, s.values[t])
+        nat.check(nat.lib.hg_policy_sample(
+            s.mu[t].data_ptr(), ac.std.data_ptr(), nat.ptr(eps), self._seed, self._sample_step,
+            s.actions[t].data_ptr(), s.actions_log_prob[t].data_ptr(), s.sigma[t].data_ptr(),
+            s.num_envs, s.actions_shape[0], st), "hg_policy_sample")
+        self._sample_step += 1
+        s.add_native(t, obs=obs, priv_obs=critic_obs if s.privileged_observations is not None else None)
+        tr = self.transition
+        tr.actions, tr.values, tr.actions_log_prob = s.actions[t], s.values[t], s.actions_log_prob[t]
+        tr.action_mean, tr.action_sigma = s.mu[t], s.sigma[t]
+        tr.observations, tr.critic_observations = s.observations[t], (
+            s.privileged_observations[t] if s.privileged_observations is not None else s.observations[t])
+        return tr.actions
+
+    def process_env_step(self, rewards, dones, infos):
+        """ppo.py:103-113: r += gamma * V * time_out, then store rewards and dones (one launch)."""
+        s = self.storage
+        t = s.step
+        time_outs = infos.get("time_outs") if isinstance(infos, dict) else None
+        d = dones if dones.dtype in (torch.bool, torch.uint8) else dones.to(torch.uint8)
+        s.add_native(t, gamma=self.gamma, rewards=rewards.contiguous(), dones=d.contiguous(),
+                     time_outs=None if time_outs is None else time_outs.contiguous())
+        s.step += 1
+        self.transition.clear()
+        self.actor_critic.reset(dones)
+
+    def compute_returns(self, last_critic_obs):
+        """ppo.py:115-117 + rollout_storage.py:122-136."""
+        s = self.storage
+        if not hasattr(self, "_last_values") or self._last_values.shape[0] != s.num_envs:
+            self._last_values = torch.empty(s.num_envs, 1, dtype=torch.float32, device=self.device)
+        self.actor_critic.native_forward("critic", last_critic_obs, self._last_values)
+        world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+        if world > 1 and self.global_advantage_norm:
+            s.compute_returns(self._last_values, self.gamma, self.lam, normalise=False)
+            dist.all_reduce(s._stats)
+            s.normalise_advantages()
+        else:
+            s.compute_returns(self._last_values, self.gamma, self.lam)
+
+    # ------------------------------------------------------------------------------------------
+    # update
+    # ------------------------------------------------------------------------------------------
+    def _scratch(self, B):
+        if B not in self._mb_scratch:
+            ac, z = self.actor_critic, dict(dtype=torch.float32, device=self.device)
+            A = ac.num_actions
+            self._mb_scratch = {B: dict(
+                mean=torch.empty(B, A, **z), value=torch.empty(B, 1, **z), d_mean=torch.empty(B, A, **z),
+                d_value=torch.empty(B, 1, **z),
+                hid_a=torch.empty(B * ac.hidden_width("actor"), **z), dhid_a=torch.empty(B * ac.hidden_width("actor"), **z),
+                hid_c=torch.empty(B * ac.hidden_width("critic"), **z), dhid_c=torch.empty(B * ac.hidden_width("critic"), **z))}
+        return self._mb_scratch[B]
+
+    def minibatch_step(self, mb, world=1):
+        """Loss forward/backward + gradient (all-reduce) + lr rule + clip + Adam for one minibatch."""
+        ac = self.actor_critic
+        flat = ac.flat_params()
+        st = nat.stream_ptr(self._dev_index)
+        obs = mb["obs"]
+        cobs = mb["priv_obs"] if mb["priv_obs"] is not None else obs
+        B = obs.shape[0]
+        w = self._scratch(B)
+        ac.native_forward("actor", obs, w["mean"], hidden=w["hid_a"])
+        ac.native_forward("critic", cobs, w["value"], hidden=w["hid_c"])
+        a = nat.PpoLossArgs()
+        a.mean, a.value, a.std = w["mean"].data_ptr(), w["value"].data_ptr(), ac.std.data_ptr()
+        a.actions, a.target_values = mb["actions"].data_ptr(), mb["values"].data_ptr()
+        a.advantages, a.returns = mb["advantages"].data_ptr(), mb["returns"].data_ptr()
+        a.old_log_prob, a.old_mu, a.old_sigma = mb["old_log_prob"].data_ptr(), mb["old_mu"].data_ptr(), mb["old_sigma"].data_ptr()
+        a.d_mean, a.d_value = w["d_mean"].data_ptr(), w["d_value"].data_ptr()
+        a.grad_std = self._grad.data_ptr() + 4 * ac._offsets["std"]
+        a.scalars = self._scalars.data_ptr()
+        a.clip_param, a.value_loss_coef, a.entropy_coef = self.clip_param, self.value_loss_coef, self.entropy_coef
+        a.use_clipped_value_loss, a.num_actions = int(self.use_clipped_value_loss), ac.num_actions
+        a.inv_B = 1.0 / (B * world)
+        nat.check(nat.lib.hg_ppo_loss_fwd_bwd(a, B, st), "hg_ppo_loss_fwd_bwd")
+        g = self._grad.data_ptr()
+        nat.check(nat.lib.hg_mlp_backward(ac._desc["actor"], flat.data_ptr(), obs.data_ptr(), obs.shape[1], w["hid_a"].data_ptr(),
+                                          w["d_mean"].data_ptr(), w["dhid_a"].data_ptr(), g, B, st), "hg_mlp_backward(actor)")
+        nat.check(nat.lib.hg_mlp_backward(ac._desc["critic"], flat.data_ptr(), cobs.data_ptr(), cobs.shape[1], w["hid_c"].data_ptr(),
+                                          w["d_value"].data_ptr(), w["dhid_c"].data_ptr(), g, B, st), "hg_mlp_backward(critic)")
+        if world > 1:
+            dist.all_reduce(self._grad)                         # the ONE collective of the update path
+        if self.desired_kl is not None and self.schedule == "adaptive":
+            nat.check(nat.lib.hg_adapt_lr(self._scalars.data_ptr() + 12, float(self.desired_kl), self._lr.data_ptr(), st), "hg_adapt_lr")
+        n = ac.num_params
+        nat.check(nat.lib.hg_grad_sqnorm(g, n, self._sqnorm.data_ptr(), st), "hg_grad_sqnorm")
+        nat.check(nat.lib.hg_clip_adam_step(flat.data_ptr(), g, self._exp_avg.data_ptr(), self._exp_avg_sq.data_ptr(),
+                                            self._sqnorm.data_ptr(), float(self.max_grad_norm), self._lr.data_ptr(),
+                                            self._adam_step.data_ptr(), 0.9, 0.999, 1e-8, 1.0, n, st), "hg_clip_adam_step")
+        self._loss_sums.add_(self._scalars)
+
+    def update(self):
+        """ppo.py:119-184."""
+        s = self.storage
+        world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+        batch_size = s.num_envs * s.num_transitions_per_env
+        mini = batch_size // self.num_mini_batches
+        indices = torch.randperm(self.num_mini_batches * mini, requires_grad=False, device=self.device)
+        self._loss_sums.zero_()
+        for _ in range(self.num_learning_epochs):
+            for i in range(self.num_mini_batches):
+                mb = s.gather(indices[i * mini:(i + 1) * mini])
+                self.minibatch_step(mb, world)
+        num_updates = self.num_learning_epochs * self.num_mini_batches
+        sums = self._loss_sums.tolist()                          # the only device->host read of the update
+        s.clear()
+        return sums[1] / num_updates, sums[0] / num_updates

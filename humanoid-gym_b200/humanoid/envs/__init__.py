@@ -1,0 +1,9 @@
+"""Task registration (mirrors reference envs/__init__.py:33-45)."""
+from humanoid import LEGGED_GYM_ROOT_DIR, LEGGED_GYM_ENVS_DIR  # noqa: F401
+from .base.legged_robot import LeggedRobot  # noqa: F401
+from .custom.humanoid_config import XBotLCfg, XBotLCfgPPO
+from .custom.humanoid_env import XBotLFreeEnv
+
+from humanoid.utils.task_registry import task_registry
+
+task_registry.register("humanoid_ppo", XBotLFreeEnv, XBotLCfg(), XBotLCfgPPO())

@@ -1,0 +1,308 @@
+"""LeggedRobot: host side of the vectorised env step.
+
+Same public surface as reference envs/base/legged_robot.py (ctor, step, reset, post_physics_step,
+check_termination, compute_reward, reset_idx, _compute_torques, the live state tensors), but every
+tensor op between the physics refresh and the return of step() is ONE launch of the fused
+sm_100a kernel `hg_env_post_physics`; this class only owns the buffers, the physics seam and the
+argument marshalling.  Rough terrain, curricula and the viewer are out of scope (XBotLCfg disables
+them: humanoid_config.py:72-76).
+"""
+import os
+
+import numpy as np
+import torch
+
+from humanoid import _native as nat
+from humanoid.envs.base.base_task import BaseTask
+from humanoid.utils.helpers import class_to_dict
+from humanoid import physics as phys
+
+
+class LeggedRobot(BaseTask):
+    def __init__(self, cfg, sim_params, physics_engine, sim_device, headless):
+        self.cfg = cfg
+        self.sim_params = sim_params
+        self.height_samples = None
+        self.debug_viz = False
+        self.init_done = False
+        self._parse_cfg(self.cfg)
+        super().__init__(self.cfg, sim_params, physics_engine, sim_device, headless)
+        self._init_buffers()
+        self._prepare_reward_function()
+        self._bind_native()
+        self.init_done = True
+
+    # ------------------------------------------------------------------------------------------
+    # configuration
+    # ------------------------------------------------------------------------------------------
+    def _parse_cfg(self, cfg):                                   # reference legged_robot.py:710-720
+        self.dt = self.cfg.control.decimation * self.sim_params.dt
+        self.obs_scales = self.cfg.normalization.obs_scales
+        self.reward_scales = class_to_dict(self.cfg.rewards.scales)
+        self.command_ranges = class_to_dict(self.cfg.commands.ranges)
+        if self.cfg.terrain.mesh_type not in ("heightfield", "trimesh"):
+            self.cfg.terrain.curriculum = False
+        else:
+            raise NotImplementedError("rough terrain is outside the humanoid_ppo hot path (plane only)")
+        if self.cfg.terrain.measure_heights:
+            raise NotImplementedError("measure_heights is outside the humanoid_ppo hot path")
+        self.max_episode_length_s = self.cfg.env.episode_length_s
+        self.max_episode_length = np.ceil(self.max_episode_length_s / self.dt)
+        self.cfg.domain_rand.push_interval = np.ceil(self.cfg.domain_rand.push_interval_s / self.dt)
+
+    def create_sim(self):
+        """Physics seam (reference humanoid_env.py:145-163 + legged_robot.py:588-681)."""
+        self.up_axis_idx = 2
+        self._get_env_origins()
+        kind = os.environ.get("HG_PHYSICS", getattr(self.cfg, "physics_backend", "auto"))
+        seed = getattr(self.cfg, "seed", 0)
+        rank = int(os.environ.get("RANK", "0"))
+        self.gym = phys.make_physics(kind, self.num_envs, self.device, self.cfg, self.env_origins, seed=seed, rank=rank)
+        self.sim = self.gym
+        self.num_dof = self.num_dofs = self.gym.num_dof
+        self.num_bodies = self.gym.num_bodies
+        self.dof_names = list(self.gym.dof_names)
+        body_names = list(self.gym.body_names)
+        dev = self.device
+
+        def indices(pattern_list):
+            names = []
+            for pat in pattern_list:
+                names.extend(s for s in body_names if pat in s)
+            return torch.tensor([body_names.index(n) for n in names], dtype=torch.long, device=dev)
+
+        self.feet_indices = indices([self.cfg.asset.foot_name])
+        self.knee_indices = indices([self.cfg.asset.knee_name])
+        self.penalised_contact_indices = indices(self.cfg.asset.penalize_contacts_on)
+        self.termination_contact_indices = indices(self.cfg.asset.terminate_after_contacts_on)
+
+        props = self.gym.dof_properties()                         # _process_dof_props :276-293
+        s = self.cfg.safety
+        self.dof_pos_limits = torch.tensor(list(zip(props["lower"], props["upper"])), dtype=torch.float, device=dev) * s.pos_limit
+        self.dof_vel_limits = torch.tensor(props["velocity"], dtype=torch.float, device=dev) * s.vel_limit
+        self.torque_limits = torch.tensor(props["effort"], dtype=torch.float, device=dev) * s.torque_limit
+
+        init = self.cfg.init_state
+        self.base_init_state = torch.tensor(init.pos + init.rot + init.lin_vel + init.ang_vel, dtype=torch.float, device=dev)
+
+        # one-time domain randomisation, drawn on the CPU like the reference (:257-270, :296-302)
+        N = self.num_envs
+        dr = self.cfg.domain_rand
+        self.env_frictions = torch.zeros(N, 1, dtype=torch.float32, device=dev)
+        if dr.randomize_friction:
+            buckets = 256
+            ids = torch.randint(0, buckets, (N, 1))
+            lo, hi = dr.friction_range
+            vals = (hi - lo) * torch.rand(buckets, 1) + lo
+            self.friction_coeffs = vals[ids]
+            self.env_frictions[:] = self.friction_coeffs.view(N, 1).to(dev)
+        self.body_mass = torch.full((N, 1), phys.robot.BASE_LINK_MASS, dtype=torch.float32, device=dev)
+        if dr.randomize_base_mass:
+            lo, hi = dr.added_mass_range
+            self.body_mass += torch.from_numpy(np.random.uniform(lo, hi, size=(N, 1)).astype(np.float32)).to(dev)
+
+    def _get_env_origins(self):                                  # :683-708 (flat-ground grid)
+        self.custom_origins = False
+        N = self.num_envs
+        cols = np.floor(np.sqrt(N))
+        rows = np.ceil(N / cols)
+        xx, yy = torch.meshgrid(torch.arange(rows), torch.arange(cols), indexing="ij")
+        sp = self.cfg.env.env_spacing
+        o = torch.zeros(N, 3)
+        o[:, 0] = sp * xx.flatten()[:N]
+        o[:, 1] = sp * yy.flatten()[:N]
+        self.env_origins = o.to(self.device)
+
+    # ------------------------------------------------------------------------------------------
+    # buffers
+    # ------------------------------------------------------------------------------------------
+    def _init_buffers(self):                                     # :434-516
+        N, dev = self.num_envs, self.device
+        g = self.gym
+        self.root_states = g.root_states
+        self.dof_state = g.dof_state
+        self.dof_pos = self.dof_state.view(N, self.num_dof, 2)[..., 0]
+        self.dof_vel = self.dof_state.view(N, self.num_dof, 2)[..., 1]
+        self.base_quat = self.root_states[:, 3:7]
+        self.contact_forces = g.contact_forces.view(N, -1, 3)
+        self.rigid_state = g.rigid_state.view(N, -1, 13)
+
+        def zeros(*shape, dtype=torch.float):
+            return torch.zeros(*shape, dtype=dtype, device=dev, requires_grad=False)
+
+        self.common_step_counter = 0
+        self.extras = {}
+        self.noise_scale_vec = self._get_noise_scale_vec(self.cfg)
+        self.gravity_vec = torch.tensor([0.0, 0.0, -1.0], device=dev).repeat((N, 1))
+        self.forward_vec = torch.tensor([1.0, 0.0, 0.0], device=dev).repeat((N, 1))
+        A = self.num_actions
+        self.torques = zeros(N, A)
+        self.p_gains = zeros(N, A)
+        self.d_gains = zeros(N, A)
+        self.actions = zeros(N, A)
+        self.last_actions = zeros(N, A)
+        self.last_last_actions = zeros(N, A)
+        self.last_rigid_state = torch.zeros_like(self.rigid_state)    # dead data in the reference (:151)
+        self.last_dof_vel = zeros(N, self.num_dof)
+        self.last_root_vel = zeros(N, 6)
+        self.commands = zeros(N, self.cfg.commands.num_commands)
+        self.commands_scale = torch.tensor([self.obs_scales.lin_vel, self.obs_scales.lin_vel, self.obs_scales.ang_vel], device=dev)
+        self.feet_air_time = zeros(N, self.feet_indices.shape[0])
+        self.last_contacts = zeros(N, len(self.feet_indices), dtype=torch.bool)
+        self.base_lin_vel = zeros(N, 3)
+        self.base_ang_vel = zeros(N, 3)
+        self.projected_gravity = zeros(N, 3)
+        self.projected_gravity[:, 2] = -1.0
+        self.base_euler_xyz = zeros(N, 3)
+        self.measured_heights = 0
+        self.feet_height = zeros(N, 2)
+        self.last_feet_z = torch.full((N, 2), 0.05, device=dev)
+        self.ref_dof_pos = zeros(N, self.num_dof)
+        self.rand_push_force = zeros(N, 3)
+        self.rand_push_torque = zeros(N, 3)
+        self.extras_time_outs = zeros(N, dtype=torch.bool)
+        self.reset_ids = zeros(N, dtype=torch.int32)
+        self._scratch = zeros(32, dtype=torch.int32)
+
+        self.default_dof_pos = zeros(self.num_dof)
+        for i, name in enumerate(self.dof_names):                # :487-501
+            self.default_dof_pos[i] = self.cfg.init_state.default_joint_angles[name]
+            for key in self.cfg.control.stiffness.keys():
+                if key in name:
+                    self.p_gains[:, i] = self.cfg.control.stiffness[key]
+                    self.d_gains[:, i] = self.cfg.control.damping[key]
+        self.default_dof_pos = self.default_dof_pos.unsqueeze(0)
+        self.default_joint_pd_target = self.default_dof_pos.clone()
+
+    def _get_noise_scale_vec(self, cfg):
+        raise NotImplementedError
+
+    def _prepare_reward_function(self):                          # :518-541
+        for key in list(self.reward_scales.keys()):
+            if self.reward_scales[key] == 0:
+                self.reward_scales.pop(key)
+            else:
+                self.reward_scales[key] *= self.dt
+        self.reward_names = [k for k in self.reward_scales.keys() if k != "termination"]
+        K = len(self.reward_names)
+        self._episode_sums = torch.zeros(K, self.num_envs, dtype=torch.float, device=self.device)
+        self._episode_means = torch.zeros(K, dtype=torch.float, device=self.device)
+        self.episode_sums = {n: self._episode_sums[k] for k, n in enumerate(self.reward_names)}
+
+    # ------------------------------------------------------------------------------------------
+    # native binding
+    # ------------------------------------------------------------------------------------------
+    def _native_params(self):
+        raise NotImplementedError
+
+    def _bind_native(self):
+        self._P = self._native_params()
+        B = nat.EnvBuffers()
+        tensors = dict(
+            root_states=self.root_states, dof_state=self.dof_state, contact_forces=self.gym.contact_forces,
+            rigid_state=self.gym.rigid_state, actions=self.actions, last_actions=self.last_actions,
+            last_last_actions=self.last_last_actions, torques=self.torques, last_dof_vel=self.last_dof_vel,
+            last_root_vel=self.last_root_vel, commands=self.commands, episode_length_buf=self._episode_length_buf,
+            reset_buf=self.reset_buf, time_out_buf=self.time_out_buf, extras_time_outs=self.extras_time_outs,
+            base_lin_vel=self.base_lin_vel, base_ang_vel=self.base_ang_vel, projected_gravity=self.projected_gravity,
+            base_euler_xyz=self.base_euler_xyz, feet_air_time=self.feet_air_time, last_contacts=self.last_contacts,
+            feet_height=self.feet_height, last_feet_z=self.last_feet_z, ref_dof_pos=self.ref_dof_pos,
+            rand_push_force=self.rand_push_force, rand_push_torque=self.rand_push_torque,
+            env_frictions=self.env_frictions, body_mass=self.body_mass, env_origins=self.env_origins,
+            episode_sums=self._episode_sums, episode_means=self._episode_means, rew_terms=None,
+            obs_buf=self.obs_buf, privileged_obs_buf=self.privileged_obs_buf, rew_buf=self.rew_buf,
+            reset_ids=self.reset_ids, scratch=self._scratch)
+        for k, t in tensors.items():
+            setattr(B, k, nat.ptr(t))
+        self._B = B
+        self._keepalive = tensors
+        self._Z = nat.EnvNoise()
+        self._Z.seed = int(getattr(self.cfg, "seed", 0)) * 0x9E3779B97F4A7C15 % (1 << 64) + int(os.environ.get("RANK", "0"))
+        self._noise_step = 0
+        self._injected = {}
+        self._dev_index = torch.device(self.device).index
+
+    def inject_noise(self, **tensors):
+        """Parity hook: dense per-env draws (u_cmd_cb, u_cmd_rs, u_dof, u_push, z_obs, u_delay, z_act)
+        used instead of in-kernel Philox for the NEXT kernel call(s) of this step."""
+        self._injected = {k: v.to(self.device, torch.float32).contiguous() for k, v in tensors.items()}
+
+    def _launch_post_physics(self, phases):
+        Z = self._Z
+        inj = self._injected
+        for k in ("u_cmd_cb", "u_cmd_rs", "u_dof", "u_push", "z_obs"):
+            setattr(Z, k, nat.ptr(inj.get(k)))
+        Z.step = self._noise_step
+        self._noise_step += 1
+        nat.check(nat.lib.hg_env_post_physics(self._B, self._P, Z, phases, int(self.common_step_counter),
+                                              self.num_envs, nat.stream_ptr(self._dev_index)), "hg_env_post_physics")
+
+    # ------------------------------------------------------------------------------------------
+    # stepping
+    # ------------------------------------------------------------------------------------------
+    def step(self, actions):                                      # :84-109
+        """`actions` are already the clipped / delayed / noised actions in self.actions when called
+        from XBotLFreeEnv.step; a direct call clips and stores them first."""
+        if actions is not self.actions:
+            clip = self.cfg.normalization.clip_actions
+            self.actions.copy_(torch.clip(actions, -clip, clip))
+        g = self.gym
+        st = nat.stream_ptr(self._dev_index)
+        for _ in range(self.cfg.control.decimation):
+            nat.check(nat.lib.hg_env_compute_torques(self._B, self._P, self.num_envs, st), "hg_env_compute_torques")
+            g.set_dof_actuation_force_tensor(self.torques)
+            g.simulate()
+            g.refresh_dof_state_tensor()
+        self.post_physics_step()
+        return self.obs_buf, self.privileged_obs_buf, self.rew_buf, self.reset_buf, self.extras
+
+    def _compute_torques(self, actions):                          # :340-356
+        if actions is not self.actions:
+            self.actions.copy_(actions)
+        nat.check(nat.lib.hg_env_compute_torques(self._B, self._P, self.num_envs, nat.stream_ptr(self._dev_index)),
+                  "hg_env_compute_torques")
+        return self.torques
+
+    def post_physics_step(self):                                  # :119-154 + the clip of :104-108
+        g = self.gym
+        g.refresh_actor_root_state_tensor()
+        g.refresh_net_contact_force_tensor()
+        g.refresh_rigid_body_state_tensor()
+        self.common_step_counter += 1
+        self._launch_post_physics(nat.PHASE_STEP_ALL)
+        self._injected = {}
+        pushed = self.cfg.domain_rand.push_robots and (self.common_step_counter % self.cfg.domain_rand.push_interval == 0)
+        g.apply_env_writes(self.reset_ids, self._scratch, pushed)
+        self._publish_extras()
+
+    def _publish_extras(self):
+        if "episode" not in self.extras:
+            self.extras["episode"] = {"rew_" + n: self._episode_means[k] for k, n in enumerate(self.reward_names)}
+        if self.cfg.env.send_timeouts:
+            self.extras["time_outs"] = self.extras_time_outs
+
+    # the individual stages stay callable, each as the same kernel with a phase mask
+    def check_termination(self):                                  # :156-161
+        self._launch_post_physics(nat.PHASE_TERMINATE)
+
+    def compute_reward(self):                                     # :217-235
+        self._launch_post_physics(nat.PHASE_REWARD)
+
+    def compute_observations(self):
+        self._launch_post_physics(nat.PHASE_OBS)
+
+    def reset_idx(self, env_ids):                                 # :163-215
+        if len(env_ids) == 0:
+            return
+        previous = self.reset_buf.clone()
+        self.reset_buf.zero_()
+        self.reset_buf[env_ids] = True                            # the kernel resets the masked envs
+        self._launch_post_physics(nat.PHASE_RESET)
+        self.reset_buf |= previous                                # reference only sets [env_ids] = 1 (:196)
+        self._injected = {}
+        self._publish_extras()
+
+    @property
+    def last_reset_count(self):
+        """Number of envs reset by the most recent step (device->host read)."""
+        return int(self._scratch[3].item())

@@ -1,0 +1,243 @@
+"""The physics seam below the hot path ("Physics boundary").
+
+The reference talks to Isaac Gym through its tensor API: four state tensors
+(`actor_root_state (N,13)`, `dof_state (N*12,2)`, `net_contact_force (N*13,3)`,
+`rigid_body_state (N*13,13)`), `simulate`, `refresh_*`, `set_*` (reference
+legged_robot.py:96-101,124-126,371-373,395-397,438-457; humanoid_env.py:97-98).
+`PhysicsBackend` keeps exactly that surface so `LeggedRobot` reads like the reference:
+
+* `IsaacGymPhysics`   -- thin adapter, used when `isaacgym` is importable (not in this image).
+* `SyntheticPhysics`  -- seeded synthetic tensor source: a ring of
+  pre-generated frames, either resident in HBM or in pinned host memory (`host_resident=True`,
+  the end-to-end bench arm: every refresh is then a host->device copy inside the step).
+
+Nothing here is on the accelerated path; it is the producer of the tensors the fused env kernel
+consumes.
+"""
+import math
+
+import torch
+
+from humanoid.envs.custom import xbot_l_model as robot
+
+
+class PhysicsBackend:
+    """Isaac-Gym-tensor-API shaped interface."""
+    num_envs: int
+    device: torch.device
+    root_states: torch.Tensor      # (N, 13)
+    dof_state: torch.Tensor        # (N*num_dof, 2)
+    contact_forces: torch.Tensor   # (N*num_bodies, 3)
+    rigid_state: torch.Tensor      # (N*num_bodies, 13)
+
+    num_dof = robot.NUM_DOF
+    num_bodies = robot.NUM_BODIES
+    dof_names = robot.DOF_NAMES
+    body_names = robot.BODY_NAMES
+
+    def dof_properties(self):
+        return dict(lower=list(robot.DOF_LOWER), upper=list(robot.DOF_UPPER),
+                    velocity=list(robot.DOF_VELOCITY), effort=list(robot.DOF_EFFORT))
+
+    # -- stepping ---------------------------------------------------------------------------
+    def set_dof_actuation_force_tensor(self, torques):
+        pass
+
+    def simulate(self):
+        raise NotImplementedError
+
+    def fetch_results(self):
+        pass
+
+    def refresh_dof_state_tensor(self):
+        pass
+
+    def refresh_actor_root_state_tensor(self):
+        pass
+
+    def refresh_net_contact_force_tensor(self):
+        pass
+
+    def refresh_rigid_body_state_tensor(self):
+        pass
+
+    # -- state injection (resets / pushes) ----------------------------------------------------
+    def set_dof_state_tensor_indexed(self, dof_state, env_ids_int32, count):
+        pass
+
+    def set_actor_root_state_tensor(self, root_states):
+        pass
+
+    def set_actor_root_state_tensor_indexed(self, root_states, env_ids_int32, count):
+        pass
+
+    def apply_env_writes(self, reset_ids, scratch, pushed):
+        """Called once per env step after the fused kernel: `reset_ids[:scratch[3]]` are the envs
+        whose dof/root rows were rewritten, `pushed` tells whether root velocities were overwritten
+        for all envs.  Backends that own a real simulator forward this to set_*_indexed."""
+        pass
+
+
+class SyntheticPhysics(PhysicsBackend):
+    """Seeded synthetic stand-in for gym.simulate() + refresh_* (SURVEY.md section 8d).
+
+    K frames are generated once (outside any timed region).  `simulate()` only advances a counter;
+    `refresh_*` copy the current frame into the live state tensors, which is what PhysX does to its
+    GPU buffers from the env's point of view."""
+
+    def __init__(self, num_envs, device, cmd_ranges, env_origins=None, decimation=10, seed=5, ring=6,
+                 host_resident=False, p_base_contact=0.002):
+        self.num_envs, self.device = num_envs, torch.device(device)
+        self.decimation, self.ring = decimation, ring
+        self.host_resident = host_resident
+        N, nb, nd = num_envs, self.num_bodies, self.num_dof
+        dev = self.device
+        g = torch.Generator(device=dev)
+        g.manual_seed(seed)
+
+        def randn(*s):
+            return torch.randn(*s, generator=g, device=dev)
+
+        def rand(*s):
+            return torch.rand(*s, generator=g, device=dev)
+
+        origins = torch.zeros(N, 3, device=dev) if env_origins is None else env_origins.to(dev)
+        lo = torch.tensor(robot.DOF_LOWER, device=dev)
+        hi = torch.tensor(robot.DOF_UPPER, device=dev)
+        K = ring
+        root = torch.zeros(K, N, 13, device=dev)
+        dof = torch.zeros(K * decimation, N, nd, 2, device=dev)
+        contact = torch.zeros(K, N, nb, 3, device=dev)
+        rigid = torch.zeros(K, N, nb, 13, device=dev)
+        feet, knees = (6, 12), (4, 10)
+        for k in range(K):
+            r = root[k]
+            r[:, 0:2] = origins[:, 0:2] + (2 * rand(N, 2) - 1)
+            r[:, 2] = 0.95 + 0.02 * randn(N)
+            rpy = 0.1 * randn(N, 3)
+            rpy[:, 2] = (2 * rand(N) - 1) * math.pi
+            cr, sr = torch.cos(rpy[:, 0] / 2), torch.sin(rpy[:, 0] / 2)
+            cp, sp = torch.cos(rpy[:, 1] / 2), torch.sin(rpy[:, 1] / 2)
+            cy, sy = torch.cos(rpy[:, 2] / 2), torch.sin(rpy[:, 2] / 2)
+            r[:, 3] = sr * cp * cy - cr * sp * sy
+            r[:, 4] = cr * sp * cy + sr * cp * sy
+            r[:, 5] = cr * cp * sy - sr * sp * cy
+            r[:, 6] = cr * cp * cy + sr * sp * sy
+            cx = cmd_ranges["lin_vel_x"][0] + (cmd_ranges["lin_vel_x"][1] - cmd_ranges["lin_vel_x"][0]) * rand(N)
+            cyv = cmd_ranges["lin_vel_y"][0] + (cmd_ranges["lin_vel_y"][1] - cmd_ranges["lin_vel_y"][0]) * rand(N)
+            yaw = rpy[:, 2]
+            r[:, 7] = torch.cos(yaw) * cx - torch.sin(yaw) * cyv + 0.2 * randn(N)
+            r[:, 8] = torch.sin(yaw) * cx + torch.cos(yaw) * cyv + 0.2 * randn(N)
+            r[:, 9] = 0.2 * randn(N)
+            r[:, 10:13] = 0.3 * randn(N, 3)
+
+            clock = math.sin(2 * math.pi * (k + 0.25) / K)
+            stance = torch.tensor([clock >= 0, clock < 0], device=dev).repeat(N, 1)
+            in_contact = stance ^ (rand(N, 2) < 0.10)
+            c = contact[k]
+            for j, b in enumerate(feet):
+                c[:, b, 2] = (200 + 400 * rand(N)) * in_contact[:, j]
+                c[:, b, 0:2] = 20 * randn(N, 2) * in_contact[:, j:j + 1]
+            hit = rand(N) < p_base_contact
+            c[:, 0, :] = hit.unsqueeze(1) * (2.0 + 5 * rand(N, 3))
+
+            rg = rigid[k]
+            swing = (~in_contact).float()
+            for j, b in enumerate(feet):
+                side = 0.15 if j == 0 else -0.15
+                rg[:, b, 0] = r[:, 0] + 0.05 * randn(N)
+                rg[:, b, 1] = r[:, 1] + side + 0.03 * randn(N)
+                rg[:, b, 2] = 0.05 + 0.06 * swing[:, j] * abs(clock)
+                rg[:, b, 7:9] = 0.3 * randn(N, 2) * swing[:, j:j + 1]
+            for j, b in enumerate(knees):
+                side = 0.12 if j == 0 else -0.12
+                rg[:, b, 0] = r[:, 0] + 0.02 * randn(N)
+                rg[:, b, 1] = r[:, 1] + side + 0.02 * randn(N)
+                rg[:, b, 2] = 0.45
+        for s in range(K * decimation):
+            q = 0.2 * randn(N, nd)
+            dof[s, :, :, 0] = torch.max(torch.min(q, hi), lo)
+            dof[s, :, :, 1] = randn(N, nd)
+
+        def place(t):
+            return t.cpu().pin_memory() if host_resident else t
+
+        self._ring_root, self._ring_dof = place(root), place(dof.view(K * decimation, N * nd, 2))
+        self._ring_contact, self._ring_rigid = place(contact.view(K, N * nb, 3)), place(rigid.view(K, N * nb, 13))
+        # live tensors handed out through acquire_*
+        self.root_states = torch.zeros(N, 13, device=dev)
+        self.root_states[:, 6] = 1.0
+        self.root_states[:, 2] = 0.95
+        self.dof_state = torch.zeros(N * nd, 2, device=dev)
+        self.contact_forces = torch.zeros(N * nb, 3, device=dev)
+        self.rigid_state = torch.zeros(N * nb, 13, device=dev)
+        self.substep = 0
+        self.h2d_bytes = 0
+
+    # how many bytes one env step moves host->device when host_resident
+    def h2d_bytes_per_step(self):
+        if not self.host_resident:
+            return 0
+        per = self._ring_root[0].numel() + self._ring_contact[0].numel() + self._ring_rigid[0].numel()
+        return 4 * (per + self.decimation * self._ring_dof[0].numel())
+
+    def _frame(self):
+        return ((self.substep - 1) // self.decimation) % self.ring if self.substep > 0 else 0
+
+    def simulate(self):
+        self.substep += 1
+
+    def refresh_dof_state_tensor(self):
+        self.dof_state.copy_(self._ring_dof[(self.substep - 1) % (self.ring * self.decimation)], non_blocking=True)
+
+    def refresh_actor_root_state_tensor(self):
+        self.root_states.copy_(self._ring_root[self._frame()], non_blocking=True)
+
+    def refresh_net_contact_force_tensor(self):
+        self.contact_forces.copy_(self._ring_contact[self._frame()], non_blocking=True)
+
+    def refresh_rigid_body_state_tensor(self):
+        self.rigid_state.copy_(self._ring_rigid[self._frame()], non_blocking=True)
+
+
+class ExternalPhysics(PhysicsBackend):
+    """State tensors written by the caller (parity tests: frames come from golden vectors)."""
+
+    def __init__(self, num_envs, device):
+        self.num_envs, self.device = num_envs, torch.device(device)
+        N, nb, nd = num_envs, self.num_bodies, self.num_dof
+        self.root_states = torch.zeros(N, 13, device=device)
+        self.root_states[:, 6] = 1.0
+        self.dof_state = torch.zeros(N * nd, 2, device=device)
+        self.contact_forces = torch.zeros(N * nb, 3, device=device)
+        self.rigid_state = torch.zeros(N * nb, 13, device=device)
+        self.on_simulate = None
+
+    def simulate(self):
+        if self.on_simulate is not None:
+            self.on_simulate(self)
+
+
+def isaacgym_available():
+    try:
+        import isaacgym  # noqa: F401
+        return True
+    except Exception:
+        return False
+
+
+def make_physics(kind, num_envs, device, cfg, env_origins, seed=5, rank=0):
+    """kind: 'auto' | 'synthetic' | 'synthetic_host' | 'external' | 'isaacgym'."""
+    if kind == "auto":
+        kind = "isaacgym" if isaacgym_available() else "synthetic"
+    ranges = {k: getattr(cfg.commands.ranges, k) for k in ("lin_vel_x", "lin_vel_y")}
+    if kind in ("synthetic", "synthetic_host"):
+        return SyntheticPhysics(num_envs, device, ranges, env_origins, decimation=cfg.control.decimation,
+                                seed=seed + rank, host_resident=(kind == "synthetic_host"))
+    if kind == "external":
+        return ExternalPhysics(num_envs, device)
+    if kind == "isaacgym":
+        raise NotImplementedError(
+            "Isaac Gym Preview 4 ships no sm_100 build; the adapter seam is PhysicsBackend "
+            "(see INTEGRATION.md) -- select HG_PHYSICS=synthetic on this image")
+    raise ValueError(f"unknown physics backend {kind!r}")

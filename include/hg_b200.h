@@ -1,0 +1,289 @@
+/* hg_b200.h -- C ABI of libhg_b200.so: the B200 (sm_100a) kernels behind the
+ * humanoid-gym `humanoid_ppo` hot path.
+ *
+ * Conventions
+ *   - plain C: POD structs, raw device pointers, sizes; no C++/torch types.
+ *   - every buffer is allocated and owned by the caller (torch tensors in the
+ *     Python host layer); the library never allocates or frees user data.
+ *   - `stream` is a cudaStream_t passed as void* (0 = legacy default stream).
+ *   - return value: 0 ok, <0 argument error (see HG_E_*), >0 a cudaError_t.
+ *     hg_last_error() returns a thread-local message for the last failure.
+ *   - all floating point data is fp32, row-major, env-major (N, ...).
+ *
+ * Each entry cites the reference function it replaces; paths are relative to
+ * roboterax/humanoid-gym `humanoid/`.
+ */
+#ifndef HG_B200_H
+#define HG_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HG_VERSION 100
+#define HG_NUM_DOF 12
+#define HG_NUM_REWARDS 22
+#define HG_OBS1 47          /* single-frame observation width   */
+#define HG_PRIV1 73         /* single-frame privileged obs width */
+#define HG_OBS_FRAMES 15
+#define HG_PRIV_FRAMES 3
+#define HG_MAX_CONTACT_BODIES 4
+#define HG_MAX_LAYERS 8
+
+#define HG_E_NULL (-1)      /* required pointer is NULL           */
+#define HG_E_ALIGN (-2)     /* pointer not 16-byte aligned        */
+#define HG_E_SIZE (-3)      /* N <= 0 or inconsistent dimensions  */
+#define HG_E_ARG (-4)       /* other invalid argument             */
+#define HG_E_STATE (-5)     /* call sequence error                */
+
+/* ------------------------------------------------------------------------ */
+/* Environment side                                                         */
+/* ------------------------------------------------------------------------ */
+
+/* Constants of XBotLCfg as LeggedRobot._parse_cfg / _init_buffers derive them
+ * (envs/base/legged_robot.py:434-541,710-720; envs/custom/humanoid_config.py). */
+typedef struct HgEnvParams {
+    float dt;                          /* float32(decimation * sim_params.dt)          */
+    float cycle_time;
+    float clip_actions, clip_obs, action_scale;
+    float action_delay, action_noise;
+    /* uniform ranges as (lo, span): torch_rand_float(lo,hi) = (hi-lo)*u + lo with the
+     * span (hi-lo) formed in DOUBLE by the host, then rounded to fp32, as Python does  */
+    float cmd_x_lo, cmd_x_span, cmd_y_lo, cmd_y_span, cmd_heading_lo, cmd_heading_span;
+    float push_vel_lo, push_vel_span, push_ang_lo, push_ang_span;
+    float dof_reset_lo, dof_reset_span;   /* q = q0 + U(-0.1, 0.1) on reset             */
+    float target_joint_pos_scale, target_feet_height, base_height_target;
+    float min_dist, max_dist, max_contact_force, tracking_sigma;
+    float obs_scale_lin_vel, obs_scale_ang_vel, obs_scale_dof_pos, obs_scale_dof_vel, obs_scale_quat;
+    float noise_level;
+    float max_episode_length_s;
+    int32_t add_noise, only_positive_rewards, heading_command, push_robots;
+    int32_t resample_period;           /* int(resampling_time / dt) = 799              */
+    int32_t push_interval;             /* ceil(push_interval_s / dt) = 400             */
+    int64_t max_episode_length;        /* ceil(episode_length_s / dt) = 2400           */
+    int32_t num_bodies;                /* 13 after fixed-joint collapse                */
+    int32_t feet[2], knees[2];
+    int32_t n_term, term_bodies[HG_MAX_CONTACT_BODIES];
+    int32_t n_pen, pen_bodies[HG_MAX_CONTACT_BODIES];
+    float reward_scales[HG_NUM_REWARDS];   /* scale*dt, alphabetical term order        */
+    float p_gains[HG_NUM_DOF], d_gains[HG_NUM_DOF], torque_limits[HG_NUM_DOF];
+    float default_dof_pos[HG_NUM_DOF];
+    float noise_scale_vec[HG_OBS1];
+    float base_init_state[13];
+} HgEnvParams;
+
+/* Live state tensors of LeggedRobot / XBotLFreeEnv. */
+typedef struct HgEnvBuffers {
+    /* physics tensors (Isaac Gym tensor-API layout) */
+    float* root_states;        /* (N,13) pos3 quat_xyzw4 linvel3 angvel3           */
+    float* dof_state;          /* (N,12,2) interleaved (pos, vel)                  */
+    const float* contact_forces;   /* (N,num_bodies,3)                             */
+    const float* rigid_state;      /* (N,num_bodies,13)                            */
+    /* env state */
+    float* actions;            /* (N,12) */
+    float* last_actions;       /* (N,12) */
+    float* last_last_actions;  /* (N,12) */
+    float* torques;            /* (N,12) */
+    float* last_dof_vel;       /* (N,12) */
+    float* last_root_vel;      /* (N,6)  */
+    float* commands;           /* (N,4)  */
+    int64_t* episode_length_buf;   /* (N) */
+    uint8_t* reset_buf;        /* (N) bool */
+    uint8_t* time_out_buf;     /* (N) bool */
+    uint8_t* extras_time_outs; /* (N) bool, refreshed only on steps with >=1 reset */
+    float* base_lin_vel;       /* (N,3) */
+    float* base_ang_vel;       /* (N,3) */
+    float* projected_gravity;  /* (N,3) */
+    float* base_euler_xyz;     /* (N,3) */
+    float* feet_air_time;      /* (N,2) */
+    uint8_t* last_contacts;    /* (N,2) bool */
+    float* feet_height;        /* (N,2) */
+    float* last_feet_z;        /* (N,2) */
+    float* ref_dof_pos;        /* (N,12) */
+    float* rand_push_force;    /* (N,3) */
+    float* rand_push_torque;   /* (N,3) */
+    const float* env_frictions;    /* (N,1) */
+    const float* body_mass;        /* (N,1) */
+    const float* env_origins;      /* (N,3) */
+    float* episode_sums;       /* (22,N) one row per reward term, alphabetical     */
+    float* episode_means;      /* (22)   extras["episode"]["rew_*"]                */
+    float* rew_terms;          /* (22,N) optional (may be NULL): per-term scaled reward of this step */
+    float* obs_buf;            /* (N,705) 15 frames oldest->newest, clipped        */
+    float* privileged_obs_buf; /* (N,219) 3 frames                                 */
+    float* rew_buf;            /* (N)                                              */
+    int32_t* reset_ids;        /* (N) compacted ids of envs reset this step (any order) */
+    int32_t* scratch;          /* (32) int32, zero-initialised once by the caller:
+                                  [0] running reset count, [1] CTA ticket, [3] reset
+                                  count of the last step, [4..5] int64 common_step_counter,
+                                  [6..7] uint64 noise step, [8..29] float accumulators  */
+} HgEnvBuffers;
+
+/* Injected random draws (parity mode).  Any pointer may be NULL: the kernel
+ * then draws the numbers itself from Philox4x32-10 keyed by (seed, step, env). */
+typedef struct HgEnvNoise {
+    const float* u_cmd_cb;     /* (N,3) U[0,1): command resample in the step callback */
+    const float* u_cmd_rs;     /* (N,3) U[0,1): command resample on reset             */
+    const float* u_dof;        /* (N,12) U[0,1): joint positions on reset             */
+    const float* u_push;       /* (N,5) U[0,1): push lin-vel xy, ang-vel xyz          */
+    const float* z_obs;        /* (N,47) N(0,1): observation noise                    */
+    uint64_t seed;
+    uint64_t step;             /* distinct per call                                   */
+    int32_t use_device_counters;   /* 1: `step` and `common_step_counter` are taken from
+                                      scratch[6..7] / scratch[4..5] (int64 each) and bumped
+                                      by the kernel -> the launch is CUDA-graph replayable */
+    int32_t _pad;
+} HgEnvNoise;
+
+/* phases of hg_env_post_physics (bit mask) */
+#define HG_PHASE_COUNTERS  0x01u  /* episode_length++ ; base-frame quantities (legged_robot.py:128-136) */
+#define HG_PHASE_CALLBACK  0x02u  /* command resample, heading command, push  (:304-320, humanoid_env.py:83-98) */
+#define HG_PHASE_TERMINATE 0x04u  /* check_termination (:156-161)                                         */
+#define HG_PHASE_REWARD    0x08u  /* compute_reward + 22 terms (:217-235, humanoid_env.py:272-540)        */
+#define HG_PHASE_RESET     0x10u  /* reset_idx for envs with reset_buf set (:163-215, humanoid_env.py:264-269) */
+#define HG_PHASE_OBS       0x20u  /* compute_observations (humanoid_env.py:200-262)                       */
+#define HG_PHASE_LAST      0x40u  /* last_* copies (:147-151) and the +-18 clip (:104-108)                */
+#define HG_PHASE_STEP_ALL  0x7Fu
+
+/* XBotLFreeEnv.step prologue (humanoid_env.py:189-197) + LeggedRobot.step clip
+ * (legged_robot.py:90-91): clip, delay-mix with the previous actions,
+ * multiplicative noise, clip.  Writes B->actions.
+ * u_delay (N,1) U[0,1) and z_act (N,12) N(0,1) may be NULL (Philox).
+ * step == UINT64_MAX: take the noise step from scratch[6..7] (device counter). */
+int32_t hg_env_pre_physics(const HgEnvBuffers* B, const HgEnvParams* P, const float* actions_in,
+                           const float* u_delay, const float* z_act, uint64_t seed, uint64_t step,
+                           int64_t N, void* stream);
+
+/* LeggedRobot._compute_torques (legged_robot.py:340-356); called once per
+ * decimation sub-step.  Reads B->actions, B->dof_state; writes B->torques. */
+int32_t hg_env_compute_torques(const HgEnvBuffers* B, const HgEnvParams* P, int64_t N, void* stream);
+
+/* LeggedRobot.post_physics_step (legged_robot.py:119-154) with everything it
+ * calls, fused into one launch; `phases` selects sub-sequences so that
+ * reset_idx() / compute_observations() stay callable on their own.
+ * `common_step_counter` is the value AFTER this step's increment. */
+int32_t hg_env_post_physics(const HgEnvBuffers* B, const HgEnvParams* P, const HgEnvNoise* Z,
+                            uint32_t phases, int64_t common_step_counter, int64_t N, void* stream);
+
+/* ------------------------------------------------------------------------ */
+/* Learning side                                                            */
+/* ------------------------------------------------------------------------ */
+
+/* One ELU-MLP (nn.Sequential(Linear, ELU, ..., Linear), algo/ppo/actor_critic.py:54-77).
+ * Parameters live in ONE flat fp32 buffer shared by actor, critic and std so
+ * that gradient all-reduce / Adam touch a single range. */
+typedef struct HgMlpDesc {
+    int32_t n_layers;                   /* number of Linear layers                   */
+    int32_t dims[HG_MAX_LAYERS + 1];    /* in, hidden..., out                        */
+    int64_t w_off[HG_MAX_LAYERS];       /* element offset of weight l (out,in) row-major in the flat buffer */
+    int64_t b_off[HG_MAX_LAYERS];       /* element offset of bias l                  */
+} HgMlpDesc;
+
+/* Y = MLP(X).  `hidden`: caller scratch receiving every hidden layer's post-ELU
+ * output, (M, sum(dims[1..n-1])) laid out layer after layer [layer l at element
+ * offset M*sum(dims[1..l-1])] (kept for the backward pass); `out` (M, dims[n])
+ * receives the network output and may point straight into a rollout-storage slab.
+ * Replaces nn.Sequential.forward as used by ActorCritic.act / evaluate
+ * (actor_critic.py:111-128). */
+int32_t hg_mlp_forward(const HgMlpDesc* net, const float* params, const float* X, int64_t ldx,
+                       float* hidden, float* out, int64_t M, void* stream);
+
+/* Backward of the same MLP.  dY (M, dims[n]) is the loss gradient w.r.t. the
+ * network output; grads (same flat layout as params) receives dW, db
+ * (overwritten, not accumulated).  dhidden: scratch of the same size as hidden.
+ * Replaces autograd through nn.Sequential in PPO.update (ppo.py:170-173). */
+int32_t hg_mlp_backward(const HgMlpDesc* net, const float* params, const float* X, int64_t ldx,
+                        const float* hidden, const float* dY, float* dhidden, float* grads,
+                        int64_t M, void* stream);
+
+/* PPO.act epilogue (ppo.py:91-101, actor_critic.py:111-120): actions =
+ * mean + std*eps, log-prob summed over actions, sigma broadcast.
+ * eps (M,A) may be NULL (Philox with seed/step). */
+int32_t hg_policy_sample(const float* mean, const float* std, const float* eps, uint64_t seed, uint64_t step,
+                         float* actions, float* log_prob, float* sigma_out, int64_t M, int32_t A, void* stream);
+
+/* RolloutStorage.add_transitions (rollout_storage.py:87-100) fused with the
+ * time-out bootstrap of PPO.process_env_step (ppo.py:107-108): copies one
+ * step's tensors into slab `t` of the (T,N,.) storage in a single launch.
+ * Any HgTransition pointer may be NULL or already equal to its slab (the
+ * producer wrote in place): that tensor is skipped. */
+typedef struct HgTransition {
+    const float* obs; const float* priv_obs; const float* actions; const float* rewards;
+    const uint8_t* dones; const uint8_t* time_outs; const float* values; const float* log_prob;
+    const float* mu; const float* sigma;
+} HgTransition;
+typedef struct HgStorage {
+    float* observations; float* privileged_observations; float* actions; float* rewards;
+    uint8_t* dones; float* values; float* actions_log_prob; float* mu; float* sigma;
+    float* returns; float* advantages;
+    int32_t T, num_obs, num_priv, num_actions;
+} HgStorage;
+int32_t hg_storage_add(const HgStorage* S, const HgTransition* tr, int32_t t, float gamma, int64_t N, void* stream);
+
+/* RolloutStorage.compute_returns (rollout_storage.py:122-136): reverse GAE
+ * scan over T for each env + global advantage normalisation (unbiased std).
+ * stats: (4) fp32+fp64-free scratch [sum, sumsq, count, pad] -- if
+ * `normalise`==0 only the raw sums are produced (multi-GPU: all-reduce them,
+ * then call hg_adv_normalise). */
+int32_t hg_gae(const HgStorage* S, const float* last_values, float gamma, float lam, double* stats,
+               int32_t normalise, int64_t N, void* stream);
+int32_t hg_adv_normalise(const HgStorage* S, const double* stats, int64_t N, void* stream);
+
+/* mini_batch_generator gather (rollout_storage.py:146-182): rows idx[0..B) of
+ * the flattened (T*N,.) storage into contiguous minibatch tensors, one launch. */
+typedef struct HgMiniBatch {
+    float* obs; float* priv_obs; float* actions; float* values; float* advantages; float* returns;
+    float* old_log_prob; float* old_mu; float* old_sigma;
+} HgMiniBatch;
+int32_t hg_minibatch_gather(const HgStorage* S, const int64_t* idx, const HgMiniBatch* mb, int64_t B, void* stream);
+
+/* PPO.update loss (ppo.py:133-168) forward + analytic backward in one kernel:
+ * log-prob, ratio, clipped surrogate, clipped value loss, entropy, KL.
+ * Outputs d loss/d mean (B,A), d loss/d value (B,1), d loss/d std (A) and
+ * `scalars` (8 fp32, zeroed by the call): [0] surrogate loss, [1] value loss,
+ * [2] entropy, [3] KL mean.  Means use `inv_B` = 1/B_global so that partial
+ * results of env-sharded ranks SUM to the single-process value. */
+typedef struct HgPpoLossArgs {
+    const float* mean; const float* value; const float* std;
+    const float* actions; const float* target_values; const float* advantages; const float* returns;
+    const float* old_log_prob; const float* old_mu; const float* old_sigma;
+    float* d_mean; float* d_value; float* grad_std; float* scalars;
+    float clip_param, value_loss_coef, entropy_coef;
+    int32_t use_clipped_value_loss;
+    int32_t num_actions;
+    float inv_B;
+} HgPpoLossArgs;
+int32_t hg_ppo_loss_fwd_bwd(const HgPpoLossArgs* a, int64_t B, void* stream);
+
+/* clip_grad_norm_ + Adam (ppo.py:172-173; torch.optim.Adam defaults) over the
+ * flat parameter buffer: a squared-norm reduction, then the fused clip+Adam
+ * update.  The learning rate (double) and the Adam step count live in DEVICE
+ * memory so that the adaptive-KL schedule needs no host sync; the update
+ * kernel increments step_dev[0] and re-zeroes sqnorm[0] for the next step.
+ * Effective gradient = grads * grad_scale (1.0 unless the caller all-reduced
+ * un-normalised partial gradients). */
+int32_t hg_grad_sqnorm(const float* grads, int64_t n, double* sqnorm_out, void* stream);
+int32_t hg_clip_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq,
+                          double* sqnorm, float max_grad_norm, const double* lr_dev, int32_t* step_dev,
+                          float beta1, float beta2, float eps, float grad_scale, int64_t n, void* stream);
+
+/* Adaptive-KL learning-rate rule (ppo.py:142-148) evaluated on the device:
+ * reads kl_mean_dev[0] (fp32 KL mean of the minibatch), updates lr_dev[0]. */
+int32_t hg_adapt_lr(const float* kl_mean_dev, double desired_kl, double* lr_dev, void* stream);
+
+/* ------------------------------------------------------------------------ */
+/* misc                                                                     */
+/* ------------------------------------------------------------------------ */
+int32_t hg_version(void);
+/* sizeof() of the ABI structs, for binding self-checks: 0 HgEnvParams, 1 HgEnvBuffers,
+ * 2 HgEnvNoise, 3 HgMlpDesc, 4 HgTransition, 5 HgStorage, 6 HgMiniBatch, 7 HgPpoLossArgs */
+int64_t hg_struct_size(int32_t which);
+const char* hg_last_error(void);
+/* number of kernel launches issued by this library in the calling process */
+int64_t hg_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HG_B200_H */

@@ -1,0 +1,198 @@
+"""GPU parity of the fused env kernels (through the C ABI, via the drop-in XBotLFreeEnv) against
+  (1) golden vectors produced by the unmodified reference, step by step, and
+  (2) the CPU oracle on seeded random states at N=4096,
+plus size-independent properties at the benchmark sizes.  Tolerance: 1e-5 relative (north_star), with an
+absolute floor of 1e-6 and a small outlier allowance ONLY for quantities that sit behind a threshold."""
+import numpy as np
+import pytest
+import torch
+
+from golden_io import Golden, oracle_state_from_golden
+from parity_utils import (make_env, random_state, random_noise, load_state, oracle_step, compare_step, env_value)
+
+pytestmark = pytest.mark.gpu
+RTOL, ATOL = 1e-5, 1e-6
+
+
+def _golden_state_after(g, S, t):
+    """Oracle-layout state == what the reference held after step t (teacher forcing for step t+1)."""
+    post = g.group(f"step{t:03d}.post.")
+    for k, v in post.items():
+        if k in S and k not in ("obs_buf", "privileged_obs_buf"):
+            S[k] = v.clone()
+    S["common_step_counter"] = int(g["init.common_step_counter"]) + t + 1
+    return S
+
+
+def test_golden_rollout_step_by_step():
+    g = Golden("env_rollout.npz")
+    n, steps = int(g["meta.n_envs"]), int(g["meta.n_steps"])
+    env = make_env(n, physics="external")
+    # derived constants must equal the reference's
+    assert env.dt == float(g["meta.dt"])
+    assert env._P.resample_period == int(g["meta.resample_period"]) == 799
+    assert env._P.max_episode_length == 2400 and env._P.push_interval == 400
+    assert env.reward_names == list(g["meta.reward_names"])
+    np.testing.assert_allclose(np.array(env._P.reward_scales[:]), g["meta.reward_scales"].astype(np.float32), rtol=0, atol=0)
+    assert env.feet_indices.tolist() == g["meta.feet_indices"].tolist()
+    assert env.knee_indices.tolist() == g["meta.knee_indices"].tolist()
+    np.testing.assert_array_equal(env.torque_limits.cpu().numpy(), g["meta.torque_limits"])
+    np.testing.assert_array_equal(env.p_gains[0].cpu().numpy(), g["meta.p_gains"])
+    np.testing.assert_array_equal(env.noise_scale_vec.cpu().numpy(), g["meta.noise_scale_vec"])
+    np.testing.assert_array_equal(env.env_origins.cpu().numpy(), g["init.env_origins"])
+
+    S = oracle_state_from_golden(g)
+    hist_o, hist_p = S["obs_hist"].clone(), S["critic_hist"].clone()
+    problems = []
+    for t in range(steps):
+        p = f"step{t:03d}."
+        noise = g.group(p + "noise.")
+        # teacher forcing: state := reference state before this step; histories are chained from our own output
+        S["obs_hist"], S["critic_hist"] = hist_o, hist_p
+        load_state(env, S)
+        frames = {k: g.t(p + "pre." + k) for k in ("root_states", "contact_forces", "rigid_state")}
+        dof_seq = [(g.t(p + "torque_in.dof_pos"), g.t(p + "torque_in.dof_vel")), (g.t(p + "pre.dof_pos"), g.t(p + "pre.dof_vel"))]
+        calls = {"n": 0}
+
+        def on_simulate(ph, frames=frames, dof_seq=dof_seq, calls=calls):
+            calls["n"] += 1
+            if calls["n"] == 9:      # state the LAST torque computation sees (sub-step 10 reads it)
+                ds = ph.dof_state.view(n, 12, 2)
+                ds[..., 0], ds[..., 1] = dof_seq[0][0].cuda(), dof_seq[0][1].cuda()
+            if calls["n"] == 10:     # state after the last sub-step == what post_physics_step reads
+                ds = ph.dof_state.view(n, 12, 2)
+                ds[..., 0], ds[..., 1] = dof_seq[1][0].cuda(), dof_seq[1][1].cuda()
+                ph.root_states.copy_(frames["root_states"].cuda())
+                ph.contact_forces.copy_(frames["contact_forces"].reshape(-1, 3).cuda())
+                ph.rigid_state.copy_(frames["rigid_state"].reshape(-1, 13).cuda())
+        env.gym.on_simulate = on_simulate
+        env.inject_noise(**noise)
+        obs, priv, rew, reset, extras = env.step(g.t(p + "actions_in").cuda())
+        torch.cuda.synchronize()
+        ref = {k: v for k, v in g.group(p + "post.").items()}
+        keys = [k for k in ref if k not in ("obs_frame", "priv_frame", "obs_buf", "privileged_obs_buf")]
+        ref["torques"] = g.t(p + "pre.torques")
+        bad = compare_step(env, ref, RTOL, ATOL, max_outlier_frac=0.0, keys=keys + ["torques"])
+        for name, got, want in (("obs_frame", obs[:, -47:], ref["obs_frame"]), ("priv_frame", priv[:, -73:], ref["priv_frame"])):
+            if not torch.allclose(got.cpu(), want, rtol=RTOL, atol=ATOL):
+                bad.append(f"{name}: max abs err {(got.cpu() - want).abs().max().item():.3g}")
+        if "obs_buf" in ref:
+            if not torch.allclose(obs.cpu(), ref["obs_buf"], rtol=RTOL, atol=ATOL):
+                bad.append("obs_buf (full 15-frame history)")
+            if not torch.allclose(priv.cpu(), ref["privileged_obs_buf"], rtol=RTOL, atol=ATOL):
+                bad.append("privileged_obs_buf (full 3-frame history)")
+        assert extras["time_outs"].dtype == torch.bool and reset.dtype == torch.bool
+        if bad:
+            problems.append((t, bad))
+        hist_o = obs.detach().cpu().view(n, 15, 47).clone()
+        hist_p = priv.detach().cpu().view(n, 3, 73).clone()
+        S = _golden_state_after(g, S, t)
+    assert not problems, problems[:3]
+
+
+@pytest.mark.parametrize("N,seed", [(4096, 1), (1000, 2), (7, 3)])
+def test_random_state_vs_oracle(N, seed):
+    """All phases, with pushes (counter 399 -> 400), time-outs, resampling, resets; ragged N included."""
+    g = torch.Generator().manual_seed(seed)
+    env = make_env(N, physics="external")
+    S, noise = random_state(N, g), random_noise(N, g)
+    actions = 3.0 * torch.randn(N, 12, generator=g)
+    actions[::9] *= 10
+    load_state(env, S)
+    env.inject_noise(**noise)
+    env.step(actions.cuda())
+    torch.cuda.synchronize()
+    ref = oracle_step(S, noise, actions)
+    assert int(ref["reset_buf"].sum()) > 0 or N < 64
+    bad = compare_step(env, ref, RTOL, ATOL, max_outlier_frac=2e-3)
+    assert not bad, bad
+    # reset_ids: the compacted list holds exactly the reset envs
+    cnt = env.last_reset_count
+    assert cnt == int(ref["reset_buf"].sum())
+    assert sorted(env.reset_ids[:cnt].tolist()) == ref["reset_buf"].nonzero().flatten().tolist()
+
+
+def test_stage_entry_points_match_oracle():
+    """reset_idx / compute_observations stay callable on their own (phase masks)."""
+    from oracle import env_oracle as eo
+    N = 256
+    g = torch.Generator().manual_seed(11)
+    env = make_env(N, physics="external")
+    S, noise = random_state(N, g), random_noise(N, g)
+    load_state(env, S)
+    ids = torch.arange(0, N, 3)
+    env.inject_noise(**noise)
+    env.reset_idx(ids.cuda())
+    P = eo.make_params()
+    R = {k: (v.clone() if isinstance(v, torch.Tensor) else v) for k, v in S.items()}
+    eo.reset_idx(R, P, ids, noise)
+    R["obs_buf"], R["privileged_obs_buf"] = R["obs_hist"].reshape(N, -1), R["critic_hist"].reshape(N, -1)
+    keys = ("root_states", "dof_pos", "dof_vel", "commands", "actions", "last_actions", "last_last_actions", "last_dof_vel",
+            "feet_air_time", "episode_length_buf", "episode_sums", "episode_means", "projected_gravity", "base_euler_xyz",
+            "obs_buf", "privileged_obs_buf")
+    bad = compare_step(env, R, RTOL, ATOL, keys=keys)
+    assert not bad, bad
+    env.inject_noise(z_obs=noise["z_obs"])
+    env.compute_observations()
+    eo.compute_observations(R, P, noise["z_obs"])
+    bad = compare_step(env, R, RTOL, ATOL, max_outlier_frac=2e-3, keys=("obs_buf", "privileged_obs_buf", "ref_dof_pos"))
+    assert not bad, bad
+
+
+@pytest.mark.parametrize("N", [4096, 65536])
+def test_properties_at_benchmark_sizes(N):
+    """Size-independent invariants with in-kernel Philox noise on the synthetic physics source."""
+    env = make_env(N, physics="synthetic")
+    env.episode_length_buf = torch.randint(0, 2400, (N,), device="cuda")
+    torch.manual_seed(0)
+    prev_obs = env.obs_buf.clone()
+    prev_priv = env.privileged_obs_buf.clone()
+    prev_ep = env.episode_length_buf.clone()
+    total_resets = 0
+    for it in range(6):
+        obs, priv, rew, reset, extras = env.step(torch.randn(N, 12, device="cuda"))
+        keep = ~reset
+        # history shift: frames 1..14 of the previous obs are frames 0..13 now (untouched envs)
+        assert torch.equal(obs[keep, :658], prev_obs[keep, 47:])
+        assert torch.equal(priv[keep, :146], prev_priv[keep, 73:])
+        # reset envs: history zeroed, episode restarted
+        assert (obs[reset, :658] == 0).all() and (priv[reset, :146] == 0).all()
+        assert (env.episode_length_buf[reset] == 0).all()
+        assert torch.equal(env.episode_length_buf[keep], prev_ep[keep] + 1)
+        assert obs.abs().max() <= 18 and priv.abs().max() <= 18
+        assert (rew >= 0).all() and torch.isfinite(rew).all() and torch.isfinite(obs).all() and torch.isfinite(priv).all()
+        # gait clock features are a unit vector
+        assert torch.allclose(obs[:, -47] ** 2 + obs[:, -46] ** 2, torch.ones(N, device="cuda"), atol=1e-5)
+        assert env.last_reset_count == int(reset.sum())
+        total_resets += int(reset.sum())
+        prev_obs, prev_priv, prev_ep = obs.clone(), priv.clone(), env.episode_length_buf.clone()
+    assert total_resets > 0
+    # Philox observation noise: per-channel std of (obs - noiseless obs) must be noise_scale_vec * 0.6
+    env2 = make_env(N, physics="external")
+    S = {k: v for k, v in random_state(N, torch.Generator().manual_seed(5)).items()}
+    load_state(env2, S)
+    env2.compute_observations()
+    noisy = env2.obs_buf[:, -47:].clone()
+    env2.cfg.noise.add_noise = False
+    env2._P = env2._native_params()
+    load_state(env2, S)
+    env2.compute_observations()
+    clean = env2.obs_buf[:, -47:]
+    d = (noisy - clean)
+    want = env2.noise_scale_vec * 0.6
+    assert torch.allclose(d.std(dim=0), want, rtol=0.03, atol=1e-6)
+    assert d.mean(dim=0).abs().max() < 4 * float(want.max()) / np.sqrt(N)
+
+
+def test_argument_errors_are_reported_not_fatal():
+    from humanoid import _native as nat
+    env = make_env(8, physics="external")
+    with pytest.raises(nat.NativeError):
+        nat.check(nat.lib.hg_env_post_physics(env._B, env._P, env._Z, 0, 1, 8, 0), "phase mask 0")
+    with pytest.raises(nat.NativeError):
+        nat.check(nat.lib.hg_env_post_physics(env._B, env._P, env._Z, nat.PHASE_STEP_ALL, 1, 0, 0), "N=0")
+    B = nat.EnvBuffers.from_buffer_copy(env._B)
+    B.obs_buf = None
+    with pytest.raises(nat.NativeError, match="NULL"):
+        nat.check(nat.lib.hg_env_post_physics(B, env._P, env._Z, nat.PHASE_STEP_ALL, 1, 8, 0), "null obs_buf")
+    env.step(torch.zeros(8, 12, device="cuda"))    # still usable afterwards
