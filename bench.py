@@ -1,0 +1,342 @@
+#!/usr/bin/env python
+"""bench.py -- env-steps/sec of the humanoid_ppo hot path (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W             # this repo's sm_100a path
+    python bench.py --impl reference --gpus N --steps K ...    # the reference's PyTorch path on the host cores
+
+A "step" is one learning iteration of `scripts/train.py --task=humanoid_ppo`: T=60 env steps of
+num_envs=4096 envs per GPU (act -> env.step -> process_env_step), compute_returns, and PPO.update
+(2 epochs x 4 minibatches), i.e. 245,760 env-steps per GPU.  metric = N*T*K*world / time, exactly
+on_policy_runner.py:199-203 aggregated over ranks.  Physics is the seeded synthetic tensor source of
+SURVEY.md section 8d (neither Isaac Gym nor MuJoCo exists in this image); its frames are pre-generated
+outside the timed region.
+
+Printed JSON (rank 0, one line): see README / DESIGN.md section 6.  `value` is timed with CUDA events around
+exactly K steps with inputs resident in HBM; `e2e` is the same loop driven through the public
+task_registry/OnPolicyRunner API with the physics frames in PINNED HOST memory (host->device copy of every
+frame inside the timed region) and a device->host read of the iteration's losses and mean reward.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "humanoid-gym_b200")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import torch  # noqa: E402
+import torch.distributed as dist  # noqa: E402
+
+T_STEPS = 60
+ENV_BYTES_PER_STEP = 7985            # algorithmic bytes of the fused post-physics kernel / env-step
+FLOPS_FWD = 1052672 + 795392         # per sample, actor + critic forward
+FLOPS_BWD = 1383424 + 1254400        # per sample, actor + critic backward
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        d = json.load(open(path))
+        return dict(hbm=d["hbm_gbs"], bf16=d["bf16_tflops"], bf16_sustained=d.get("bf16_tflops_sustained", d["bf16_tflops"]),
+                    src="measured (MEASURED_PEAKS.json)")
+    return dict(hbm=6650.0, bf16=1590.0, bf16_sustained=1400.0, src="fallback (B200_PROFILING.md)")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region."""
+
+    def __init__(self, index=0):
+        self.samples, self.reasons, self._stop, self.index = [], set(), threading.Event(), index
+        self.max_mhz = None
+
+    def _run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                                     capture_output=True, text=True, timeout=5).stdout.strip().split(",")
+                self.samples.append(float(out[0]))
+                self.max_mhz = float(out[1])
+                for n, v in zip(names, out[2:]):
+                    if v.strip().lower().startswith("active"):
+                        self.reasons.add(n)
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def __enter__(self):
+        self.th = threading.Thread(target=self._run, daemon=True)
+        self.th.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        self.th.join(timeout=3)
+
+    def summary(self):
+        s = sorted(self.samples)
+        return dict(sm_mhz=s[len(s) // 2] if s else None, sm_max_mhz=self.max_mhz, reasons=sorted(self.reasons), samples=len(s))
+
+
+# ----------------------------------------------------------------------------------------------
+# product arm
+# ----------------------------------------------------------------------------------------------
+def _make_runner(num_envs, device, physics, seed=5):
+    os.environ["HG_PHYSICS"] = physics
+    os.environ.setdefault("WANDB_MODE", "disabled")
+    from humanoid.envs import XBotLCfg  # noqa: F401  (registers humanoid_ppo)
+    from humanoid.utils import task_registry
+    from humanoid.utils.helpers import get_args
+    args = get_args(["--task=humanoid_ppo", "--headless", f"--num_envs={num_envs}", f"--sim_device={device}",
+                     f"--rl_device={device}", f"--seed={seed}"])
+    env, _ = task_registry.make_env("humanoid_ppo", args=args)
+    runner, _ = task_registry.make_alg_runner(env, name="humanoid_ppo", args=args, log_root=None)
+    env.episode_length_buf = torch.randint_like(env.episode_length_buf, high=int(env.max_episode_length))
+    return env, runner
+
+
+def _iterate(runner, state):
+    obs, cobs = state
+    with torch.inference_mode():
+        obs, cobs = runner.rollout(obs, cobs)
+        vl, sl = runner.alg.update()
+    return (obs, cobs), (vl, sl)
+
+
+def _time_iterations(runner, state, steps, device, world, e2e=False):
+    """CUDA-event time of exactly `steps` iterations, barrier + synchronize on both sides, max over ranks."""
+    from humanoid import _native as nat
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize(device)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    n0 = nat.launch_count()
+    w0 = time.time()
+    ev0.record()
+    results = []
+    for _ in range(steps):
+        state, losses = _iterate(runner, state)
+        if e2e:   # device->host read of the step's result
+            results.append((losses, float(runner.env.rew_buf.mean().item())))
+    ev1.record()
+    torch.cuda.synchronize(device)
+    if world > 1:
+        dist.barrier()
+    ms = ev0.elapsed_time(ev1)
+    wall = (time.time() - w0) * 1e3
+    launches = nat.launch_count() - n0
+    t = torch.tensor([ms], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item()), wall, launches, state
+
+
+def _kernel_rooflines(runner, device, pk):
+    """Live CUDA-event timing of the two kernels that bound the path: the MLP GEMM chain of one PPO
+    minibatch (tensor roofline) and the fused post-physics env kernel (HBM roofline)."""
+    from humanoid import _native as nat
+    env, alg = runner.env, runner.alg
+    N = env.num_envs
+    out = {}
+    # -- fused env kernel: time K back-to-back launches on the launching stream -------------------------
+    st = torch.cuda.current_stream(device)
+    reps = 20
+    for _ in range(3):
+        env._launch_post_physics(nat.PHASE_STEP_ALL)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    flush = torch.empty(192 * 1024 * 1024 // 4, device=device)     # > 126 MB L2
+    tot = 0.0
+    for _ in range(reps):
+        flush.zero_()                                              # L2 flush between timed launches
+        e0.record(st)
+        env._launch_post_physics(nat.PHASE_STEP_ALL)
+        e1.record(st)
+        torch.cuda.synchronize(device)
+        tot += e0.elapsed_time(e1)
+    t_env = tot / reps * 1e-3
+    gbs = ENV_BYTES_PER_STEP * N / t_env / 1e9
+    out["roofline_env"] = dict(kernel="post_physics_kernel", bound="hbm", achieved=round(gbs, 1), peak=pk["hbm"], unit="GB/s",
+                               frac=round(gbs / pk["hbm"], 4), traffic=None, us_per_launch=round(t_env * 1e6, 2),
+                               bytes_per_launch=ENV_BYTES_PER_STEP * N, peak_source=pk["src"], l2="flushed between launches")
+    # -- MLP fwd+bwd chain of one minibatch (inputs 237 MB > L2) -------------------------------------------
+    s = alg.storage
+    B = (s.num_envs * s.num_transitions_per_env) // alg.num_mini_batches
+    idx = torch.randperm(s.num_envs * s.num_transitions_per_env, device=device)[:B]
+    mb = s.gather(idx)
+    ac = alg.actor_critic
+    flat = ac.flat_params()
+    w = alg._scratch(B)
+    sp = nat.stream_ptr(device.index)
+
+    def chain():
+        ac.native_forward("actor", mb["obs"], w["mean"], hidden=w["hid_a"])
+        ac.native_forward("critic", mb["priv_obs"], w["value"], hidden=w["hid_c"])
+        g = alg._grad.data_ptr()
+        nat.check(nat.lib.hg_mlp_backward(ac._desc["actor"], flat.data_ptr(), mb["obs"].data_ptr(), 705, w["hid_a"].data_ptr(),
+                                          w["d_mean"].data_ptr(), w["dhid_a"].data_ptr(), g, B, sp))
+        nat.check(nat.lib.hg_mlp_backward(ac._desc["critic"], flat.data_ptr(), mb["priv_obs"].data_ptr(), 219, w["hid_c"].data_ptr(),
+                                          w["d_value"].data_ptr(), w["dhid_c"].data_ptr(), g, B, sp))
+    w["d_mean"].normal_()
+    w["d_value"].normal_()
+    for _ in range(3):
+        chain()
+    torch.cuda.synchronize(device)
+    e0.record(st)
+    reps = 5
+    for _ in range(reps):
+        chain()
+    e1.record(st)
+    torch.cuda.synchronize(device)
+    t = e0.elapsed_time(e1) / reps * 1e-3
+    flops = (FLOPS_FWD + FLOPS_BWD) * B
+    tf = flops / t / 1e12
+    peak_tf32 = pk["bf16_sustained"] / 2.0
+    out["roofline"] = dict(kernel="ActorCritic fwd+bwd GEMM chain (gemm_kernel, fp32 CUDA-core path)", bound="tensor",
+                           achieved=round(tf, 2), peak=round(peak_tf32, 1), unit="TFLOP/s", frac=round(tf / peak_tf32, 4),
+                           traffic=None, ms_per_minibatch=round(t * 1e3, 3), flops_per_launch_group=flops,
+                           peak_source=pk["src"] + "; TF32 dense = bf16_sustained/2", share_of_step=None)
+    return out
+
+
+def run_product(args):
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world} (launch with torch.distributed.run)"
+    device = torch.device("cuda", local)
+    pk = peaks()
+    N = args.num_envs
+
+    # ---- device-resident arm (value) -----------------------------------------------------------------
+    env, runner = _make_runner(N, str(device), "synthetic")
+    state = (env.get_observations(), env.get_privileged_observations())
+    for _ in range(args.warmup):
+        state, _ = _iterate(runner, state)
+    with ClockSampler(local) as clocks:
+        ms, wall_ms, launches, state = _time_iterations(runner, state, args.steps, device, world)
+    env_steps = N * T_STEPS * args.steps * world
+    value = env_steps / (ms * 1e-3)
+    extra = _kernel_rooflines(runner, device, pk) if rank == 0 else {}
+    perf = dict(runner.last_perf)
+    del runner, env
+    torch.cuda.empty_cache()
+
+    # ---- end-to-end arm (host-resident physics frames, D2H of results) ---------------------------------
+    env, runner = _make_runner(N, str(device), "synthetic_host")
+    state = (env.get_observations(), env.get_privileged_observations())
+    for _ in range(max(1, args.warmup)):
+        state, _ = _iterate(runner, state)
+    ms_e, _, _, state = _time_iterations(runner, state, args.steps, device, world, e2e=True)
+    e2e_value = env_steps / (ms_e * 1e-3)
+    h2d = env.gym.h2d_bytes_per_step() * T_STEPS
+    d2h = 8 * 4 + 4
+    del runner, env
+
+    if rank != 0:
+        return
+    line = {
+        "metric": "env_steps_per_sec", "value": round(value, 1), "unit": "env-steps/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms / args.steps, 3),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "humanoid_ppo XBot-L, %d envs/GPU x T=60 steps + PPO update (2 epochs x 4 minibatches) per step"
+                               % N, "num_envs_per_gpu": N, "num_steps_per_env": T_STEPS, "global_envs": N * world,
+                   "parallelism": f"env-sharded dp{world}, one NCCL all-reduce of the flat gradient per optimizer step",
+                   "physics": "synthetic tensor source (SURVEY.md 8d), frames pre-generated outside the timed region",
+                   "l2": "per-step working set (rollout storage 947 MB + minibatch 237 MB) exceeds the 126 MB L2"},
+        "e2e": {"value": round(e2e_value, 1), "unit": "env-steps/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": d2h,
+                "ms_per_step": round(ms_e / args.steps, 3),
+                "note": "physics frames staged from pinned host memory every env step; losses + mean reward read back"},
+        "gpu_launches": int(launches // args.steps),
+        "clocks": clocks.summary(),
+        "host_wall_ms_per_step": round(wall_ms / args.steps, 3),
+        "last_iteration": {k: round(v, 5) for k, v in perf.items()},
+    }
+    line.update(extra)
+    if world == 1 and not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline(N, sample_T=T_STEPS)
+    print(json.dumps(line))
+
+
+# ----------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the reference's PyTorch path (oracle port) on the host cores
+# ----------------------------------------------------------------------------------------------
+def _oracle_trainer(num_envs, T, device="cpu"):
+    from humanoid.physics import SyntheticPhysics
+    from oracle.runner_oracle import OracleTrainer
+    from oracle import env_oracle as eo
+    torch.set_num_threads(os.cpu_count())
+    ranges = {"lin_vel_x": [-0.3, 0.6], "lin_vel_y": [-0.3, 0.3]}
+    ph = SyntheticPhysics(num_envs, device, ranges, eo.grid_origins(num_envs), decimation=10, seed=5)
+    return OracleTrainer(num_envs, ph, T=T)
+
+
+def cpu_baseline(num_envs, sample_T):
+    tr = _oracle_trainer(num_envs, sample_T)
+    c, l = tr.iteration()
+    v = num_envs * sample_T / (c + l)
+    return {"value": round(v, 1), "unit": "env-steps/s", "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"1 learning iteration of the oracle port (reference PyTorch path), N={num_envs}, T={sample_T}, "
+                      f"collection {c:.2f}s + learn {l:.2f}s, torch CPU fp32",
+            "collection_s": round(c, 3), "learn_s": round(l, 3)}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    N = args.num_envs
+    T = args.ref_T
+    tr = _oracle_trainer(N, T)
+    for _ in range(args.warmup):
+        tr.iteration()
+    t0 = time.time()
+    c = l = 0.0
+    for _ in range(args.steps):
+        a, b = tr.iteration()
+        c, l = c + a, l + b
+    dt = time.time() - t0
+    v = N * T * args.steps / dt
+    cores = torch.get_num_threads()
+    sample = (f"each step = one learning iteration of the reference PyTorch path (oracle port) at N={N} with T={T} of the 60 "
+              f"env steps (bounded sample; the metric is a rate), 2 epochs x 4 minibatches, {cores} host threads")
+    print(json.dumps({
+        "impl": "reference", "metric": "env_steps_per_sec", "value": round(v, 1), "unit": "env-steps/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(dt / args.steps * 1e3, 2),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "humanoid_ppo XBot-L, %d envs, reference PyTorch path on host CPU" % N, "num_envs_per_gpu": N,
+                   "num_steps_per_env": T},
+        "cpu_baseline": {"value": round(v, 1), "unit": "env-steps/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": round(v, 1), "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "collection_s": round(c / args.steps, 3), "learn_s": round(l / args.steps, 3)}))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--num-envs", type=int, default=4096, help="envs per GPU (BASELINE.json configs[1])")
+    ap.add_argument("--ref-T", type=int, default=60, help="env steps per iteration in the reference arm's bounded sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_product(args)
+    if dist.is_available() and dist.is_initialized():
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
