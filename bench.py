@@ -226,8 +226,17 @@ def run_product(args):
         ms, wall_ms, launches, state = _time_iterations(runner, state, args.steps, device, world)
     env_steps = N * T_STEPS * args.steps * world
     value = env_steps / (ms * 1e-3)
-    extra = _kernel_rooflines(runner, device, pk) if rank == 0 else {}
-    perf = dict(runner.last_perf)
+    print(f"[bench] rank {rank}: {value:.0f} env-steps/s, {ms / args.steps:.2f} ms/step, host wall {wall_ms / args.steps:.2f} ms/step",
+          file=sys.stderr, flush=True)
+    if args.quick:
+        if rank == 0:
+            print(json.dumps({"metric": "env_steps_per_sec", "value": round(value, 1), "unit": "env-steps/s", "n_gpus": world,
+                              "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms / args.steps, 3), "quick": True,
+                              "gpu_launches": int(launches // args.steps)}))
+        return
+    with torch.inference_mode():
+        extra = _kernel_rooflines(runner, device, pk) if rank == 0 else {}
+    perf = {}
     del runner, env
     torch.cuda.empty_cache()
 
@@ -259,7 +268,6 @@ def run_product(args):
         "gpu_launches": int(launches // args.steps),
         "clocks": clocks.summary(),
         "host_wall_ms_per_step": round(wall_ms / args.steps, 3),
-        "last_iteration": {k: round(v, 5) for k, v in perf.items()},
     }
     line.update(extra)
     if world == 1 and not args.no_cpu_baseline:
@@ -329,6 +337,7 @@ def main():
     ap.add_argument("--num-envs", type=int, default=4096, help="envs per GPU (BASELINE.json configs[1])")
     ap.add_argument("--ref-T", type=int, default=60, help="env steps per iteration in the reference arm's bounded sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--quick", action="store_true", help="value arm only (for ncu launch lists): no e2e, rooflines, cpu baseline")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

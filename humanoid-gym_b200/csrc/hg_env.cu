@@ -237,6 +237,8 @@ post_physics_kernel(HgEnvBuffers B, HgEnvNoise Z, uint32_t phases, int64_t commo
             p = B.projected_gravity + (size_t)e * 3; pg = {p[0], p[1], p[2]};
             p = B.base_euler_xyz + (size_t)e * 3; eul = {p[0], p[1], p[2]};
             reset = B.reset_buf[e] != 0;
+            // stand-alone reset_idx refreshes the euler angles of ALL envs (legged_robot.py:213)
+            if (do_reset) eul = euler_xyz_wrapped(root + 3);
         }
 
         if (phases & HG_PHASE_CALLBACK) {                       // legged_robot.py:304-320

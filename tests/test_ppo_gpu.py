@@ -199,8 +199,11 @@ def test_flagship_gradients_vs_autograd():
     torch.nn.utils.clip_grad_norm_([L.p[k] for k in L.names], 1.0)
     L.opt.step()
     want = torch.cat([L.p[k].detach().reshape(-1) for k in L.names])
+    # the fp32 update (~1e-5) is only a few ulp of the weights it lands on, so compare the new parameters
+    # tightly and the update itself within that quantisation
+    assert torch.allclose(ac.flat_params().cpu(), want, rtol=1e-6, atol=1e-9)
     upd_got, upd_want = (ac.flat_params().cpu() - w_before.cpu()), (want - w_before.cpu())
-    assert _rel(upd_got, upd_want) < 1e-4, _rel(upd_got, upd_want)
+    assert _rel(upd_got, upd_want) < 1e-3, _rel(upd_got, upd_want)
     assert abs(alg.learning_rate - L.lr) < 1e-18
 
 
