@@ -6,24 +6,34 @@
 //                          legged_robot.py:119-235,304-336,359-397 + humanoid_env.py:83-142,200-540
 //
 // Data layout: the reference's own env-major row-major tensors (Isaac Gym tensor API), untouched.
-// A CTA owns HG_ENVS_PER_CTA consecutive envs.  Because rows of consecutive envs are contiguous,
-// every per-CTA tile (root 13, dof 24, actions 12, obs 705, priv 219 floats per env) is one
-// contiguous, 16-byte aligned range: it is staged into shared memory with coalesced float4 loads,
-// one thread per env then evaluates the (branchy, transcendental-heavy) step, and the outputs --
-// dominated by the 15x47 / 3x73 observation histories (87 % of the bytes) -- are written back with
-// coalesced float4 stores, the one-frame shift being resolved on the shared-memory side.
+// A CTA owns 32 consecutive envs (one warp's worth).  Rows of consecutive envs are contiguous, so every
+// per-CTA tile of per-env state (root 13, dof 24, actions 12, contacts 39, ... floats per env) is ONE
+// contiguous 16-byte-aligned range: all 8 warps stage those tiles into shared memory with coalesced
+// float4 loads.  Then the CTA splits by role:
+//   * warp 0, one lane per env, evaluates the branchy / transcendental-heavy step entirely out of shared
+//     memory (no dependent global loads on its critical path) and publishes the per-env reset flags early;
+//   * warps 1-7 stream the observation histories -- 87 % of the kernel's bytes: obs_out[e][0:658] =
+//     obs_in[e][47:705], priv likewise -- straight through registers with many independent 128-byte
+//     requests in flight; input and output histories are distinct (ping-pong) buffers, so the shift has no
+//     in-place hazard and needs no staging.
+// The newest frame (47 / 73 floats per env), the observation noise and the +-18 clip are applied by all
+// warps after the compute warp finishes.
 //
-// Compiled with -fmad=false: the reference is a chain of separate fp32 torch ops, so every
-// multiply and add rounds on its own; op order below follows the cited lines.
+// Compiled with -fmad=false: the reference is a chain of separate fp32 torch ops, so every multiply and add
+// rounds on its own; op order below follows the cited lines.
 #include "hg_common.cuh"
 
-#define HG_ENVS_PER_CTA 8
+#define HG_ENVS_PER_CTA 32
 #define HG_ENV_THREADS 256
+#define HG_MAX_BODIES 16
 
 namespace {
 
+constexpr int E = HG_ENVS_PER_CTA;
 constexpr int OBS_W = HG_OBS1 * HG_OBS_FRAMES;      // 705
 constexpr int PRIV_W = HG_PRIV1 * HG_PRIV_FRAMES;   // 219
+constexpr int OBS_KEEP = OBS_W - HG_OBS1;           // 658 floats survive the shift
+constexpr int PRIV_KEEP = PRIV_W - HG_PRIV1;        // 146
 constexpr float kTwoPi = 6.283185307179586f;        // float32(2*np.pi)
 constexpr float kPi = 3.141592653589793f;           // float32(np.pi)
 
@@ -75,7 +85,7 @@ __device__ __forceinline__ float two_point_distance_reward(float ax, float ay, f
     return (expf(-fabsf(dmin) * 100.0f) + expf(-fabsf(dmax) * 100.0f)) / 2.0f;
 }
 
-// cooperative global <-> shared copies of a contiguous float range
+// cooperative (whole CTA) global -> shared copy of a contiguous float range
 __device__ __forceinline__ void tile_load(float* s, const float* g, int n) {
     if ((reinterpret_cast<uintptr_t>(g) & 15u) == 0) {
         int n4 = n >> 2;
@@ -87,71 +97,36 @@ __device__ __forceinline__ void tile_load(float* s, const float* g, int n) {
         for (int i = threadIdx.x; i < n; i += HG_ENV_THREADS) s[i] = __ldg(g + i);
     }
 }
-__device__ __forceinline__ void tile_store(float* g, const float* s, int n) {
-    if ((reinterpret_cast<uintptr_t>(g) & 15u) == 0) {
-        int n4 = n >> 2;
-        float4* g4 = reinterpret_cast<float4*>(g);
-        const float4* s4 = reinterpret_cast<const float4*>(s);
-        for (int i = threadIdx.x; i < n4; i += HG_ENV_THREADS) g4[i] = s4[i];
-        for (int i = (n4 << 2) + threadIdx.x; i < n; i += HG_ENV_THREADS) g[i] = s[i];
-    } else {
-        for (int i = threadIdx.x; i < n; i += HG_ENV_THREADS) g[i] = s[i];
-    }
-}
 
+// every array length is a multiple of 4 floats so that each member stays 16-byte aligned
 struct __align__(16) EnvSmem {
-    float obs[HG_ENVS_PER_CTA * OBS_W];
-    float priv[HG_ENVS_PER_CTA * PRIV_W];
-    float root[HG_ENVS_PER_CTA * 13 + 4];
-    float dof[HG_ENVS_PER_CTA * 24];
-    float act[HG_ENVS_PER_CTA * 12];
-    float lact[HG_ENVS_PER_CTA * 12];
-    float ldv[HG_ENVS_PER_CTA * 12];
-    float tau[HG_ENVS_PER_CTA * 12];
-    float llact[HG_ENVS_PER_CTA * 12];
-    float newobs[HG_ENVS_PER_CTA * HG_OBS1];
-    float newpriv[HG_ENVS_PER_CTA * HG_PRIV1];
-    float acc[HG_NUM_REWARDS];
+    float root[E * 13];
+    float dof[E * 24];
+    float act[E * 12];
+    float lact[E * 12];
+    float llact[E * 12];
+    float ldv[E * 12];
+    float tau[E * 12];
+    float ref[E * 12];
+    float lrv[E * 6];
+    float cmd[E * 4];
+    float cf[E * HG_MAX_BODIES * 3];
+    float rg[E * 4 * 13];               // feet L/R, knee L/R rows of rigid_state
+    float fat[E * 2], fh[E * 2], lfz[E * 2];
+    float rpf[E * 3], rpt[E * 3], org[E * 3];
+    float fric[E], mass[E];
+    float sums[HG_NUM_REWARDS * E];
+    float newobs[E * HG_OBS1];
+    float newpriv[E * HG_PRIV1];
+    float acc[HG_NUM_REWARDS + 2];
+    long long ep[E];
     int cnt;
     int is_last;
-    unsigned char reset[HG_ENVS_PER_CTA];
-    unsigned char root_dirty[HG_ENVS_PER_CTA];
+    unsigned char lc[E * 2];
+    unsigned char reset_in[E];
+    unsigned char reset[E];
+    unsigned char root_dirty[E];
 };
-
-// one output element of a shifted history tile
-template <int FRAME, int WIDTH>
-__device__ __forceinline__ float hist_elem(const float* s_hist, const float* s_new, const unsigned char* s_reset,
-                                           int i, int shift, bool clip) {
-    int e = i / WIDTH, k = i - e * WIDTH;
-    int src = k + shift;
-    if (src < WIDTH) return s_reset[e] ? 0.0f : s_hist[e * WIDTH + src];
-    float v = s_new[e * FRAME + (src - WIDTH)];
-    return clip ? clampf(v, -cP.clip_obs, cP.clip_obs) : v;
-}
-
-template <int FRAME, int WIDTH>
-__device__ __forceinline__ void hist_store(float* g, const float* s_hist, const float* s_new,
-                                           const unsigned char* s_reset, int n_env, int shift, bool clip) {
-    int n = n_env * WIDTH;
-    if ((reinterpret_cast<uintptr_t>(g) & 15u) == 0) {
-        int n4 = n >> 2;
-        float4* g4 = reinterpret_cast<float4*>(g);
-        for (int j = threadIdx.x; j < n4; j += HG_ENV_THREADS) {
-            int i = j << 2;
-            float4 v;
-            v.x = hist_elem<FRAME, WIDTH>(s_hist, s_new, s_reset, i, shift, clip);
-            v.y = hist_elem<FRAME, WIDTH>(s_hist, s_new, s_reset, i + 1, shift, clip);
-            v.z = hist_elem<FRAME, WIDTH>(s_hist, s_new, s_reset, i + 2, shift, clip);
-            v.w = hist_elem<FRAME, WIDTH>(s_hist, s_new, s_reset, i + 3, shift, clip);
-            g4[j] = v;
-        }
-        for (int i = (n4 << 2) + threadIdx.x; i < n; i += HG_ENV_THREADS)
-            g[i] = hist_elem<FRAME, WIDTH>(s_hist, s_new, s_reset, i, shift, clip);
-    } else {
-        for (int i = threadIdx.x; i < n; i += HG_ENV_THREADS)
-            g[i] = hist_elem<FRAME, WIDTH>(s_hist, s_new, s_reset, i, shift, clip);
-    }
-}
 
 __device__ __forceinline__ float draw_u(const float* inj, int64_t idx, uint64_t seed, uint64_t step, uint32_t env,
                                         uint32_t stream, uint32_t k) {
@@ -171,24 +146,51 @@ __device__ __forceinline__ void resample_commands(float* cmd, float u0, float u1
     cmd[1] *= keep;
 }
 
-__global__ void __launch_bounds__(HG_ENV_THREADS)
+__device__ __forceinline__ void bar_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+__device__ __forceinline__ void bar_arrive(int id, int count) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+
+// history rows w, w+nw, ... of one CTA tile: out[r][0:KEEP] = in[r][FRAME:FRAME+KEEP] (0 if the env reset)
+template <int FRAME, int KEEP, int WIDTH>
+__device__ __forceinline__ void stream_history(float* __restrict__ out, const float* __restrict__ in,
+                                               const unsigned char* s_reset, int nE, int w, int nw, int lane) {
+    constexpr int CH = (KEEP + 31) / 32;            // 21 (obs) / 5 (priv) independent 128-byte requests per row
+    for (int r = w; r < nE; r += nw) {
+        const float* src = in + (size_t)r * WIDTH + FRAME;
+        float* dst = out + (size_t)r * WIDTH;
+        float v[CH];
+        if (s_reset[r]) {
+#pragma unroll
+            for (int c = 0; c < CH; ++c) v[c] = 0.0f;
+        } else {
+#pragma unroll
+            for (int c = 0; c < CH; ++c) {
+                int k = c * 32 + lane;
+                v[c] = (k < KEEP) ? __ldcs(src + k) : 0.0f;          // streaming: read once
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < CH; ++c) {
+            int k = c * 32 + lane;
+            if (k < KEEP) dst[k] = v[c];
+        }
+    }
+}
+
+__global__ void __launch_bounds__(HG_ENV_THREADS, 3)
 post_physics_kernel(HgEnvBuffers B, HgEnvNoise Z, uint32_t phases, int64_t common_step, int N) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     EnvSmem& S = *reinterpret_cast<EnvSmem*>(smem_raw);
-    const int tid = threadIdx.x;
-    const int e0 = blockIdx.x * HG_ENVS_PER_CTA;
-    const int nE = min(HG_ENVS_PER_CTA, N - e0);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int e0 = blockIdx.x * E;
+    const int nE = min(E, N - e0);
     const bool do_obs = phases & HG_PHASE_OBS, do_reset = phases & HG_PHASE_RESET, do_last = phases & HG_PHASE_LAST;
+    const int nb = cP.num_bodies;
     if (Z.use_device_counters) {   // CUDA-graph friendly: counters live in scratch[4..7], bumped by the last CTA
         common_step = *reinterpret_cast<const volatile int64_t*>(B.scratch + 4) + ((phases & HG_PHASE_COUNTERS) ? 1 : 0);
         Z.step = *reinterpret_cast<const volatile uint64_t*>(B.scratch + 6);
     }
 
-    // ---- 1. stage the per-CTA tiles (coalesced float4) -------------------------------------------
-    if (do_obs) {
-        tile_load(S.obs, B.obs_buf + (size_t)e0 * OBS_W, nE * OBS_W);
-        tile_load(S.priv, B.privileged_obs_buf + (size_t)e0 * PRIV_W, nE * PRIV_W);
-    }
+    // ---- 1. stage every per-env input (all warps, coalesced) -------------------------------------------
     tile_load(S.root, B.root_states + (size_t)e0 * 13, nE * 13);
     tile_load(S.dof, B.dof_state + (size_t)e0 * 24, nE * 24);
     tile_load(S.act, B.actions + (size_t)e0 * 12, nE * 12);
@@ -196,391 +198,437 @@ post_physics_kernel(HgEnvBuffers B, HgEnvNoise Z, uint32_t phases, int64_t commo
     tile_load(S.llact, B.last_last_actions + (size_t)e0 * 12, nE * 12);
     tile_load(S.ldv, B.last_dof_vel + (size_t)e0 * 12, nE * 12);
     tile_load(S.tau, B.torques + (size_t)e0 * 12, nE * 12);
+    tile_load(S.ref, B.ref_dof_pos + (size_t)e0 * 12, nE * 12);
+    tile_load(S.lrv, B.last_root_vel + (size_t)e0 * 6, nE * 6);
+    tile_load(S.cmd, B.commands + (size_t)e0 * 4, nE * 4);
+    tile_load(S.cf, B.contact_forces + (size_t)e0 * nb * 3, nE * nb * 3);
+    tile_load(S.fat, B.feet_air_time + (size_t)e0 * 2, nE * 2);
+    tile_load(S.fh, B.feet_height + (size_t)e0 * 2, nE * 2);
+    tile_load(S.lfz, B.last_feet_z + (size_t)e0 * 2, nE * 2);
+    tile_load(S.rpf, B.rand_push_force + (size_t)e0 * 3, nE * 3);
+    tile_load(S.rpt, B.rand_push_torque + (size_t)e0 * 3, nE * 3);
+    tile_load(S.org, B.env_origins + (size_t)e0 * 3, nE * 3);
+    tile_load(S.fric, B.env_frictions + e0, nE);
+    tile_load(S.mass, B.body_mass + e0, nE);
+    for (int i = tid; i < nE * 52; i += HG_ENV_THREADS) {          // feet / knee rows of rigid_state (52-byte runs)
+        int le = i / 52, r = i - le * 52, b = r / 13, c = r - b * 13;
+        int body = (b < 2) ? cP.feet[b] : cP.knees[b - 2];
+        S.rg[i] = __ldg(B.rigid_state + ((size_t)(e0 + le) * nb + body) * 13 + c);
+    }
+    for (int i = tid; i < HG_NUM_REWARDS * nE; i += HG_ENV_THREADS) {   // episode sums are (22, N): 128-byte runs
+        int k = i / nE, le = i - k * nE;
+        S.sums[k * E + le] = B.episode_sums[(size_t)k * N + e0 + le];
+    }
+    if (tid < nE) {
+        S.ep[tid] = B.episode_length_buf[e0 + tid];
+        S.reset_in[tid] = B.reset_buf[e0 + tid];
+        S.lc[2 * tid] = B.last_contacts[(size_t)(e0 + tid) * 2];
+        S.lc[2 * tid + 1] = B.last_contacts[(size_t)(e0 + tid) * 2 + 1];
+    }
     if (tid < HG_NUM_REWARDS) S.acc[tid] = 0.0f;
     if (tid == 0) { S.cnt = 0; S.is_last = 0; }
-    if (tid < HG_ENVS_PER_CTA) { S.reset[tid] = 0; S.root_dirty[tid] = 0; }
+    if (tid < E) { S.reset[tid] = 0; S.root_dirty[tid] = 0; }
     __syncthreads();
 
-    // ---- 2. one thread per env ---------------------------------------------------------------------
-    if (tid < nE) {
-        const int le = tid;
+    if (warp == 0) {
+        // ---- 2a. compute warp: one lane per env, everything out of shared memory -----------------------------
+        const int le = lane;
         const int e = e0 + le;
+        const bool active = le < nE;
+        bool reset = false, timeout = false;
+        V3 blv{0, 0, 0}, bav{0, 0, 0}, pg{0, 0, 0}, eul{0, 0, 0};
+        float cmd[4] = {0, 0, 0, 0};
+        long long ep = 0;
+        bool cmd_dirty = false;
         float* root = S.root + le * 13;
         float* dof = S.dof + le * 24;
         float* act = S.act + le * 12;
-        const float* lact = S.lact + le * 12;
-        const float* llact = S.llact + le * 12;
-        const float* ldv = S.ldv + le * 12;
-        const float* tau = S.tau + le * 12;
-        const float* cf = B.contact_forces + (size_t)e * cP.num_bodies * 3;
-        const float* rs = B.rigid_state + (size_t)e * cP.num_bodies * 13;
-
-        int64_t ep = B.episode_length_buf[e];
-        float cmd[4];
-        {
-            float4 c4 = *reinterpret_cast<const float4*>(B.commands + (size_t)e * 4);
-            cmd[0] = c4.x; cmd[1] = c4.y; cmd[2] = c4.z; cmd[3] = c4.w;
-        }
-        V3 blv, bav, pg, eul;
-        bool reset = false, timeout = false;
-        bool cmd_dirty = false;
-
-        if (phases & HG_PHASE_COUNTERS) {                       // legged_robot.py:128-136
-            ep += 1;
-            blv = quat_rotate_inverse(root + 3, V3{root[7], root[8], root[9]});
-            bav = quat_rotate_inverse(root + 3, V3{root[10], root[11], root[12]});
-            pg = quat_rotate_inverse(root + 3, V3{0.0f, 0.0f, -1.0f});
-            eul = euler_xyz_wrapped(root + 3);
-        } else {
-            const float* p = B.base_lin_vel + (size_t)e * 3; blv = {p[0], p[1], p[2]};
-            p = B.base_ang_vel + (size_t)e * 3; bav = {p[0], p[1], p[2]};
-            p = B.projected_gravity + (size_t)e * 3; pg = {p[0], p[1], p[2]};
-            p = B.base_euler_xyz + (size_t)e * 3; eul = {p[0], p[1], p[2]};
-            reset = B.reset_buf[e] != 0;
-            // stand-alone reset_idx refreshes the euler angles of ALL envs (legged_robot.py:213)
-            if (do_reset) eul = euler_xyz_wrapped(root + 3);
-        }
-
-        if (phases & HG_PHASE_CALLBACK) {                       // legged_robot.py:304-320
-            if (ep % cP.resample_period == 0) {
-                float u0 = draw_u(Z.u_cmd_cb, (int64_t)e * 3 + 0, Z.seed, Z.step, e, HG_RNG_CMD_CB, 0);
-                float u1 = draw_u(Z.u_cmd_cb, (int64_t)e * 3 + 1, Z.seed, Z.step, e, HG_RNG_CMD_CB, 1);
-                float u2 = draw_u(Z.u_cmd_cb, (int64_t)e * 3 + 2, Z.seed, Z.step, e, HG_RNG_CMD_CB, 2);
-                resample_commands(cmd, u0, u1, u2);
+        const float* cf = S.cf + le * nb * 3;
+        const float* fL = S.rg + le * 52;
+        const float* fR = fL + 13;
+        if (active) {
+            ep = S.ep[le];
+            cmd[0] = S.cmd[le * 4]; cmd[1] = S.cmd[le * 4 + 1]; cmd[2] = S.cmd[le * 4 + 2]; cmd[3] = S.cmd[le * 4 + 3];
+            if (phases & HG_PHASE_COUNTERS) {                       // legged_robot.py:128-136
+                ep += 1;
+                blv = quat_rotate_inverse(root + 3, V3{root[7], root[8], root[9]});
+                bav = quat_rotate_inverse(root + 3, V3{root[10], root[11], root[12]});
+                pg = quat_rotate_inverse(root + 3, V3{0.0f, 0.0f, -1.0f});
+                eul = euler_xyz_wrapped(root + 3);
+            } else {
+                const float* p = B.base_lin_vel + (size_t)e * 3; blv = {p[0], p[1], p[2]};
+                p = B.base_ang_vel + (size_t)e * 3; bav = {p[0], p[1], p[2]};
+                p = B.projected_gravity + (size_t)e * 3; pg = {p[0], p[1], p[2]};
+                p = B.base_euler_xyz + (size_t)e * 3; eul = {p[0], p[1], p[2]};
+                reset = S.reset_in[le] != 0;
+                // stand-alone reset_idx refreshes the euler angles of ALL envs (legged_robot.py:213)
+                if (do_reset) eul = euler_xyz_wrapped(root + 3);
             }
-            if (cP.heading_command) {
-                // forward = quat_apply(q, (1,0,0)) = v + w t + u x t,  t = 2 (u x v)
-                float ux = root[3], uy = root[4], uz = root[5], w = root[6];
-                float tx = (uy * 0.0f - uz * 0.0f) * 2.0f, ty = (uz * 1.0f - ux * 0.0f) * 2.0f, tz = (ux * 0.0f - uy * 1.0f) * 2.0f;
-                float fx = 1.0f + w * tx + (uy * tz - uz * ty);
-                float fy = 0.0f + w * ty + (uz * tx - ux * tz);
-                float heading = atan2f(fy, fx);
-                float a = remainder_pos(cmd[3] - heading, kTwoPi);          // utils/math.py:47-50
-                a = a - kTwoPi * (a > kPi ? 1.0f : 0.0f);
-                cmd[2] = clampf(0.5f * a, -1.0f, 1.0f);
+            if (phases & HG_PHASE_TERMINATE) {                      // legged_robot.py:156-161
+                for (int b = 0; b < cP.n_term; ++b) {
+                    const float* f = cf + cP.term_bodies[b] * 3;
+                    reset |= sqrtf(f[0] * f[0] + f[1] * f[1] + f[2] * f[2]) > 1.0f;
+                }
+                timeout = ep > cP.max_episode_length;
+                reset |= timeout;
+                B.time_out_buf[e] = timeout;
             }
-            cmd_dirty = true;
-            if (cP.push_robots && (common_step % cP.push_interval == 0)) {   // humanoid_env.py:83-98
-                float u[5];
+            S.reset[le] = (do_reset && reset) ? 1 : 0;
+        }
+        // the reset mask depends only on this step's contacts and the episode clock: publish it now so that
+        // the streaming warps can start on the histories while the rewards are being evaluated
+        __syncwarp();
+        bar_arrive(1, HG_ENV_THREADS);
+
+        if (active) {
+            if (phases & HG_PHASE_CALLBACK) {                       // legged_robot.py:304-320
+                if (ep % cP.resample_period == 0) {
+                    float u0 = draw_u(Z.u_cmd_cb, (int64_t)e * 3 + 0, Z.seed, Z.step, e, HG_RNG_CMD_CB, 0);
+                    float u1 = draw_u(Z.u_cmd_cb, (int64_t)e * 3 + 1, Z.seed, Z.step, e, HG_RNG_CMD_CB, 1);
+                    float u2 = draw_u(Z.u_cmd_cb, (int64_t)e * 3 + 2, Z.seed, Z.step, e, HG_RNG_CMD_CB, 2);
+                    resample_commands(cmd, u0, u1, u2);
+                }
+                if (cP.heading_command) {
+                    // forward = quat_apply(q, (1,0,0)) = v + w t + u x t,  t = 2 (u x v)
+                    float ux = root[3], uy = root[4], uz = root[5], w = root[6];
+                    float tx = (uy * 0.0f - uz * 0.0f) * 2.0f, ty = (uz * 1.0f - ux * 0.0f) * 2.0f, tz = (ux * 0.0f - uy * 1.0f) * 2.0f;
+                    float fx = 1.0f + w * tx + (uy * tz - uz * ty);
+                    float fy = 0.0f + w * ty + (uz * tx - ux * tz);
+                    float heading = atan2f(fy, fx);
+                    float a = remainder_pos(cmd[3] - heading, kTwoPi);          // utils/math.py:47-50
+                    a = a - kTwoPi * (a > kPi ? 1.0f : 0.0f);
+                    cmd[2] = clampf(0.5f * a, -1.0f, 1.0f);
+                }
+                cmd_dirty = true;
+                if (cP.push_robots && (common_step % cP.push_interval == 0)) {   // humanoid_env.py:83-98
+                    float u[5];
 #pragma unroll
-                for (int k = 0; k < 5; ++k) u[k] = draw_u(Z.u_push, (int64_t)e * 5 + k, Z.seed, Z.step, e, HG_RNG_PUSH, k);
-                float f0 = cP.push_vel_span * u[0] + cP.push_vel_lo, f1 = cP.push_vel_span * u[1] + cP.push_vel_lo;
-                float t0 = cP.push_ang_span * u[2] + cP.push_ang_lo, t1 = cP.push_ang_span * u[3] + cP.push_ang_lo;
-                float t2 = cP.push_ang_span * u[4] + cP.push_ang_lo;
-                float* rpf = B.rand_push_force + (size_t)e * 3;
-                float* rpt = B.rand_push_torque + (size_t)e * 3;
-                rpf[0] = f0; rpf[1] = f1;
-                rpt[0] = t0; rpt[1] = t1; rpt[2] = t2;
-                root[7] = f0; root[8] = f1;
-                root[10] = t0; root[11] = t1; root[12] = t2;
+                    for (int k = 0; k < 5; ++k) u[k] = draw_u(Z.u_push, (int64_t)e * 5 + k, Z.seed, Z.step, e, HG_RNG_PUSH, k);
+                    float f0 = cP.push_vel_span * u[0] + cP.push_vel_lo, f1 = cP.push_vel_span * u[1] + cP.push_vel_lo;
+                    float t0 = cP.push_ang_span * u[2] + cP.push_ang_lo, t1 = cP.push_ang_span * u[3] + cP.push_ang_lo;
+                    float t2 = cP.push_ang_span * u[4] + cP.push_ang_lo;
+                    S.rpf[le * 3] = f0; S.rpf[le * 3 + 1] = f1;
+                    S.rpt[le * 3] = t0; S.rpt[le * 3 + 1] = t1; S.rpt[le * 3 + 2] = t2;
+                    float* rpf = B.rand_push_force + (size_t)e * 3;
+                    float* rpt = B.rand_push_torque + (size_t)e * 3;
+                    rpf[0] = f0; rpf[1] = f1;
+                    rpt[0] = t0; rpt[1] = t1; rpt[2] = t2;
+                    root[7] = f0; root[8] = f1;
+                    root[10] = t0; root[11] = t1; root[12] = t2;
+                    S.root_dirty[le] = 1;
+                }
+            }
+
+            // feet contacts used by rewards and observations
+            const float cLz = cf[cP.feet[0] * 3 + 2], cRz = cf[cP.feet[1] * 3 + 2];
+            const bool contact0 = cLz > 5.0f, contact1 = cRz > 5.0f;
+
+            if (phases & HG_PHASE_REWARD) {                         // legged_robot.py:217-235
+                const float* lact = S.lact + le * 12;
+                const float* llact = S.llact + le * 12;
+                const float* ldv = S.ldv + le * 12;
+                const float* tau = S.tau + le * 12;
+                float phase = (float)ep * cP.dt / cP.cycle_time;    // humanoid_env.py:100-103
+                float s = sinf(kTwoPi * phase);
+                float st0 = s >= 0.0f ? 1.0f : 0.0f, st1 = s < 0.0f ? 1.0f : 0.0f;   // :105-118
+                if (fabsf(s) < 0.1f) { st0 = 1.0f; st1 = 1.0f; }
+                float total = 0.0f;
+                int kk = 0;
+                auto add_term = [&](float rv) {                     // alphabetical accumulation, :222-230
+                    float rk = rv * cP.reward_scales[kk];
+                    total += rk;
+                    S.sums[kk * E + le] += rk;
+                    if (B.rew_terms) B.rew_terms[(size_t)kk * N + e] = rk;
+                    ++kk;
+                };
+                {   // 0 action_smoothness, humanoid_env.py:530-540
+                    float t1 = 0.0f, t2 = 0.0f, t3 = 0.0f;
+                    for (int j = 0; j < 12; ++j) {
+                        float d1 = lact[j] - act[j];
+                        t1 += d1 * d1;
+                        float d2 = act[j] + llact[j] - 2.0f * lact[j];
+                        t2 += d2 * d2;
+                        t3 += fabsf(act[j]);
+                    }
+                    add_term(t1 + t2 + 0.05f * t3);
+                }
+                {   // 1 base_acc :386-393
+                    const float* lrv = S.lrv + le * 6;
+                    float a = 0.0f;
+                    for (int j = 0; j < 6; ++j) { float d = lrv[j] - root[7 + j]; a += d * d; }
+                    add_term(expf(-sqrtf(a) * 3.0f));
+                }
+                {   // 2 base_height :374-384
+                    float measured = (fL[2] * st0 + fR[2] * st1) / (st0 + st1);
+                    float h = root[2] - (measured - 0.05f);
+                    add_term(expf(-fabsf(h - cP.base_height_target) * 100.0f));
+                }
+                {   // 3 collision :523-528
+                    float c = 0.0f;
+                    for (int b = 0; b < cP.n_pen; ++b) {
+                        const float* f = cf + cP.pen_bodies[b] * 3;
+                        c += (sqrtf(f[0] * f[0] + f[1] * f[1] + f[2] * f[2]) > 0.1f) ? 1.0f : 0.0f;
+                    }
+                    add_term(c);
+                }
+                float dq2 = 0.0f, dacc = 0.0f, qerr = 0.0f, jall = 0.0f, tq = 0.0f;
+                {
+                    const float* ref = S.ref + le * 12;              // STALE reference pose (hazard 2)
+                    for (int j = 0; j < 12; ++j) {
+                        float q = dof[2 * j], v = dof[2 * j + 1];
+                        float d = q - cP.default_dof_pos[j];
+                        jall += d * d;
+                        dq2 += v * v;
+                        float a = (ldv[j] - v) / cP.dt;
+                        dacc += a * a;
+                        float er = q - ref[j];
+                        qerr += er * er;
+                        tq += tau[j] * tau[j];
+                    }
+                }
+                {   // 4 default_joint_pos :362-372
+                    float d0 = dof[0] - cP.default_dof_pos[0], d1 = dof[2] - cP.default_dof_pos[1];
+                    float d6 = dof[12] - cP.default_dof_pos[6], d7 = dof[14] - cP.default_dof_pos[7];
+                    float yr = sqrtf(d0 * d0 + d1 * d1) + sqrtf(d6 * d6 + d7 * d7);
+                    yr = clampf(yr - 0.1f, 0.0f, 50.0f);
+                    add_term(expf(-yr * 100.0f) - 0.01f * sqrtf(jall));
+                }
+                add_term(dacc);                                      // 5 dof_acc :516-521
+                add_term(dq2);                                       // 6 dof_vel :509-514
+                {   // 7 feet_air_time :320-334 (stateful)
+                    bool filt0 = contact0 || (st0 != 0.0f) || S.lc[2 * le];
+                    bool filt1 = contact1 || (st1 != 0.0f) || S.lc[2 * le + 1];
+                    B.last_contacts[(size_t)e * 2] = contact0;
+                    B.last_contacts[(size_t)e * 2 + 1] = contact1;
+                    float a0 = S.fat[2 * le], a1 = S.fat[2 * le + 1];
+                    bool first0 = (a0 > 0.0f) && filt0, first1 = (a1 > 0.0f) && filt1;
+                    a0 += cP.dt; a1 += cP.dt;
+                    add_term(clampf(a0, 0.0f, 0.5f) * (first0 ? 1.0f : 0.0f) + clampf(a1, 0.0f, 0.5f) * (first1 ? 1.0f : 0.0f));
+                    S.fat[2 * le] = a0 * (filt0 ? 0.0f : 1.0f);
+                    S.fat[2 * le + 1] = a1 * (filt1 ? 0.0f : 1.0f);
+                }
+                {   // 8 feet_clearance :446-467 (stateful; never reset, hazard 4)
+                    float z0 = fL[2] - 0.05f, z1 = fR[2] - 0.05f;
+                    float h0 = S.fh[2 * le] + (z0 - S.lfz[2 * le]), h1 = S.fh[2 * le + 1] + (z1 - S.lfz[2 * le + 1]);
+                    float hit0 = fabsf(h0 - cP.target_feet_height) < 0.01f ? 1.0f : 0.0f;
+                    float hit1 = fabsf(h1 - cP.target_feet_height) < 0.01f ? 1.0f : 0.0f;
+                    add_term(hit0 * (1.0f - st0) + hit1 * (1.0f - st1));
+                    float2* gh = reinterpret_cast<float2*>(B.feet_height) + e;
+                    float2* gz = reinterpret_cast<float2*>(B.last_feet_z) + e;
+                    *gh = make_float2(h0 * (contact0 ? 0.0f : 1.0f), h1 * (contact1 ? 0.0f : 1.0f));
+                    *gz = make_float2(z0, z1);
+                }
+                {   // 9 feet_contact_forces :355-360
+                    const float* a = cf + cP.feet[0] * 3;
+                    const float* b = cf + cP.feet[1] * 3;
+                    float na = sqrtf(a[0] * a[0] + a[1] * a[1] + a[2] * a[2]);
+                    float nbn = sqrtf(b[0] * b[0] + b[1] * b[1] + b[2] * b[2]);
+                    add_term(clampf(na - cP.max_contact_force, 0.0f, 400.0f) + clampf(nbn - cP.max_contact_force, 0.0f, 400.0f));
+                }
+                {   // 10 feet_contact_number :336-344
+                    float m0 = ((contact0 ? 1.0f : 0.0f) == st0) ? 1.0f : -0.3f;
+                    float m1 = ((contact1 ? 1.0f : 0.0f) == st1) ? 1.0f : -0.3f;
+                    add_term((m0 + m1) / 2.0f);
+                }
+                add_term(two_point_distance_reward(fL[0], fL[1], fR[0], fR[1], cP.min_dist, cP.max_dist));   // 11 :282-292
+                {   // 12 foot_slip :308-318
+                    float v0 = sqrtf(sqrtf(fL[7] * fL[7] + fL[8] * fL[8]));
+                    float v1 = sqrtf(sqrtf(fR[7] * fR[7] + fR[8] * fR[8]));
+                    add_term(v0 * (contact0 ? 1.0f : 0.0f) + v1 * (contact1 ? 1.0f : 0.0f));
+                }
+                {   // 13 joint_pos :272-280
+                    float er = sqrtf(qerr);
+                    add_term(expf(-2.0f * er) - 0.2f * clampf(er, 0.0f, 0.5f));
+                }
+                {   // 14 knee_distance :295-305
+                    const float* kL = fL + 26;
+                    const float* kR = fL + 39;
+                    add_term(two_point_distance_reward(kL[0], kL[1], kR[0], kR[1], cP.min_dist, cP.max_dist / 2.0f));
+                }
+                {   // 15 low_speed :469-500
+                    float v = blv.x, c = cmd[0];
+                    float av = fabsf(v), ac = fabsf(c);
+                    bool low = av < 0.5f * ac, high = av > 1.2f * ac;
+                    float rr = 0.0f;
+                    if (low) rr = -1.0f;
+                    if (high) rr = 0.0f;
+                    if (!(low || high)) rr = 1.2f;
+                    float sv = (v > 0.0f) - (v < 0.0f), sc = (c > 0.0f) - (c < 0.0f);
+                    if (sv != sc) rr = -2.0f;
+                    add_term(rr * (ac > 0.1f ? 1.0f : 0.0f));
+                }
+                {   // 16 orientation :346-353
+                    float a = expf(-(fabsf(eul.x) + fabsf(eul.y)) * 10.0f);
+                    float b = expf(-sqrtf(pg.x * pg.x + pg.y * pg.y) * 20.0f);
+                    add_term((a + b) / 2.0f);
+                }
+                add_term(tq);                                        // 17 torques :502-507
+                {
+                    float ex = cmd[0] - blv.x, ey = cmd[1] - blv.y;
+                    float le2 = ex * ex + ey * ey;
+                    float lin = sqrtf(le2);
+                    float ang = fabsf(cmd[2] - bav.z);
+                    add_term((expf(-lin * 10.0f) + expf(-ang * 10.0f)) / 2.0f - 0.2f * (lin + ang));   // 18 track_vel_hard :408-425
+                    float da = cmd[2] - bav.z;
+                    add_term(expf(-(da * da) * cP.tracking_sigma));                                    // 19 tracking_ang_vel :436-444
+                    add_term(expf(-le2 * cP.tracking_sigma));                                          // 20 tracking_lin_vel :427-434
+                }
+                {   // 21 vel_mismatch_exp :396-406
+                    float a = expf(-(blv.z * blv.z) * 10.0f);
+                    float b = expf(-sqrtf(bav.x * bav.x + bav.y * bav.y) * 5.0f);
+                    add_term((a + b) / 2.0f);
+                }
+                if (cP.only_positive_rewards) total = fmaxf(total, 0.0f);
+                B.rew_buf[e] = total;
+            }
+
+            if (do_reset && reset) {                                // legged_robot.py:163-215
+                for (int j = 0; j < 12; ++j) {                      // _reset_dofs :359-373
+                    float u = draw_u(Z.u_dof, (int64_t)e * 12 + j, Z.seed, Z.step, e, HG_RNG_DOF, j);
+                    dof[2 * j] = cP.default_dof_pos[j] + (cP.dof_reset_span * u + cP.dof_reset_lo);
+                    dof[2 * j + 1] = 0.0f;
+                    act[j] = 0.0f;
+                }
+                for (int j = 0; j < 13; ++j) root[j] = cP.base_init_state[j];      // _reset_root_states :374-397
+                root[0] += S.org[le * 3]; root[1] += S.org[le * 3 + 1]; root[2] += S.org[le * 3 + 2];
                 S.root_dirty[le] = 1;
-            }
-        }
-
-        if (phases & HG_PHASE_TERMINATE) {                      // legged_robot.py:156-161
-            for (int b = 0; b < cP.n_term; ++b) {
-                const float* f = cf + cP.term_bodies[b] * 3;
-                reset |= sqrtf(f[0] * f[0] + f[1] * f[1] + f[2] * f[2]) > 1.0f;
-            }
-            timeout = ep > cP.max_episode_length;
-            reset |= timeout;
-            B.time_out_buf[e] = timeout;
-        }
-
-        // feet / knee kinematics and contacts used by rewards and observations
-        const float* fL = rs + cP.feet[0] * 13;
-        const float* fR = rs + cP.feet[1] * 13;
-        const float cLz = cf[cP.feet[0] * 3 + 2], cRz = cf[cP.feet[1] * 3 + 2];
-        const bool contact0 = cLz > 5.0f, contact1 = cRz > 5.0f;
-
-        if (phases & HG_PHASE_REWARD) {                         // legged_robot.py:217-235
-            float phase = (float)ep * cP.dt / cP.cycle_time;    // humanoid_env.py:100-103
-            float s = sinf(kTwoPi * phase);
-            float st0 = s >= 0.0f ? 1.0f : 0.0f, st1 = s < 0.0f ? 1.0f : 0.0f;   // :105-118
-            if (fabsf(s) < 0.1f) { st0 = 1.0f; st1 = 1.0f; }
-            float r[HG_NUM_REWARDS];
-            {   // 0 action_smoothness, humanoid_env.py:530-540
-                float t1 = 0.0f, t2 = 0.0f, t3 = 0.0f;
-                for (int j = 0; j < 12; ++j) {
-                    float d1 = lact[j] - act[j];
-                    t1 += d1 * d1;
-                    float d2 = act[j] + llact[j] - 2.0f * lact[j];
-                    t2 += d2 * d2;
-                    t3 += fabsf(act[j]);
+                float u0 = draw_u(Z.u_cmd_rs, (int64_t)e * 3 + 0, Z.seed, Z.step, e, HG_RNG_CMD_RS, 0);
+                float u1 = draw_u(Z.u_cmd_rs, (int64_t)e * 3 + 1, Z.seed, Z.step, e, HG_RNG_CMD_RS, 1);
+                float u2 = draw_u(Z.u_cmd_rs, (int64_t)e * 3 + 2, Z.seed, Z.step, e, HG_RNG_CMD_RS, 2);
+                resample_commands(cmd, u0, u1, u2);
+                cmd_dirty = true;
+                S.fat[2 * le] = 0.0f; S.fat[2 * le + 1] = 0.0f;
+                ep = 0;
+                for (int k = 0; k < HG_NUM_REWARDS; ++k) {          // extras["episode"] :198-202
+                    atomicAdd(&S.acc[k], S.sums[k * E + le]);
+                    S.sums[k * E + le] = 0.0f;
                 }
-                r[0] = t1 + t2 + 0.05f * t3;
+                atomicAdd(&S.cnt, 1);
+                B.reset_ids[atomicAdd(&B.scratch[0], 1)] = e;
+                eul = euler_xyz_wrapped(root + 3);                   // "fix reset gravity bug" :212-215
+                pg = quat_rotate_inverse(root + 3, V3{0.0f, 0.0f, -1.0f});
             }
-            {   // 1 base_acc :386-393
-                const float* lrv = B.last_root_vel + (size_t)e * 6;
-                float a = 0.0f;
-                for (int j = 0; j < 6; ++j) { float d = lrv[j] - root[7 + j]; a += d * d; }
-                r[1] = expf(-sqrtf(a) * 3.0f);
-            }
-            {   // 2 base_height :374-384
-                float measured = (fL[2] * st0 + fR[2] * st1) / (st0 + st1);
-                float h = root[2] - (measured - 0.05f);
-                r[2] = expf(-fabsf(h - cP.base_height_target) * 100.0f);
-            }
-            {   // 3 collision :523-528
-                float c = 0.0f;
-                for (int b = 0; b < cP.n_pen; ++b) {
-                    const float* f = cf + cP.pen_bodies[b] * 3;
-                    c += (sqrtf(f[0] * f[0] + f[1] * f[1] + f[2] * f[2]) > 0.1f) ? 1.0f : 0.0f;
-                }
-                r[3] = c;
-            }
-            float dq2 = 0.0f, dacc = 0.0f, qerr = 0.0f, jall = 0.0f, tq = 0.0f;
-            {
-                const float* ref = B.ref_dof_pos + (size_t)e * 12;   // STALE reference pose (hazard 2)
+            if (phases & (HG_PHASE_TERMINATE | HG_PHASE_RESET)) B.reset_buf[e] = reset;
+
+            if (do_obs) {                                           // humanoid_env.py:200-262
+                float phase = (float)ep * cP.dt / cP.cycle_time;
+                float ang = kTwoPi * phase;
+                float s = sinf(ang), c = cosf(ang);
+                float st0 = s >= 0.0f ? 1.0f : 0.0f, st1 = s < 0.0f ? 1.0f : 0.0f;
+                bool dbl = fabsf(s) < 0.1f;
+                if (dbl) { st0 = 1.0f; st1 = 1.0f; }
+                float sl = s > 0.0f ? 0.0f : s, sr = s < 0.0f ? 0.0f : s;   // compute_ref_state :121-142
+                float k1 = cP.target_joint_pos_scale, k2 = 2.0f * k1;
+                float* o = S.newobs + le * HG_OBS1;
+                float* p = S.newpriv + le * HG_PRIV1;
+                float ci[5] = {s, c, cmd[0] * cP.obs_scale_lin_vel, cmd[1] * cP.obs_scale_lin_vel, cmd[2] * cP.obs_scale_ang_vel};
+#pragma unroll
+                for (int j = 0; j < 5; ++j) { o[j] = ci[j]; p[j] = ci[j]; }
+                float* gref = B.ref_dof_pos + (size_t)e * 12;
+#pragma unroll
                 for (int j = 0; j < 12; ++j) {
+                    float rj = 0.0f;
+                    if (!dbl) {
+                        if (j == 2 || j == 4) rj = sl * k1;
+                        if (j == 3) rj = sl * k2;
+                        if (j == 8 || j == 10) rj = sr * k1;
+                        if (j == 9) rj = sr * k2;
+                    }
                     float q = dof[2 * j], v = dof[2 * j + 1];
-                    float d = q - cP.default_dof_pos[j];
-                    jall += d * d;
-                    dq2 += v * v;
-                    float a = (ldv[j] - v) / cP.dt;
-                    dacc += a * a;
-                    float er = q - ref[j];
-                    qerr += er * er;
-                    tq += tau[j] * tau[j];
+                    float qs = (q - cP.default_dof_pos[j]) * cP.obs_scale_dof_pos;
+                    float vs = v * cP.obs_scale_dof_vel;
+                    o[5 + j] = qs; o[17 + j] = vs; o[29 + j] = act[j];
+                    p[5 + j] = qs; p[17 + j] = vs; p[29 + j] = act[j];
+                    p[41 + j] = q - rj;
+                    gref[j] = rj;
                 }
+                o[41] = bav.x * cP.obs_scale_ang_vel; o[42] = bav.y * cP.obs_scale_ang_vel; o[43] = bav.z * cP.obs_scale_ang_vel;
+                o[44] = eul.x * cP.obs_scale_quat; o[45] = eul.y * cP.obs_scale_quat; o[46] = eul.z * cP.obs_scale_quat;
+                p[53] = blv.x * cP.obs_scale_lin_vel; p[54] = blv.y * cP.obs_scale_lin_vel; p[55] = blv.z * cP.obs_scale_lin_vel;
+                p[56] = o[41]; p[57] = o[42]; p[58] = o[43];
+                p[59] = o[44]; p[60] = o[45]; p[61] = o[46];
+                p[62] = S.rpf[le * 3]; p[63] = S.rpf[le * 3 + 1];
+                p[64] = S.rpt[le * 3]; p[65] = S.rpt[le * 3 + 1]; p[66] = S.rpt[le * 3 + 2];
+                p[67] = S.fric[le];
+                p[68] = S.mass[le] / 30.0f;
+                p[69] = st0; p[70] = st1;
+                p[71] = contact0 ? 1.0f : 0.0f; p[72] = contact1 ? 1.0f : 0.0f;
             }
-            {   // 4 default_joint_pos :362-372
-                float d0 = dof[0] - cP.default_dof_pos[0], d1 = dof[2] - cP.default_dof_pos[1];
-                float d6 = dof[12] - cP.default_dof_pos[6], d7 = dof[14] - cP.default_dof_pos[7];
-                float yr = sqrtf(d0 * d0 + d1 * d1) + sqrtf(d6 * d6 + d7 * d7);
-                yr = clampf(yr - 0.1f, 0.0f, 50.0f);
-                r[4] = expf(-yr * 100.0f) - 0.01f * sqrtf(jall);
-            }
-            r[5] = dacc;                                         // dof_acc :516-521
-            r[6] = dq2;                                          // dof_vel :509-514
-            {   // 7 feet_air_time :320-334 (stateful)
-                float* fat = B.feet_air_time + (size_t)e * 2;
-                unsigned char* lc = B.last_contacts + (size_t)e * 2;
-                bool filt0 = contact0 || (st0 != 0.0f) || lc[0];
-                bool filt1 = contact1 || (st1 != 0.0f) || lc[1];
-                lc[0] = contact0; lc[1] = contact1;
-                float a0 = fat[0], a1 = fat[1];
-                bool first0 = (a0 > 0.0f) && filt0, first1 = (a1 > 0.0f) && filt1;
-                a0 += cP.dt; a1 += cP.dt;
-                r[7] = clampf(a0, 0.0f, 0.5f) * (first0 ? 1.0f : 0.0f) + clampf(a1, 0.0f, 0.5f) * (first1 ? 1.0f : 0.0f);
-                fat[0] = a0 * (filt0 ? 0.0f : 1.0f);
-                fat[1] = a1 * (filt1 ? 0.0f : 1.0f);
-            }
-            {   // 8 feet_clearance :446-467 (stateful; never reset, hazard 4)
-                float* fh = B.feet_height + (size_t)e * 2;
-                float* lz = B.last_feet_z + (size_t)e * 2;
-                float z0 = fL[2] - 0.05f, z1 = fR[2] - 0.05f;
-                float h0 = fh[0] + (z0 - lz[0]), h1 = fh[1] + (z1 - lz[1]);
-                lz[0] = z0; lz[1] = z1;
-                float hit0 = fabsf(h0 - cP.target_feet_height) < 0.01f ? 1.0f : 0.0f;
-                float hit1 = fabsf(h1 - cP.target_feet_height) < 0.01f ? 1.0f : 0.0f;
-                r[8] = hit0 * (1.0f - st0) + hit1 * (1.0f - st1);
-                fh[0] = h0 * (contact0 ? 0.0f : 1.0f);
-                fh[1] = h1 * (contact1 ? 0.0f : 1.0f);
-            }
-            {   // 9 feet_contact_forces :355-360
-                const float* a = cf + cP.feet[0] * 3;
-                const float* b = cf + cP.feet[1] * 3;
-                float na = sqrtf(a[0] * a[0] + a[1] * a[1] + a[2] * a[2]);
-                float nb = sqrtf(b[0] * b[0] + b[1] * b[1] + b[2] * b[2]);
-                r[9] = clampf(na - cP.max_contact_force, 0.0f, 400.0f) + clampf(nb - cP.max_contact_force, 0.0f, 400.0f);
-            }
-            {   // 10 feet_contact_number :336-344
-                float m0 = ((contact0 ? 1.0f : 0.0f) == st0) ? 1.0f : -0.3f;
-                float m1 = ((contact1 ? 1.0f : 0.0f) == st1) ? 1.0f : -0.3f;
-                r[10] = (m0 + m1) / 2.0f;
-            }
-            r[11] = two_point_distance_reward(fL[0], fL[1], fR[0], fR[1], cP.min_dist, cP.max_dist);   // :282-292
-            {   // 12 foot_slip :308-318
-                float v0 = sqrtf(sqrtf(fL[7] * fL[7] + fL[8] * fL[8]));
-                float v1 = sqrtf(sqrtf(fR[7] * fR[7] + fR[8] * fR[8]));
-                r[12] = v0 * (contact0 ? 1.0f : 0.0f) + v1 * (contact1 ? 1.0f : 0.0f);
-            }
-            {   // 13 joint_pos :272-280
-                float er = sqrtf(qerr);
-                r[13] = expf(-2.0f * er) - 0.2f * clampf(er, 0.0f, 0.5f);
-            }
-            {   // 14 knee_distance :295-305
-                const float* kL = rs + cP.knees[0] * 13;
-                const float* kR = rs + cP.knees[1] * 13;
-                r[14] = two_point_distance_reward(kL[0], kL[1], kR[0], kR[1], cP.min_dist, cP.max_dist / 2.0f);
-            }
-            {   // 15 low_speed :469-500
-                float v = blv.x, c = cmd[0];
-                float av = fabsf(v), ac = fabsf(c);
-                bool low = av < 0.5f * ac, high = av > 1.2f * ac;
-                float rr = 0.0f;
-                if (low) rr = -1.0f;
-                if (high) rr = 0.0f;
-                if (!(low || high)) rr = 1.2f;
-                float sv = (v > 0.0f) - (v < 0.0f), sc = (c > 0.0f) - (c < 0.0f);
-                if (sv != sc) rr = -2.0f;
-                r[15] = rr * (ac > 0.1f ? 1.0f : 0.0f);
-            }
-            {   // 16 orientation :346-353
-                float a = expf(-(fabsf(eul.x) + fabsf(eul.y)) * 10.0f);
-                float b = expf(-sqrtf(pg.x * pg.x + pg.y * pg.y) * 20.0f);
-                r[16] = (a + b) / 2.0f;
-            }
-            r[17] = tq;                                          // torques :502-507
-            {
-                float ex = cmd[0] - blv.x, ey = cmd[1] - blv.y;
-                float le2 = ex * ex + ey * ey;
-                float lin = sqrtf(le2);
-                float ang = fabsf(cmd[2] - bav.z);
-                // 18 track_vel_hard :408-425
-                r[18] = (expf(-lin * 10.0f) + expf(-ang * 10.0f)) / 2.0f - 0.2f * (lin + ang);
-                // 19 tracking_ang_vel :436-444
-                float da = cmd[2] - bav.z;
-                r[19] = expf(-(da * da) * cP.tracking_sigma);
-                // 20 tracking_lin_vel :427-434
-                r[20] = expf(-le2 * cP.tracking_sigma);
-            }
-            {   // 21 vel_mismatch_exp :396-406
-                float a = expf(-(blv.z * blv.z) * 10.0f);
-                float b = expf(-sqrtf(bav.x * bav.x + bav.y * bav.y) * 5.0f);
-                r[21] = (a + b) / 2.0f;
-            }
-            float total = 0.0f;
-#pragma unroll
-            for (int k = 0; k < HG_NUM_REWARDS; ++k) {
-                float rk = r[k] * cP.reward_scales[k];
-                total += rk;
-                B.episode_sums[(size_t)k * N + e] += rk;
-                if (B.rew_terms) B.rew_terms[(size_t)k * N + e] = rk;
-            }
-            if (cP.only_positive_rewards) total = fmaxf(total, 0.0f);
-            B.rew_buf[e] = total;
-        }
 
-        if (do_reset && reset) {                                // legged_robot.py:163-215
-            for (int j = 0; j < 12; ++j) {                      // _reset_dofs :359-373
-                float u = draw_u(Z.u_dof, (int64_t)e * 12 + j, Z.seed, Z.step, e, HG_RNG_DOF, j);
-                dof[2 * j] = cP.default_dof_pos[j] + (cP.dof_reset_span * u + cP.dof_reset_lo);
-                dof[2 * j + 1] = 0.0f;
-                act[j] = 0.0f;
+            // ---- small per-env outputs (fire-and-forget stores) ------------------------------------------
+            if (phases & (HG_PHASE_COUNTERS | HG_PHASE_RESET)) {
+                B.episode_length_buf[e] = ep;
+                float* q;
+                q = B.projected_gravity + (size_t)e * 3; q[0] = pg.x; q[1] = pg.y; q[2] = pg.z;
+                q = B.base_euler_xyz + (size_t)e * 3; q[0] = eul.x; q[1] = eul.y; q[2] = eul.z;
             }
-            const float* org = B.env_origins + (size_t)e * 3;   // _reset_root_states :374-397
-            for (int j = 0; j < 13; ++j) root[j] = cP.base_init_state[j];
-            root[0] += org[0]; root[1] += org[1]; root[2] += org[2];
-            S.root_dirty[le] = 1;
-            float u0 = draw_u(Z.u_cmd_rs, (int64_t)e * 3 + 0, Z.seed, Z.step, e, HG_RNG_CMD_RS, 0);
-            float u1 = draw_u(Z.u_cmd_rs, (int64_t)e * 3 + 1, Z.seed, Z.step, e, HG_RNG_CMD_RS, 1);
-            float u2 = draw_u(Z.u_cmd_rs, (int64_t)e * 3 + 2, Z.seed, Z.step, e, HG_RNG_CMD_RS, 2);
-            resample_commands(cmd, u0, u1, u2);
-            cmd_dirty = true;
-            B.feet_air_time[(size_t)e * 2] = 0.0f;
-            B.feet_air_time[(size_t)e * 2 + 1] = 0.0f;
-            ep = 0;
-            for (int k = 0; k < HG_NUM_REWARDS; ++k) {          // extras["episode"] :198-202
-                float* p = B.episode_sums + (size_t)k * N + e;
-                atomicAdd(&S.acc[k], *p);
-                *p = 0.0f;
+            if (phases & HG_PHASE_COUNTERS) {
+                float* q;
+                q = B.base_lin_vel + (size_t)e * 3; q[0] = blv.x; q[1] = blv.y; q[2] = blv.z;
+                q = B.base_ang_vel + (size_t)e * 3; q[0] = bav.x; q[1] = bav.y; q[2] = bav.z;
             }
-            atomicAdd(&S.cnt, 1);
-            B.reset_ids[atomicAdd(&B.scratch[0], 1)] = e;
-            eul = euler_xyz_wrapped(root + 3);                   // "fix reset gravity bug" :212-215
-            pg = quat_rotate_inverse(root + 3, V3{0.0f, 0.0f, -1.0f});
-            S.reset[le] = 1;
-        }
-        if (phases & (HG_PHASE_TERMINATE | HG_PHASE_RESET)) B.reset_buf[e] = reset;
-
-        if (do_obs) {                                           // humanoid_env.py:200-262
-            float phase = (float)ep * cP.dt / cP.cycle_time;
-            float ang = kTwoPi * phase;
-            float s = sinf(ang), c = cosf(ang);
-            float st0 = s >= 0.0f ? 1.0f : 0.0f, st1 = s < 0.0f ? 1.0f : 0.0f;
-            bool dbl = fabsf(s) < 0.1f;
-            if (dbl) { st0 = 1.0f; st1 = 1.0f; }
-            float sl = s > 0.0f ? 0.0f : s, sr = s < 0.0f ? 0.0f : s;   // compute_ref_state :121-142
-            float k1 = cP.target_joint_pos_scale, k2 = 2.0f * k1;
-            float ref[12];
+            if (phases & (HG_PHASE_REWARD | HG_PHASE_RESET))
+                *(reinterpret_cast<float2*>(B.feet_air_time) + e) = make_float2(S.fat[2 * le], S.fat[2 * le + 1]);
+            if (cmd_dirty) *reinterpret_cast<float4*>(B.commands + (size_t)e * 4) = make_float4(cmd[0], cmd[1], cmd[2], cmd[3]);
+            if (do_last) {                                          // legged_robot.py:150
+                float* lrv = B.last_root_vel + (size_t)e * 6;
 #pragma unroll
-            for (int j = 0; j < 12; ++j) ref[j] = 0.0f;
-            if (!dbl) {
-                ref[2] = sl * k1; ref[3] = sl * k2; ref[4] = sl * k1;
-                ref[8] = sr * k1; ref[9] = sr * k2; ref[10] = sr * k1;
+                for (int j = 0; j < 6; ++j) lrv[j] = root[7 + j];
             }
-            float* o = S.newobs + le * HG_OBS1;
-            float* p = S.newpriv + le * HG_PRIV1;
-            float ci[5] = {s, c, cmd[0] * cP.obs_scale_lin_vel, cmd[1] * cP.obs_scale_lin_vel, cmd[2] * cP.obs_scale_ang_vel};
-#pragma unroll
-            for (int j = 0; j < 5; ++j) { o[j] = ci[j]; p[j] = ci[j]; }
-            float* gref = B.ref_dof_pos + (size_t)e * 12;
-            for (int j = 0; j < 12; ++j) {
-                float q = dof[2 * j], v = dof[2 * j + 1];
-                float qs = (q - cP.default_dof_pos[j]) * cP.obs_scale_dof_pos;
-                float vs = v * cP.obs_scale_dof_vel;
-                o[5 + j] = qs; o[17 + j] = vs; o[29 + j] = act[j];
-                p[5 + j] = qs; p[17 + j] = vs; p[29 + j] = act[j];
-                p[41 + j] = q - ref[j];
-                gref[j] = ref[j];
-            }
-            o[41] = bav.x * cP.obs_scale_ang_vel; o[42] = bav.y * cP.obs_scale_ang_vel; o[43] = bav.z * cP.obs_scale_ang_vel;
-            o[44] = eul.x * cP.obs_scale_quat; o[45] = eul.y * cP.obs_scale_quat; o[46] = eul.z * cP.obs_scale_quat;
-            p[53] = blv.x * cP.obs_scale_lin_vel; p[54] = blv.y * cP.obs_scale_lin_vel; p[55] = blv.z * cP.obs_scale_lin_vel;
-            p[56] = o[41]; p[57] = o[42]; p[58] = o[43];
-            p[59] = o[44]; p[60] = o[45]; p[61] = o[46];
-            const float* rpf = B.rand_push_force + (size_t)e * 3;
-            const float* rpt = B.rand_push_torque + (size_t)e * 3;
-            p[62] = rpf[0]; p[63] = rpf[1];
-            p[64] = rpt[0]; p[65] = rpt[1]; p[66] = rpt[2];
-            p[67] = B.env_frictions[e];
-            p[68] = B.body_mass[e] / 30.0f;
-            p[69] = st0; p[70] = st1;
-            p[71] = contact0 ? 1.0f : 0.0f; p[72] = contact1 ? 1.0f : 0.0f;
         }
-
-        // ---- small per-env outputs ---------------------------------------------------------------
-        if (phases & (HG_PHASE_COUNTERS | HG_PHASE_RESET)) {
-            B.episode_length_buf[e] = ep;
-            float* q;
-            q = B.projected_gravity + (size_t)e * 3; q[0] = pg.x; q[1] = pg.y; q[2] = pg.z;
-            q = B.base_euler_xyz + (size_t)e * 3; q[0] = eul.x; q[1] = eul.y; q[2] = eul.z;
-        }
-        if (phases & HG_PHASE_COUNTERS) {
-            float* q;
-            q = B.base_lin_vel + (size_t)e * 3; q[0] = blv.x; q[1] = blv.y; q[2] = blv.z;
-            q = B.base_ang_vel + (size_t)e * 3; q[0] = bav.x; q[1] = bav.y; q[2] = bav.z;
-        }
-        if (cmd_dirty) *reinterpret_cast<float4*>(B.commands + (size_t)e * 4) = make_float4(cmd[0], cmd[1], cmd[2], cmd[3]);
-        if (do_last) {                                          // legged_robot.py:150
-            float* lrv = B.last_root_vel + (size_t)e * 6;
-#pragma unroll
-            for (int j = 0; j < 6; ++j) lrv[j] = root[7 + j];
+    } else {
+        // ---- 2b. streaming warps: history shift, overlapped with the reward / observation math ---------------
+        bar_sync(1, HG_ENV_THREADS);                                 // reset mask is ready
+        if (do_obs) {
+            stream_history<HG_OBS1, OBS_KEEP, OBS_W>(B.obs_out + (size_t)e0 * OBS_W, B.obs_buf + (size_t)e0 * OBS_W, S.reset,
+                                                      nE, warp - 1, 7, lane);
+            stream_history<HG_PRIV1, PRIV_KEEP, PRIV_W>(B.priv_out + (size_t)e0 * PRIV_W, B.privileged_obs_buf + (size_t)e0 * PRIV_W,
+                                                        S.reset, nE, warp - 1, 7, lane);
         }
     }
     __syncthreads();
 
-    // ---- 3. observation noise (humanoid_env.py:249-252), spread over the CTA ----------------------
-    if (do_obs && cP.add_noise) {
+    // ---- 3. newest frame: noise (humanoid_env.py:249-252), +-18 clip (legged_robot.py:104-108), store ---------
+    if (do_obs) {
         for (int i = tid; i < nE * HG_OBS1; i += HG_ENV_THREADS) {
             int le = i / HG_OBS1, k = i - le * HG_OBS1;
-            float sc = cP.noise_scale_vec[k];
-            if (sc != 0.0f || Z.z_obs) {
-                int e = e0 + le;
-                float z;
-                if (Z.z_obs) z = Z.z_obs[(size_t)e * HG_OBS1 + k];
-                else {
-                    HgPhilox r = hg_philox(Z.seed, (uint32_t)e, (uint32_t)Z.step, HG_RNG_OBS | ((uint32_t)(Z.step >> 32) << 8), (uint32_t)k);
-                    z = hg_normal(r.c[0], r.c[1]);
+            float v = S.newobs[i];
+            if (cP.add_noise) {
+                float sc = cP.noise_scale_vec[k];
+                if (sc != 0.0f || Z.z_obs) {
+                    int e = e0 + le;
+                    float z;
+                    if (Z.z_obs) z = Z.z_obs[(size_t)e * HG_OBS1 + k];
+                    else {
+                        HgPhilox r = hg_philox(Z.seed, (uint32_t)e, (uint32_t)Z.step, HG_RNG_OBS | ((uint32_t)(Z.step >> 32) << 8), (uint32_t)k);
+                        z = hg_normal(r.c[0], r.c[1]);
+                    }
+                    v = v + z * sc * cP.noise_level;
                 }
-                S.newobs[i] = S.newobs[i] + z * sc * cP.noise_level;
             }
+            if (do_last) v = clampf(v, -cP.clip_obs, cP.clip_obs);
+            B.obs_out[(size_t)(e0 + le) * OBS_W + OBS_KEEP + k] = v;
         }
-        __syncthreads();
+        for (int i = tid; i < nE * HG_PRIV1; i += HG_ENV_THREADS) {
+            int le = i / HG_PRIV1, k = i - le * HG_PRIV1;
+            float v = S.newpriv[i];
+            if (do_last) v = clampf(v, -cP.clip_obs, cP.clip_obs);
+            B.priv_out[(size_t)(e0 + le) * PRIV_W + PRIV_KEEP + k] = v;
+        }
+    } else if (do_reset) {
+        // stand-alone reset_idx: zero the history rows of the reset envs in place (humanoid_env.py:264-269)
+        for (int i = tid; i < nE * OBS_W; i += HG_ENV_THREADS)
+            if (S.reset[i / OBS_W]) B.obs_buf[(size_t)e0 * OBS_W + i] = 0.0f;
+        for (int i = tid; i < nE * PRIV_W; i += HG_ENV_THREADS)
+            if (S.reset[i / PRIV_W]) B.privileged_obs_buf[(size_t)e0 * PRIV_W + i] = 0.0f;
     }
 
-    // ---- 4. coalesced write-back -------------------------------------------------------------------
-    if (do_obs || do_reset) {
-        const int shift_o = do_obs ? HG_OBS1 : 0, shift_p = do_obs ? HG_PRIV1 : 0;
-        if (!do_obs) {   // stand-alone reset_idx: rows must come from HBM (not staged above)
-            tile_load(S.obs, B.obs_buf + (size_t)e0 * OBS_W, nE * OBS_W);
-            tile_load(S.priv, B.privileged_obs_buf + (size_t)e0 * PRIV_W, nE * PRIV_W);
-            __syncthreads();
+    // ---- 4. coalesced write-back of the tiles the step modified ------------------------------------------------
+    if (phases & (HG_PHASE_REWARD | HG_PHASE_RESET)) {
+        for (int i = tid; i < HG_NUM_REWARDS * nE; i += HG_ENV_THREADS) {
+            int k = i / nE, le = i - k * nE;
+            B.episode_sums[(size_t)k * N + e0 + le] = S.sums[k * E + le];
         }
-        hist_store<HG_OBS1, OBS_W>(B.obs_buf + (size_t)e0 * OBS_W, S.obs, S.newobs, S.reset, nE, shift_o, do_last);
-        hist_store<HG_PRIV1, PRIV_W>(B.privileged_obs_buf + (size_t)e0 * PRIV_W, S.priv, S.newpriv, S.reset, nE, shift_p, do_last);
     }
     if (do_reset || (phases & HG_PHASE_CALLBACK)) {
         // root / dof rows change only on push or reset: write back the dirty rows
@@ -697,6 +745,7 @@ int32_t check_buffers(const HgEnvBuffers* B) {
     HG_REQUIRE(B->rand_push_force); HG_REQUIRE(B->rand_push_torque); HG_REQUIRE(B->env_frictions); HG_REQUIRE(B->body_mass);
     HG_REQUIRE(B->env_origins); HG_REQUIRE(B->episode_sums); HG_REQUIRE(B->episode_means); HG_REQUIRE(B->obs_buf);
     HG_REQUIRE(B->privileged_obs_buf); HG_REQUIRE(B->rew_buf); HG_REQUIRE(B->reset_ids); HG_REQUIRE(B->scratch);
+    HG_REQUIRE(B->obs_out); HG_REQUIRE(B->priv_out);
     if (!hg_aligned16(B->commands)) return hg_fail(HG_E_ALIGN, "commands must be 16-byte aligned");
     if (!hg_aligned16(B->dof_state)) return hg_fail(HG_E_ALIGN, "dof_state must be 16-byte aligned");
     return 0;
@@ -733,6 +782,9 @@ extern "C" int32_t hg_env_post_physics(const HgEnvBuffers* B, const HgEnvParams*
     if (int32_t rc = check_buffers(B)) return rc;
     HG_REQUIRE(P); HG_REQUIRE(Z);
     if (N <= 0 || N > (1 << 26)) return hg_fail(HG_E_SIZE, "hg_env_post_physics: bad N");
+    if ((phases & HG_PHASE_OBS) && (B->obs_out == B->obs_buf || B->priv_out == B->privileged_obs_buf))
+        return hg_fail(HG_E_ARG, "hg_env_post_physics: obs_out / priv_out must not alias the history inputs");
+    if (P->num_bodies > HG_MAX_BODIES) return hg_fail(HG_E_SIZE, "hg_env_post_physics: num_bodies > 16");
     if (P->num_bodies <= 0 || P->n_term > HG_MAX_CONTACT_BODIES || P->n_pen > HG_MAX_CONTACT_BODIES)
         return hg_fail(HG_E_ARG, "hg_env_post_physics: bad body indices");
     if ((phases & ~HG_PHASE_STEP_ALL) || phases == 0) return hg_fail(HG_E_ARG, "hg_env_post_physics: bad phase mask");

@@ -58,7 +58,8 @@ _ENV_BUFFER_NAMES = (
     "reset_buf", "time_out_buf", "extras_time_outs", "base_lin_vel", "base_ang_vel", "projected_gravity",
     "base_euler_xyz", "feet_air_time", "last_contacts", "feet_height", "last_feet_z", "ref_dof_pos",
     "rand_push_force", "rand_push_torque", "env_frictions", "body_mass", "env_origins", "episode_sums",
-    "episode_means", "rew_terms", "obs_buf", "privileged_obs_buf", "rew_buf", "reset_ids", "scratch")
+    "episode_means", "rew_terms", "obs_buf", "privileged_obs_buf", "obs_out", "priv_out", "rew_buf", "reset_ids",
+    "scratch")
 
 
 class EnvBuffers(C.Structure):

@@ -212,6 +212,11 @@ class LeggedRobot(BaseTask):
             episode_sums=self._episode_sums, episode_means=self._episode_means, rew_terms=None,
             obs_buf=self.obs_buf, privileged_obs_buf=self.privileged_obs_buf, rew_buf=self.rew_buf,
             reset_ids=self.reset_ids, scratch=self._scratch)
+        # observation histories are a ping-pong pair: the kernel reads frames 1..14 of one buffer and writes
+        # frames 0..13 (+ the new frame) of the other -- like the reference, env.obs_buf is rebound every step
+        self._obs_pp = [self.obs_buf, torch.zeros_like(self.obs_buf)]
+        self._priv_pp = [self.privileged_obs_buf, torch.zeros_like(self.privileged_obs_buf)]
+        tensors["obs_out"], tensors["priv_out"] = self._obs_pp[1], self._priv_pp[1]
         for k, t in tensors.items():
             setattr(B, k, nat.ptr(t))
         self._B = B
@@ -234,8 +239,23 @@ class LeggedRobot(BaseTask):
             setattr(Z, k, nat.ptr(inj.get(k)))
         Z.step = self._noise_step
         self._noise_step += 1
-        nat.check(nat.lib.hg_env_post_physics(self._B, self._P, Z, phases, int(self.common_step_counter),
+        B = self._B
+        if self.obs_buf is self._obs_pp[0]:
+            src, dst = 0, 1
+        elif self.obs_buf is self._obs_pp[1]:
+            src, dst = 1, 0
+        else:       # user code rebound env.obs_buf: adopt its contents
+            self._obs_pp[0].copy_(self.obs_buf)
+            self._priv_pp[0].copy_(self.privileged_obs_buf)
+            src, dst = 0, 1
+        B.obs_buf, B.privileged_obs_buf = self._obs_pp[src].data_ptr(), self._priv_pp[src].data_ptr()
+        B.obs_out, B.priv_out = self._obs_pp[dst].data_ptr(), self._priv_pp[dst].data_ptr()
+        nat.check(nat.lib.hg_env_post_physics(B, self._P, Z, phases, int(self.common_step_counter),
                                               self.num_envs, nat.stream_ptr(self._dev_index)), "hg_env_post_physics")
+        if phases & nat.PHASE_OBS:
+            self.obs_buf, self.privileged_obs_buf = self._obs_pp[dst], self._priv_pp[dst]
+        else:
+            self.obs_buf, self.privileged_obs_buf = self._obs_pp[src], self._priv_pp[src]
 
     # ------------------------------------------------------------------------------------------
     # stepping

@@ -110,8 +110,11 @@ typedef struct HgEnvBuffers {
     float* episode_sums;       /* (22,N) one row per reward term, alphabetical     */
     float* episode_means;      /* (22)   extras["episode"]["rew_*"]                */
     float* rew_terms;          /* (22,N) optional (may be NULL): per-term scaled reward of this step */
-    float* obs_buf;            /* (N,705) 15 frames oldest->newest, clipped        */
-    float* privileged_obs_buf; /* (N,219) 3 frames                                 */
+    float* obs_buf;            /* (N,705) 15 frames oldest->newest, clipped: history INPUT  */
+    float* privileged_obs_buf; /* (N,219) 3 frames: history INPUT                           */
+    float* obs_out;            /* (N,705) shifted history + new frame is written here; must
+                                  not alias obs_buf (ping-pong pair, or a rollout-storage slab) */
+    float* priv_out;           /* (N,219) likewise                                          */
     float* rew_buf;            /* (N)                                              */
     int32_t* reset_ids;        /* (N) compacted ids of envs reset this step (any order) */
     int32_t* scratch;          /* (32) int32, zero-initialised once by the caller:
