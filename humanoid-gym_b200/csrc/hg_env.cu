@@ -53,20 +53,23 @@ __device__ __forceinline__ V3 quat_rotate_inverse(const float* q, V3 v) {
     return {a.x - b.x + e.x, a.y - b.y + e.y, a.z - b.z + e.z};
 }
 
-// torch.remainder for a positive divisor
+// torch.remainder for a positive divisor.  fmod is exact, and for |a| < m it is the identity: that covers
+// every angle on this path (atan2 / asin outputs, heading errors); the general case is kept out of line.
+__device__ __noinline__ float fmod_general(float a, float m) { return fmodf(a, m); }
 __device__ __forceinline__ float remainder_pos(float a, float m) {
-    float r = fmodf(a, m);
+    float r = (fabsf(a) < m) ? a : fmod_general(a, m);
     if (r != 0.0f && r < 0.0f) r += m;
     return r;
 }
+__device__ __noinline__ float atan2_call(float y, float x) { return atan2f(y, x); }
 
 // get_euler_xyz + fold of (pi, 2pi) to negative angles (legged_robot.py:50-55)
-__device__ __forceinline__ V3 euler_xyz_wrapped(const float* q) {
+__device__ __noinline__ V3 euler_xyz_wrapped(const float* q) {
     float x = q[0], y = q[1], z = q[2], w = q[3];
-    float roll = atan2f(2.0f * (w * x + y * z), w * w - x * x - y * y + z * z);
+    float roll = atan2_call(2.0f * (w * x + y * z), w * w - x * x - y * y + z * z);
     float sinp = 2.0f * (w * y - z * x);
     float pitch = (fabsf(sinp) >= 1.0f) ? copysignf(1.5707963267948966f, sinp) : asinf(sinp);
-    float yaw = atan2f(2.0f * (w * z + x * y), w * w + x * x - y * y - z * z);
+    float yaw = atan2_call(2.0f * (w * z + x * y), w * w + x * x - y * y - z * z);
     V3 e = {remainder_pos(roll, kTwoPi), remainder_pos(pitch, kTwoPi), remainder_pos(yaw, kTwoPi)};
     if (e.x > kPi) e.x -= kTwoPi;
     if (e.y > kPi) e.y -= kTwoPi;
@@ -85,16 +88,42 @@ __device__ __forceinline__ float two_point_distance_reward(float ax, float ay, f
     return (expf(-fabsf(dmin) * 100.0f) + expf(-fabsf(dmax) * 100.0f)) / 2.0f;
 }
 
-// cooperative (whole CTA) global -> shared copy of a contiguous float range
-__device__ __forceinline__ void tile_load(float* s, const float* g, int n) {
+// cooperative (whole CTA) ASYNCHRONOUS global -> shared copy of a contiguous float range (cp.async / LDGSTS):
+// no register round trip, so the staging loop issues every tile's requests back to back and pays the
+// memory latency once (cp_async_wait_all + __syncthreads) instead of once per tile.
+__device__ __forceinline__ void cp_async4(float* sdst, const float* gsrc) {
+    unsigned sa = (unsigned)__cvta_generic_to_shared(sdst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(sa), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async16(float* sdst, const float* gsrc) {
+    unsigned sa = (unsigned)__cvta_generic_to_shared(sdst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
+}
+// the calling thread's arrival on `bar` is triggered when all of its earlier cp.async copies have landed
+__device__ __forceinline__ void mbar_arrive_on_cp_async(unsigned long long* bar) {
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+    unsigned sa = (unsigned)__cvta_generic_to_shared(bar);
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" ::"r"(sa), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tile_load(float* s, const float* g, int n, int t, int nt) {
     if ((reinterpret_cast<uintptr_t>(g) & 15u) == 0) {
         int n4 = n >> 2;
-        const float4* g4 = reinterpret_cast<const float4*>(g);
-        float4* s4 = reinterpret_cast<float4*>(s);
-        for (int i = threadIdx.x; i < n4; i += HG_ENV_THREADS) s4[i] = __ldg(g4 + i);
-        for (int i = (n4 << 2) + threadIdx.x; i < n; i += HG_ENV_THREADS) s[i] = __ldg(g + i);
+        for (int i = t; i < n4; i += nt) cp_async16(s + 4 * i, g + 4 * i);
+        for (int i = (n4 << 2) + t; i < n; i += nt) cp_async4(s + i, g + i);
     } else {
-        for (int i = threadIdx.x; i < n; i += HG_ENV_THREADS) s[i] = __ldg(g + i);
+        for (int i = t; i < n; i += nt) cp_async4(s + i, g + i);
     }
 }
 
@@ -116,10 +145,12 @@ struct __align__(16) EnvSmem {
     float rpf[E * 3], rpt[E * 3], org[E * 3];
     float fric[E], mass[E];
     float sums[HG_NUM_REWARDS * E];
+    float rterm[HG_NUM_REWARDS * E];    // unscaled reward terms of this step
     float newobs[E * HG_OBS1];
     float newpriv[E * HG_PRIV1];
     float acc[HG_NUM_REWARDS + 2];
     long long ep[E];
+    unsigned long long mbar;
     int cnt;
     int is_last;
     unsigned char lc[E * 2];
@@ -128,10 +159,27 @@ struct __align__(16) EnvSmem {
     unsigned char root_dirty[E];
 };
 
+#define FIELD(f) (int)(offsetof(HgEnvBuffers, f) / sizeof(void*))
+#define SMEMF(f) (int)(offsetof(EnvSmem, f) / sizeof(float))
+constexpr int kNumTiles = 19;
+__constant__ int kTileField[kNumTiles] = {
+    FIELD(root_states), FIELD(dof_state), FIELD(actions), FIELD(last_actions), FIELD(last_last_actions), FIELD(last_dof_vel),
+    FIELD(torques), FIELD(ref_dof_pos), FIELD(last_root_vel), FIELD(commands), FIELD(contact_forces), FIELD(feet_air_time),
+    FIELD(feet_height), FIELD(last_feet_z), FIELD(rand_push_force), FIELD(rand_push_torque), FIELD(env_origins),
+    FIELD(env_frictions), FIELD(body_mass)};
+__constant__ int kTileSmem[kNumTiles] = {
+    SMEMF(root), SMEMF(dof), SMEMF(act), SMEMF(lact), SMEMF(llact), SMEMF(ldv), SMEMF(tau), SMEMF(ref), SMEMF(lrv), SMEMF(cmd),
+    SMEMF(cf), SMEMF(fat), SMEMF(fh), SMEMF(lfz), SMEMF(rpf), SMEMF(rpt), SMEMF(org), SMEMF(fric), SMEMF(mass)};
+__constant__ int kTileWidth[kNumTiles] = {13, 24, 12, 12, 12, 12, 12, 12, 6, 4, 0 /* num_bodies*3 */, 2, 2, 2, 3, 3, 3, 1, 1};
+
+__device__ __noinline__ HgPhilox philox_call(uint64_t seed, uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3) {
+    return hg_philox(seed, c0, c1, c2, c3);
+}
+
 __device__ __forceinline__ float draw_u(const float* inj, int64_t idx, uint64_t seed, uint64_t step, uint32_t env,
                                         uint32_t stream, uint32_t k) {
     if (inj) return inj[idx];
-    HgPhilox r = hg_philox(seed, env, (uint32_t)step, stream | ((uint32_t)(step >> 32) << 8), k);
+    HgPhilox r = philox_call(seed, env, (uint32_t)step, stream | ((uint32_t)(step >> 32) << 8), k);
     return hg_u01(r.c[0]);
 }
 
@@ -146,32 +194,38 @@ __device__ __forceinline__ void resample_commands(float* cmd, float u0, float u1
     cmd[1] *= keep;
 }
 
-__device__ __forceinline__ void bar_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
-__device__ __forceinline__ void bar_arrive(int id, int count) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory"); }
 
-// history rows w, w+nw, ... of one CTA tile: out[r][0:KEEP] = in[r][FRAME:FRAME+KEEP] (0 if the env reset)
-template <int FRAME, int KEEP, int WIDTH>
+// history rows w, w+nw, ... of one CTA tile: out[r][0:KEEP] = in[r][FRAME:FRAME+KEEP] (0 if the env reset).
+// ROWS rows are in flight per iteration: ROWS * ceil(KEEP/32) independent 128-byte requests per warp.
+template <int FRAME, int KEEP, int WIDTH, int ROWS>
 __device__ __forceinline__ void stream_history(float* __restrict__ out, const float* __restrict__ in,
                                                const unsigned char* s_reset, int nE, int w, int nw, int lane) {
-    constexpr int CH = (KEEP + 31) / 32;            // 21 (obs) / 5 (priv) independent 128-byte requests per row
-    for (int r = w; r < nE; r += nw) {
-        const float* src = in + (size_t)r * WIDTH + FRAME;
-        float* dst = out + (size_t)r * WIDTH;
-        float v[CH];
-        if (s_reset[r]) {
+    constexpr int CH = (KEEP + 31) / 32;            // 21 (obs) / 5 (priv)
+#pragma unroll 1
+    for (int r0 = w; r0 < nE; r0 += nw * ROWS) {
+        float v[ROWS][CH];
 #pragma unroll
-            for (int c = 0; c < CH; ++c) v[c] = 0.0f;
-        } else {
+        for (int q = 0; q < ROWS; ++q) {
+            const int r = r0 + q * nw;
+            const bool live = (r < nE);
+            const float* src = in + (size_t)r * WIDTH + FRAME;
 #pragma unroll
             for (int c = 0; c < CH; ++c) {
                 int k = c * 32 + lane;
-                v[c] = (k < KEEP) ? __ldcs(src + k) : 0.0f;          // streaming: read once
+                v[q][c] = (live && k < KEEP) ? __ldcs(src + k) : 0.0f;      // streaming: read once
             }
         }
 #pragma unroll
-        for (int c = 0; c < CH; ++c) {
-            int k = c * 32 + lane;
-            if (k < KEEP) dst[k] = v[c];
+        for (int q = 0; q < ROWS; ++q) {
+            const int r = r0 + q * nw;
+            if (r < nE) {
+                float* dst = out + (size_t)r * WIDTH;
+#pragma unroll
+                for (int c = 0; c < CH; ++c) {
+                    int k = c * 32 + lane;
+                    if (k < KEEP) dst[k] = v[q][c];
+                }
+            }
         }
     }
 }
@@ -181,8 +235,7 @@ post_physics_kernel(HgEnvBuffers B, HgEnvNoise Z, uint32_t phases, int64_t commo
     extern __shared__ __align__(16) unsigned char smem_raw[];
     EnvSmem& S = *reinterpret_cast<EnvSmem*>(smem_raw);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int e0 = blockIdx.x * E;
-    const int nE = min(E, N - e0);
+    const int num_tiles = (N + E - 1) / E;
     const bool do_obs = phases & HG_PHASE_OBS, do_reset = phases & HG_PHASE_RESET, do_last = phases & HG_PHASE_LAST;
     const int nb = cP.num_bodies;
     if (Z.use_device_counters) {   // CUDA-graph friendly: counters live in scratch[4..7], bumped by the last CTA
@@ -190,47 +243,57 @@ post_physics_kernel(HgEnvBuffers B, HgEnvNoise Z, uint32_t phases, int64_t commo
         Z.step = *reinterpret_cast<const volatile uint64_t*>(B.scratch + 6);
     }
 
-    // ---- 1. stage every per-env input (all warps, coalesced) -------------------------------------------
-    tile_load(S.root, B.root_states + (size_t)e0 * 13, nE * 13);
-    tile_load(S.dof, B.dof_state + (size_t)e0 * 24, nE * 24);
-    tile_load(S.act, B.actions + (size_t)e0 * 12, nE * 12);
-    tile_load(S.lact, B.last_actions + (size_t)e0 * 12, nE * 12);
-    tile_load(S.llact, B.last_last_actions + (size_t)e0 * 12, nE * 12);
-    tile_load(S.ldv, B.last_dof_vel + (size_t)e0 * 12, nE * 12);
-    tile_load(S.tau, B.torques + (size_t)e0 * 12, nE * 12);
-    tile_load(S.ref, B.ref_dof_pos + (size_t)e0 * 12, nE * 12);
-    tile_load(S.lrv, B.last_root_vel + (size_t)e0 * 6, nE * 6);
-    tile_load(S.cmd, B.commands + (size_t)e0 * 4, nE * 4);
-    tile_load(S.cf, B.contact_forces + (size_t)e0 * nb * 3, nE * nb * 3);
-    tile_load(S.fat, B.feet_air_time + (size_t)e0 * 2, nE * 2);
-    tile_load(S.fh, B.feet_height + (size_t)e0 * 2, nE * 2);
-    tile_load(S.lfz, B.last_feet_z + (size_t)e0 * 2, nE * 2);
-    tile_load(S.rpf, B.rand_push_force + (size_t)e0 * 3, nE * 3);
-    tile_load(S.rpt, B.rand_push_torque + (size_t)e0 * 3, nE * 3);
-    tile_load(S.org, B.env_origins + (size_t)e0 * 3, nE * 3);
-    tile_load(S.fric, B.env_frictions + e0, nE);
-    tile_load(S.mass, B.body_mass + e0, nE);
-    for (int i = tid; i < nE * 52; i += HG_ENV_THREADS) {          // feet / knee rows of rigid_state (52-byte runs)
-        int le = i / 52, r = i - le * 52, b = r / 13, c = r - b * 13;
-        int body = (b < 2) ? cP.feet[b] : cP.knees[b - 2];
-        S.rg[i] = __ldg(B.rigid_state + ((size_t)(e0 + le) * nb + body) * 13 + c);
-    }
-    for (int i = tid; i < HG_NUM_REWARDS * nE; i += HG_ENV_THREADS) {   // episode sums are (22, N): 128-byte runs
-        int k = i / nE, le = i - k * nE;
-        S.sums[k * E + le] = B.episode_sums[(size_t)k * N + e0 + le];
-    }
-    if (tid < nE) {
-        S.ep[tid] = B.episode_length_buf[e0 + tid];
-        S.reset_in[tid] = B.reset_buf[e0 + tid];
-        S.lc[2 * tid] = B.last_contacts[(size_t)(e0 + tid) * 2];
-        S.lc[2 * tid + 1] = B.last_contacts[(size_t)(e0 + tid) * 2 + 1];
+    // ---- 1. stage every per-env input: all 8 warps ISSUE the asynchronous copies, nobody blocks on them here.
+    // Completion is tracked by an mbarrier (cp.async.mbarrier.arrive.noinc): only the compute warp waits for
+    // it; the streaming warps go straight to the history shift, which depends on none of the staged data.
+    // Table-driven (one rolled loop) to keep the instruction footprint small: a CTA executes this code once,
+    // cold, so straight-line code costs an instruction-cache miss per 128 bytes.
+    if (tid == 0) {
+        mbar_init(&S.mbar, HG_ENV_THREADS);
+        S.cnt = 0;
+        S.is_last = 0;
     }
     if (tid < HG_NUM_REWARDS) S.acc[tid] = 0.0f;
-    if (tid == 0) { S.cnt = 0; S.is_last = 0; }
+    // tile loop (grid-stride over 32-env tiles; with the default grid each CTA runs exactly one tile)
+    unsigned tile_parity = 0;
+#pragma unroll 1
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, tile_parity ^= 1u) {
+    const int e0 = tile * E;
+    const int nE = min(E, N - e0);
     if (tid < E) { S.reset[tid] = 0; S.root_dirty[tid] = 0; }
     __syncthreads();
+    {
+        const float* const* fields = reinterpret_cast<const float* const*>(&B);
+        float* sbase = reinterpret_cast<float*>(&S);
+#pragma unroll 1
+        for (int t = 0; t < kNumTiles; ++t) {
+            int w = kTileWidth[t] ? kTileWidth[t] : nb * 3;
+            tile_load(sbase + kTileSmem[t], fields[kTileField[t]] + (size_t)e0 * w, nE * w, tid, HG_ENV_THREADS);
+        }
+    }
+#pragma unroll 1
+    for (int i = tid; i < nE * 52; i += HG_ENV_THREADS) {              // feet / knee rows of rigid_state (52-byte runs)
+        int le = i / 52, r = i - le * 52, b = r / 13, c = r - b * 13;
+        int body = (b < 2) ? cP.feet[b] : cP.knees[b - 2];
+        cp_async4(S.rg + i, B.rigid_state + ((size_t)(e0 + le) * nb + body) * 13 + c);
+    }
+#pragma unroll 1
+    for (int i = tid; i < HG_NUM_REWARDS * E; i += HG_ENV_THREADS) {    // episode sums are (22, N): 128-byte runs
+        int k = i / E, le = i % E;
+        if (le < nE) cp_async4(S.sums + i, B.episode_sums + (size_t)k * N + e0 + le);
+    }
+    mbar_arrive_on_cp_async(&S.mbar);
 
     if (warp == 0) {
+        if (lane < nE) {
+            S.ep[lane] = B.episode_length_buf[e0 + lane];
+            S.reset_in[lane] = B.reset_buf[e0 + lane];
+            S.lc[2 * lane] = B.last_contacts[(size_t)(e0 + lane) * 2];
+            S.lc[2 * lane + 1] = B.last_contacts[(size_t)(e0 + lane) * 2 + 1];
+        }
+        mbar_wait(&S.mbar, tile_parity);
+        __syncwarp();
+
         // ---- 2a. compute warp: one lane per env, everything out of shared memory -----------------------------
         const int le = lane;
         const int e = e0 + le;
@@ -265,6 +328,7 @@ post_physics_kernel(HgEnvBuffers B, HgEnvNoise Z, uint32_t phases, int64_t commo
                 if (do_reset) eul = euler_xyz_wrapped(root + 3);
             }
             if (phases & HG_PHASE_TERMINATE) {                      // legged_robot.py:156-161
+#pragma unroll 1
                 for (int b = 0; b < cP.n_term; ++b) {
                     const float* f = cf + cP.term_bodies[b] * 3;
                     reset |= sqrtf(f[0] * f[0] + f[1] * f[1] + f[2] * f[2]) > 1.0f;
@@ -275,10 +339,7 @@ post_physics_kernel(HgEnvBuffers B, HgEnvNoise Z, uint32_t phases, int64_t commo
             }
             S.reset[le] = (do_reset && reset) ? 1 : 0;
         }
-        // the reset mask depends only on this step's contacts and the episode clock: publish it now so that
-        // the streaming warps can start on the histories while the rewards are being evaluated
         __syncwarp();
-        bar_arrive(1, HG_ENV_THREADS);
 
         if (active) {
             if (phases & HG_PHASE_CALLBACK) {                       // legged_robot.py:304-320
@@ -294,7 +355,7 @@ post_physics_kernel(HgEnvBuffers B, HgEnvNoise Z, uint32_t phases, int64_t commo
                     float tx = (uy * 0.0f - uz * 0.0f) * 2.0f, ty = (uz * 1.0f - ux * 0.0f) * 2.0f, tz = (ux * 0.0f - uy * 1.0f) * 2.0f;
                     float fx = 1.0f + w * tx + (uy * tz - uz * ty);
                     float fy = 0.0f + w * ty + (uz * tx - ux * tz);
-                    float heading = atan2f(fy, fx);
+                    float heading = atan2_call(fy, fx);
                     float a = remainder_pos(cmd[3] - heading, kTwoPi);          // utils/math.py:47-50
                     a = a - kTwoPi * (a > kPi ? 1.0f : 0.0f);
                     cmd[2] = clampf(0.5f * a, -1.0f, 1.0f);
@@ -332,17 +393,11 @@ post_physics_kernel(HgEnvBuffers B, HgEnvNoise Z, uint32_t phases, int64_t commo
                 float s = sinf(kTwoPi * phase);
                 float st0 = s >= 0.0f ? 1.0f : 0.0f, st1 = s < 0.0f ? 1.0f : 0.0f;   // :105-118
                 if (fabsf(s) < 0.1f) { st0 = 1.0f; st1 = 1.0f; }
-                float total = 0.0f;
                 int kk = 0;
-                auto add_term = [&](float rv) {                     // alphabetical accumulation, :222-230
-                    float rk = rv * cP.reward_scales[kk];
-                    total += rk;
-                    S.sums[kk * E + le] += rk;
-                    if (B.rew_terms) B.rew_terms[(size_t)kk * N + e] = rk;
-                    ++kk;
-                };
+                auto add_term = [&](float rv) { S.rterm[kk * E + le] = rv; ++kk; };   // kk is a compile-time index
                 {   // 0 action_smoothness, humanoid_env.py:530-540
                     float t1 = 0.0f, t2 = 0.0f, t3 = 0.0f;
+#pragma unroll 1
                     for (int j = 0; j < 12; ++j) {
                         float d1 = lact[j] - act[j];
                         t1 += d1 * d1;
@@ -365,6 +420,7 @@ post_physics_kernel(HgEnvBuffers B, HgEnvNoise Z, uint32_t phases, int64_t commo
                 }
                 {   // 3 collision :523-528
                     float c = 0.0f;
+#pragma unroll 1
                     for (int b = 0; b < cP.n_pen; ++b) {
                         const float* f = cf + cP.pen_bodies[b] * 3;
                         c += (sqrtf(f[0] * f[0] + f[1] * f[1] + f[2] * f[2]) > 0.1f) ? 1.0f : 0.0f;
@@ -374,6 +430,7 @@ post_physics_kernel(HgEnvBuffers B, HgEnvNoise Z, uint32_t phases, int64_t commo
                 float dq2 = 0.0f, dacc = 0.0f, qerr = 0.0f, jall = 0.0f, tq = 0.0f;
                 {
                     const float* ref = S.ref + le * 12;              // STALE reference pose (hazard 2)
+#pragma unroll 1
                     for (int j = 0; j < 12; ++j) {
                         float q = dof[2 * j], v = dof[2 * j + 1];
                         float d = q - cP.default_dof_pos[j];
@@ -478,11 +535,20 @@ post_physics_kernel(HgEnvBuffers B, HgEnvNoise Z, uint32_t phases, int64_t commo
                     float b = expf(-sqrtf(bav.x * bav.x + bav.y * bav.y) * 5.0f);
                     add_term((a + b) / 2.0f);
                 }
+                float total = 0.0f;
+#pragma unroll 1
+                for (int k = 0; k < HG_NUM_REWARDS; ++k) {          // alphabetical accumulation, legged_robot.py:222-230
+                    float rk = S.rterm[k * E + le] * cP.reward_scales[k];
+                    total += rk;
+                    S.sums[k * E + le] += rk;
+                    if (B.rew_terms) B.rew_terms[(size_t)k * N + e] = rk;
+                }
                 if (cP.only_positive_rewards) total = fmaxf(total, 0.0f);
                 B.rew_buf[e] = total;
             }
 
             if (do_reset && reset) {                                // legged_robot.py:163-215
+#pragma unroll 1
                 for (int j = 0; j < 12; ++j) {                      // _reset_dofs :359-373
                     float u = draw_u(Z.u_dof, (int64_t)e * 12 + j, Z.seed, Z.step, e, HG_RNG_DOF, j);
                     dof[2 * j] = cP.default_dof_pos[j] + (cP.dof_reset_span * u + cP.dof_reset_lo);
@@ -499,6 +565,7 @@ post_physics_kernel(HgEnvBuffers B, HgEnvNoise Z, uint32_t phases, int64_t commo
                 cmd_dirty = true;
                 S.fat[2 * le] = 0.0f; S.fat[2 * le + 1] = 0.0f;
                 ep = 0;
+#pragma unroll 1
                 for (int k = 0; k < HG_NUM_REWARDS; ++k) {          // extras["episode"] :198-202
                     atomicAdd(&S.acc[k], S.sums[k * E + le]);
                     S.sums[k * E + le] = 0.0f;
@@ -525,7 +592,7 @@ post_physics_kernel(HgEnvBuffers B, HgEnvNoise Z, uint32_t phases, int64_t commo
 #pragma unroll
                 for (int j = 0; j < 5; ++j) { o[j] = ci[j]; p[j] = ci[j]; }
                 float* gref = B.ref_dof_pos + (size_t)e * 12;
-#pragma unroll
+#pragma unroll 1
                 for (int j = 0; j < 12; ++j) {
                     float rj = 0.0f;
                     if (!dbl) {
@@ -577,12 +644,12 @@ post_physics_kernel(HgEnvBuffers B, HgEnvNoise Z, uint32_t phases, int64_t commo
             }
         }
     } else {
-        // ---- 2b. streaming warps: history shift, overlapped with the reward / observation math ---------------
-        bar_sync(1, HG_ENV_THREADS);                                 // reset mask is ready
+        // ---- 2b. streaming warps: history shift, overlapped with staging and the reward / observation math.
+        // They copy every row unconditionally; rows of envs that turn out to reset are zeroed in step 3.
         if (do_obs) {
-            stream_history<HG_OBS1, OBS_KEEP, OBS_W>(B.obs_out + (size_t)e0 * OBS_W, B.obs_buf + (size_t)e0 * OBS_W, S.reset,
+            stream_history<HG_OBS1, OBS_KEEP, OBS_W, 1>(B.obs_out + (size_t)e0 * OBS_W, B.obs_buf + (size_t)e0 * OBS_W, S.reset,
                                                       nE, warp - 1, 7, lane);
-            stream_history<HG_PRIV1, PRIV_KEEP, PRIV_W>(B.priv_out + (size_t)e0 * PRIV_W, B.privileged_obs_buf + (size_t)e0 * PRIV_W,
+            stream_history<HG_PRIV1, PRIV_KEEP, PRIV_W, 5>(B.priv_out + (size_t)e0 * PRIV_W, B.privileged_obs_buf + (size_t)e0 * PRIV_W,
                                                         S.reset, nE, warp - 1, 7, lane);
         }
     }
@@ -600,7 +667,7 @@ post_physics_kernel(HgEnvBuffers B, HgEnvNoise Z, uint32_t phases, int64_t commo
                     float z;
                     if (Z.z_obs) z = Z.z_obs[(size_t)e * HG_OBS1 + k];
                     else {
-                        HgPhilox r = hg_philox(Z.seed, (uint32_t)e, (uint32_t)Z.step, HG_RNG_OBS | ((uint32_t)(Z.step >> 32) << 8), (uint32_t)k);
+                        HgPhilox r = philox_call(Z.seed, (uint32_t)e, (uint32_t)Z.step, HG_RNG_OBS | ((uint32_t)(Z.step >> 32) << 8), (uint32_t)k);
                         z = hg_normal(r.c[0], r.c[1]);
                     }
                     v = v + z * sc * cP.noise_level;
@@ -615,6 +682,14 @@ post_physics_kernel(HgEnvBuffers B, HgEnvNoise Z, uint32_t phases, int64_t commo
             if (do_last) v = clampf(v, -cP.clip_obs, cP.clip_obs);
             B.priv_out[(size_t)(e0 + le) * PRIV_W + PRIV_KEEP + k] = v;
         }
+        if (do_reset) {   // reset envs restart with an all-zero history (humanoid_env.py:264-269); rare
+#pragma unroll 1
+            for (int le = 0; le < nE; ++le) {
+                if (!S.reset[le]) continue;
+                for (int k = tid; k < OBS_KEEP; k += HG_ENV_THREADS) B.obs_out[(size_t)(e0 + le) * OBS_W + k] = 0.0f;
+                for (int k = tid; k < PRIV_KEEP; k += HG_ENV_THREADS) B.priv_out[(size_t)(e0 + le) * PRIV_W + k] = 0.0f;
+            }
+        }
     } else if (do_reset) {
         // stand-alone reset_idx: zero the history rows of the reset envs in place (humanoid_env.py:264-269)
         for (int i = tid; i < nE * OBS_W; i += HG_ENV_THREADS)
@@ -625,9 +700,10 @@ post_physics_kernel(HgEnvBuffers B, HgEnvNoise Z, uint32_t phases, int64_t commo
 
     // ---- 4. coalesced write-back of the tiles the step modified ------------------------------------------------
     if (phases & (HG_PHASE_REWARD | HG_PHASE_RESET)) {
-        for (int i = tid; i < HG_NUM_REWARDS * nE; i += HG_ENV_THREADS) {
-            int k = i / nE, le = i - k * nE;
-            B.episode_sums[(size_t)k * N + e0 + le] = S.sums[k * E + le];
+#pragma unroll 1
+        for (int i = tid; i < HG_NUM_REWARDS * E; i += HG_ENV_THREADS) {
+            int k = i / E, le = i % E;
+            if (le < nE) B.episode_sums[(size_t)k * N + e0 + le] = S.sums[i];
         }
     }
     if (do_reset || (phases & HG_PHASE_CALLBACK)) {
@@ -657,6 +733,9 @@ post_physics_kernel(HgEnvBuffers B, HgEnvNoise Z, uint32_t phases, int64_t commo
         }
     }
 
+    __syncthreads();      // smem tiles are reused by the next tile of this CTA
+    }                     // tile loop
+
     // ---- 5. extras["episode"] means + stale-able time_outs: last CTA finalises -------------------
     {
         if (S.cnt > 0 && tid < HG_NUM_REWARDS) atomicAdd(reinterpret_cast<float*>(B.scratch + 8) + tid, S.acc[tid]);
@@ -672,7 +751,18 @@ post_physics_kernel(HgEnvBuffers B, HgEnvNoise Z, uint32_t phases, int64_t commo
                     float sum = *(reinterpret_cast<volatile float*>(B.scratch + 8) + tid);
                     B.episode_means[tid] = sum / (float)total / cP.max_episode_length_s;
                 }
-                for (int i = tid; i < N; i += HG_ENV_THREADS) B.extras_time_outs[i] = B.time_out_buf[i];
+                // N-byte copy by ONE CTA: 16-byte vectors, 4 independent requests per thread in flight
+                if (((reinterpret_cast<uintptr_t>(B.extras_time_outs) | reinterpret_cast<uintptr_t>(B.time_out_buf)) & 15u) == 0) {
+                    const uint4* src = reinterpret_cast<const uint4*>(B.time_out_buf);
+                    uint4* dst = reinterpret_cast<uint4*>(B.extras_time_outs);
+                    const int n16 = N >> 4;
+#pragma unroll 4
+                    for (int i = tid; i < n16; i += HG_ENV_THREADS) dst[i] = src[i];
+                    for (int i = (n16 << 4) + tid; i < N; i += HG_ENV_THREADS) B.extras_time_outs[i] = B.time_out_buf[i];
+                } else {
+#pragma unroll 4
+                    for (int i = tid; i < N; i += HG_ENV_THREADS) B.extras_time_outs[i] = B.time_out_buf[i];
+                }
             }
             __syncthreads();
             if (tid < HG_NUM_REWARDS) reinterpret_cast<float*>(B.scratch + 8)[tid] = 0.0f;
@@ -796,6 +886,8 @@ extern "C" int32_t hg_env_post_physics(const HgEnvBuffers* B, const HgEnvParams*
         attr_set = true;
     }
     int grid = (int)((N + HG_ENVS_PER_CTA - 1) / HG_ENVS_PER_CTA);
+    // one CTA per 32-env tile; the kernel body is a tile loop, so a capped (persistent) grid also works, but
+    // measured no gain on B200: the per-tile time is the compute warp's dependent-instruction latency
     post_physics_kernel<<<grid, HG_ENV_THREADS, sizeof(EnvSmem), st>>>(*B, *Z, phases, common_step_counter, (int)N);
     HG_LAUNCHED(1);
     return hg_cuda_status("hg_env_post_physics");
