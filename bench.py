@@ -179,9 +179,9 @@ def _kernel_rooflines(runner, device, pk):
         ac.native_forward("actor", mb["obs"], w["mean"], hidden=w["hid_a"])
         ac.native_forward("critic", mb["priv_obs"], w["value"], hidden=w["hid_c"])
         g = alg._grad.data_ptr()
-        nat.check(nat.lib.hg_mlp_backward(ac._desc["actor"], flat.data_ptr(), mb["obs"].data_ptr(), 705, w["hid_a"].data_ptr(),
+        nat.check(nat.lib.hg_mlp_backward(ac._desc["actor"], flat.data_ptr(), mb["obs"].data_ptr(), mb["obs"].stride(0), w["hid_a"].data_ptr(),
                                           w["d_mean"].data_ptr(), w["dhid_a"].data_ptr(), g, B, sp))
-        nat.check(nat.lib.hg_mlp_backward(ac._desc["critic"], flat.data_ptr(), mb["priv_obs"].data_ptr(), 219, w["hid_c"].data_ptr(),
+        nat.check(nat.lib.hg_mlp_backward(ac._desc["critic"], flat.data_ptr(), mb["priv_obs"].data_ptr(), mb["priv_obs"].stride(0), w["hid_c"].data_ptr(),
                                           w["d_value"].data_ptr(), w["dhid_c"].data_ptr(), g, B, sp))
     w["d_mean"].normal_()
     w["d_value"].normal_()

@@ -17,6 +17,7 @@ extern "C" int64_t hg_struct_size(int32_t which) {
         case 5: return sizeof(HgStorage);
         case 6: return sizeof(HgMiniBatch);
         case 7: return sizeof(HgPpoLossArgs);
+        case 8: return sizeof(HgGemm);
         default: return -1;
     }
 }

@@ -8,6 +8,8 @@
 // share one kernel, with the bias+ELU and ELU' epilogues fused.  It is the bit-for-bit-fp32 reference
 // for the tcgen05 path (hg_gemm_tc.cu) and the fallback for shapes the tensor-core tiles do not cover
 // (K = 219 / 705 row pitches that TMA cannot address, N = 12 / 1 output layers).
+#include <stdlib.h>
+
 #include "hg_common.cuh"
 
 namespace {
@@ -138,15 +140,51 @@ __global__ void colsum_kernel(const float* __restrict__ dZ, float* __restrict__ 
     atomicAdd(db + n, s);
 }
 
+int g_gemm_mode = -1;   // -1: read HG_GEMM on first use
+int gemm_mode() {
+    if (g_gemm_mode < 0) {
+        const char* e = getenv("HG_GEMM");
+        g_gemm_mode = 1;
+        if (e && (!strcmp(e, "simt") || !strcmp(e, "0"))) g_gemm_mode = 0;
+        if (e && (!strcmp(e, "tf32") || !strcmp(e, "2"))) g_gemm_mode = 2;
+    }
+    return g_gemm_mode;
+}
+
+// Try the tensor-core kernel for C = A x B; returns HG_E_ALIGN-style "not eligible" as 1 so the caller falls back.
+// a_mn / b_mn: operand is stored with its M / N index contiguous (see HgGemm).
+int32_t try_tc(const float* A, int64_t lda, bool a_mn, const float* B, int64_t ldb, bool b_mn, float* C, int64_t ldc, int M, int N,
+               int K, int epi, const float* bias, const float* H, int64_t ldh, int split_k, cudaStream_t st) {
+    const int mode = gemm_mode();
+    if (mode == 0) return 1;
+    if ((lda & 3) || (ldb & 3) || !hg_aligned16(A) || !hg_aligned16(B)) return 1;
+    HgGemm d{};
+    d.A = A; d.B = B; d.C = C; d.bias = bias; d.H = H;
+    d.M = M; d.N = N; d.K = K;
+    d.lda = lda; d.ldb = ldb; d.ldc = ldc; d.ldh = ldh;
+    d.a_mn_major = a_mn; d.b_mn_major = b_mn;
+    d.epilogue = epi; d.passes = (mode == 2) ? 1 : 3; d.split_k = split_k;
+    d.trust_hw_truncation = 1;      // verified on B200: kind::tf32 ignores the low 13 mantissa bits (tests/test_gemm_tc_gpu.py)
+    return hg_gemm_tf32(&d, (void*)st);
+}
+
 int32_t check_net(const HgMlpDesc* net) {
     HG_REQUIRE(net);
     if (net->n_layers < 1 || net->n_layers > HG_MAX_LAYERS) return hg_fail(HG_E_ARG, "HgMlpDesc: bad n_layers");
     for (int l = 0; l <= net->n_layers; ++l)
         if (net->dims[l] < 1) return hg_fail(HG_E_SIZE, "HgMlpDesc: bad layer width");
+    for (int l = 0; l < net->n_layers; ++l)
+        if (net->ldw[l] < net->dims[l]) return hg_fail(HG_E_SIZE, "HgMlpDesc: ldw < layer input width");
     return 0;
 }
 
 }  // namespace
+
+extern "C" int32_t hg_set_gemm_mode(int32_t mode) {
+    int prev = gemm_mode();
+    if (mode >= 0 && mode <= 2) g_gemm_mode = mode;
+    return prev;
+}
 
 extern "C" int32_t hg_mlp_forward(const HgMlpDesc* net, const float* params, const float* X, int64_t ldx,
                                   float* hidden, float* out, int64_t M, void* stream) {
@@ -161,13 +199,19 @@ extern "C" int32_t hg_mlp_forward(const HgMlpDesc* net, const float* params, con
     for (int l = 0; l < net->n_layers; ++l) {
         const int K = net->dims[l], N = net->dims[l + 1];
         const bool last = (l + 1 == net->n_layers);
-        GemmArgs g{};
-        g.A = in; g.sai = ld_in; g.sap = 1;
-        g.B = params + net->w_off[l]; g.sbp = 1; g.sbj = K;
-        g.C = last ? out : h; g.ldc = N;
-        g.bias = params + net->b_off[l];
-        g.M = (int)M; g.N = N; g.K = K; g.k_chunk = K;
-        int32_t rc = last ? launch_gemm<EPI_BIAS>(g, 1, st) : launch_gemm<EPI_BIAS_ELU>(g, 1, st);
+        const float* W = params + net->w_off[l];
+        const int64_t ldw = net->ldw[l];
+        float* dst = last ? out : h;
+        int32_t rc = try_tc(in, ld_in, false, W, ldw, false, dst, N, (int)M, N, K, last ? 1 : 2, params + net->b_off[l], nullptr, 0, 1, st);
+        if (rc == 1) {
+            GemmArgs g{};
+            g.A = in; g.sai = ld_in; g.sap = 1;
+            g.B = W; g.sbp = 1; g.sbj = ldw;
+            g.C = dst; g.ldc = N;
+            g.bias = params + net->b_off[l];
+            g.M = (int)M; g.N = N; g.K = K; g.k_chunk = K;
+            rc = last ? launch_gemm<EPI_BIAS>(g, 1, st) : launch_gemm<EPI_BIAS_ELU>(g, 1, st);
+        }
         if (rc) return rc;
         in = h; ld_in = N;
         h += M * N;
@@ -195,21 +239,29 @@ extern "C" int32_t hg_mlp_backward(const HgMlpDesc* net, const float* params, co
         const int64_t ld_in = (l == 0) ? ldx : K;
         float* dW = grads + net->w_off[l];
         float* db = grads + net->b_off[l];
-        cudaMemsetAsync(dW, 0, sizeof(float) * (size_t)N * K, st);
+        const int64_t ldw = net->ldw[l];
+        cudaMemsetAsync(dW, 0, sizeof(float) * (size_t)N * ldw, st);
         cudaMemsetAsync(db, 0, sizeof(float) * (size_t)N, st);
         {   // dW[n][k] = sum_m dZ[m][n] X[m][k]
-            GemmArgs g{};
-            g.A = dZ; g.sai = 1; g.sap = N;
-            g.B = in; g.sbp = ld_in; g.sbj = 1;
-            g.C = dW; g.ldc = K;
-            g.M = N; g.N = K; g.K = (int)M;
             int tiles = ((N + BM - 1) / BM) * ((K + BN - 1) / BN);
-            int64_t want = (4 * HG_NUM_SMS + tiles - 1) / tiles, cap = (M + 255) / 256;
-            int splits = (int)(want < cap ? want : cap);
-            if (splits < 1) splits = 1;
-            g.k_chunk = (int)(((M + splits - 1) / splits + BK - 1) / BK * BK);
-            splits = (int)((M + g.k_chunk - 1) / g.k_chunk);
-            if (int32_t rc = launch_gemm<EPI_ATOMIC>(g, splits, st)) return rc;
+            int64_t want_tc = (2 * HG_NUM_SMS + tiles - 1) / tiles, cap_tc = (M + 511) / 512;
+            int split_tc = (int)(want_tc < cap_tc ? want_tc : cap_tc);
+            if (split_tc < 1) split_tc = 1;
+            int32_t rc = try_tc(dZ, N, true, in, ld_in, true, dW, ldw, N, K, (int)M, 4, nullptr, nullptr, 0, split_tc, st);
+            if (rc == 1) {
+                GemmArgs g{};
+                g.A = dZ; g.sai = 1; g.sap = N;
+                g.B = in; g.sbp = ld_in; g.sbj = 1;
+                g.C = dW; g.ldc = ldw;
+                g.M = N; g.N = K; g.K = (int)M;
+                int64_t want = (4 * HG_NUM_SMS + tiles - 1) / tiles, cap = (M + 255) / 256;
+                int splits = (int)(want < cap ? want : cap);
+                if (splits < 1) splits = 1;
+                g.k_chunk = (int)(((M + splits - 1) / splits + BK - 1) / BK * BK);
+                splits = (int)((M + g.k_chunk - 1) / g.k_chunk);
+                rc = launch_gemm<EPI_ATOMIC>(g, splits, st);
+            }
+            if (rc) return rc;
         }
         {
             int rows = 512;
@@ -218,13 +270,18 @@ extern "C" int32_t hg_mlp_backward(const HgMlpDesc* net, const float* params, co
             HG_LAUNCHED(1);
         }
         if (l > 0) {   // dZ_{l-1} = (dZ_l W_l) * ELU'(h_{l-1})
-            GemmArgs g{};
-            g.A = dZ; g.sai = N; g.sap = 1;
-            g.B = params + net->w_off[l]; g.sbp = K; g.sbj = 1;
-            g.C = dhidden + off[l]; g.ldc = K;
-            g.h = hidden + off[l]; g.ldh = K;
-            g.M = (int)M; g.N = K; g.K = N; g.k_chunk = N;
-            if (int32_t rc = launch_gemm<EPI_MUL_DELU>(g, 1, st)) return rc;
+            const float* W = params + net->w_off[l];
+            int32_t rc = try_tc(dZ, N, false, W, ldw, true, dhidden + off[l], K, (int)M, K, N, 3, nullptr, hidden + off[l], K, 1, st);
+            if (rc == 1) {
+                GemmArgs g{};
+                g.A = dZ; g.sai = N; g.sap = 1;
+                g.B = W; g.sbp = ldw; g.sbj = 1;
+                g.C = dhidden + off[l]; g.ldc = K;
+                g.h = hidden + off[l]; g.ldh = K;
+                g.M = (int)M; g.N = K; g.K = N; g.k_chunk = N;
+                rc = launch_gemm<EPI_MUL_DELU>(g, 1, st);
+            }
+            if (rc) return rc;
             dZ = dhidden + off[l];
         }
     }

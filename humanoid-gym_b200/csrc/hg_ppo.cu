@@ -155,11 +155,11 @@ __global__ void gather_kernel(HgStorage S, const int64_t* __restrict__ idx, HgMi
     if (row >= B) return;
     size_t src = (size_t)idx[row];
     const float* o = S.observations + src * S.num_obs;
-    float* od = mb.obs + (size_t)row * S.num_obs;
+    float* od = mb.obs + (size_t)row * (mb.ld_obs ? mb.ld_obs : S.num_obs);
     for (int k = lane; k < S.num_obs; k += 32) od[k] = __ldg(o + k);
     if (S.privileged_observations) {
         const float* p = S.privileged_observations + src * S.num_priv;
-        float* pd = mb.priv_obs + (size_t)row * S.num_priv;
+        float* pd = mb.priv_obs + (size_t)row * (mb.ld_priv ? mb.ld_priv : S.num_priv);
         for (int k = lane; k < S.num_priv; k += 32) pd[k] = __ldg(p + k);
     }
     int A = S.num_actions;

@@ -73,7 +73,7 @@ class EnvNoise(C.Structure):
 
 class MlpDesc(C.Structure):
     _fields_ = [("n_layers", i32), ("dims", i32 * (MAX_LAYERS + 1)),
-                ("w_off", i64 * MAX_LAYERS), ("b_off", i64 * MAX_LAYERS)]
+                ("w_off", i64 * MAX_LAYERS), ("b_off", i64 * MAX_LAYERS), ("ldw", i64 * MAX_LAYERS)]
 
 
 class Transition(C.Structure):
@@ -89,7 +89,7 @@ class Storage(C.Structure):
 
 class MiniBatch(C.Structure):
     _fields_ = [(n, PF) for n in ("obs", "priv_obs", "actions", "values", "advantages", "returns",
-                                  "old_log_prob", "old_mu", "old_sigma")]
+                                  "old_log_prob", "old_mu", "old_sigma")] + [("ld_obs", i64), ("ld_priv", i64)]
 
 
 class PpoLossArgs(C.Structure):
@@ -100,7 +100,13 @@ class PpoLossArgs(C.Structure):
                 ("use_clipped_value_loss", i32), ("num_actions", i32), ("inv_B", f32)]
 
 
-_STRUCTS = (EnvParams, EnvBuffers, EnvNoise, MlpDesc, Transition, Storage, MiniBatch, PpoLossArgs)
+class Gemm(C.Structure):
+    _fields_ = [("A", PF), ("B", PF), ("C", PF), ("bias", PF), ("H", PF), ("M", i32), ("N", i32), ("K", i32),
+                ("lda", i64), ("ldb", i64), ("ldc", i64), ("ldh", i64), ("a_mn_major", i32), ("b_mn_major", i32),
+                ("epilogue", i32), ("passes", i32), ("split_k", i32), ("trust_hw_truncation", i32)]
+
+
+_STRUCTS = (EnvParams, EnvBuffers, EnvNoise, MlpDesc, Transition, Storage, MiniBatch, PpoLossArgs, Gemm)
 
 
 class NativeError(RuntimeError):
@@ -124,6 +130,8 @@ def _load():
         "hg_env_post_physics": (i32, [P(EnvBuffers), P(EnvParams), P(EnvNoise), C.c_uint32, i64, i64, PF]),
         "hg_mlp_forward": (i32, [P(MlpDesc), PF, PF, i64, PF, PF, i64, PF]),
         "hg_mlp_backward": (i32, [P(MlpDesc), PF, PF, i64, PF, PF, PF, PF, i64, PF]),
+        "hg_gemm_tf32": (i32, [P(Gemm), PF]),
+        "hg_set_gemm_mode": (i32, [i32]),
         "hg_policy_sample": (i32, [PF, PF, PF, u64, u64, PF, PF, PF, i64, i32, PF]),
         "hg_storage_add": (i32, [P(Storage), P(Transition), i32, f32, i64, PF]),
         "hg_gae": (i32, [P(Storage), PF, f32, f32, PF, i32, i64, PF]),

@@ -46,23 +46,36 @@ class ActorCritic(nn.Module):
     # flat parameter buffer + native descriptors
     # ------------------------------------------------------------------------------------------
     def _flatten(self):
-        """(Re)alias every parameter into one contiguous buffer on its current device."""
+        """(Re)alias every parameter into one contiguous buffer on its current device.
+
+        Weight rows are laid out with a pitch rounded up to 4 floats and every block starts on a 16-byte
+        boundary, so that TMA can address each matrix directly (tensor-core path); the parameters themselves
+        are (out, in) views of that storage, the pad floats stay zero for ever (zero gradient)."""
         params = list(self.parameters())
         dev = params[0].device
         if dev.type != "cuda":
             raise nat.NativeError("ActorCritic must live on a CUDA device: no CPU fallback for the hot path")
-        n = sum(p.numel() for p in params)
-        flat = torch.empty(n, dtype=torch.float32, device=dev)
+        self._layout = {}
         off = 0
-        self._offsets = {}
         for name, p in self.named_parameters():
-            k = p.numel()
-            flat[off:off + k].copy_(p.data.reshape(-1))
-            p.data = flat[off:off + k].view(p.shape)
-            self._offsets[name] = off
-            off += k
+            if p.dim() == 2:
+                rows, cols = p.shape
+                ld = (cols + 3) // 4 * 4
+                self._layout[name] = (off, (rows, cols), ld)
+                off += rows * ld
+            else:
+                self._layout[name] = (off, tuple(p.shape), None)
+                off += (p.numel() + 3) // 4 * 4
+        n = off
+        flat = torch.zeros(n, dtype=torch.float32, device=dev)
+        for name, p in self.named_parameters():
+            v = self.view_of(flat, name)
+            v.copy_(p.data)
+            p.data = v
+        self._offsets = {k: v[0] for k, v in self._layout.items()}
         self._flat = flat
-        self.num_params = n
+        self.num_params = n                       # allocated floats (incl. pads) == length of every flat buffer
+        self.num_real_params = sum(p.numel() for p in params)
         self._desc = {}
         for prefix, dims in (("actor", self._actor_dims), ("critic", self._critic_dims)):
             d = nat.MlpDesc()
@@ -70,10 +83,21 @@ class ActorCritic(nn.Module):
             for i, w in enumerate(dims):
                 d.dims[i] = w
             for l in range(d.n_layers):
-                d.w_off[l] = self._offsets[f"{prefix}.{2 * l}.weight"]
-                d.b_off[l] = self._offsets[f"{prefix}.{2 * l}.bias"]
+                d.w_off[l], _, d.ldw[l] = self._layout[f"{prefix}.{2 * l}.weight"]
+                d.b_off[l] = self._layout[f"{prefix}.{2 * l}.bias"][0]
             self._desc[prefix] = d
         self._scratch = {}
+
+    def view_of(self, flat, name):
+        """The (possibly row-padded) view of parameter `name` inside a flat buffer with this module's layout."""
+        off, shape, ld = self._layout[name]
+        if ld is None:
+            k = 1
+            for s_ in shape:
+                k *= s_
+            return flat[off:off + k].view(shape)
+        rows, cols = shape
+        return flat[off:off + rows * ld].view(rows, ld)[:, :cols]
 
     def flat_params(self):
         first = next(self.parameters())
@@ -95,10 +119,10 @@ class ActorCritic(nn.Module):
         """out (M, dims[-1]) <- MLP_which(x); returns the hidden-activation scratch."""
         flat = self.flat_params()
         M = x.shape[0]
-        assert x.is_contiguous() and x.dtype == torch.float32
+        assert x.dtype == torch.float32 and x.stride(1) == 1
         if hidden is None:
             hidden = self._hidden_scratch(which, M)
-        nat.check(nat.lib.hg_mlp_forward(self._desc[which], flat.data_ptr(), x.data_ptr(), x.shape[1],
+        nat.check(nat.lib.hg_mlp_forward(self._desc[which], flat.data_ptr(), x.data_ptr(), x.stride(0),
                                          hidden.data_ptr(), out.data_ptr(), M, nat.stream_ptr(flat.device.index)),
                   "hg_mlp_forward")
         return hidden

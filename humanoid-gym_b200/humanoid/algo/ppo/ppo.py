@@ -61,10 +61,9 @@ class PPO:
         """p.grad and the torch Adam state become views of the flat buffers (checkpoint compatibility)."""
         ac = self.actor_critic
         for name, p in ac.named_parameters():
-            off, k = ac._offsets[name], p.numel()
-            p.grad = self._grad[off:off + k].view(p.shape)
-            self.optimizer.state[p] = dict(step=torch.tensor(0.0), exp_avg=self._exp_avg[off:off + k].view(p.shape),
-                                           exp_avg_sq=self._exp_avg_sq[off:off + k].view(p.shape))
+            p.grad = ac.view_of(self._grad, name)
+            self.optimizer.state[p] = dict(step=torch.tensor(0.0), exp_avg=ac.view_of(self._exp_avg, name),
+                                           exp_avg_sq=ac.view_of(self._exp_avg_sq, name))
 
     def sync_optimizer_container(self):
         """Refresh the torch.optim.Adam container from the device-resident lr / step (before save)."""
@@ -82,9 +81,8 @@ class PPO:
             st = self.optimizer.state.get(p)
             if not st:
                 continue
-            off, k = ac._offsets[name], p.numel()
-            self._exp_avg[off:off + k].copy_(st["exp_avg"].reshape(-1))
-            self._exp_avg_sq[off:off + k].copy_(st["exp_avg_sq"].reshape(-1))
+            ac.view_of(self._exp_avg, name).copy_(st["exp_avg"])
+            ac.view_of(self._exp_avg_sq, name).copy_(st["exp_avg_sq"])
             step = float(st["step"])
         self._adam_step.fill_(int(step))
         self._lr.fill_(self.optimizer.param_groups[0]["lr"])
@@ -199,9 +197,9 @@ class PPO:
         a.inv_B = 1.0 / (B * world)
         nat.check(nat.lib.hg_ppo_loss_fwd_bwd(a, B, st), "hg_ppo_loss_fwd_bwd")
         g = self._grad.data_ptr()
-        nat.check(nat.lib.hg_mlp_backward(ac._desc["actor"], flat.data_ptr(), obs.data_ptr(), obs.shape[1], w["hid_a"].data_ptr(),
+        nat.check(nat.lib.hg_mlp_backward(ac._desc["actor"], flat.data_ptr(), obs.data_ptr(), obs.stride(0), w["hid_a"].data_ptr(),
                                           w["d_mean"].data_ptr(), w["dhid_a"].data_ptr(), g, B, st), "hg_mlp_backward(actor)")
-        nat.check(nat.lib.hg_mlp_backward(ac._desc["critic"], flat.data_ptr(), cobs.data_ptr(), cobs.shape[1], w["hid_c"].data_ptr(),
+        nat.check(nat.lib.hg_mlp_backward(ac._desc["critic"], flat.data_ptr(), cobs.data_ptr(), cobs.stride(0), w["hid_c"].data_ptr(),
                                           w["d_value"].data_ptr(), w["dhid_c"].data_ptr(), g, B, st), "hg_mlp_backward(critic)")
         if world > 1:
             dist.all_reduce(self._grad)                         # the ONE collective of the update path

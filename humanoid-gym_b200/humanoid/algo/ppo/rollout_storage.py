@@ -119,15 +119,19 @@ class RolloutStorage:
         if self._mb is None or self._mb["obs"].shape[0] != B:
             z = dict(device=self.device, dtype=torch.float32)
             A = self.actions_shape[0]
+            def padded(width):      # row pitch rounded up to 4 floats: TMA-addressable by the tensor-core MLP path
+                return torch.zeros(B, (width + 3) // 4 * 4, **z)[:, :width]
             self._mb = dict(
-                obs=torch.empty(B, self.obs_shape[0], **z),
-                priv_obs=torch.empty(B, self.privileged_obs_shape[0], **z) if self.privileged_observations is not None else None,
+                obs=padded(self.obs_shape[0]),
+                priv_obs=padded(self.privileged_obs_shape[0]) if self.privileged_observations is not None else None,
                 actions=torch.empty(B, A, **z), values=torch.empty(B, 1, **z), advantages=torch.empty(B, 1, **z),
                 returns=torch.empty(B, 1, **z), old_log_prob=torch.empty(B, 1, **z), old_mu=torch.empty(B, A, **z),
                 old_sigma=torch.empty(B, A, **z))
             m = nat.MiniBatch()
             for k, v in self._mb.items():
-                setattr(m, k, nat.ptr(v))
+                setattr(m, k, None if v is None else v.data_ptr())
+            m.ld_obs = self._mb["obs"].stride(0)
+            m.ld_priv = self._mb["priv_obs"].stride(0) if self._mb["priv_obs"] is not None else 0
             self._mbs = m
         return self._mb
 

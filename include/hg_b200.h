@@ -181,6 +181,8 @@ typedef struct HgMlpDesc {
     int32_t dims[HG_MAX_LAYERS + 1];    /* in, hidden..., out                        */
     int64_t w_off[HG_MAX_LAYERS];       /* element offset of weight l (out,in) row-major in the flat buffer */
     int64_t b_off[HG_MAX_LAYERS];       /* element offset of bias l                  */
+    int64_t ldw[HG_MAX_LAYERS];         /* row pitch of weight l in elements (>= dims[l]); a multiple of 4 with a
+                                           16-byte aligned w_off lets TMA address it -> tensor-core path         */
 } HgMlpDesc;
 
 /* Y = MLP(X).  `hidden`: caller scratch receiving every hidden layer's post-ELU
@@ -199,6 +201,27 @@ int32_t hg_mlp_forward(const HgMlpDesc* net, const float* params, const float* X
 int32_t hg_mlp_backward(const HgMlpDesc* net, const float* params, const float* X, int64_t ldx,
                         const float* hidden, const float* dY, float* dhidden, float* grads,
                         int64_t M, void* stream);
+
+/* Tensor-core GEMM building block of hg_mlp_forward / hg_mlp_backward (tcgen05.mma kind::tf32, accumulator
+ * in TMEM, operands by TMA):  C (M x N, pitch ldc) = A x B reduced over K, fp32 in / fp32 out.
+ *   a_mn_major = 0: A is (M, K) row-major  (pitch lda);  1: A is (K, M) row-major, i.e. the M index is contiguous
+ *   b_mn_major = 0: B is (N, K) row-major  (pitch ldb);  1: B is (K, N) row-major
+ *   passes     = 3: 3xTF32 split compensation (fp32-class accuracy);  1: plain TF32
+ *   epilogue   : 0 store, 1 +bias[N], 2 +bias then ELU, 3 multiply by ELU'(z) recovered from H = ELU(z) (pitch ldh),
+ *                4 atomicAdd into C (required when split_k > 1; C must be zeroed by the caller)
+ *   trust_hw_truncation: 1 = feed the raw fp32 tile as the "hi" operand (the tensor core drops the low 13
+ *                mantissa bits itself); 0 = rewrite it with an explicit truncation first
+ * Requirements: A, B 16-byte aligned with lda, ldb multiples of 4 (TMA); violations return HG_E_ALIGN. */
+typedef struct HgGemm {
+    const float* A; const float* B; float* C; const float* bias; const float* H;
+    int32_t M, N, K;
+    int64_t lda, ldb, ldc, ldh;
+    int32_t a_mn_major, b_mn_major, epilogue, passes, split_k, trust_hw_truncation;
+} HgGemm;
+int32_t hg_gemm_tf32(const HgGemm* d, void* stream);
+/* GEMM engine of hg_mlp_forward / hg_mlp_backward: 0 = exact-fp32 CUDA-core path, 1 = tcgen05 3xTF32 (default),
+ * 2 = tcgen05 plain TF32.  Layers whose operands TMA cannot address fall back to 0.  Returns the previous mode. */
+int32_t hg_set_gemm_mode(int32_t mode);
 
 /* PPO.act epilogue (ppo.py:91-101, actor_critic.py:111-120): actions =
  * mean + std*eps, log-prob summed over actions, sigma broadcast.
@@ -238,6 +261,8 @@ int32_t hg_adv_normalise(const HgStorage* S, const double* stats, int64_t N, voi
 typedef struct HgMiniBatch {
     float* obs; float* priv_obs; float* actions; float* values; float* advantages; float* returns;
     float* old_log_prob; float* old_mu; float* old_sigma;
+    int64_t ld_obs, ld_priv;            /* row pitch of obs / priv_obs in elements (0 = dense); a multiple of 4
+                                           makes the rows TMA-addressable for the tensor-core MLP path        */
 } HgMiniBatch;
 int32_t hg_minibatch_gather(const HgStorage* S, const int64_t* idx, const HgMiniBatch* mb, int64_t B, void* stream);
 
@@ -280,7 +305,7 @@ int32_t hg_adapt_lr(const float* kl_mean_dev, double desired_kl, double* lr_dev,
 /* ------------------------------------------------------------------------ */
 int32_t hg_version(void);
 /* sizeof() of the ABI structs, for binding self-checks: 0 HgEnvParams, 1 HgEnvBuffers,
- * 2 HgEnvNoise, 3 HgMlpDesc, 4 HgTransition, 5 HgStorage, 6 HgMiniBatch, 7 HgPpoLossArgs */
+ * 2 HgEnvNoise, 3 HgMlpDesc, 4 HgTransition, 5 HgStorage, 6 HgMiniBatch, 7 HgPpoLossArgs, 8 HgGemm */
 int64_t hg_struct_size(int32_t which);
 const char* hg_last_error(void);
 /* number of kernel launches issued by this library in the calling process */
