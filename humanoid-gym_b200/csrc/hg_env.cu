@@ -199,7 +199,7 @@ __device__ __forceinline__ void resample_commands(float* cmd, float u0, float u1
 // ROWS rows are in flight per iteration: ROWS * ceil(KEEP/32) independent 128-byte requests per warp.
 template <int FRAME, int KEEP, int WIDTH, int ROWS>
 __device__ __forceinline__ void stream_history(float* __restrict__ out, const float* __restrict__ in,
-                                               const unsigned char* s_reset, int nE, int w, int nw, int lane) {
+                                               const unsigned char* s_reset, int nE, int w, int nw, int lane, int64_t pitch) {
     constexpr int CH = (KEEP + 31) / 32;            // 21 (obs) / 5 (priv)
 #pragma unroll 1
     for (int r0 = w; r0 < nE; r0 += nw * ROWS) {
@@ -208,7 +208,7 @@ __device__ __forceinline__ void stream_history(float* __restrict__ out, const fl
         for (int q = 0; q < ROWS; ++q) {
             const int r = r0 + q * nw;
             const bool live = (r < nE);
-            const float* src = in + (size_t)r * WIDTH + FRAME;
+            const float* src = in + (size_t)r * pitch + FRAME;
 #pragma unroll
             for (int c = 0; c < CH; ++c) {
                 int k = c * 32 + lane;
@@ -219,7 +219,7 @@ __device__ __forceinline__ void stream_history(float* __restrict__ out, const fl
         for (int q = 0; q < ROWS; ++q) {
             const int r = r0 + q * nw;
             if (r < nE) {
-                float* dst = out + (size_t)r * WIDTH;
+                float* dst = out + (size_t)r * pitch;
 #pragma unroll
                 for (int c = 0; c < CH; ++c) {
                     int k = c * 32 + lane;
@@ -238,6 +238,7 @@ post_physics_kernel(HgEnvBuffers B, HgEnvNoise Z, uint32_t phases, int64_t commo
     const int num_tiles = (N + E - 1) / E;
     const bool do_obs = phases & HG_PHASE_OBS, do_reset = phases & HG_PHASE_RESET, do_last = phases & HG_PHASE_LAST;
     const int nb = cP.num_bodies;
+    const int64_t opitch = B.obs_pitch ? B.obs_pitch : OBS_W, ppitch = B.priv_pitch ? B.priv_pitch : PRIV_W;
     if (Z.use_device_counters) {   // CUDA-graph friendly: counters live in scratch[4..7], bumped by the last CTA
         common_step = *reinterpret_cast<const volatile int64_t*>(B.scratch + 4) + ((phases & HG_PHASE_COUNTERS) ? 1 : 0);
         Z.step = *reinterpret_cast<const volatile uint64_t*>(B.scratch + 6);
@@ -647,10 +648,10 @@ post_physics_kernel(HgEnvBuffers B, HgEnvNoise Z, uint32_t phases, int64_t commo
         // ---- 2b. streaming warps: history shift, overlapped with staging and the reward / observation math.
         // They copy every row unconditionally; rows of envs that turn out to reset are zeroed in step 3.
         if (do_obs) {
-            stream_history<HG_OBS1, OBS_KEEP, OBS_W, 1>(B.obs_out + (size_t)e0 * OBS_W, B.obs_buf + (size_t)e0 * OBS_W, S.reset,
-                                                      nE, warp - 1, 7, lane);
-            stream_history<HG_PRIV1, PRIV_KEEP, PRIV_W, 5>(B.priv_out + (size_t)e0 * PRIV_W, B.privileged_obs_buf + (size_t)e0 * PRIV_W,
-                                                        S.reset, nE, warp - 1, 7, lane);
+            stream_history<HG_OBS1, OBS_KEEP, OBS_W, 1>(B.obs_out + (size_t)e0 * opitch, B.obs_buf + (size_t)e0 * opitch, S.reset,
+                                                        nE, warp - 1, 7, lane, opitch);
+            stream_history<HG_PRIV1, PRIV_KEEP, PRIV_W, 5>(B.priv_out + (size_t)e0 * ppitch, B.privileged_obs_buf + (size_t)e0 * ppitch,
+                                                           S.reset, nE, warp - 1, 7, lane, ppitch);
         }
     }
     __syncthreads();
@@ -674,28 +675,28 @@ post_physics_kernel(HgEnvBuffers B, HgEnvNoise Z, uint32_t phases, int64_t commo
                 }
             }
             if (do_last) v = clampf(v, -cP.clip_obs, cP.clip_obs);
-            B.obs_out[(size_t)(e0 + le) * OBS_W + OBS_KEEP + k] = v;
+            B.obs_out[(size_t)(e0 + le) * opitch + OBS_KEEP + k] = v;
         }
         for (int i = tid; i < nE * HG_PRIV1; i += HG_ENV_THREADS) {
             int le = i / HG_PRIV1, k = i - le * HG_PRIV1;
             float v = S.newpriv[i];
             if (do_last) v = clampf(v, -cP.clip_obs, cP.clip_obs);
-            B.priv_out[(size_t)(e0 + le) * PRIV_W + PRIV_KEEP + k] = v;
+            B.priv_out[(size_t)(e0 + le) * ppitch + PRIV_KEEP + k] = v;
         }
         if (do_reset) {   // reset envs restart with an all-zero history (humanoid_env.py:264-269); rare
 #pragma unroll 1
             for (int le = 0; le < nE; ++le) {
                 if (!S.reset[le]) continue;
-                for (int k = tid; k < OBS_KEEP; k += HG_ENV_THREADS) B.obs_out[(size_t)(e0 + le) * OBS_W + k] = 0.0f;
-                for (int k = tid; k < PRIV_KEEP; k += HG_ENV_THREADS) B.priv_out[(size_t)(e0 + le) * PRIV_W + k] = 0.0f;
+                for (int k = tid; k < OBS_KEEP; k += HG_ENV_THREADS) B.obs_out[(size_t)(e0 + le) * opitch + k] = 0.0f;
+                for (int k = tid; k < PRIV_KEEP; k += HG_ENV_THREADS) B.priv_out[(size_t)(e0 + le) * ppitch + k] = 0.0f;
             }
         }
     } else if (do_reset) {
         // stand-alone reset_idx: zero the history rows of the reset envs in place (humanoid_env.py:264-269)
         for (int i = tid; i < nE * OBS_W; i += HG_ENV_THREADS)
-            if (S.reset[i / OBS_W]) B.obs_buf[(size_t)e0 * OBS_W + i] = 0.0f;
+            if (S.reset[i / OBS_W]) B.obs_buf[(size_t)(e0 + i / OBS_W) * opitch + i % OBS_W] = 0.0f;
         for (int i = tid; i < nE * PRIV_W; i += HG_ENV_THREADS)
-            if (S.reset[i / PRIV_W]) B.privileged_obs_buf[(size_t)e0 * PRIV_W + i] = 0.0f;
+            if (S.reset[i / PRIV_W]) B.privileged_obs_buf[(size_t)(e0 + i / PRIV_W) * ppitch + i % PRIV_W] = 0.0f;
     }
 
     // ---- 4. coalesced write-back of the tiles the step modified ------------------------------------------------
@@ -874,6 +875,8 @@ extern "C" int32_t hg_env_post_physics(const HgEnvBuffers* B, const HgEnvParams*
     if (N <= 0 || N > (1 << 26)) return hg_fail(HG_E_SIZE, "hg_env_post_physics: bad N");
     if ((phases & HG_PHASE_OBS) && (B->obs_out == B->obs_buf || B->priv_out == B->privileged_obs_buf))
         return hg_fail(HG_E_ARG, "hg_env_post_physics: obs_out / priv_out must not alias the history inputs");
+    if ((B->obs_pitch && B->obs_pitch < 705) || (B->priv_pitch && B->priv_pitch < 219))
+        return hg_fail(HG_E_SIZE, "hg_env_post_physics: observation pitch smaller than the row width");
     if (P->num_bodies > HG_MAX_BODIES) return hg_fail(HG_E_SIZE, "hg_env_post_physics: num_bodies > 16");
     if (P->num_bodies <= 0 || P->n_term > HG_MAX_CONTACT_BODIES || P->n_pen > HG_MAX_CONTACT_BODIES)
         return hg_fail(HG_E_ARG, "hg_env_post_physics: bad body indices");

@@ -9,12 +9,13 @@
 //     wgrad    dW = dZ^T X   A = dZ (MN-major)   B = X  (MN-major), split-K over the batch, fp32 atomics
 // (UMMA instruction-descriptor bits 15/16 select K- vs MN-major per operand.)
 //
-// CTA = 128 x BN output tile, 10 warps, warp-specialised:
+// CTA = 128 x BN output tile, 14 warps, warp-specialised:
 //     warps 0-3  epilogue     tcgen05.ld 32 TMEM lanes each -> bias / ELU / ELU' / atomics -> global
 //     warp  4    TMA producer cp.async.bulk.tensor (128B-swizzled 128x32 fp32 tiles, OOB zero fill)
 //     warp  5    MMA issuer   one lane issues tcgen05.mma.kind::tf32 (M=128, N=BN, K=8), accumulator in TMEM
-//     warps 6-9  splitter     raw fp32 tile -> (hi in place, lo tile), elementwise so the swizzle is untouched
-// 3-stage ring of {A, B, A_lo, B_lo} tiles (64 KB / stage) with full / ready / empty mbarriers.
+//     warps 6-13 splitter     raw fp32 tile -> lo tile (x - tf32(x)), elementwise so the swizzle is untouched
+// 3-stage ring of {A, B, A_lo, B_lo} tiles (64 KB / stage) with full / ready / empty mbarriers; CTAs are
+// persistent (one per SM) and the accumulator is double-buffered in TMEM so that epilogue and main loop overlap.
 #include <cuda.h>
 
 #include "hg_common.cuh"
@@ -24,7 +25,8 @@ namespace {
 constexpr int BM = 128, BK = 32, STAGES = 3;
 constexpr int TILE_BYTES = BM * BK * 4;              // 16 KB: 128 rows (or 4 MN-boxes) x 128 B
 constexpr int STAGE_BYTES = 4 * TILE_BYTES;          // A, B, A_lo, B_lo
-constexpr int TC_THREADS = 320;
+constexpr int SPLIT_WARPS = 8;
+constexpr int TC_THREADS = (6 + SPLIT_WARPS) * 32;   // 4 epilogue + TMA + MMA + splitters
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
 
 enum { EPI_STORE = 0, EPI_BIAS = 1, EPI_BIAS_ELU = 2, EPI_MUL_DELU = 3, EPI_ATOMIC = 4 };
@@ -36,7 +38,8 @@ struct TcArgs {
     int BN;                          // 32 / 64 / 96 / 128
     int a_mn, b_mn;                  // operand majorness (0 = K-major, 1 = MN-major)
     int epi, passes;
-    int kb_per_split;                // k-blocks (of 32) per blockIdx.z
+    int kb_per_split;                // k-blocks (of 32) per split
+    int splits;
     int hi_in_place;                 // 1: splitter rewrites the raw tile with its tf32 truncation
 };
 
@@ -143,65 +146,93 @@ __device__ __forceinline__ uint32_t make_idesc(int N, bool a_mn, bool b_mn) {
     return d;
 }
 
+// Work item w = (m_tile, n_tile, split).  CTAs are persistent: CTA c processes items c, c + gridDim.x, ...;
+// the {A,B,A_lo,B_lo} stage ring keeps rolling across items and the accumulator is double-buffered in TMEM
+// (2 x 128 columns), so the epilogue of item i overlaps the main loop of item i + 1.
+struct Work { int m0, n0, kb_begin, num_kb; };
+__device__ __forceinline__ Work decode_work(const TcArgs& g, int w, int tiles_n, int tiles_mn, int num_kb_total) {
+    Work r;
+    const int split = w / tiles_mn, t = w - split * tiles_mn;
+    const int tm = t / tiles_n, tn = t - tm * tiles_n;
+    r.m0 = tm * BM;
+    r.n0 = tn * g.BN;
+    r.kb_begin = split * g.kb_per_split;
+    r.num_kb = min(num_kb_total, r.kb_begin + g.kb_per_split) - r.kb_begin;
+    return r;
+}
+
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcArgs g) {
     extern __shared__ unsigned char smem_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
-    uint64_t* full = bars;                 // TMA -> splitter
-    uint64_t* ready = bars + STAGES;       // splitter -> MMA
-    uint64_t* empty = bars + 2 * STAGES;   // MMA -> TMA
-    uint64_t* tmem_full = bars + 3 * STAGES;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * STAGES + 1);
+    uint64_t* full = bars;                     // TMA -> splitter
+    uint64_t* ready = bars + STAGES;           // splitter -> MMA
+    uint64_t* empty = bars + 2 * STAGES;       // MMA -> TMA
+    uint64_t* tmem_full = bars + 3 * STAGES;   // [2] MMA -> epilogue
+    uint64_t* tmem_empty = tmem_full + 2;      // [2] epilogue -> MMA
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int m0 = blockIdx.y * BM, n0 = blockIdx.x * g.BN;
     const int num_kb_total = (g.K + BK - 1) / BK;
-    const int kb_begin = blockIdx.z * g.kb_per_split;
-    const int kb_end = min(num_kb_total, kb_begin + g.kb_per_split);
-    const int num_kb = kb_end - kb_begin;
+    const int tiles_n = (g.N + g.BN - 1) / g.BN, tiles_m = (g.M + BM - 1) / BM;
+    const int tiles_mn = tiles_n * tiles_m;
+    const int total_work = tiles_mn * g.splits;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; ++s) {
             mbar_init(&full[s], 1);
-            mbar_init(&ready[s], 4);
+            mbar_init(&ready[s], SPLIT_WARPS);
             mbar_init(&empty[s], 1);
         }
-        mbar_init(tmem_full, 1);
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(&tmem_full[a], 1);
+            mbar_init(&tmem_empty[a], 4);
+        }
         fence_barrier_init();
     }
-    if (warp == 5) tmem_alloc(tmem_slot, 128);
+    if (warp == 5) tmem_alloc(tmem_slot, 256);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    if (num_kb > 0) {
-        if (warp == 4) {
-            // ===== TMA producer =====
-            if (lane == 0) {
-                asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
-                asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
-                const uint32_t tx = TILE_BYTES + (uint32_t)g.BN * BK * 4;
-                for (int it = 0; it < num_kb; ++it) {
-                    const int s = it % STAGES, k0 = (kb_begin + it) * BK;
+    if (warp == 4) {
+        // ===== TMA producer =====
+        if (lane == 0) {
+            asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+            asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+            const uint32_t tx = TILE_BYTES + (uint32_t)g.BN * BK * 4;
+            int it = 0;
+            for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
+                const Work wk = decode_work(g, w, tiles_n, tiles_mn, num_kb_total);
+                for (int kb = 0; kb < wk.num_kb; ++kb, ++it) {
+                    const int s = it % STAGES, k0 = (wk.kb_begin + kb) * BK;
                     mbar_wait(&empty[s], ((it / STAGES) & 1) ^ 1);
                     unsigned char* st = smem + s * STAGE_BYTES;
                     mbar_expect_tx(&full[s], tx);
-                    if (!g.a_mn) tma_load_2d(st, &tmA, &full[s], k0, m0);
+                    if (!g.a_mn) tma_load_2d(st, &tmA, &full[s], k0, wk.m0);
                     else
-                        for (int j = 0; j < BM / 32; ++j) tma_load_2d(st + j * 4096, &tmA, &full[s], m0 + 32 * j, k0);
-                    if (!g.b_mn) tma_load_2d(st + TILE_BYTES, &tmB, &full[s], k0, n0);
+                        for (int j = 0; j < BM / 32; ++j) tma_load_2d(st + j * 4096, &tmA, &full[s], wk.m0 + 32 * j, k0);
+                    if (!g.b_mn) tma_load_2d(st + TILE_BYTES, &tmB, &full[s], k0, wk.n0);
                     else
-                        for (int j = 0; j < g.BN / 32; ++j) tma_load_2d(st + TILE_BYTES + j * 4096, &tmB, &full[s], n0 + 32 * j, k0);
+                        for (int j = 0; j < g.BN / 32; ++j) tma_load_2d(st + TILE_BYTES + j * 4096, &tmB, &full[s], wk.n0 + 32 * j, k0);
                 }
             }
-        } else if (warp == 5) {
-            // ===== MMA issuer =====
-            if (lane == 0) {
-                const uint32_t idesc = make_idesc(g.BN, g.a_mn, g.b_mn);
-                const uint32_t kstep_a = g.a_mn ? 1024 : 32, kstep_b = g.b_mn ? 1024 : 32;   // bytes per K = 8
-                for (int it = 0; it < num_kb; ++it) {
+        }
+    } else if (warp == 5) {
+        // ===== MMA issuer =====
+        if (lane == 0) {
+            const uint32_t idesc = make_idesc(g.BN, g.a_mn, g.b_mn);
+            const uint32_t kstep_a = g.a_mn ? 1024 : 32, kstep_b = g.b_mn ? 1024 : 32;   // bytes per K = 8
+            int it = 0, item = 0;
+            for (int w = blockIdx.x; w < total_work; w += gridDim.x, ++item) {
+                const Work wk = decode_work(g, w, tiles_n, tiles_mn, num_kb_total);
+                const int acc_stage = item & 1;
+                mbar_wait(&tmem_empty[acc_stage], ((item >> 1) & 1) ^ 1);       // epilogue has drained this accumulator
+                tc_fence_after();
+                const uint32_t tmem_d = tmem_base + (uint32_t)(acc_stage * 128);
+                for (int kb = 0; kb < wk.num_kb; ++kb, ++it) {
                     const int s = it % STAGES;
                     mbar_wait(&ready[s], (it / STAGES) & 1);
                     tc_fence_after();
@@ -210,26 +241,31 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     for (int kk = 0; kk < BK / 8; ++kk) {
                         const uint64_t a_hi = make_desc(base + kk * kstep_a, g.a_mn);
                         const uint64_t b_hi = make_desc(base + TILE_BYTES + kk * kstep_b, g.b_mn);
-                        const uint32_t acc = (it > 0 || kk > 0) ? 1u : 0u;
+                        const uint32_t acc = (kb > 0 || kk > 0) ? 1u : 0u;
                         if (g.passes == 3) {
                             const uint64_t a_lo = make_desc(base + 2 * TILE_BYTES + kk * kstep_a, g.a_mn);
                             const uint64_t b_lo = make_desc(base + 3 * TILE_BYTES + kk * kstep_b, g.b_mn);
-                            umma_tf32(tmem_base, a_lo, b_hi, idesc, acc);      // small terms first
-                            umma_tf32(tmem_base, a_hi, b_lo, idesc, 1u);
-                            umma_tf32(tmem_base, a_hi, b_hi, idesc, 1u);
+                            umma_tf32(tmem_d, a_lo, b_hi, idesc, acc);          // small terms first
+                            umma_tf32(tmem_d, a_hi, b_lo, idesc, 1u);
+                            umma_tf32(tmem_d, a_hi, b_hi, idesc, 1u);
                         } else {
-                            umma_tf32(tmem_base, a_hi, b_hi, idesc, acc);
+                            umma_tf32(tmem_d, a_hi, b_hi, idesc, acc);
                         }
                     }
-                    umma_commit(&empty[s]);                                   // stage reusable once these MMAs retire
+                    umma_commit(&empty[s]);                                     // stage reusable once these MMAs retire
                 }
-                umma_commit(tmem_full);
+                umma_commit(&tmem_full[acc_stage]);
             }
-        } else if (warp >= 6) {
-            // ===== splitter: x -> (tf32(x), x - tf32(x)), elementwise (swizzle-agnostic) =====
-            const int t = threadIdx.x - 6 * 32;                               // 0..127
-            const int nB4 = g.BN * BK / 4;                                    // float4 count of the B tile
-            for (int it = 0; it < num_kb; ++it) {
+        }
+    } else if (warp >= 6) {
+        // ===== splitter: x -> (tf32(x), x - tf32(x)), elementwise (swizzle-agnostic) =====
+        const int t = threadIdx.x - 6 * 32;                                     // 0 .. 32*SPLIT_WARPS-1
+        constexpr int NT = 32 * SPLIT_WARPS;
+        const int nB4 = g.BN * BK / 4;                                          // float4 count of the B tile
+        int it = 0;
+        for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
+            const Work wk = decode_work(g, w, tiles_n, tiles_mn, num_kb_total);
+            for (int kb = 0; kb < wk.num_kb; ++kb, ++it) {
                 const int s = it % STAGES;
                 mbar_wait(&full[s], (it / STAGES) & 1);
                 if (g.passes == 3) {
@@ -249,24 +285,29 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         if (g.hi_in_place) raw[i] = h;
                     };
 #pragma unroll 4
-                    for (int i = t; i < TILE_BYTES / 16; i += 128) split(a, alo, i);
+                    for (int i = t; i < TILE_BYTES / 16; i += NT) split(a, alo, i);
 #pragma unroll 4
-                    for (int i = t; i < nB4; i += 128) split(b, blo, i);
-                    fence_proxy_async();                                      // generic-proxy writes -> tensor-core reads
+                    for (int i = t; i < nB4; i += NT) split(b, blo, i);
+                    fence_proxy_async();                                        // generic-proxy writes -> tensor-core reads
                 }
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&ready[s]);
             }
-        } else {
-            // ===== epilogue (warps 0-3 <-> TMEM lanes 32*warp .. +31) =====
-            mbar_wait(tmem_full, 0);
+        }
+    } else {
+        // ===== epilogue (warps 0-3 <-> TMEM lanes 32*warp .. +31) =====
+        int item = 0;
+        for (int w = blockIdx.x; w < total_work; w += gridDim.x, ++item) {
+            const Work wk = decode_work(g, w, tiles_n, tiles_mn, num_kb_total);
+            const int acc_stage = item & 1;
+            mbar_wait(&tmem_full[acc_stage], (item >> 1) & 1);
             tc_fence_after();
-            const int row = m0 + warp * 32 + lane;
+            const int row = wk.m0 + warp * 32 + lane;
             const bool row_ok = row < g.M;
             for (int c0 = 0; c0 < g.BN; c0 += 32) {
                 float v[32];
-                tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, v);
-                const int col0 = n0 + c0;
+                tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(acc_stage * 128 + c0), v);
+                const int col0 = wk.n0 + c0;
                 if (!row_ok || col0 >= g.N) continue;
                 float* dst = g.C + (int64_t)row * g.ldc + col0;
                 const int nvalid = min(32, g.N - col0);
@@ -300,12 +341,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 }
             }
             tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty[acc_stage]);                 // accumulator free for item + 2
         }
     }
+    tc_fence_before();
     __syncthreads();
     if (warp == 5) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, 128);
+        tmem_dealloc(tmem_base, 256);
     }
 }
 
@@ -393,7 +437,9 @@ extern "C" int32_t hg_gemm_tf32(const HgGemm* d, void* stream) {
         if (e != cudaSuccess) return hg_fail((int32_t)e, cudaGetErrorString(e));
         attr_set = true;
     }
-    dim3 grid((d->N + g.BN - 1) / g.BN, (d->M + BM - 1) / BM, splits);
+    g.splits = splits;
+    const int total_work = ((d->N + g.BN - 1) / g.BN) * ((d->M + BM - 1) / BM) * splits;
+    const int grid = total_work < HG_NUM_SMS ? total_work : HG_NUM_SMS;       // persistent: one CTA per SM
     gemm_tc_kernel<<<grid, TC_THREADS, SMEM_BYTES, st>>>(tmA, tmB, g);
     HG_LAUNCHED(1);
     return hg_cuda_status("hg_gemm_tf32");

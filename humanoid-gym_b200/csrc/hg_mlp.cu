@@ -130,14 +130,33 @@ int32_t launch_gemm(const GemmArgs& g, int splits, cudaStream_t st) {
     return hg_cuda_status("hg gemm");
 }
 
-// db[n] = sum_m dZ[m][n]
-__global__ void colsum_kernel(const float* __restrict__ dZ, float* __restrict__ db, int M, int N, int rows_per_block) {
-    int n = blockIdx.x * blockDim.x + threadIdx.x;
-    int m0 = blockIdx.y * rows_per_block, m1 = min(M, m0 + rows_per_block);
-    if (n >= N) return;
-    float s = 0.0f;
-    for (int m = m0; m < m1; ++m) s += dZ[(int64_t)m * N + n];
-    atomicAdd(db + n, s);
+// db[n] = sum_m dZ[m][n].  Block = 32 columns x 8 row-lanes; each warp reads 128-byte row segments (coalesced),
+// 4 independent loads in flight per thread; partial sums meet in shared memory, one atomicAdd per column per block.
+constexpr int CS_ROWS = 2048;
+__global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ dZ, float* __restrict__ db, int M, int N) {
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int n = blockIdx.x * 32 + tx;
+    const int m0 = blockIdx.y * CS_ROWS, m1 = min(M, m0 + CS_ROWS);
+    float s0 = 0.0f, s1 = 0.0f, s2 = 0.0f, s3 = 0.0f;
+    if (n < N) {
+        int m = m0 + ty;
+        for (; m + 24 < m1; m += 32) {
+            s0 += __ldg(dZ + (int64_t)m * N + n);
+            s1 += __ldg(dZ + (int64_t)(m + 8) * N + n);
+            s2 += __ldg(dZ + (int64_t)(m + 16) * N + n);
+            s3 += __ldg(dZ + (int64_t)(m + 24) * N + n);
+        }
+        for (; m < m1; m += 8) s0 += __ldg(dZ + (int64_t)m * N + n);
+    }
+    __shared__ float sh[8][33];
+    sh[ty][tx] = (s0 + s1) + (s2 + s3);
+    __syncthreads();
+    if (ty == 0 && n < N) {
+        float t = 0.0f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) t += sh[k][tx];
+        atomicAdd(db + n, t);
+    }
 }
 
 int g_gemm_mode = -1;   // -1: read HG_GEMM on first use
@@ -264,9 +283,8 @@ extern "C" int32_t hg_mlp_backward(const HgMlpDesc* net, const float* params, co
             if (rc) return rc;
         }
         {
-            int rows = 512;
-            dim3 grid((N + 127) / 128, (unsigned)((M + rows - 1) / rows));
-            colsum_kernel<<<grid, 128, 0, st>>>(dZ, db, (int)M, N, rows);
+            dim3 grid((N + 31) / 32, (unsigned)((M + CS_ROWS - 1) / CS_ROWS));
+            colsum_kernel<<<grid, 256, 0, st>>>(dZ, db, (int)M, N);
             HG_LAUNCHED(1);
         }
         if (l > 0) {   // dZ_{l-1} = (dZ_l W_l) * ELU'(h_{l-1})

@@ -72,12 +72,22 @@ __device__ __forceinline__ void copy_f32(float* dst, const float* src, size_t n)
 __device__ __forceinline__ void copy_slab(float* dst, const float* src, size_t n) {
     if (src != nullptr && src != dst) copy_f32(dst, src, n);
 }
+// rows of `width` floats from a pitched source into a dense destination
+__device__ __forceinline__ void copy_rows(float* dst, const float* src, size_t rows, size_t width, size_t pitch) {
+    if (src == nullptr || src == dst) return;
+    if (pitch == 0 || pitch == width) { copy_f32(dst, src, rows * width); return; }
+    size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, nt = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = tid; i < rows * width; i += nt) {
+        size_t r = i / width, c = i - r * width;
+        dst[i] = __ldg(src + r * pitch + c);
+    }
+}
 __global__ void storage_add_kernel(AddArgs a) {
     const size_t N = a.N, t = a.t;
     const HgStorage& S = a.S;
     switch (blockIdx.y) {
-        case 0: copy_slab(S.observations + t * N * S.num_obs, a.tr.obs, N * S.num_obs); break;
-        case 1: if (S.privileged_observations) copy_slab(S.privileged_observations + t * N * S.num_priv, a.tr.priv_obs, N * S.num_priv); break;
+        case 0: copy_rows(S.observations + t * N * S.num_obs, a.tr.obs, N, S.num_obs, a.tr.obs_pitch); break;
+        case 1: if (S.privileged_observations) copy_rows(S.privileged_observations + t * N * S.num_priv, a.tr.priv_obs, N, S.num_priv, a.tr.priv_pitch); break;
         case 2: copy_slab(S.actions + t * N * S.num_actions, a.tr.actions, N * S.num_actions); break;
         case 3: copy_slab(S.mu + t * N * S.num_actions, a.tr.mu, N * S.num_actions); break;
         case 4: copy_slab(S.sigma + t * N * S.num_actions, a.tr.sigma, N * S.num_actions); break;

@@ -63,7 +63,7 @@ _ENV_BUFFER_NAMES = (
 
 
 class EnvBuffers(C.Structure):
-    _fields_ = [(n, PF) for n in _ENV_BUFFER_NAMES]
+    _fields_ = [(n, PF) for n in _ENV_BUFFER_NAMES] + [("obs_pitch", i64), ("priv_pitch", i64)]
 
 
 class EnvNoise(C.Structure):
@@ -78,7 +78,7 @@ class MlpDesc(C.Structure):
 
 class Transition(C.Structure):
     _fields_ = [(n, PF) for n in ("obs", "priv_obs", "actions", "rewards", "dones", "time_outs", "values",
-                                  "log_prob", "mu", "sigma")]
+                                  "log_prob", "mu", "sigma")] + [("obs_pitch", i64), ("priv_pitch", i64)]
 
 
 class Storage(C.Structure):

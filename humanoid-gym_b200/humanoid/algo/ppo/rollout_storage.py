@@ -75,7 +75,12 @@ class RolloutStorage:
         tr = nat.Transition()
         for k, v in tensors.items():
             if v is not None:
-                assert v.is_cuda and v.is_contiguous()
+                assert v.is_cuda
+                if k in ("obs", "priv_obs"):            # row-pitched views (env buffers) are fine
+                    assert v.dim() == 2 and v.stride(1) == 1
+                    setattr(tr, "obs_pitch" if k == "obs" else "priv_pitch", v.stride(0))
+                else:
+                    assert v.is_contiguous()
                 setattr(tr, k, v.data_ptr())
         nat.check(nat.lib.hg_storage_add(self._native(), tr, t, gamma, self.num_envs, nat.stream_ptr(self._dev_index)),
                   "hg_storage_add")
@@ -83,7 +88,8 @@ class RolloutStorage:
     def add_transitions(self, transition):
         if self.step >= self.num_transitions_per_env:
             raise AssertionError("Rollout buffer overflow")
-        f = lambda x: None if x is None else x.to(torch.float32).contiguous()          # noqa: E731
+        f = lambda x: None if x is None else (x if (x.dtype == torch.float32 and x.dim() == 2 and x.stride(1) == 1)  # noqa: E731
+                                              else x.to(torch.float32).contiguous())
         d = transition.dones
         self.add_native(
             self.step, obs=f(transition.observations),

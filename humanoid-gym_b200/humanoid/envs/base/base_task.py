@@ -27,7 +27,11 @@ class BaseTask:
         self.num_actions = cfg.env.num_actions
 
         z = dict(device=self.device)
-        self.obs_buf = torch.zeros(self.num_envs, self.num_obs, dtype=torch.float, **z)
+        # observation rows are stored with a pitch rounded up to 4 floats (705 -> 708, 219 -> 220) so that TMA can
+        # feed them to the tensor-core actor / critic; obs_buf / privileged_obs_buf are the (N, 705) / (N, 219) views
+        def pitched(width):
+            return torch.zeros(self.num_envs, (width + 3) // 4 * 4, dtype=torch.float, **z)[:, :width]
+        self.obs_buf = pitched(self.num_obs)
         self.rew_buf = torch.zeros(self.num_envs, dtype=torch.float, **z)
         # the reference allocates int64 ones but rebinds a bool tensor on every step
         # (legged_robot.py:159); the fused kernel always writes bool
@@ -35,7 +39,7 @@ class BaseTask:
         self._episode_length_buf = torch.zeros(self.num_envs, dtype=torch.long, **z)
         self.time_out_buf = torch.zeros(self.num_envs, dtype=torch.bool, **z)
         if self.num_privileged_obs is not None:
-            self.privileged_obs_buf = torch.zeros(self.num_envs, self.num_privileged_obs, dtype=torch.float, **z)
+            self.privileged_obs_buf = pitched(self.num_privileged_obs)
         else:
             self.privileged_obs_buf = None
         self.extras = {}

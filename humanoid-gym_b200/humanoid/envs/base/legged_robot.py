@@ -210,15 +210,18 @@ class LeggedRobot(BaseTask):
             rand_push_force=self.rand_push_force, rand_push_torque=self.rand_push_torque,
             env_frictions=self.env_frictions, body_mass=self.body_mass, env_origins=self.env_origins,
             episode_sums=self._episode_sums, episode_means=self._episode_means, rew_terms=None,
-            obs_buf=self.obs_buf, privileged_obs_buf=self.privileged_obs_buf, rew_buf=self.rew_buf,
-            reset_ids=self.reset_ids, scratch=self._scratch)
+            rew_buf=self.rew_buf, reset_ids=self.reset_ids, scratch=self._scratch)
         # observation histories are a ping-pong pair: the kernel reads frames 1..14 of one buffer and writes
         # frames 0..13 (+ the new frame) of the other -- like the reference, env.obs_buf is rebound every step
-        self._obs_pp = [self.obs_buf, torch.zeros_like(self.obs_buf)]
-        self._priv_pp = [self.privileged_obs_buf, torch.zeros_like(self.privileged_obs_buf)]
-        tensors["obs_out"], tensors["priv_out"] = self._obs_pp[1], self._priv_pp[1]
+        def twin(v):        # same pitch, fresh storage
+            return torch.zeros(v.shape[0], v.stride(0), dtype=v.dtype, device=v.device)[:, :v.shape[1]]
+        self._obs_pp = [self.obs_buf, twin(self.obs_buf)]
+        self._priv_pp = [self.privileged_obs_buf, twin(self.privileged_obs_buf)]
         for k, t in tensors.items():
             setattr(B, k, nat.ptr(t))
+        B.obs_buf, B.obs_out = self._obs_pp[0].data_ptr(), self._obs_pp[1].data_ptr()
+        B.privileged_obs_buf, B.priv_out = self._priv_pp[0].data_ptr(), self._priv_pp[1].data_ptr()
+        B.obs_pitch, B.priv_pitch = self.obs_buf.stride(0), self.privileged_obs_buf.stride(0)
         self._B = B
         self._keepalive = tensors
         self._Z = nat.EnvNoise()

@@ -121,6 +121,9 @@ typedef struct HgEnvBuffers {
                                   [0] running reset count, [1] CTA ticket, [3] reset
                                   count of the last step, [4..5] int64 common_step_counter,
                                   [6..7] uint64 noise step, [8..29] float accumulators  */
+    int64_t obs_pitch;         /* row pitch (elements) of obs_buf AND obs_out; 0 = dense 705.  A multiple of 4
+                                  (708) makes the rows TMA-addressable for the tensor-core actor forward      */
+    int64_t priv_pitch;        /* likewise for privileged_obs_buf / priv_out; 0 = dense 219 (220 for TMA)     */
 } HgEnvBuffers;
 
 /* Injected random draws (parity mode).  Any pointer may be NULL: the kernel
@@ -238,6 +241,7 @@ typedef struct HgTransition {
     const float* obs; const float* priv_obs; const float* actions; const float* rewards;
     const uint8_t* dones; const uint8_t* time_outs; const float* values; const float* log_prob;
     const float* mu; const float* sigma;
+    int64_t obs_pitch, priv_pitch;      /* row pitch of obs / priv_obs in elements (0 = dense)            */
 } HgTransition;
 typedef struct HgStorage {
     float* observations; float* privileged_observations; float* actions; float* rewards;

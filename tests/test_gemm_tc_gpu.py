@@ -72,7 +72,8 @@ def test_wgrad_layout(Nout, Kin, batch, split):
     X = _pad4(torch.randn(batch, Kin, device="cuda", generator=g))
     ref = dZ.double().t() @ X.double()
     C = _run(dZ, X, Nout, Kin, batch, 1, 1, 3, epilogue=4, split_k=split)
-    assert _rel(C, ref) < 1e-5, _rel(C, ref)
+    # fp32 accumulation over `batch` terms: the error floor grows like sqrt(batch) * 2^-24
+    assert _rel(C, ref) < max(1e-5, 2e-7 * batch ** 0.5), _rel(C, ref)
 
 
 def test_hardware_truncates_tf32_operands():

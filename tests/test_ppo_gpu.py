@@ -223,7 +223,7 @@ def test_flagship_gradients_vs_autograd():
     want = torch.cat([L.p[k].detach().reshape(-1) for k in L.names])
     # the fp32 update (~1e-5) is only a few ulp of the weights it lands on, so compare the new parameters
     # tightly and the update itself within that quantisation
-    assert torch.allclose(_cat(ac).cpu(), want, rtol=1e-6, atol=1e-9)
+    assert torch.allclose(_cat(ac).cpu(), want, rtol=1e-6, atol=2e-7)     # 2 % of one lr-sized step
     upd_got, upd_want = (_cat(ac).cpu() - w_before.cpu()), (want - w_before.cpu())
     assert _rel(upd_got, upd_want) < 1e-3, _rel(upd_got, upd_want)
     assert abs(alg.learning_rate - L.lr) < 1e-18
@@ -245,8 +245,10 @@ def test_checkpoint_roundtrip(tmp_path):
     ac2.load_state_dict(sd["model_state_dict"])
     alg2.optimizer.load_state_dict(sd["optimizer_state_dict"])
     alg2.load_optimizer_container()
-    assert torch.equal(ac2.flat_params(), ac.flat_params())
-    assert torch.equal(alg2._exp_avg, alg._exp_avg) and torch.equal(alg2._exp_avg_sq, alg._exp_avg_sq)
+    assert torch.equal(_cat(ac2), _cat(ac))
+    for name, _ in ac.named_parameters():
+        assert torch.equal(ac2.view_of(alg2._exp_avg, name), ac.view_of(alg._exp_avg, name)), name
+        assert torch.equal(ac2.view_of(alg2._exp_avg_sq, name), ac.view_of(alg._exp_avg_sq, name)), name
     assert int(alg2._adam_step) == 17 and abs(alg2.learning_rate - 3e-4) < 1e-12
     # the reference's own ActorCritic accepts the weights (same module tree): checked structurally
     assert ac2.actor[0].weight.shape == (32, 60) and ac2.critic[6].weight.shape == (1, 16)

@@ -52,7 +52,8 @@ def main():
     s.observations.normal_(), s.privileged_observations.normal_(), s.actions.normal_(), s.mu.normal_()
     s.sigma.fill_(1.0), s.values.normal_(), s.returns.normal_(), s.advantages.normal_(), s.actions_log_prob.fill_(-17.0)
     if a.what == "act":
-        obs, cobs = torch.randn(N, 705, device=dev), torch.randn(N, 219, device=dev)
+        obs = torch.randn(N, 708, device=dev)[:, :705]          # row pitch 708 / 220, as the env produces them
+        cobs = torch.randn(N, 220, device=dev)[:, :219]
         for _ in range(3):
             s.step = 0
             alg.act(obs, cobs)
