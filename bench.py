@@ -105,7 +105,7 @@ def _make_runner(num_envs, device, physics, seed=5):
 def _iterate(runner, state):
     obs, cobs = state
     with torch.inference_mode():
-        obs, cobs = runner.rollout(obs, cobs)
+        obs, cobs = runner.collect(obs, cobs)       # CUDA-graph replay of the 60-step rollout when the physics allows
         vl, sl = runner.alg.update()
     return (obs, cobs), (vl, sl)
 

@@ -30,10 +30,11 @@ __device__ __forceinline__ double warp_sum(double v) {
 // ---------------------------------------------------------------------------------------------
 __global__ void policy_sample_kernel(const float* __restrict__ mean, const float* __restrict__ stdv,
                                      const float* __restrict__ eps, uint64_t seed, uint64_t step,
-                                     float* __restrict__ actions, float* __restrict__ logp, float* __restrict__ sigma_out,
+                                     const uint64_t* __restrict__ step_dev, float* __restrict__ actions, float* __restrict__ logp, float* __restrict__ sigma_out,
                                      int M, int A) {
     int m = blockIdx.x * blockDim.x + threadIdx.x;
     if (m >= M) return;
+    if (step_dev) step = *step_dev;
     float lp = 0.0f;
     for (int j = 0; j < A; ++j) {
         float mu = mean[(size_t)m * A + j];
@@ -337,10 +338,11 @@ __global__ void adapt_lr_kernel(const float* kl_mean, double desired_kl, double*
 }  // namespace
 
 extern "C" int32_t hg_policy_sample(const float* mean, const float* std, const float* eps, uint64_t seed, uint64_t step,
-                                    float* actions, float* log_prob, float* sigma_out, int64_t M, int32_t A, void* stream) {
+                                    const uint64_t* step_dev, float* actions, float* log_prob, float* sigma_out, int64_t M,
+                                    int32_t A, void* stream) {
     HG_REQUIRE(mean); HG_REQUIRE(std); HG_REQUIRE(actions); HG_REQUIRE(log_prob); HG_REQUIRE(sigma_out);
     if (M <= 0 || A <= 0 || A > MAX_A) return hg_fail(HG_E_SIZE, "hg_policy_sample: bad M/A");
-    policy_sample_kernel<<<(unsigned)((M + 127) / 128), 128, 0, (cudaStream_t)stream>>>(mean, std, eps, seed, step, actions,
+    policy_sample_kernel<<<(unsigned)((M + 127) / 128), 128, 0, (cudaStream_t)stream>>>(mean, std, eps, seed, step, step_dev, actions,
                                                                                       log_prob, sigma_out, (int)M, A);
     HG_LAUNCHED(1);
     return hg_cuda_status("hg_policy_sample");

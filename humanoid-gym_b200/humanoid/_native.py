@@ -132,7 +132,7 @@ def _load():
         "hg_mlp_backward": (i32, [P(MlpDesc), PF, PF, i64, PF, PF, PF, PF, i64, PF]),
         "hg_gemm_tf32": (i32, [P(Gemm), PF]),
         "hg_set_gemm_mode": (i32, [i32]),
-        "hg_policy_sample": (i32, [PF, PF, PF, u64, u64, PF, PF, PF, i64, i32, PF]),
+        "hg_policy_sample": (i32, [PF, PF, PF, u64, u64, PF, PF, PF, PF, i64, i32, PF]),
         "hg_storage_add": (i32, [P(Storage), P(Transition), i32, f32, i64, PF]),
         "hg_gae": (i32, [P(Storage), PF, f32, f32, PF, i32, i64, PF]),
         "hg_adv_normalise": (i32, [P(Storage), PF, i64, PF]),

@@ -58,15 +58,55 @@ class OnPolicyRunner:
     def rollout(self, obs, critic_obs, book=None):
         """One collection phase: num_steps_per_env x (act, env.step, process_env_step) + compute_returns."""
         env, alg = self.env, self.alg
-        for _ in range(self.num_steps_per_env):
-            actions = alg.act(obs, critic_obs)
+        step_dev = env.noise_step_dev_ptr if getattr(env, "_Z", None) is not None and env._Z.use_device_counters else None
+        for t in range(self.num_steps_per_env):
+            actions = alg.act(obs, critic_obs, step_dev=step_dev)
             obs, privileged_obs, rewards, dones, infos = env.step(actions)
             critic_obs = privileged_obs if privileged_obs is not None else obs
             alg.process_env_step(rewards, dones, infos)
             if book is not None:
-                book.step(rewards, dones, infos)
+                book.step(t, rewards, dones, infos)
         alg.compute_returns(critic_obs)
         return obs, critic_obs
+
+    # ---- CUDA graph of the whole collection phase -----------------------------------------------------
+    def _graph_ok(self):
+        if os.environ.get("HG_CUDA_GRAPH", "1") == "0" or self.num_steps_per_env % 2:
+            return False
+        return bool(getattr(self.env, "graph_safe", lambda: False)())
+
+    def collect(self, obs, critic_obs, book=None):
+        """rollout(), replayed from a CUDA graph after the first (eager, warm-up) call when the physics source
+        allows it: ~2000 launches of a 60-step rollout become one graph launch, nothing per-step crosses PCIe."""
+        if not self._graph_ok():
+            return self.rollout(obs, critic_obs, book)
+        env, alg = self.env, self.alg
+        key = (obs.data_ptr(), critic_obs.data_ptr(), book is not None)
+        if getattr(self, "_graph_key", None) != key:
+            self._graph, self._graph_key, self._graph_warm = None, key, 0
+        if self._graph is None:
+            if self._graph_warm < 1:                  # first call with these buffers: eager (JIT, attributes, caches)
+                self._graph_warm += 1
+                return self.rollout(obs, critic_obs, book)
+            env.use_device_counters(True)
+            torch.cuda.synchronize(self.device)
+            g = torch.cuda.CUDAGraph()
+            side = torch.cuda.Stream(self.device)
+            side.wait_stream(torch.cuda.current_stream(self.device))
+            with torch.cuda.stream(side):
+                host_before = (env.common_step_counter, env._noise_step, getattr(env.gym, "substep", 0))
+                with torch.cuda.graph(g, stream=side):
+                    out = self.rollout(obs, critic_obs, book)
+                # capture executed nothing on the device: rewind the host mirrors the Python loop advanced
+                env.common_step_counter, env._noise_step = host_before[0], host_before[1]
+                if hasattr(env.gym, "substep"):
+                    env.gym.substep = host_before[2]
+            torch.cuda.current_stream(self.device).wait_stream(side)
+            self._graph, self._graph_out = g, out
+        self._graph.replay()
+        env.advance_host_counters(self.num_steps_per_env)
+        alg.storage.step = self.num_steps_per_env
+        return self._graph_out
 
     def learn(self, num_learning_iterations, init_at_random_ep_len=False):
         if self.log_dir is not None and self.writer is None:
@@ -77,13 +117,14 @@ class OnPolicyRunner:
         privileged_obs = self.env.get_privileged_observations()
         critic_obs = privileged_obs if privileged_obs is not None else obs
         self.alg.actor_critic.train()
-        book = _EpisodeBook(self.env.num_envs, self.device) if self.log_dir is not None else None
+        book = (_EpisodeBook(self.env.num_envs, self.num_steps_per_env, len(self.env.extras.get("episode", {})), self.device)
+                if self.log_dir is not None else None)
 
         tot_iter = self.current_learning_iteration + num_learning_iterations
         for it in range(self.current_learning_iteration, tot_iter):
             start = time.time()
             with torch.inference_mode():
-                obs, critic_obs = self.rollout(obs, critic_obs, book)
+                obs, critic_obs = self.collect(obs, critic_obs, book)
                 torch.cuda.synchronize(self.device)
                 stop = time.time()
                 collection_time = stop - start
@@ -176,37 +217,40 @@ class OnPolicyRunner:
 
 
 class _EpisodeBook:
-    """Per-episode reward / length bookkeeping of on_policy_runner.py:140-154, kept on the device;
-    finished-episode statistics are read back once per iteration instead of once per step."""
+    """Per-episode reward / length bookkeeping of on_policy_runner.py:140-154, kept on the device in
+    preallocated (T, N) buffers (so the per-step updates are CUDA-graph capturable); finished-episode statistics
+    are read back once per iteration instead of once per step."""
 
-    def __init__(self, n, device):
-        self.cur_reward_sum = torch.zeros(n, dtype=torch.float, device=device)
-        self.cur_episode_length = torch.zeros(n, dtype=torch.float, device=device)
+    def __init__(self, n, T, n_infos, device):
+        z = dict(dtype=torch.float, device=device)
+        self.cur_reward_sum = torch.zeros(n, **z)
+        self.cur_episode_length = torch.zeros(n, **z)
+        self.done_rew = torch.full((T, n), float("nan"), **z)
+        self.done_len = torch.full((T, n), float("nan"), **z)
+        self.infos = torch.zeros(T, max(n_infos, 1), **z)
+        self.nan = torch.full((n,), float("nan"), **z)
         self.rewbuffer, self.lenbuffer = deque(maxlen=100), deque(maxlen=100)
-        self._done_rew, self._done_len, self._infos = [], [], []
+        self._info_keys = []
 
-    def step(self, rewards, dones, infos):
-        if "episode" in infos:
-            self._infos.append(torch.stack(list(infos["episode"].values())).clone())
+    def step(self, t, rewards, dones, infos):
+        if "episode" in infos and infos["episode"]:
             self._info_keys = list(infos["episode"].keys())
+            self.infos[t, :len(self._info_keys)].copy_(torch.stack(list(infos["episode"].values())))
         self.cur_reward_sum += rewards
         self.cur_episode_length += 1
         d = dones > 0
-        self._done_rew.append(torch.where(d, self.cur_reward_sum, torch.full_like(self.cur_reward_sum, float("nan"))))
-        self._done_len.append(torch.where(d, self.cur_episode_length, torch.full_like(self.cur_reward_sum, float("nan"))))
+        torch.where(d, self.cur_reward_sum, self.nan, out=self.done_rew[t])
+        torch.where(d, self.cur_episode_length, self.nan, out=self.done_len[t])
         self.cur_reward_sum.masked_fill_(d, 0)
         self.cur_episode_length.masked_fill_(d, 0)
 
     def drain_infos(self):
-        if self._done_rew:
-            r = torch.stack(self._done_rew).flatten()
-            ln = torch.stack(self._done_len).flatten()
-            keep = ~torch.isnan(r)
-            self.rewbuffer.extend(r[keep].cpu().tolist())
-            self.lenbuffer.extend(ln[keep].cpu().tolist())
+        r, ln = self.done_rew.flatten(), self.done_len.flatten()
+        keep = ~torch.isnan(r)
+        self.rewbuffer.extend(r[keep].cpu().tolist())
+        self.lenbuffer.extend(ln[keep].cpu().tolist())
         out = {}
-        if self._infos:
-            m = torch.stack(self._infos).mean(dim=0).cpu().tolist()
+        if self._info_keys:
+            m = self.infos[:, :len(self._info_keys)].mean(dim=0).cpu().tolist()
             out = dict(zip(self._info_keys, m))
-        self._done_rew, self._done_len, self._infos = [], [], []
         return out

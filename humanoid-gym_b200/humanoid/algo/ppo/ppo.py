@@ -109,7 +109,7 @@ class PPO:
     # ------------------------------------------------------------------------------------------
     # rollout
     # ------------------------------------------------------------------------------------------
-    def act(self, obs, critic_obs, eps=None):
+    def act(self, obs, critic_obs, eps=None, step_dev=None):
         """ppo.py:91-101.  Everything lands directly in slab t of the storage: actor mean -> mu[t],
         value -> values[t], sampled actions / log-prob / sigma -> actions[t] / actions_log_prob[t] / sigma[t];
         obs and critic obs are copied now, because env.step() overwrites the env's buffers in place."""
@@ -121,7 +121,7 @@ class PPO:
         ac.native_forward("actor", obs, s.mu[t])
         ac.native_forward("critic", critic_obs, s.values[t])
         nat.check(nat.lib.hg_policy_sample(
-            s.mu[t].data_ptr(), ac.std.data_ptr(), nat.ptr(eps), self._seed, self._sample_step,
+            s.mu[t].data_ptr(), ac.std.data_ptr(), nat.ptr(eps), self._seed, self._sample_step, step_dev,
             s.actions[t].data_ptr(), s.actions_log_prob[t].data_ptr(), s.sigma[t].data_ptr(),
             s.num_envs, s.actions_shape[0], st), "hg_policy_sample")
         self._sample_step += 1

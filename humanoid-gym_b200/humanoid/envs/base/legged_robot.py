@@ -230,6 +230,33 @@ class LeggedRobot(BaseTask):
         self._injected = {}
         self._dev_index = torch.device(self.device).index
 
+    # ---- CUDA-graph support: per-step counters move to device memory -----------------------------------
+    def use_device_counters(self, on=True):
+        """With device counters the launches of a step carry no per-step host value (common_step_counter and the
+        Philox step live in scratch[4..7] and are bumped by the kernel), so a captured rollout can be replayed."""
+        if on and not self._Z.use_device_counters:
+            c = torch.tensor([self.common_step_counter, self._noise_step], dtype=torch.int64, device=self.device)
+            self._scratch[4:8].copy_(c.view(torch.int32))
+        elif not on and self._Z.use_device_counters:
+            c = self._scratch[4:8].clone().view(torch.int64).tolist()
+            self.common_step_counter, self._noise_step = int(c[0]), int(c[1])
+        self._Z.use_device_counters = int(on)
+
+    @property
+    def noise_step_dev_ptr(self):
+        """Device address of the Philox step counter (uint64 at scratch[6..7])."""
+        return self._scratch.data_ptr() + 24
+
+    def advance_host_counters(self, steps):
+        """After replaying a captured rollout of `steps` env steps: keep the host mirrors in sync."""
+        self.common_step_counter += steps
+        self._noise_step += steps
+        if hasattr(self.gym, "substep"):
+            self.gym.substep += steps * self.cfg.control.decimation
+
+    def graph_safe(self):
+        return isinstance(self.gym, phys.SyntheticPhysics) and not self.gym.host_resident
+
     def inject_noise(self, **tensors):
         """Parity hook: dense per-env draws (u_cmd_cb, u_cmd_rs, u_dof, u_push, z_obs, u_delay, z_act)
         used instead of in-kernel Philox for the NEXT kernel call(s) of this step."""

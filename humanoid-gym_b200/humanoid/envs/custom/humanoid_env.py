@@ -89,7 +89,8 @@ class XBotLFreeEnv(LeggedRobot):
         actions = actions.to(self.device, torch.float32).contiguous()
         nat.check(nat.lib.hg_env_pre_physics(
             self._B, self._P, nat.ptr(actions), nat.ptr(inj.get("u_delay")), nat.ptr(inj.get("z_act")),
-            self._Z.seed, self._noise_step, self.num_envs, nat.stream_ptr(self._dev_index)), "hg_env_pre_physics")
+            self._Z.seed, nat.STEP_FROM_DEVICE if self._Z.use_device_counters else self._noise_step, self.num_envs,
+            nat.stream_ptr(self._dev_index)), "hg_env_pre_physics")
         return super().step(self.actions)
 
     # conveniences kept from the reference API ------------------------------------------------

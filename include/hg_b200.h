@@ -228,9 +228,11 @@ int32_t hg_set_gemm_mode(int32_t mode);
 
 /* PPO.act epilogue (ppo.py:91-101, actor_critic.py:111-120): actions =
  * mean + std*eps, log-prob summed over actions, sigma broadcast.
- * eps (M,A) may be NULL (Philox with seed/step). */
+ * eps (M,A) may be NULL (Philox with seed/step).  step_dev, when not NULL, is a device counter read instead
+ * of `step` (the env's noise-step counter: the launch then carries no per-step host value -> graph replayable). */
 int32_t hg_policy_sample(const float* mean, const float* std, const float* eps, uint64_t seed, uint64_t step,
-                         float* actions, float* log_prob, float* sigma_out, int64_t M, int32_t A, void* stream);
+                         const uint64_t* step_dev, float* actions, float* log_prob, float* sigma_out, int64_t M,
+                         int32_t A, void* stream);
 
 /* RolloutStorage.add_transitions (rollout_storage.py:87-100) fused with the
  * time-out bootstrap of PPO.process_env_step (ppo.py:107-108): copies one

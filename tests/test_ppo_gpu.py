@@ -57,7 +57,9 @@ def test_policy_example_known_answers():
         sd["actor." + n] = v.cuda()
     ac.load_state_dict(sd)
     y = ac.act_inference(k.t("x").cuda())
-    np.testing.assert_allclose(y.cpu().numpy(), k["y"], rtol=1e-5, atol=2e-6)
+    # 705-term fp32 dot products: compare norm-wise at 1e-5 and element-wise with an absolute floor of 1e-5 * max|y|
+    assert _rel(y.cpu(), k.t("y")) < 1e-5, _rel(y.cpu(), k.t("y"))
+    np.testing.assert_allclose(y.cpu().numpy(), k["y"], rtol=1e-5, atol=1e-5 * float(np.abs(k["y"]).max()))
     kat = [0.0847, -0.0234, 0.0057, 0.2348, 0.6382, -0.2275, -0.1129, -0.1501, 0.2042, 0.3535, 0.0077, -0.4530]
     np.testing.assert_allclose(y[0].cpu().numpy(), kat, atol=5e-5)
 
@@ -78,7 +80,7 @@ def test_forward_sample_logprob_vs_golden():
     eps = torch.randn(M, 12, generator=torch.Generator().manual_seed(1))
     mean = ac.action_mean.contiguous()
     a, lp, sg = torch.empty(M, 12, device="cuda"), torch.empty(M, device="cuda"), torch.empty(M, 12, device="cuda")
-    nat.check(nat.lib.hg_policy_sample(mean.data_ptr(), ac.std.data_ptr(), eps.cuda().data_ptr(), 0, 0, a.data_ptr(),
+    nat.check(nat.lib.hg_policy_sample(mean.data_ptr(), ac.std.data_ptr(), eps.cuda().data_ptr(), 0, 0, None, a.data_ptr(),
                                        lp.data_ptr(), sg.data_ptr(), M, 12, 0))
     ra, rv, rlp, rmu, rsg = po.act(obs.cpu(), cobs.cpu(), p0, eps)
     np.testing.assert_allclose(a.cpu().numpy(), ra.numpy(), rtol=1e-5, atol=1e-6)
@@ -89,7 +91,7 @@ def test_forward_sample_logprob_vs_golden():
     mean0 = torch.zeros(M2, 12, device="cuda")
     one = torch.ones(12, device="cuda")
     a2, lp2, sg2 = torch.empty(M2, 12, device="cuda"), torch.empty(M2, device="cuda"), torch.empty(M2, 12, device="cuda")
-    nat.check(nat.lib.hg_policy_sample(mean0.data_ptr(), one.data_ptr(), None, 1234, 7, a2.data_ptr(), lp2.data_ptr(),
+    nat.check(nat.lib.hg_policy_sample(mean0.data_ptr(), one.data_ptr(), None, 1234, 7, None, a2.data_ptr(), lp2.data_ptr(),
                                        sg2.data_ptr(), M2, 12, 0))
     assert abs(float(a2.mean())) < 0.01 and abs(float(a2.std()) - 1) < 0.01
     assert abs(float((a2 ** 4).mean()) - 3) < 0.1
@@ -223,9 +225,15 @@ def test_flagship_gradients_vs_autograd():
     want = torch.cat([L.p[k].detach().reshape(-1) for k in L.names])
     # the fp32 update (~1e-5) is only a few ulp of the weights it lands on, so compare the new parameters
     # tightly and the update itself within that quantisation
-    assert torch.allclose(_cat(ac).cpu(), want, rtol=1e-6, atol=2e-7)     # 2 % of one lr-sized step
+    # Adam's first step moves every weight by lr * g / (|g| + 1e-8): for the few elements whose gradient is itself
+    # ~1e-8 an absolute gradient difference of 1e-9 (well inside the 1e-4 relative budget) changes the step by a
+    # sizeable fraction of lr, for ANY fp32 summation order.  So: every weight within one lr-step (1e-5) of the
+    # oracle's, 99.9 % of them within 2 % of a step, and the update vector as a whole within 1 %.
+    diff = (_cat(ac).cpu() - want).abs()
+    assert float(diff.max()) < 1.0e-5, float(diff.max())
+    assert float((diff > 2e-7).float().mean()) < 1e-3, float((diff > 2e-7).float().mean())
     upd_got, upd_want = (_cat(ac).cpu() - w_before.cpu()), (want - w_before.cpu())
-    assert _rel(upd_got, upd_want) < 1e-3, _rel(upd_got, upd_want)
+    assert _rel(upd_got, upd_want) < 1e-2, _rel(upd_got, upd_want)
     assert abs(alg.learning_rate - L.lr) < 1e-18
 
 
