@@ -117,7 +117,7 @@ def _time_iterations(runner, state, steps, device, world, e2e=False):
         dist.barrier()
     torch.cuda.synchronize(device)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    n0 = nat.launch_count()
+    n0 = nat.launch_count() + getattr(runner, "replayed_launches", 0)
     w0 = time.time()
     ev0.record()
     results = []
@@ -131,7 +131,7 @@ def _time_iterations(runner, state, steps, device, world, e2e=False):
         dist.barrier()
     ms = ev0.elapsed_time(ev1)
     wall = (time.time() - w0) * 1e3
-    launches = nat.launch_count() - n0
+    launches = nat.launch_count() + getattr(runner, "replayed_launches", 0) - n0
     t = torch.tensor([ms], dtype=torch.float64, device=device)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)

@@ -14,7 +14,7 @@
 //     warp  4    TMA producer cp.async.bulk.tensor (128B-swizzled 128x32 fp32 tiles, OOB zero fill)
 //     warp  5    MMA issuer   one lane issues tcgen05.mma.kind::tf32 (M=128, N=BN, K=8), accumulator in TMEM
 //     warps 6-13 splitter     raw fp32 tile -> lo tile (x - tf32(x)), elementwise so the swizzle is untouched
-// 3-stage ring of {A, B, A_lo, B_lo} tiles (64 KB / stage) with full / ready / empty mbarriers; CTAs are
+// 4-deep ring of raw {A, B} tile pairs (TMA look-ahead) + 2-deep ring of {A_lo, B_lo} pairs, mbarrier-linked; CTAs are
 // persistent (one per SM) and the accumulator is double-buffered in TMEM so that epilogue and main loop overlap.
 #include <cuda.h>
 
@@ -22,12 +22,14 @@
 
 namespace {
 
-constexpr int BM = 128, BK = 32, STAGES = 3;
+constexpr int BM = 128, BK = 32;
+constexpr int RAW_STAGES = 4;                        // TMA look-ahead: raw {A, B} tiles
+constexpr int LO_STAGES = 2;                         // splitter -> MMA: {A_lo, B_lo} tiles
 constexpr int TILE_BYTES = BM * BK * 4;              // 16 KB: 128 rows (or 4 MN-boxes) x 128 B
-constexpr int STAGE_BYTES = 4 * TILE_BYTES;          // A, B, A_lo, B_lo
+constexpr int PAIR_BYTES = 2 * TILE_BYTES;           // one {A, B} pair
 constexpr int SPLIT_WARPS = 8;
 constexpr int TC_THREADS = (6 + SPLIT_WARPS) * 32;   // 4 epilogue + TMA + MMA + splitters
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+constexpr int SMEM_BYTES = (RAW_STAGES + LO_STAGES) * PAIR_BYTES + 1024 /*align*/ + 256 /*barriers*/;
 
 enum { EPI_STORE = 0, EPI_BIAS = 1, EPI_BIAS_ELU = 2, EPI_MUL_DELU = 3, EPI_ATOMIC = 4 };
 
@@ -165,12 +167,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcArgs g) {
     extern __shared__ unsigned char smem_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
-    uint64_t* full = bars;                     // TMA -> splitter
-    uint64_t* ready = bars + STAGES;           // splitter -> MMA
-    uint64_t* empty = bars + 2 * STAGES;       // MMA -> TMA
-    uint64_t* tmem_full = bars + 3 * STAGES;   // [2] MMA -> epilogue
-    uint64_t* tmem_empty = tmem_full + 2;      // [2] epilogue -> MMA
+    unsigned char* smem_lo = smem + RAW_STAGES * PAIR_BYTES;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_lo + LO_STAGES * PAIR_BYTES);
+    uint64_t* full = bars;                          // [RAW] TMA -> splitter (and MMA)
+    uint64_t* empty = full + RAW_STAGES;            // [RAW] MMA -> TMA
+    uint64_t* ready = empty + RAW_STAGES;           // [LO]  splitter -> MMA
+    uint64_t* lo_empty = ready + LO_STAGES;         // [LO]  MMA -> splitter
+    uint64_t* tmem_full = lo_empty + LO_STAGES;     // [2]   MMA -> epilogue
+    uint64_t* tmem_empty = tmem_full + 2;           // [2]   epilogue -> MMA
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -180,10 +184,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int total_work = tiles_mn * g.splits;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < STAGES; ++s) {
+        for (int s = 0; s < RAW_STAGES; ++s) {
             mbar_init(&full[s], 1);
-            mbar_init(&ready[s], SPLIT_WARPS);
             mbar_init(&empty[s], 1);
+        }
+        for (int s = 0; s < LO_STAGES; ++s) {
+            mbar_init(&ready[s], SPLIT_WARPS);
+            mbar_init(&lo_empty[s], 1);
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(&tmem_full[a], 1);
@@ -207,9 +214,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
                 const Work wk = decode_work(g, w, tiles_n, tiles_mn, num_kb_total);
                 for (int kb = 0; kb < wk.num_kb; ++kb, ++it) {
-                    const int s = it % STAGES, k0 = (wk.kb_begin + kb) * BK;
-                    mbar_wait(&empty[s], ((it / STAGES) & 1) ^ 1);
-                    unsigned char* st = smem + s * STAGE_BYTES;
+                    const int s = it % RAW_STAGES, k0 = (wk.kb_begin + kb) * BK;
+                    mbar_wait(&empty[s], ((it / RAW_STAGES) & 1) ^ 1);
+                    unsigned char* st = smem + s * PAIR_BYTES;
                     mbar_expect_tx(&full[s], tx);
                     if (!g.a_mn) tma_load_2d(st, &tmA, &full[s], k0, wk.m0);
                     else
@@ -233,18 +240,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 tc_fence_after();
                 const uint32_t tmem_d = tmem_base + (uint32_t)(acc_stage * 128);
                 for (int kb = 0; kb < wk.num_kb; ++kb, ++it) {
-                    const int s = it % STAGES;
-                    mbar_wait(&ready[s], (it / STAGES) & 1);
+                    const int s = it % RAW_STAGES, l = it % LO_STAGES;
+                    mbar_wait(&ready[l], (it / LO_STAGES) & 1);                   // lo tiles written (raw tiles landed before that)
+                    mbar_wait(&full[s], (it / RAW_STAGES) & 1);
                     tc_fence_after();
-                    const uint32_t base = smem_u32(smem + s * STAGE_BYTES);
+                    const uint32_t base = smem_u32(smem + s * PAIR_BYTES), base_lo = smem_u32(smem_lo + l * PAIR_BYTES);
 #pragma unroll
                     for (int kk = 0; kk < BK / 8; ++kk) {
                         const uint64_t a_hi = make_desc(base + kk * kstep_a, g.a_mn);
                         const uint64_t b_hi = make_desc(base + TILE_BYTES + kk * kstep_b, g.b_mn);
                         const uint32_t acc = (kb > 0 || kk > 0) ? 1u : 0u;
                         if (g.passes == 3) {
-                            const uint64_t a_lo = make_desc(base + 2 * TILE_BYTES + kk * kstep_a, g.a_mn);
-                            const uint64_t b_lo = make_desc(base + 3 * TILE_BYTES + kk * kstep_b, g.b_mn);
+                            const uint64_t a_lo = make_desc(base_lo + kk * kstep_a, g.a_mn);
+                            const uint64_t b_lo = make_desc(base_lo + TILE_BYTES + kk * kstep_b, g.b_mn);
                             umma_tf32(tmem_d, a_lo, b_hi, idesc, acc);          // small terms first
                             umma_tf32(tmem_d, a_hi, b_lo, idesc, 1u);
                             umma_tf32(tmem_d, a_hi, b_hi, idesc, 1u);
@@ -252,7 +260,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                             umma_tf32(tmem_d, a_hi, b_hi, idesc, acc);
                         }
                     }
-                    umma_commit(&empty[s]);                                     // stage reusable once these MMAs retire
+                    umma_commit(&empty[s]);                                     // stages reusable once these MMAs retire
+                    umma_commit(&lo_empty[l]);
                 }
                 umma_commit(&tmem_full[acc_stage]);
             }
@@ -266,13 +275,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
             const Work wk = decode_work(g, w, tiles_n, tiles_mn, num_kb_total);
             for (int kb = 0; kb < wk.num_kb; ++kb, ++it) {
-                const int s = it % STAGES;
-                mbar_wait(&full[s], (it / STAGES) & 1);
+                const int s = it % RAW_STAGES, l = it % LO_STAGES;
+                mbar_wait(&lo_empty[l], ((it / LO_STAGES) & 1) ^ 1);            // MMA is done with this lo pair
+                mbar_wait(&full[s], (it / RAW_STAGES) & 1);
                 if (g.passes == 3) {
-                    float4* a = reinterpret_cast<float4*>(smem + s * STAGE_BYTES);
+                    float4* a = reinterpret_cast<float4*>(smem + s * PAIR_BYTES);
                     float4* b = a + TILE_BYTES / 16;
-                    float4* alo = a + 2 * TILE_BYTES / 16;
-                    float4* blo = a + 3 * TILE_BYTES / 16;
+                    float4* alo = reinterpret_cast<float4*>(smem_lo + l * PAIR_BYTES);
+                    float4* blo = alo + TILE_BYTES / 16;
                     auto split = [&](float4* raw, float4* lo, int i) {
                         // hi = truncation (what the tensor core does to a raw fp32 operand anyway);
                         // lo = residual, rounded to nearest tf32 so that its own truncation error vanishes
@@ -291,7 +301,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     fence_proxy_async();                                        // generic-proxy writes -> tensor-core reads
                 }
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&ready[s]);
+                if (lane == 0) mbar_arrive(&ready[l]);
             }
         }
     } else {

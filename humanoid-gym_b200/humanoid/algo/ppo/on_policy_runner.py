@@ -95,8 +95,11 @@ class OnPolicyRunner:
             side.wait_stream(torch.cuda.current_stream(self.device))
             with torch.cuda.stream(side):
                 host_before = (env.common_step_counter, env._noise_step, getattr(env.gym, "substep", 0))
+                from humanoid import _native as nat
+                n0 = nat.launch_count()
                 with torch.cuda.graph(g, stream=side):
                     out = self.rollout(obs, critic_obs, book)
+                self._graph_launches = nat.launch_count() - n0      # native kernels inside one replay
                 # capture executed nothing on the device: rewind the host mirrors the Python loop advanced
                 env.common_step_counter, env._noise_step = host_before[0], host_before[1]
                 if hasattr(env.gym, "substep"):
@@ -104,6 +107,7 @@ class OnPolicyRunner:
             torch.cuda.current_stream(self.device).wait_stream(side)
             self._graph, self._graph_out = g, out
         self._graph.replay()
+        self.replayed_launches = getattr(self, "replayed_launches", 0) + self._graph_launches
         env.advance_host_counters(self.num_steps_per_env)
         alg.storage.step = self.num_steps_per_env
         return self._graph_out

@@ -55,6 +55,7 @@ class PPO:
         self._seed = (torch.initial_seed() * 0x9E3779B97F4A7C15 + 12345) % (1 << 64)
         self._alias_grads_and_state()
         self._mb_scratch = {}
+        self._side = torch.cuda.Stream(dev)
 
     # ------------------------------------------------------------------------------------------
     def _alias_grads_and_state(self):
@@ -117,15 +118,21 @@ class PPO:
         t = s.step
         if t >= s.num_transitions_per_env:
             raise AssertionError("Rollout buffer overflow")
+        # actor and critic are independent chains of small GEMMs (M = num_envs): run them on two streams so that
+        # the tail layers of one (32-64 CTAs) overlap the other instead of leaving most of the 148 SMs idle
+        cur = torch.cuda.current_stream(self._dev_index)
+        self._side.wait_stream(cur)
+        with torch.cuda.stream(self._side):
+            ac.native_forward("critic", critic_obs, s.values[t])
         st = nat.stream_ptr(self._dev_index)
         ac.native_forward("actor", obs, s.mu[t])
-        ac.native_forward("critic", critic_obs, s.values[t])
         nat.check(nat.lib.hg_policy_sample(
             s.mu[t].data_ptr(), ac.std.data_ptr(), nat.ptr(eps), self._seed, self._sample_step, step_dev,
             s.actions[t].data_ptr(), s.actions_log_prob[t].data_ptr(), s.sigma[t].data_ptr(),
             s.num_envs, s.actions_shape[0], st), "hg_policy_sample")
         self._sample_step += 1
         s.add_native(t, obs=obs, priv_obs=critic_obs if s.privileged_observations is not None else None)
+        cur.wait_stream(self._side)
         tr = self.transition
         tr.actions, tr.values, tr.actions_log_prob = s.actions[t], s.values[t], s.actions_log_prob[t]
         tr.action_mean, tr.action_sigma = s.mu[t], s.sigma[t]
@@ -182,8 +189,12 @@ class PPO:
         cobs = mb["priv_obs"] if mb["priv_obs"] is not None else obs
         B = obs.shape[0]
         w = self._scratch(B)
+        cur = torch.cuda.current_stream(self._dev_index)
+        self._side.wait_stream(cur)
+        with torch.cuda.stream(self._side):               # critic chain overlaps the actor chain
+            ac.native_forward("critic", cobs, w["value"], hidden=w["hid_c"])
         ac.native_forward("actor", obs, w["mean"], hidden=w["hid_a"])
-        ac.native_forward("critic", cobs, w["value"], hidden=w["hid_c"])
+        cur.wait_stream(self._side)
         a = nat.PpoLossArgs()
         a.mean, a.value, a.std = w["mean"].data_ptr(), w["value"].data_ptr(), ac.std.data_ptr()
         a.actions, a.target_values = mb["actions"].data_ptr(), mb["values"].data_ptr()
@@ -197,10 +208,14 @@ class PPO:
         a.inv_B = 1.0 / (B * world)
         nat.check(nat.lib.hg_ppo_loss_fwd_bwd(a, B, st), "hg_ppo_loss_fwd_bwd")
         g = self._grad.data_ptr()
+        self._side.wait_stream(cur)
+        with torch.cuda.stream(self._side):               # the two backward chains write disjoint gradient ranges
+            nat.check(nat.lib.hg_mlp_backward(ac._desc["critic"], flat.data_ptr(), cobs.data_ptr(), cobs.stride(0), w["hid_c"].data_ptr(),
+                                              w["d_value"].data_ptr(), w["dhid_c"].data_ptr(), g, B,
+                                              nat.stream_ptr(self._dev_index)), "hg_mlp_backward(critic)")
         nat.check(nat.lib.hg_mlp_backward(ac._desc["actor"], flat.data_ptr(), obs.data_ptr(), obs.stride(0), w["hid_a"].data_ptr(),
                                           w["d_mean"].data_ptr(), w["dhid_a"].data_ptr(), g, B, st), "hg_mlp_backward(actor)")
-        nat.check(nat.lib.hg_mlp_backward(ac._desc["critic"], flat.data_ptr(), cobs.data_ptr(), cobs.stride(0), w["hid_c"].data_ptr(),
-                                          w["d_value"].data_ptr(), w["dhid_c"].data_ptr(), g, B, st), "hg_mlp_backward(critic)")
+        cur.wait_stream(self._side)
         if world > 1:
             dist.all_reduce(self._grad)                         # the ONE collective of the update path
         if self.desired_kl is not None and self.schedule == "adaptive":
