@@ -234,8 +234,10 @@ def run_product(args):
                               "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms / args.steps, 3), "quick": True,
                               "gpu_launches": int(launches // args.steps)}))
         return
+    _log("value arm done; kernel rooflines")
     with torch.inference_mode():
         extra = _kernel_rooflines(runner, device, pk) if rank == 0 else {}
+    _log("rooflines done; e2e arm (host-resident physics frames)")
     perf = {}
     del runner, env
     torch.cuda.empty_cache()
@@ -247,6 +249,7 @@ def run_product(args):
         state, _ = _iterate(runner, state)
     ms_e, _, _, state = _time_iterations(runner, state, args.steps, device, world, e2e=True)
     e2e_value = env_steps / (ms_e * 1e-3)
+    _log("e2e arm done")
     h2d = env.gym.h2d_bytes_per_step() * T_STEPS
     d2h = 8 * 4 + 4
     del runner, env
@@ -271,26 +274,38 @@ def run_product(args):
     }
     line.update(extra)
     if world == 1 and not args.no_cpu_baseline:
-        line["cpu_baseline"] = cpu_baseline(N, sample_T=T_STEPS)
+        line["cpu_baseline"] = cpu_baseline(N, sample_T=args.cpu_T)
     print(json.dumps(line))
 
 
 # ----------------------------------------------------------------------------------------------
 # reference arm / cpu baseline: the reference's PyTorch path (oracle port) on the host cores
 # ----------------------------------------------------------------------------------------------
+def _log(msg):
+    print(f"[bench {time.strftime('%H:%M:%S')}] {msg}", file=sys.stderr, flush=True)
+
+
+def _cpu_threads():
+    """Host threads for the reference PyTorch path.  Its tensors are small (N x 12 .. N x 705 fp32), so intra-op
+    parallelism stops paying long before a 100+-core host is full; more threads only add fork/join overhead."""
+    return int(os.environ.get("HG_REF_THREADS", min(os.cpu_count() or 1, 32)))
+
+
 def _oracle_trainer(num_envs, T, device="cpu"):
     from humanoid.physics import SyntheticPhysics
     from oracle.runner_oracle import OracleTrainer
     from oracle import env_oracle as eo
-    torch.set_num_threads(os.cpu_count())
+    torch.set_num_threads(_cpu_threads())
     ranges = {"lin_vel_x": [-0.3, 0.6], "lin_vel_y": [-0.3, 0.3]}
     ph = SyntheticPhysics(num_envs, device, ranges, eo.grid_origins(num_envs), decimation=10, seed=5)
     return OracleTrainer(num_envs, ph, T=T)
 
 
 def cpu_baseline(num_envs, sample_T):
+    _log(f"cpu_baseline: oracle port, N={num_envs}, T={sample_T}, {_cpu_threads()} threads")
     tr = _oracle_trainer(num_envs, sample_T)
     c, l = tr.iteration()
+    _log(f"cpu_baseline done: collection {c:.2f}s learn {l:.2f}s")
     v = num_envs * sample_T / (c + l)
     return {"value": round(v, 1), "unit": "env-steps/s", "cores": torch.get_num_threads(), "kind": "port",
             "sample": f"1 learning iteration of the oracle port (reference PyTorch path), N={num_envs}, T={sample_T}, "
@@ -316,7 +331,8 @@ def run_reference(args):
     v = N * T * args.steps / dt
     cores = torch.get_num_threads()
     sample = (f"each step = one learning iteration of the reference PyTorch path (oracle port) at N={N} with T={T} of the 60 "
-              f"env steps (bounded sample; the metric is a rate), 2 epochs x 4 minibatches, {cores} host threads")
+              f"env steps (bounded sample; the metric is a rate: env-steps/s = N*T/(collection+learn)), 2 epochs x 4 "
+              f"minibatches, {cores} host threads")
     print(json.dumps({
         "impl": "reference", "metric": "env_steps_per_sec", "value": round(v, 1), "unit": "env-steps/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(dt / args.steps * 1e3, 2),
@@ -335,7 +351,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--num-envs", type=int, default=4096, help="envs per GPU (BASELINE.json configs[1])")
-    ap.add_argument("--ref-T", type=int, default=60, help="env steps per iteration in the reference arm's bounded sample")
+    ap.add_argument("--ref-T", type=int, default=12, help="env steps per iteration in the reference arm's bounded sample")
+    ap.add_argument("--cpu-T", type=int, default=12, help="env steps of the cpu_baseline sample (one iteration)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--quick", action="store_true", help="value arm only (for ncu launch lists): no e2e, rooflines, cpu baseline")
     args = ap.parse_args()
