@@ -162,7 +162,7 @@ def _kernel_rooflines(runner, device, pk):
         tot += e0.elapsed_time(e1)
     t_env = tot / reps * 1e-3
     gbs = ENV_BYTES_PER_STEP * N / t_env / 1e9
-    out["roofline_env"] = dict(kernel="post_physics_kernel", bound="hbm", achieved=round(gbs, 1), peak=pk["hbm"], unit="GB/s",
+    out["roofline_env"] = dict(num_envs=N, kernel="post_physics_kernel", bound="hbm", achieved=round(gbs, 1), peak=pk["hbm"], unit="GB/s",
                                frac=round(gbs / pk["hbm"], 4), traffic=None, us_per_launch=round(t_env * 1e6, 2),
                                bytes_per_launch=ENV_BYTES_PER_STEP * N, peak_source=pk["src"], l2="flushed between launches")
     # -- MLP fwd+bwd chain of one minibatch (inputs 237 MB > L2) -------------------------------------------
@@ -198,11 +198,53 @@ def _kernel_rooflines(runner, device, pk):
     flops = (FLOPS_FWD + FLOPS_BWD) * B
     tf = flops / t / 1e12
     peak_tf32 = pk["bf16_sustained"] / 2.0
-    out["roofline"] = dict(kernel="ActorCritic fwd+bwd GEMM chain (gemm_kernel, fp32 CUDA-core path)", bound="tensor",
+    mode = nat.lib.hg_set_gemm_mode(-1)
+    passes = {0: 0, 1: 3, 2: 1}[mode]
+    engine = {0: "gemm_kernel (exact-fp32 CUDA-core path)", 1: "gemm_tc_kernel (tcgen05 kind::tf32, 3xTF32)",
+              2: "gemm_tc_kernel (tcgen05 kind::tf32, 1 pass)"}[mode]
+    out["roofline"] = dict(kernel="ActorCritic fwd+bwd GEMM chain of one 61,440-sample minibatch: " + engine, bound="tensor",
                            achieved=round(tf, 2), peak=round(peak_tf32, 1), unit="TFLOP/s", frac=round(tf / peak_tf32, 4),
                            traffic=None, ms_per_minibatch=round(t * 1e3, 3), flops_per_launch_group=flops,
-                           peak_source=pk["src"] + "; TF32 dense = bf16_sustained/2", share_of_step=None)
+                           mma_passes=passes, tensor_pipe_tflops=round(tf * max(passes, 1), 2),
+                           tensor_pipe_frac=round(tf * max(passes, 1) / peak_tf32, 4),
+                           note="achieved = ALGORITHMIC fp32 FLOPs (4.486 MFLOP/sample, SURVEY 8d) / time; 3xTF32 issues 3 tensor "
+                                "MMAs per algorithmic product, so the tensor pipe runs at tensor_pipe_tflops",
+                           peak_source=pk["src"] + "; TF32 dense peak taken as bf16_tflops_sustained/2")
     return out
+
+
+def env_roofline_large(device, pk, N=65536):
+    """The fused env kernel at the size where it is bandwidth- rather than latency-bound (BASELINE.json sweep config)."""
+    from humanoid import _native as nat
+    env, _ = _make_env_only(N, str(device))
+    st = torch.cuda.current_stream(device)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    flush = torch.empty(192 * 1024 * 1024 // 4, device=device)
+    for _ in range(3):
+        env.step(torch.randn(N, 12, device=device))
+    tot, reps = 0.0, 10
+    for _ in range(reps):
+        flush.zero_()
+        e0.record(st)
+        env._launch_post_physics(nat.PHASE_STEP_ALL)
+        e1.record(st)
+        torch.cuda.synchronize(device)
+        tot += e0.elapsed_time(e1)
+    t = tot / reps * 1e-3
+    gbs = ENV_BYTES_PER_STEP * N / t / 1e9
+    return dict(kernel="post_physics_kernel", num_envs=N, bound="hbm", achieved=round(gbs, 1), peak=pk["hbm"], unit="GB/s",
+                frac=round(gbs / pk["hbm"], 4), traffic=None, us_per_launch=round(t * 1e6, 2),
+                bytes_per_launch=ENV_BYTES_PER_STEP * N, peak_source=pk["src"], l2="flushed between launches")
+
+
+def _make_env_only(num_envs, device, seed=5):
+    os.environ["HG_PHYSICS"] = "synthetic"
+    from humanoid.envs import XBotLCfg  # noqa: F401
+    from humanoid.utils import task_registry
+    from humanoid.utils.helpers import get_args
+    args = get_args(["--task=humanoid_ppo", "--headless", f"--num_envs={num_envs}", f"--sim_device={device}",
+                     f"--rl_device={device}", f"--seed={seed}"])
+    return task_registry.make_env("humanoid_ppo", args=args)
 
 
 def run_product(args):
@@ -273,6 +315,9 @@ def run_product(args):
         "host_wall_ms_per_step": round(wall_ms / args.steps, 3),
     }
     line.update(extra)
+    if world == 1 and not args.no_env_sweep:
+        _log("env kernel at N=65536 (its bandwidth regime)")
+        line["roofline_env_65536"] = env_roofline_large(device, pk)
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(N, sample_T=args.cpu_T)
     print(json.dumps(line))
@@ -354,6 +399,7 @@ def main():
     ap.add_argument("--ref-T", type=int, default=12, help="env steps per iteration in the reference arm's bounded sample")
     ap.add_argument("--cpu-T", type=int, default=12, help="env steps of the cpu_baseline sample (one iteration)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-env-sweep", action="store_true")
     ap.add_argument("--quick", action="store_true", help="value arm only (for ncu launch lists): no e2e, rooflines, cpu baseline")
     args = ap.parse_args()
     if args.impl == "reference":

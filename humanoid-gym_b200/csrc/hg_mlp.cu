@@ -201,7 +201,7 @@ int32_t check_net(const HgMlpDesc* net) {
 
 extern "C" int32_t hg_set_gemm_mode(int32_t mode) {
     int prev = gemm_mode();
-    if (mode >= 0 && mode <= 2) g_gemm_mode = mode;
+    if (mode >= 0 && mode <= 2) g_gemm_mode = mode;      // any other value: query only
     return prev;
 }
 
