@@ -318,30 +318,51 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 float v[32];
                 tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(acc_stage * 128 + c0), v);
                 const int col0 = wk.n0 + c0;
-                if (!row_ok || col0 >= g.N) continue;
+                if (col0 >= g.N) continue;                                  // warp-uniform
                 float* dst = g.C + (int64_t)row * g.ldc + col0;
                 const int nvalid = min(32, g.N - col0);
+                const bool vec_ok = (nvalid == 32);
                 if (g.epi == EPI_BIAS || g.epi == EPI_BIAS_ELU) {
+                    // one coalesced load of the 32 bias values of this chunk, then warp shuffles
+                    const float bl = (lane < nvalid) ? __ldg(g.bias + col0 + lane) : 0.0f;
 #pragma unroll
-                    for (int j = 0; j < 32; ++j)
-                        if (j < nvalid) {
-                            float x = v[j] + __ldg(g.bias + col0 + j);
-                            v[j] = (g.epi == EPI_BIAS_ELU) ? (x > 0.0f ? x : expm1f(x)) : x;
-                        }
+                    for (int j = 0; j < 32; ++j) {
+                        float x = v[j] + __shfl_sync(0xffffffffu, bl, j);
+                        // nn.ELU(alpha=1): exp(x) - 1 for x <= 0 (absolute error ~1e-7, same form as torch's CUDA kernel)
+                        v[j] = (g.epi == EPI_BIAS_ELU) ? (x > 0.0f ? x : __expf(x) - 1.0f) : x;
+                    }
                 } else if (g.epi == EPI_MUL_DELU) {
                     const float* h = g.H + (int64_t)row * g.ldh + col0;
+                    if (row_ok && vec_ok && ((reinterpret_cast<uintptr_t>(h) & 15u) == 0)) {
 #pragma unroll
-                    for (int j = 0; j < 32; ++j)
-                        if (j < nvalid) {
-                            float hv = __ldg(h + j);
-                            v[j] *= (hv > 0.0f) ? 1.0f : (hv + 1.0f);
+                        for (int j = 0; j < 32; j += 4) {
+                            const float4 hv = __ldg(reinterpret_cast<const float4*>(h + j));
+                            v[j] *= (hv.x > 0.0f) ? 1.0f : (hv.x + 1.0f);
+                            v[j + 1] *= (hv.y > 0.0f) ? 1.0f : (hv.y + 1.0f);
+                            v[j + 2] *= (hv.z > 0.0f) ? 1.0f : (hv.z + 1.0f);
+                            v[j + 3] *= (hv.w > 0.0f) ? 1.0f : (hv.w + 1.0f);
                         }
-                }
-                if (g.epi == EPI_ATOMIC) {
+                    } else if (row_ok) {
 #pragma unroll
-                    for (int j = 0; j < 32; ++j)
-                        if (j < nvalid) atomicAdd(dst + j, v[j]);
-                } else if (nvalid == 32 && ((reinterpret_cast<uintptr_t>(dst) & 15u) == 0)) {
+                        for (int j = 0; j < 32; ++j)
+                            if (j < nvalid) {
+                                float hv = __ldg(h + j);
+                                v[j] *= (hv > 0.0f) ? 1.0f : (hv + 1.0f);
+                            }
+                    }
+                }
+                if (!row_ok) continue;
+                if (g.epi == EPI_ATOMIC) {
+                    if (vec_ok && ((reinterpret_cast<uintptr_t>(dst) & 15u) == 0)) {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4)
+                            atomicAdd(reinterpret_cast<float4*>(dst + j), make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]));
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            if (j < nvalid) atomicAdd(dst + j, v[j]);
+                    }
+                } else if (vec_ok && ((reinterpret_cast<uintptr_t>(dst) & 15u) == 0)) {
 #pragma unroll
                     for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
                 } else {
