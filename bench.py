@@ -69,7 +69,7 @@ class ClockSampler:
                         self.reasons.add(n)
             except Exception:
                 pass
-            self._stop.wait(0.2)
+            self._stop.wait(0.02)
 
     def __enter__(self):
         self.th = threading.Thread(target=self._run, daemon=True)
