@@ -9,10 +9,13 @@
 // A CTA owns 32 consecutive envs (one warp's worth).  Rows of consecutive envs are contiguous, so every
 // per-CTA tile of per-env state (root 13, dof 24, actions 12, contacts 39, ... floats per env) is ONE
 // contiguous 16-byte-aligned range: all 8 warps stage those tiles into shared memory with coalesced
-// float4 loads.  Then the CTA splits by role:
+// cp.async copies.  A CTA is small (4 warps, ~27 KB of shared memory: tiles that are dead by the time the new
+// observation frames are assembled are aliased with them) so that 7 CTAs -- 7 compute warps -- are resident per SM;
+// the kernel's critical path is the ~4k dependent instructions of the per-env program, and only many concurrent
+// compute warps hide it.  Then the CTA splits by role:
 //   * warp 0, one lane per env, evaluates the branchy / transcendental-heavy step entirely out of shared
 //     memory (no dependent global loads on its critical path) and publishes the per-env reset flags early;
-//   * warps 1-7 stream the observation histories -- 87 % of the kernel's bytes: obs_out[e][0:658] =
+//   * warps 1-3 stream the observation histories -- 87 % of the kernel's bytes: obs_out[e][0:658] =
 //     obs_in[e][47:705], priv likewise -- straight through registers with many independent 128-byte
 //     requests in flight; input and output histories are distinct (ping-pong) buffers, so the shift has no
 //     in-place hazard and needs no staging.
@@ -24,7 +27,7 @@
 #include "hg_common.cuh"
 
 #define HG_ENVS_PER_CTA 32
-#define HG_ENV_THREADS 256
+#define HG_ENV_THREADS 128
 #define HG_MAX_BODIES 16
 
 namespace {
@@ -99,7 +102,6 @@ __device__ __forceinline__ void cp_async16(float* sdst, const float* gsrc) {
     unsigned sa = (unsigned)__cvta_generic_to_shared(sdst);
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gsrc) : "memory");
 }
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 __device__ __forceinline__ void mbar_init(unsigned long long* bar, int count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
 }
@@ -127,11 +129,11 @@ __device__ __forceinline__ void tile_load(float* s, const float* g, int n, int t
     }
 }
 
-// every array length is a multiple of 4 floats so that each member stays 16-byte aligned
-struct __align__(16) EnvSmem {
-    float root[E * 13];
-    float dof[E * 24];
-    float act[E * 12];
+// every array length is a multiple of 4 floats so that each member stays 16-byte aligned.
+// Aliasing: the tiles in `in_a` / `rg` are last read by the reward section; after a __syncwarp the observation
+// section reuses their storage for the new privileged / actor frames.
+constexpr int HG_CF_SLOTS = 2 + 2 * HG_MAX_CONTACT_BODIES;          // feet, termination bodies, penalised bodies
+struct InA {
     float lact[E * 12];
     float llact[E * 12];
     float ldv[E * 12];
@@ -139,15 +141,23 @@ struct __align__(16) EnvSmem {
     float ref[E * 12];
     float lrv[E * 6];
     float cmd[E * 4];
-    float cf[E * HG_MAX_BODIES * 3];
-    float rg[E * 4 * 13];               // feet L/R, knee L/R rows of rigid_state
     float fat[E * 2], fh[E * 2], lfz[E * 2];
+};
+struct __align__(16) EnvSmem {
+    float root[E * 13];
+    float dof[E * 24];
+    float act[E * 12];
+    union {
+        InA in_a;                                                   // 2432 floats
+        float newpriv[E * HG_PRIV1];                                // 2336 floats
+    };
+    union {
+        float rg[E * 4 * 13];                                       // feet L/R, knee L/R rows of rigid_state
+        float newobs[E * HG_OBS1];
+    };
+    float cf[E * HG_CF_SLOTS * 3];                                  // contact forces of the bodies the step reads
     float rpf[E * 3], rpt[E * 3], org[E * 3];
     float fric[E], mass[E];
-    float sums[HG_NUM_REWARDS * E];
-    float rterm[HG_NUM_REWARDS * E];    // unscaled reward terms of this step
-    float newobs[E * HG_OBS1];
-    float newpriv[E * HG_PRIV1];
     float acc[HG_NUM_REWARDS + 2];
     long long ep[E];
     unsigned long long mbar;
@@ -158,19 +168,22 @@ struct __align__(16) EnvSmem {
     unsigned char reset[E];
     unsigned char root_dirty[E];
 };
+static_assert(sizeof(InA) >= sizeof(float) * E * HG_PRIV1, "aliased region too small for the privileged frame");
+static_assert(sizeof(float) * E * 4 * 13 >= sizeof(float) * E * HG_OBS1, "aliased region too small for the actor frame");
 
 #define FIELD(f) (int)(offsetof(HgEnvBuffers, f) / sizeof(void*))
 #define SMEMF(f) (int)(offsetof(EnvSmem, f) / sizeof(float))
-constexpr int kNumTiles = 19;
+constexpr int kNumTiles = 18;
 __constant__ int kTileField[kNumTiles] = {
     FIELD(root_states), FIELD(dof_state), FIELD(actions), FIELD(last_actions), FIELD(last_last_actions), FIELD(last_dof_vel),
-    FIELD(torques), FIELD(ref_dof_pos), FIELD(last_root_vel), FIELD(commands), FIELD(contact_forces), FIELD(feet_air_time),
+    FIELD(torques), FIELD(ref_dof_pos), FIELD(last_root_vel), FIELD(commands), FIELD(feet_air_time),
     FIELD(feet_height), FIELD(last_feet_z), FIELD(rand_push_force), FIELD(rand_push_torque), FIELD(env_origins),
     FIELD(env_frictions), FIELD(body_mass)};
 __constant__ int kTileSmem[kNumTiles] = {
-    SMEMF(root), SMEMF(dof), SMEMF(act), SMEMF(lact), SMEMF(llact), SMEMF(ldv), SMEMF(tau), SMEMF(ref), SMEMF(lrv), SMEMF(cmd),
-    SMEMF(cf), SMEMF(fat), SMEMF(fh), SMEMF(lfz), SMEMF(rpf), SMEMF(rpt), SMEMF(org), SMEMF(fric), SMEMF(mass)};
-__constant__ int kTileWidth[kNumTiles] = {13, 24, 12, 12, 12, 12, 12, 12, 6, 4, 0 /* num_bodies*3 */, 2, 2, 2, 3, 3, 3, 1, 1};
+    SMEMF(root), SMEMF(dof), SMEMF(act), SMEMF(in_a.lact), SMEMF(in_a.llact), SMEMF(in_a.ldv), SMEMF(in_a.tau), SMEMF(in_a.ref),
+    SMEMF(in_a.lrv), SMEMF(in_a.cmd), SMEMF(in_a.fat), SMEMF(in_a.fh), SMEMF(in_a.lfz), SMEMF(rpf), SMEMF(rpt), SMEMF(org),
+    SMEMF(fric), SMEMF(mass)};
+__constant__ int kTileWidth[kNumTiles] = {13, 24, 12, 12, 12, 12, 12, 12, 6, 4, 2, 2, 2, 3, 3, 3, 1, 1};
 
 __device__ __noinline__ HgPhilox philox_call(uint64_t seed, uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3) {
     return hg_philox(seed, c0, c1, c2, c3);
@@ -230,7 +243,7 @@ __device__ __forceinline__ void stream_history(float* __restrict__ out, const fl
     }
 }
 
-__global__ void __launch_bounds__(HG_ENV_THREADS, 3)
+__global__ void __launch_bounds__(HG_ENV_THREADS, 7)
 post_physics_kernel(HgEnvBuffers B, HgEnvNoise Z, uint32_t phases, int64_t common_step, int N) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     EnvSmem& S = *reinterpret_cast<EnvSmem*>(smem_raw);
@@ -268,7 +281,7 @@ post_physics_kernel(HgEnvBuffers B, HgEnvNoise Z, uint32_t phases, int64_t commo
         float* sbase = reinterpret_cast<float*>(&S);
 #pragma unroll 1
         for (int t = 0; t < kNumTiles; ++t) {
-            int w = kTileWidth[t] ? kTileWidth[t] : nb * 3;
+            int w = kTileWidth[t];
             tile_load(sbase + kTileSmem[t], fields[kTileField[t]] + (size_t)e0 * w, nE * w, tid, HG_ENV_THREADS);
         }
     }
@@ -278,10 +291,12 @@ post_physics_kernel(HgEnvBuffers B, HgEnvNoise Z, uint32_t phases, int64_t commo
         int body = (b < 2) ? cP.feet[b] : cP.knees[b - 2];
         cp_async4(S.rg + i, B.rigid_state + ((size_t)(e0 + le) * nb + body) * 13 + c);
     }
+    const int n_slots = 2 + cP.n_term + cP.n_pen;                      // contact-force rows the step reads
 #pragma unroll 1
-    for (int i = tid; i < HG_NUM_REWARDS * E; i += HG_ENV_THREADS) {    // episode sums are (22, N): 128-byte runs
-        int k = i / E, le = i % E;
-        if (le < nE) cp_async4(S.sums + i, B.episode_sums + (size_t)k * N + e0 + le);
+    for (int i = tid; i < nE * n_slots * 3; i += HG_ENV_THREADS) {
+        int le = i / (n_slots * 3), r = i - le * (n_slots * 3), sl = r / 3, c = r - sl * 3;
+        int body = sl < 2 ? cP.feet[sl] : (sl < 2 + cP.n_term ? cP.term_bodies[sl - 2] : cP.pen_bodies[sl - 2 - cP.n_term]);
+        cp_async4(S.cf + le * (HG_CF_SLOTS * 3) + sl * 3 + c, B.contact_forces + ((size_t)(e0 + le) * nb + body) * 3 + c);
     }
     mbar_arrive_on_cp_async(&S.mbar);
 
@@ -304,15 +319,18 @@ post_physics_kernel(HgEnvBuffers B, HgEnvNoise Z, uint32_t phases, int64_t commo
         float cmd[4] = {0, 0, 0, 0};
         long long ep = 0;
         bool cmd_dirty = false;
+        float fat0 = 0.0f, fat1 = 0.0f;
+        bool contact0 = false, contact1 = false;
         float* root = S.root + le * 13;
         float* dof = S.dof + le * 24;
         float* act = S.act + le * 12;
-        const float* cf = S.cf + le * nb * 3;
+        const float* cf = S.cf + le * (HG_CF_SLOTS * 3);          // slots: feet L, feet R, termination bodies, penalised bodies
         const float* fL = S.rg + le * 52;
         const float* fR = fL + 13;
         if (active) {
             ep = S.ep[le];
-            cmd[0] = S.cmd[le * 4]; cmd[1] = S.cmd[le * 4 + 1]; cmd[2] = S.cmd[le * 4 + 2]; cmd[3] = S.cmd[le * 4 + 3];
+            cmd[0] = S.in_a.cmd[le * 4]; cmd[1] = S.in_a.cmd[le * 4 + 1]; cmd[2] = S.in_a.cmd[le * 4 + 2]; cmd[3] = S.in_a.cmd[le * 4 + 3];
+            fat0 = S.in_a.fat[2 * le]; fat1 = S.in_a.fat[2 * le + 1];
             if (phases & HG_PHASE_COUNTERS) {                       // legged_robot.py:128-136
                 ep += 1;
                 blv = quat_rotate_inverse(root + 3, V3{root[7], root[8], root[9]});
@@ -331,7 +349,7 @@ post_physics_kernel(HgEnvBuffers B, HgEnvNoise Z, uint32_t phases, int64_t commo
             if (phases & HG_PHASE_TERMINATE) {                      // legged_robot.py:156-161
 #pragma unroll 1
                 for (int b = 0; b < cP.n_term; ++b) {
-                    const float* f = cf + cP.term_bodies[b] * 3;
+                    const float* f = cf + (2 + b) * 3;
                     reset |= sqrtf(f[0] * f[0] + f[1] * f[1] + f[2] * f[2]) > 1.0f;
                 }
                 timeout = ep > cP.max_episode_length;
@@ -382,20 +400,27 @@ post_physics_kernel(HgEnvBuffers B, HgEnvNoise Z, uint32_t phases, int64_t commo
             }
 
             // feet contacts used by rewards and observations
-            const float cLz = cf[cP.feet[0] * 3 + 2], cRz = cf[cP.feet[1] * 3 + 2];
-            const bool contact0 = cLz > 5.0f, contact1 = cRz > 5.0f;
+            const float cLz = cf[2], cRz = cf[5];
+            contact0 = cLz > 5.0f; contact1 = cRz > 5.0f;
 
             if (phases & HG_PHASE_REWARD) {                         // legged_robot.py:217-235
-                const float* lact = S.lact + le * 12;
-                const float* llact = S.llact + le * 12;
-                const float* ldv = S.ldv + le * 12;
-                const float* tau = S.tau + le * 12;
+                const float* lact = S.in_a.lact + le * 12;
+                const float* llact = S.in_a.llact + le * 12;
+                const float* ldv = S.in_a.ldv + le * 12;
+                const float* tau = S.in_a.tau + le * 12;
                 float phase = (float)ep * cP.dt / cP.cycle_time;    // humanoid_env.py:100-103
                 float s = sinf(kTwoPi * phase);
                 float st0 = s >= 0.0f ? 1.0f : 0.0f, st1 = s < 0.0f ? 1.0f : 0.0f;   // :105-118
                 if (fabsf(s) < 0.1f) { st0 = 1.0f; st1 = 1.0f; }
-                int kk = 0;
-                auto add_term = [&](float rv) { S.rterm[kk * E + le] = rv; ++kk; };   // kk is a compile-time index
+                float total = 0.0f;
+                int kk = 0;                                          // compile-time index after inlining
+                auto add_term = [&](float rv) {                      // alphabetical accumulation, legged_robot.py:222-230
+                    float rk = rv * cP.reward_scales[kk];
+                    total += rk;
+                    atomicAdd(B.episode_sums + (size_t)kk * N + e, rk);   // RED: fire-and-forget, no load on the critical path
+                    if (B.rew_terms) B.rew_terms[(size_t)kk * N + e] = rk;
+                    ++kk;
+                };
                 {   // 0 action_smoothness, humanoid_env.py:530-540
                     float t1 = 0.0f, t2 = 0.0f, t3 = 0.0f;
 #pragma unroll 1
@@ -409,7 +434,7 @@ post_physics_kernel(HgEnvBuffers B, HgEnvNoise Z, uint32_t phases, int64_t commo
                     add_term(t1 + t2 + 0.05f * t3);
                 }
                 {   // 1 base_acc :386-393
-                    const float* lrv = S.lrv + le * 6;
+                    const float* lrv = S.in_a.lrv + le * 6;
                     float a = 0.0f;
                     for (int j = 0; j < 6; ++j) { float d = lrv[j] - root[7 + j]; a += d * d; }
                     add_term(expf(-sqrtf(a) * 3.0f));
@@ -423,14 +448,14 @@ post_physics_kernel(HgEnvBuffers B, HgEnvNoise Z, uint32_t phases, int64_t commo
                     float c = 0.0f;
 #pragma unroll 1
                     for (int b = 0; b < cP.n_pen; ++b) {
-                        const float* f = cf + cP.pen_bodies[b] * 3;
+                        const float* f = cf + (2 + cP.n_term + b) * 3;
                         c += (sqrtf(f[0] * f[0] + f[1] * f[1] + f[2] * f[2]) > 0.1f) ? 1.0f : 0.0f;
                     }
                     add_term(c);
                 }
                 float dq2 = 0.0f, dacc = 0.0f, qerr = 0.0f, jall = 0.0f, tq = 0.0f;
                 {
-                    const float* ref = S.ref + le * 12;              // STALE reference pose (hazard 2)
+                    const float* ref = S.in_a.ref + le * 12;         // STALE reference pose (hazard 2)
 #pragma unroll 1
                     for (int j = 0; j < 12; ++j) {
                         float q = dof[2 * j], v = dof[2 * j + 1];
@@ -458,16 +483,16 @@ post_physics_kernel(HgEnvBuffers B, HgEnvNoise Z, uint32_t phases, int64_t commo
                     bool filt1 = contact1 || (st1 != 0.0f) || S.lc[2 * le + 1];
                     B.last_contacts[(size_t)e * 2] = contact0;
                     B.last_contacts[(size_t)e * 2 + 1] = contact1;
-                    float a0 = S.fat[2 * le], a1 = S.fat[2 * le + 1];
+                    float a0 = fat0, a1 = fat1;
                     bool first0 = (a0 > 0.0f) && filt0, first1 = (a1 > 0.0f) && filt1;
                     a0 += cP.dt; a1 += cP.dt;
                     add_term(clampf(a0, 0.0f, 0.5f) * (first0 ? 1.0f : 0.0f) + clampf(a1, 0.0f, 0.5f) * (first1 ? 1.0f : 0.0f));
-                    S.fat[2 * le] = a0 * (filt0 ? 0.0f : 1.0f);
-                    S.fat[2 * le + 1] = a1 * (filt1 ? 0.0f : 1.0f);
+                    fat0 = a0 * (filt0 ? 0.0f : 1.0f);
+                    fat1 = a1 * (filt1 ? 0.0f : 1.0f);
                 }
                 {   // 8 feet_clearance :446-467 (stateful; never reset, hazard 4)
                     float z0 = fL[2] - 0.05f, z1 = fR[2] - 0.05f;
-                    float h0 = S.fh[2 * le] + (z0 - S.lfz[2 * le]), h1 = S.fh[2 * le + 1] + (z1 - S.lfz[2 * le + 1]);
+                    float h0 = S.in_a.fh[2 * le] + (z0 - S.in_a.lfz[2 * le]), h1 = S.in_a.fh[2 * le + 1] + (z1 - S.in_a.lfz[2 * le + 1]);
                     float hit0 = fabsf(h0 - cP.target_feet_height) < 0.01f ? 1.0f : 0.0f;
                     float hit1 = fabsf(h1 - cP.target_feet_height) < 0.01f ? 1.0f : 0.0f;
                     add_term(hit0 * (1.0f - st0) + hit1 * (1.0f - st1));
@@ -477,8 +502,8 @@ post_physics_kernel(HgEnvBuffers B, HgEnvNoise Z, uint32_t phases, int64_t commo
                     *gz = make_float2(z0, z1);
                 }
                 {   // 9 feet_contact_forces :355-360
-                    const float* a = cf + cP.feet[0] * 3;
-                    const float* b = cf + cP.feet[1] * 3;
+                    const float* a = cf;
+                    const float* b = cf + 3;
                     float na = sqrtf(a[0] * a[0] + a[1] * a[1] + a[2] * a[2]);
                     float nbn = sqrtf(b[0] * b[0] + b[1] * b[1] + b[2] * b[2]);
                     add_term(clampf(na - cP.max_contact_force, 0.0f, 400.0f) + clampf(nbn - cP.max_contact_force, 0.0f, 400.0f));
@@ -536,14 +561,6 @@ post_physics_kernel(HgEnvBuffers B, HgEnvNoise Z, uint32_t phases, int64_t commo
                     float b = expf(-sqrtf(bav.x * bav.x + bav.y * bav.y) * 5.0f);
                     add_term((a + b) / 2.0f);
                 }
-                float total = 0.0f;
-#pragma unroll 1
-                for (int k = 0; k < HG_NUM_REWARDS; ++k) {          // alphabetical accumulation, legged_robot.py:222-230
-                    float rk = S.rterm[k * E + le] * cP.reward_scales[k];
-                    total += rk;
-                    S.sums[k * E + le] += rk;
-                    if (B.rew_terms) B.rew_terms[(size_t)k * N + e] = rk;
-                }
                 if (cP.only_positive_rewards) total = fmaxf(total, 0.0f);
                 B.rew_buf[e] = total;
             }
@@ -564,12 +581,12 @@ post_physics_kernel(HgEnvBuffers B, HgEnvNoise Z, uint32_t phases, int64_t commo
                 float u2 = draw_u(Z.u_cmd_rs, (int64_t)e * 3 + 2, Z.seed, Z.step, e, HG_RNG_CMD_RS, 2);
                 resample_commands(cmd, u0, u1, u2);
                 cmd_dirty = true;
-                S.fat[2 * le] = 0.0f; S.fat[2 * le + 1] = 0.0f;
+                fat0 = 0.0f; fat1 = 0.0f;
                 ep = 0;
 #pragma unroll 1
                 for (int k = 0; k < HG_NUM_REWARDS; ++k) {          // extras["episode"] :198-202
-                    atomicAdd(&S.acc[k], S.sums[k * E + le]);
-                    S.sums[k * E + le] = 0.0f;
+                    // read-and-zero in one strongly-ordered op (it follows this thread's REDs to the same address)
+                    atomicAdd(&S.acc[k], atomicExch(B.episode_sums + (size_t)k * N + e, 0.0f));
                 }
                 atomicAdd(&S.cnt, 1);
                 B.reset_ids[atomicAdd(&B.scratch[0], 1)] = e;
@@ -577,6 +594,16 @@ post_physics_kernel(HgEnvBuffers B, HgEnvNoise Z, uint32_t phases, int64_t commo
                 pg = quat_rotate_inverse(root + 3, V3{0.0f, 0.0f, -1.0f});
             }
             if (phases & (HG_PHASE_TERMINATE | HG_PHASE_RESET)) B.reset_buf[e] = reset;
+            if (do_last) {     // last_last_actions <- last_actions (0 if reset), legged_robot.py:147 (+ :190); its tile is about to be reused
+                const float4* la = reinterpret_cast<const float4*>(S.in_a.lact + le * 12);
+                float4* dst = reinterpret_cast<float4*>(B.last_last_actions + (size_t)e * 12);
+                const float4 z4 = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                const bool rz = do_reset && reset;
+                dst[0] = rz ? z4 : la[0]; dst[1] = rz ? z4 : la[1]; dst[2] = rz ? z4 : la[2];
+            }
+        }
+        __syncwarp();          // every lane is done with the aliased input tiles (in_a, rg) before newpriv / newobs are written
+        if (active) {
 
             if (do_obs) {                                           // humanoid_env.py:200-262
                 float phase = (float)ep * cP.dt / cP.cycle_time;
@@ -636,7 +663,7 @@ post_physics_kernel(HgEnvBuffers B, HgEnvNoise Z, uint32_t phases, int64_t commo
                 q = B.base_ang_vel + (size_t)e * 3; q[0] = bav.x; q[1] = bav.y; q[2] = bav.z;
             }
             if (phases & (HG_PHASE_REWARD | HG_PHASE_RESET))
-                *(reinterpret_cast<float2*>(B.feet_air_time) + e) = make_float2(S.fat[2 * le], S.fat[2 * le + 1]);
+                *(reinterpret_cast<float2*>(B.feet_air_time) + e) = make_float2(fat0, fat1);
             if (cmd_dirty) *reinterpret_cast<float4*>(B.commands + (size_t)e * 4) = make_float4(cmd[0], cmd[1], cmd[2], cmd[3]);
             if (do_last) {                                          // legged_robot.py:150
                 float* lrv = B.last_root_vel + (size_t)e * 6;
@@ -649,9 +676,9 @@ post_physics_kernel(HgEnvBuffers B, HgEnvNoise Z, uint32_t phases, int64_t commo
         // They copy every row unconditionally; rows of envs that turn out to reset are zeroed in step 3.
         if (do_obs) {
             stream_history<HG_OBS1, OBS_KEEP, OBS_W, 1>(B.obs_out + (size_t)e0 * opitch, B.obs_buf + (size_t)e0 * opitch, S.reset,
-                                                        nE, warp - 1, 7, lane, opitch);
+                                                        nE, warp - 1, 3, lane, opitch);
             stream_history<HG_PRIV1, PRIV_KEEP, PRIV_W, 5>(B.priv_out + (size_t)e0 * ppitch, B.privileged_obs_buf + (size_t)e0 * ppitch,
-                                                           S.reset, nE, warp - 1, 7, lane, ppitch);
+                                                           S.reset, nE, warp - 1, 3, lane, ppitch);
         }
     }
     __syncthreads();
@@ -700,13 +727,6 @@ post_physics_kernel(HgEnvBuffers B, HgEnvNoise Z, uint32_t phases, int64_t commo
     }
 
     // ---- 4. coalesced write-back of the tiles the step modified ------------------------------------------------
-    if (phases & (HG_PHASE_REWARD | HG_PHASE_RESET)) {
-#pragma unroll 1
-        for (int i = tid; i < HG_NUM_REWARDS * E; i += HG_ENV_THREADS) {
-            int k = i / E, le = i % E;
-            if (le < nE) B.episode_sums[(size_t)k * N + e0 + le] = S.sums[i];
-        }
-    }
     if (do_reset || (phases & HG_PHASE_CALLBACK)) {
         // root / dof rows change only on push or reset: write back the dirty rows
         for (int i = tid; i < nE * 13; i += HG_ENV_THREADS)
@@ -720,7 +740,6 @@ post_physics_kernel(HgEnvBuffers B, HgEnvNoise Z, uint32_t phases, int64_t commo
             int le = i / 12, j = i - le * 12;
             bool rz = S.reset[le];
             size_t gi = (size_t)e0 * 12 + i;
-            B.last_last_actions[gi] = rz ? 0.0f : S.lact[i];
             B.last_actions[gi] = S.act[i];
             B.last_dof_vel[gi] = S.dof[le * 24 + 2 * j + 1];
             if (rz) B.actions[gi] = 0.0f;

@@ -27,10 +27,11 @@ class BaseTask:
         self.num_actions = cfg.env.num_actions
 
         z = dict(device=self.device)
-        # observation rows are stored with a pitch rounded up to 4 floats (705 -> 708, 219 -> 220) so that TMA can
-        # feed them to the tensor-core actor / critic; obs_buf / privileged_obs_buf are the (N, 705) / (N, 219) views
+        # observation rows are stored with a pitch rounded up to 32 floats (705 -> 736, 219 -> 224): every row starts on
+        # a 128-byte line (the env kernel's warp-wide stores then write whole lines) and TMA can feed the rows to the
+        # tensor-core actor / critic; obs_buf / privileged_obs_buf are the (N, 705) / (N, 219) views
         def pitched(width):
-            return torch.zeros(self.num_envs, (width + 3) // 4 * 4, dtype=torch.float, **z)[:, :width]
+            return torch.zeros(self.num_envs, (width + 31) // 32 * 32, dtype=torch.float, **z)[:, :width]
         self.obs_buf = pitched(self.num_obs)
         self.rew_buf = torch.zeros(self.num_envs, dtype=torch.float, **z)
         # the reference allocates int64 ones but rebinds a bool tensor on every step

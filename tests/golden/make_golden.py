@@ -387,13 +387,25 @@ def make_policy_kat(out_path):
     print(f"wrote {out_path}: {os.path.getsize(out_path) / 1e6:.2f} MB; y[0]={np.round(data['y'][0], 4)}")
 
 
+def make_cfg_golden(out_path):
+    """class_to_dict() dumps of the reference's registered configs (the config tree IS the API)."""
+    import json
+    from humanoid.envs import XBotLCfg, XBotLCfgPPO
+    from humanoid.utils.helpers import class_to_dict
+    json.dump({"XBotLCfg": class_to_dict(XBotLCfg()), "XBotLCfgPPO": class_to_dict(XBotLCfgPPO())}, open(out_path, "w"),
+              indent=1, sort_keys=True)
+    print(f"wrote {out_path}")
+
+
 if __name__ == "__main__":
     _install_shims()
     torch.set_num_threads(1)
-    which = sys.argv[1:] or ["env", "ppo", "kat"]
+    which = sys.argv[1:] or ["env", "ppo", "kat", "cfg"]
     if "env" in which:
         make_env_golden(os.path.join(HERE, "env_rollout.npz"))
     if "ppo" in which:
         make_ppo_golden(os.path.join(HERE, "ppo_learning.npz"))
+    if "cfg" in which:
+        make_cfg_golden(os.path.join(HERE, "cfg_dump.json"))
     if "kat" in which:
         make_policy_kat(os.path.join(HERE, "policy_example_kat.npz"))
