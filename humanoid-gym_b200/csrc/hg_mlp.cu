@@ -159,6 +159,121 @@ __global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ d
     }
 }
 
+// 128-bit variant (N % 4 == 0, 16-byte aligned dZ): a warp reads 512 contiguous bytes of a row, every thread keeps
+// 8 independent 16-byte loads in flight (32 KB per block), so the kernel runs at HBM / L2 rate instead of at
+// load latency.  Block = 128 columns x 512 rows; partial sums meet in shared memory, 128 atomicAdds per block.
+constexpr int CS4_ROWS = 512;
+__global__ void __launch_bounds__(256) colsum4_kernel(const float* __restrict__ dZ, float* __restrict__ db, int M, int N) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int nc4 = N >> 2;
+    const int c4 = blockIdx.x * 32 + lane;
+    const int m0 = blockIdx.y * CS4_ROWS, m1 = min(M, m0 + CS4_ROWS);
+    float4 acc = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    if (c4 < nc4) {
+        const float4* p = reinterpret_cast<const float4*>(dZ) + c4;
+        int m = m0 + w;
+        for (; m + 56 < m1; m += 64) {
+            float4 v[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] = __ldcs(p + (int64_t)(m + 8 * i) * nc4);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { acc.x += v[i].x; acc.y += v[i].y; acc.z += v[i].z; acc.w += v[i].w; }
+        }
+        for (; m < m1; m += 8) {
+            float4 v = __ldcs(p + (int64_t)m * nc4);
+            acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+        }
+    }
+    __shared__ float4 sh[8][33];
+    sh[w][lane] = acc;
+    __syncthreads();
+    if (w == 0 && c4 < nc4) {
+        float4 t = sh[0][lane];
+#pragma unroll
+        for (int k = 1; k < 8; ++k) { t.x += sh[k][lane].x; t.y += sh[k][lane].y; t.z += sh[k][lane].z; t.w += sh[k][lane].w; }
+        float* d = db + 4 * c4;
+        atomicAdd(d, t.x); atomicAdd(d + 1, t.y); atomicAdd(d + 2, t.z); atomicAdd(d + 3, t.w);
+    }
+}
+
+// ---- skinny layers (N_out <= 16: the 128 -> 12 / 128 -> 1 heads) -----------------------------------------------
+// A 128-row MMA tile would be > 87 % padding here and the generic CUDA-core GEMM splits K into hundreds of
+// atomically-merged slices; both backward products of such a layer are really one streaming pass over the
+// (M, K) activation matrix, so they get their own HBM-rate kernels.
+constexpr int SK_ROWS = 128;
+// dW[n][k] += sum_{m in chunk} dZ[m][n] X[m][k];  grid (ceil(K/128), ceil(M/SK_ROWS)), block 128 (one k per thread)
+template <int NO>
+__global__ void __launch_bounds__(128) wgrad_skinny_kernel(const float* __restrict__ dZ, const float* __restrict__ X, int64_t ldx,
+                                                           float* __restrict__ dW, int64_t ldw, int M, int N, int K) {
+    __shared__ float dz[SK_ROWS][NO];
+    const int m0 = blockIdx.y * SK_ROWS, rows = min(SK_ROWS, M - m0);
+    for (int i = threadIdx.x; i < SK_ROWS * NO; i += 128) {
+        int r = i / NO, n = i - r * NO;
+        dz[r][n] = (r < rows && n < N) ? dZ[(int64_t)(m0 + r) * N + n] : 0.0f;
+    }
+    __syncthreads();
+    const int k = blockIdx.x * 128 + threadIdx.x;
+    if (k >= K) return;
+    float acc[NO];
+#pragma unroll
+    for (int n = 0; n < NO; ++n) acc[n] = 0.0f;
+    const float* xp = X + (int64_t)m0 * ldx + k;
+    int r = 0;
+    for (; r + 8 <= rows; r += 8) {
+        float x[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) x[i] = __ldcs(xp + (int64_t)(r + i) * ldx);
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+            for (int n = 0; n < NO; ++n) acc[n] += dz[r + i][n] * x[i];
+    }
+    for (; r < rows; ++r) {
+        float x = __ldcs(xp + (int64_t)r * ldx);
+#pragma unroll
+        for (int n = 0; n < NO; ++n) acc[n] += dz[r][n] * x;
+    }
+#pragma unroll
+    for (int n = 0; n < NO; ++n)
+        if (n < N) atomicAdd(dW + (int64_t)n * ldw + k, acc[n]);
+}
+
+// dH[m][k] = (sum_n dZ[m][n] W[n][k]) * ELU'(h[m][k]);  one float4 of k per thread, K % 4 == 0, 16-byte aligned rows
+template <int NO>
+__global__ void __launch_bounds__(256) dgrad_skinny_kernel(const float* __restrict__ dZ, const float* __restrict__ W, int64_t ldw,
+                                                           const float* __restrict__ H, float* __restrict__ dH, int M, int N, int K) {
+    const int kq = K >> 2;
+    const int64_t idx = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (idx >= (int64_t)M * kq) return;
+    const int m = (int)(idx / kq), k4 = (int)(idx - (int64_t)m * kq);
+    float4 v = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+#pragma unroll
+    for (int n = 0; n < NO; ++n) {
+        if (n < N) {
+            const float d = __ldg(dZ + (int64_t)m * N + n);
+            const float4 w = __ldg(reinterpret_cast<const float4*>(W + (int64_t)n * ldw) + k4);
+            v.x += d * w.x; v.y += d * w.y; v.z += d * w.z; v.w += d * w.w;
+        }
+    }
+    const float4 h = __ldcs(reinterpret_cast<const float4*>(H + (int64_t)m * K) + k4);
+    v.x *= (h.x > 0.0f) ? 1.0f : (h.x + 1.0f);
+    v.y *= (h.y > 0.0f) ? 1.0f : (h.y + 1.0f);
+    v.z *= (h.z > 0.0f) ? 1.0f : (h.z + 1.0f);
+    v.w *= (h.w > 0.0f) ? 1.0f : (h.w + 1.0f);
+    reinterpret_cast<float4*>(dH + (int64_t)m * K)[k4] = v;
+}
+
+template <int NO>
+void launch_wgrad_skinny(const float* dZ, const float* X, int64_t ldx, float* dW, int64_t ldw, int M, int N, int K, cudaStream_t st) {
+    dim3 grid((K + 127) / 128, (M + SK_ROWS - 1) / SK_ROWS);
+    wgrad_skinny_kernel<NO><<<grid, 128, 0, st>>>(dZ, X, ldx, dW, ldw, M, N, K);
+}
+template <int NO>
+void launch_dgrad_skinny(const float* dZ, const float* W, int64_t ldw, const float* H, float* dH, int M, int N, int K, cudaStream_t st) {
+    int64_t total = (int64_t)M * (K >> 2);
+    dgrad_skinny_kernel<NO><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(dZ, W, ldw, H, dH, M, N, K);
+}
+
 int g_gemm_mode = -1;   // -1: read HG_GEMM on first use
 int gemm_mode() {
     if (g_gemm_mode < 0) {
@@ -251,6 +366,19 @@ extern "C" int32_t hg_mlp_backward(const HgMlpDesc* net, const float* params, co
     int64_t off[HG_MAX_LAYERS + 1];
     off[0] = 0; off[1] = 0;
     for (int l = 1; l < L; ++l) off[l + 1] = off[l] + M * net->dims[l];
+    // zero this net's gradients: one memset when its blocks are laid out back to back (w0 b0 w1 b1 ...), else per block
+    bool contiguous = true;
+    int64_t end = net->w_off[0];
+    for (int l = 0; l < L && contiguous; ++l) {
+        const int64_t n_out = net->dims[l + 1];
+        contiguous = net->w_off[l] == end && net->b_off[l] == net->w_off[l] + n_out * net->ldw[l];
+        end = net->b_off[l] + (n_out + 3) / 4 * 4;
+    }
+    if (contiguous) {
+        // the last bias block is zeroed to its exact length (what follows it may belong to somebody else)
+        const int64_t last = net->b_off[L - 1] + net->dims[L];
+        cudaMemsetAsync(grads + net->w_off[0], 0, sizeof(float) * (size_t)(last - net->w_off[0]), st);
+    }
     const float* dZ = dY;                                   // gradient w.r.t. layer l's pre-activation
     for (int l = L - 1; l >= 0; --l) {
         const int K = net->dims[l], N = net->dims[l + 1];
@@ -259,15 +387,24 @@ extern "C" int32_t hg_mlp_backward(const HgMlpDesc* net, const float* params, co
         float* dW = grads + net->w_off[l];
         float* db = grads + net->b_off[l];
         const int64_t ldw = net->ldw[l];
-        cudaMemsetAsync(dW, 0, sizeof(float) * (size_t)N * ldw, st);
-        cudaMemsetAsync(db, 0, sizeof(float) * (size_t)N, st);
+        if (!contiguous) {
+            cudaMemsetAsync(dW, 0, sizeof(float) * (size_t)N * ldw, st);
+            cudaMemsetAsync(db, 0, sizeof(float) * (size_t)N, st);
+        }
         {   // dW[n][k] = sum_m dZ[m][n] X[m][k]
             int tiles = ((N + BM - 1) / BM) * ((K + BN - 1) / BN);
             int64_t want_tc = (2 * HG_NUM_SMS + tiles - 1) / tiles, cap_tc = (M + 511) / 512;
             int split_tc = (int)(want_tc < cap_tc ? want_tc : cap_tc);
             if (split_tc < 1) split_tc = 1;
             int32_t rc = try_tc(dZ, N, true, in, ld_in, true, dW, ldw, N, K, (int)M, 4, nullptr, nullptr, 0, split_tc, st);
-            if (rc == 1) {
+            if (rc == 1 && N <= 16) {
+                if (N == 1) launch_wgrad_skinny<1>(dZ, in, ld_in, dW, ldw, (int)M, N, K, st);
+                else if (N <= 4) launch_wgrad_skinny<4>(dZ, in, ld_in, dW, ldw, (int)M, N, K, st);
+                else if (N <= 8) launch_wgrad_skinny<8>(dZ, in, ld_in, dW, ldw, (int)M, N, K, st);
+                else launch_wgrad_skinny<16>(dZ, in, ld_in, dW, ldw, (int)M, N, K, st);
+                HG_LAUNCHED(1);
+                rc = hg_cuda_status("hg wgrad (skinny)");
+            } else if (rc == 1) {
                 GemmArgs g{};
                 g.A = dZ; g.sai = 1; g.sap = N;
                 g.B = in; g.sbp = ld_in; g.sbj = 1;
@@ -282,7 +419,11 @@ extern "C" int32_t hg_mlp_backward(const HgMlpDesc* net, const float* params, co
             }
             if (rc) return rc;
         }
-        {
+        if ((N & 3) == 0 && (reinterpret_cast<uintptr_t>(dZ) & 15u) == 0) {
+            dim3 grid((N / 4 + 31) / 32, (unsigned)((M + CS4_ROWS - 1) / CS4_ROWS));
+            colsum4_kernel<<<grid, 256, 0, st>>>(dZ, db, (int)M, N);
+            HG_LAUNCHED(1);
+        } else {
             dim3 grid((N + 31) / 32, (unsigned)((M + CS_ROWS - 1) / CS_ROWS));
             colsum_kernel<<<grid, 256, 0, st>>>(dZ, db, (int)M, N);
             HG_LAUNCHED(1);
@@ -290,7 +431,17 @@ extern "C" int32_t hg_mlp_backward(const HgMlpDesc* net, const float* params, co
         if (l > 0) {   // dZ_{l-1} = (dZ_l W_l) * ELU'(h_{l-1})
             const float* W = params + net->w_off[l];
             int32_t rc = try_tc(dZ, N, false, W, ldw, true, dhidden + off[l], K, (int)M, K, N, 3, nullptr, hidden + off[l], K, 1, st);
-            if (rc == 1) {
+            if (rc == 1 && N <= 16 && (K & 3) == 0 && (ldw & 3) == 0 && hg_aligned16(W) && hg_aligned16(hidden + off[l]) &&
+                hg_aligned16(dhidden + off[l])) {
+                float* dH = dhidden + off[l];
+                const float* H = hidden + off[l];
+                if (N == 1) launch_dgrad_skinny<1>(dZ, W, ldw, H, dH, (int)M, N, K, st);
+                else if (N <= 4) launch_dgrad_skinny<4>(dZ, W, ldw, H, dH, (int)M, N, K, st);
+                else if (N <= 8) launch_dgrad_skinny<8>(dZ, W, ldw, H, dH, (int)M, N, K, st);
+                else launch_dgrad_skinny<16>(dZ, W, ldw, H, dH, (int)M, N, K, st);
+                HG_LAUNCHED(1);
+                rc = hg_cuda_status("hg dgrad (skinny)");
+            } else if (rc == 1) {
                 GemmArgs g{};
                 g.A = dZ; g.sai = N; g.sap = 1;
                 g.B = W; g.sbp = ldw; g.sbj = 1;
