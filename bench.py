@@ -309,7 +309,7 @@ def run_product(args):
                    "l2": "per-step working set (rollout storage 947 MB + minibatch 237 MB) exceeds the 126 MB L2"},
         "e2e": {"value": round(e2e_value, 1), "unit": "env-steps/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": d2h,
                 "ms_per_step": round(ms_e / args.steps, 3),
-                "note": "physics frames staged from pinned host memory every env step; losses + mean reward read back"},
+                "note": "physics frames staged from pinned host memory every env step through a double buffer (the H2D of step s+1 overlaps step s; memcpy nodes of the rollout graph); losses + mean reward read back"},
         "gpu_launches": int(launches // args.steps),
         "clocks": clocks.summary(),
         "host_wall_ms_per_step": round(wall_ms / args.steps, 3),

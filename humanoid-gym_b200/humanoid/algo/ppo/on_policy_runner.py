@@ -59,6 +59,9 @@ class OnPolicyRunner:
         """One collection phase: num_steps_per_env x (act, env.step, process_env_step) + compute_returns."""
         env, alg = self.env, self.alg
         step_dev = env.noise_step_dev_ptr if getattr(env, "_Z", None) is not None and env._Z.use_device_counters else None
+        begin = getattr(getattr(env, "gym", None), "begin_rollout", None)
+        if begin is not None:
+            begin(self.num_steps_per_env)                 # host-resident frames: a self-contained prefetch schedule
         for t in range(self.num_steps_per_env):
             actions = alg.act(obs, critic_obs, step_dev=step_dev)
             obs, privileged_obs, rewards, dones, infos = env.step(actions)
@@ -73,7 +76,8 @@ class OnPolicyRunner:
     def _graph_ok(self):
         if os.environ.get("HG_CUDA_GRAPH", "1") == "0" or self.num_steps_per_env % 2:
             return False
-        return bool(getattr(self.env, "graph_safe", lambda: False)())
+        fn = getattr(self.env, "graph_safe", None)
+        return bool(fn(self.num_steps_per_env)) if fn is not None else False
 
     def collect(self, obs, critic_obs, book=None):
         """rollout(), replayed from a CUDA graph after the first (eager, warm-up) call when the physics source

@@ -254,8 +254,13 @@ class LeggedRobot(BaseTask):
         if hasattr(self.gym, "substep"):
             self.gym.substep += steps * self.cfg.control.decimation
 
-    def graph_safe(self):
-        return isinstance(self.gym, phys.SyntheticPhysics) and not self.gym.host_resident
+    def graph_safe(self, steps=None):
+        """A rollout of `steps` env steps may be captured once and replayed: the synthetic source is a ring, so every
+        replay must start at the same ring phase (device-resident frames and pinned host frames alike: the H2D
+        copies become memcpy nodes of the graph)."""
+        if not isinstance(self.gym, phys.SyntheticPhysics):
+            return False
+        return steps is None or steps % self.gym.ring == 0
 
     def inject_noise(self, **tensors):
         """Parity hook: dense per-env draws (u_cmd_cb, u_cmd_rs, u_dof, u_push, z_obs, u_delay, z_act)

@@ -173,6 +173,69 @@ class SyntheticPhysics(PhysicsBackend):
         self.rigid_state = torch.zeros(N * nb, 13, device=dev)
         self.substep = 0
         self.h2d_bytes = 0
+        # host-resident frames are staged through a double buffer in HBM by a copy stream: the frames of env step
+        # s+1 cross PCIe while step s computes (the synthetic source is open-loop, so the next frames are known)
+        self._rollout_left = None            # env steps left in the rollout announced by begin_rollout()
+        if host_resident:
+            self._stage = [dict(dof=torch.empty(decimation, N * nd, 2, device=dev), root=torch.empty(N, 13, device=dev),
+                                contact=torch.empty(N * nb, 3, device=dev), rigid=torch.empty(N * nb, 13, device=dev))
+                           for _ in range(2)]
+            self._copy_stream = torch.cuda.Stream(dev)
+            self._ready = [torch.cuda.Event(), torch.cuda.Event()]
+            self._free = [torch.cuda.Event(), torch.cuda.Event()]
+            self._staged_step = [-1, -1]     # which env step each slot holds (host mirror)
+            self._ready_pending = [False, False]
+            self._free_recorded = [False, False]
+            self._cur_step = -1
+
+    # ---- host-resident staging ---------------------------------------------------------------------------
+    def _enqueue_stage(self, step, stream):
+        """Copy the frames of env step `step` (ring indices follow from it) into slot step % 2 on `stream`."""
+        slot = step % 2
+        st = self._stage[slot]
+        k = step % self.ring
+        d0 = (step * self.decimation) % (self.ring * self.decimation)
+        with torch.cuda.stream(stream):
+            st["dof"].copy_(self._ring_dof[d0:d0 + self.decimation], non_blocking=True)
+            st["root"].copy_(self._ring_root[k], non_blocking=True)
+            st["contact"].copy_(self._ring_contact[k], non_blocking=True)
+            st["rigid"].copy_(self._ring_rigid[k], non_blocking=True)
+        self._staged_step[slot] = step
+
+    def begin_rollout(self, steps):
+        """The next `steps` env steps form one collection phase (possibly being captured into a CUDA graph): its first
+        step loads its frames in line, its last step does not prefetch, and no event recorded before this call is
+        waited on afterwards -- so the phase is self-contained and can be replayed."""
+        self._rollout_left = int(steps)
+        if self.host_resident:
+            self._ready_pending = [False, False]
+            self._free_recorded = [False, False]
+            self._cur_step = -1
+
+    def _begin_step(self, step):
+        """Called at the first substep of env step `step`: make its frames available, start fetching the next."""
+        cur = torch.cuda.current_stream(self.device)
+        slot = step % 2
+        if self._cur_step >= 0:
+            self._free[(step - 1) % 2].record(cur)           # every read of the previous step's slot is enqueued by now
+            self._free_recorded[(step - 1) % 2] = True
+        if not (self._staged_step[slot] == step and self._ready_pending[slot]):
+            self._enqueue_stage(step, cur)                   # not prefetched (first step of a rollout): load in line
+        else:
+            cur.wait_event(self._ready[slot])
+        self._ready_pending[slot] = False
+        self._cur_step = step
+        nxt = step + 1
+        if self._rollout_left is not None:
+            self._rollout_left -= 1
+            if self._rollout_left <= 0:
+                self._rollout_left = None
+                return                                       # the next rollout loads its first step itself
+        cp = self._copy_stream
+        cp.wait_event(self._free[nxt % 2]) if self._free_recorded[nxt % 2] else cp.wait_stream(cur)
+        self._enqueue_stage(nxt, cp)
+        self._ready[nxt % 2].record(cp)
+        self._ready_pending[nxt % 2] = True
 
     # how many bytes one env step moves host->device when host_resident
     def h2d_bytes_per_step(self):
@@ -186,18 +249,29 @@ class SyntheticPhysics(PhysicsBackend):
 
     def simulate(self):
         self.substep += 1
+        if self.host_resident and (self.substep - 1) % self.decimation == 0:
+            self._begin_step((self.substep - 1) // self.decimation)
+
+    def _slot(self):
+        return self._stage[((self.substep - 1) // self.decimation) % 2]
 
     def refresh_dof_state_tensor(self):
-        self.dof_state.copy_(self._ring_dof[(self.substep - 1) % (self.ring * self.decimation)], non_blocking=True)
+        if self.host_resident and self.substep > 0:
+            self.dof_state.copy_(self._slot()["dof"][(self.substep - 1) % self.decimation], non_blocking=True)
+        else:
+            self.dof_state.copy_(self._ring_dof[(self.substep - 1) % (self.ring * self.decimation)], non_blocking=True)
 
     def refresh_actor_root_state_tensor(self):
-        self.root_states.copy_(self._ring_root[self._frame()], non_blocking=True)
+        src = self._slot()["root"] if (self.host_resident and self.substep > 0) else self._ring_root[self._frame()]
+        self.root_states.copy_(src, non_blocking=True)
 
     def refresh_net_contact_force_tensor(self):
-        self.contact_forces.copy_(self._ring_contact[self._frame()], non_blocking=True)
+        src = self._slot()["contact"] if (self.host_resident and self.substep > 0) else self._ring_contact[self._frame()]
+        self.contact_forces.copy_(src, non_blocking=True)
 
     def refresh_rigid_body_state_tensor(self):
-        self.rigid_state.copy_(self._ring_rigid[self._frame()], non_blocking=True)
+        src = self._slot()["rigid"] if (self.host_resident and self.substep > 0) else self._ring_rigid[self._frame()]
+        self.rigid_state.copy_(src, non_blocking=True)
 
 
 class ExternalPhysics(PhysicsBackend):

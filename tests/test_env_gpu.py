@@ -196,3 +196,27 @@ def test_argument_errors_are_reported_not_fatal():
     with pytest.raises(nat.NativeError, match="NULL"):
         nat.check(nat.lib.hg_env_post_physics(B, env._P, env._Z, nat.PHASE_STEP_ALL, 1, 8, 0), "null obs_buf")
     env.step(torch.zeros(8, 12, device="cuda"))    # still usable afterwards
+
+
+def test_host_resident_frames_match_device_resident():
+    """The end-to-end arm stages the physics frames from pinned host memory through a double buffer (a copy
+    stream prefetches step s+1 while step s runs).  Same seed, same actions: bit-identical to the HBM-resident
+    ring, across a ring wrap and collection-phase boundaries."""
+    N, steps = 256, 15
+    torch.manual_seed(0)                      # the constructor draws frictions / masses from the global generators
+    np.random.seed(0)
+    a = make_env(N, physics="synthetic")
+    torch.manual_seed(0)
+    np.random.seed(0)
+    b = make_env(N, physics="synthetic_host")
+    g = torch.Generator(device="cuda").manual_seed(3)
+    for t in range(steps):
+        if t % 6 == 2:
+            b.gym.begin_rollout(6)             # a collection phase boundary: in-line load, no prefetch on its last step
+        act = torch.randn(N, 12, device="cuda", generator=g)
+        oa, pa, ra, da, _ = a.step(act.clone())
+        ob, pb, rb, db, _ = b.step(act.clone())
+        assert torch.equal(oa, ob) and torch.equal(pa, pb), t
+        assert torch.equal(ra, rb) and torch.equal(da, db), t
+    torch.cuda.synchronize()
+    assert b.gym.h2d_bytes_per_step() > 0 and a.gym.h2d_bytes_per_step() == 0

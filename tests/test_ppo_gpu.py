@@ -237,6 +237,48 @@ def test_flagship_gradients_vs_autograd():
     assert abs(alg.learning_rate - L.lr) < 1e-18
 
 
+def test_ragged_small_net_gradients():
+    """Odd sizes on purpose: batch not a multiple of any tile, widths that are not multiples of 4 (scalar bias
+    sums, the generic GEMM fallback) next to ones that are (128-bit sums, skinny-head kernels)."""
+    from humanoid.algo import PPO
+    torch.manual_seed(11)
+    na, nc, nact, B = 37, 29, 3, 777
+    ac = _make_ac(na, nc, nact, [52, 20], [24, 8])
+    with torch.no_grad():
+        ac.std.copy_(0.5 + torch.rand(nact, device="cuda"))
+    alg = PPO(ac, num_learning_epochs=1, num_mini_batches=1, learning_rate=1e-5, schedule="adaptive", entropy_coef=0.001,
+              gamma=0.994, lam=0.9, device="cuda:0")
+    gen = torch.Generator().manual_seed(12)
+    p = {k: v.detach().cpu().clone() for k, v in ac.state_dict().items()}
+    obs = torch.randn(B, na, generator=gen)
+    cobs = torch.randn(B, nc, generator=gen)
+    with torch.no_grad():
+        mu_old, sg_old = po.actor_dist(obs, p)
+        mu_old = mu_old + 0.05 * torch.randn(B, nact, generator=gen)
+        acts = mu_old + sg_old * torch.randn(B, nact, generator=gen)
+        old_lp = po.log_prob(acts, mu_old, sg_old).unsqueeze(1)
+        val = po.mlp(cobs, p, "critic")
+    tv = val + 0.3 * torch.randn(B, 1, generator=gen)
+    ret = val + 0.5 * torch.randn(B, 1, generator=gen)
+    adv = torch.randn(B, 1, generator=gen)
+    L = po.Learner(p, lr=1e-5)
+    loss, sur, vl, kl = po.ppo_loss(L.p, (obs, cobs, acts, tv, adv, ret, old_lp, mu_old, sg_old))
+    loss.backward()
+    ref = L.flat_grad()
+    mb = dict(obs=obs, priv_obs=cobs, actions=acts, values=tv, advantages=adv, returns=ret, old_log_prob=old_lp,
+              old_mu=mu_old, old_sigma=sg_old)
+    mb = {k: v.cuda().contiguous() for k, v in mb.items()}
+    mb["obs"], mb["priv_obs"] = _pad4(mb["obs"]), _pad4(mb["priv_obs"])
+    alg.minibatch_step(mb)
+    torch.cuda.synchronize()
+    got = _cat(ac, "grad").cpu()
+    off = 0
+    for name in L.names:
+        k = L.p[name].numel()
+        assert _rel(got[off:off + k], ref[off:off + k]) < 1e-4, (name, _rel(got[off:off + k], ref[off:off + k]))
+        off += k
+
+
 def test_checkpoint_roundtrip(tmp_path):
     """model_<it>.pt keeps the reference's format: keys and optimizer state reload into fresh objects."""
     from humanoid.algo import PPO
