@@ -121,9 +121,13 @@ class PPO:
         # actor and critic are independent chains of small GEMMs (M = num_envs): run them on two streams so that
         # the tail layers of one (32-64 CTAs) overlap the other instead of leaving most of the 148 SMs idle
         cur = torch.cuda.current_stream(self._dev_index)
+        self._join_critic(cur)                             # (only if the caller skipped process_env_step)
         self._side.wait_stream(cur)
         with torch.cuda.stream(self._side):
             ac.native_forward("critic", critic_obs, s.values[t])
+            # the 15 MB observation copy into slab t rides on the side stream too: nothing before the update reads it
+            s.add_native(t, obs=obs, priv_obs=critic_obs if s.privileged_observations is not None else None)
+        self._critic_pending = True
         st = nat.stream_ptr(self._dev_index)
         ac.native_forward("actor", obs, s.mu[t])
         nat.check(nat.lib.hg_policy_sample(
@@ -131,8 +135,9 @@ class PPO:
             s.actions[t].data_ptr(), s.actions_log_prob[t].data_ptr(), s.sigma[t].data_ptr(),
             s.num_envs, s.actions_shape[0], st), "hg_policy_sample")
         self._sample_step += 1
-        s.add_native(t, obs=obs, priv_obs=critic_obs if s.privileged_observations is not None else None)
-        cur.wait_stream(self._side)
+        # The value estimate is not needed before process_env_step (r += gamma * V * time_out), so the critic chain is
+        # joined there: it overlaps the whole env step instead of sitting on the act -> step critical path.  The env
+        # writes its next observations into the OTHER half of its ping-pong buffers, so critic_obs stays intact.
         tr = self.transition
         tr.actions, tr.values, tr.actions_log_prob = s.actions[t], s.values[t], s.actions_log_prob[t]
         tr.action_mean, tr.action_sigma = s.mu[t], s.sigma[t]
@@ -140,10 +145,16 @@ class PPO:
             s.privileged_observations[t] if s.privileged_observations is not None else s.observations[t])
         return tr.actions
 
+    def _join_critic(self, cur):
+        if getattr(self, "_critic_pending", False):
+            cur.wait_stream(self._side)
+            self._critic_pending = False
+
     def process_env_step(self, rewards, dones, infos):
         """ppo.py:103-113: r += gamma * V * time_out, then store rewards and dones (one launch)."""
         s = self.storage
         t = s.step
+        self._join_critic(torch.cuda.current_stream(self._dev_index))
         time_outs = infos.get("time_outs") if isinstance(infos, dict) else None
         d = dones if dones.dtype in (torch.bool, torch.uint8) else dones.to(torch.uint8)
         s.add_native(t, gamma=self.gamma, rewards=rewards.contiguous(), dones=d.contiguous(),
