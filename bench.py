@@ -138,6 +138,17 @@ def _time_iterations(runner, state, steps, device, world, e2e=False):
     return float(t.item()), wall, launches, state
 
 
+# dram__bytes_read.sum + dram__bytes_write.sum of post_physics_kernel from the committed `ncu --set full` captures
+# (profiles/r01_env_v5_n*_ncu_full.md).  At N=4096 the 16.8 MB the kernel writes are still in the 126 MB L2 when it
+# ends, so only the reads reach DRAM inside the launch.
+NCU_TRAFFIC_SOURCE = "profiles/r01_env_v5_n4096_ncu_full.md, profiles/r01_env_v5_n65536_ncu_full.md (ncu --set full, one launch)"
+_NCU_ENV_TRAFFIC = {4096: 19808512 + 2560, 65536: 321089792 + 215574784}
+
+
+def _ncu_traffic(num_envs):
+    return _NCU_ENV_TRAFFIC.get(int(num_envs))
+
+
 def _kernel_rooflines(runner, device, pk):
     """Live CUDA-event timing of the two kernels that bound the path: the MLP GEMM chain of one PPO
     minibatch (tensor roofline) and the fused post-physics env kernel (HBM roofline)."""
@@ -163,8 +174,9 @@ def _kernel_rooflines(runner, device, pk):
     t_env = tot / reps * 1e-3
     gbs = ENV_BYTES_PER_STEP * N / t_env / 1e9
     out["roofline_env"] = dict(num_envs=N, kernel="post_physics_kernel", bound="hbm", achieved=round(gbs, 1), peak=pk["hbm"], unit="GB/s",
-                               frac=round(gbs / pk["hbm"], 4), traffic=None, us_per_launch=round(t_env * 1e6, 2),
-                               bytes_per_launch=ENV_BYTES_PER_STEP * N, peak_source=pk["src"], l2="flushed between launches")
+                               frac=round(gbs / pk["hbm"], 4), traffic=_ncu_traffic(N), us_per_launch=round(t_env * 1e6, 2),
+                               bytes_per_launch=ENV_BYTES_PER_STEP * N, peak_source=pk["src"], l2="flushed between launches",
+                               traffic_source=NCU_TRAFFIC_SOURCE if _ncu_traffic(N) else None)
     # -- MLP fwd+bwd chain of one minibatch (inputs 237 MB > L2) -------------------------------------------
     s = alg.storage
     B = (s.num_envs * s.num_transitions_per_env) // alg.num_mini_batches
@@ -233,8 +245,9 @@ def env_roofline_large(device, pk, N=65536):
     t = tot / reps * 1e-3
     gbs = ENV_BYTES_PER_STEP * N / t / 1e9
     return dict(kernel="post_physics_kernel", num_envs=N, bound="hbm", achieved=round(gbs, 1), peak=pk["hbm"], unit="GB/s",
-                frac=round(gbs / pk["hbm"], 4), traffic=None, us_per_launch=round(t * 1e6, 2),
-                bytes_per_launch=ENV_BYTES_PER_STEP * N, peak_source=pk["src"], l2="flushed between launches")
+                frac=round(gbs / pk["hbm"], 4), traffic=_ncu_traffic(N), us_per_launch=round(t * 1e6, 2),
+                bytes_per_launch=ENV_BYTES_PER_STEP * N, peak_source=pk["src"], l2="flushed between launches",
+                traffic_source=NCU_TRAFFIC_SOURCE if _ncu_traffic(N) else None)
 
 
 def _make_env_only(num_envs, device, seed=5):

@@ -156,6 +156,7 @@ struct __align__(16) EnvSmem {
         float newobs[E * HG_OBS1];
     };
     float cf[E * HG_CF_SLOTS * 3];                                  // contact forces of the bodies the step reads
+    float sums[HG_NUM_REWARDS * E];                                 // episode sums tile, (22, 32)
     float rpf[E * 3], rpt[E * 3], org[E * 3];
     float fric[E], mass[E];
     float acc[HG_NUM_REWARDS + 2];
@@ -243,7 +244,10 @@ __device__ __forceinline__ void stream_history(float* __restrict__ out, const fl
     }
 }
 
-__global__ void __launch_bounds__(HG_ENV_THREADS, 7)
+// T = threads per CTA (warp 0 computes, the other T/32 - 1 warps stream): 128 when the grid is several waves deep
+// (7 CTAs / SM), 256 or 512 when there are only a few tiles per SM, so that a lone CTA still keeps many rows in flight.
+template <int T>
+__global__ void __launch_bounds__(T, (T == 128 ? 7 : (T == 256 ? 3 : 1)))
 post_physics_kernel(HgEnvBuffers B, HgEnvNoise Z, uint32_t phases, int64_t common_step, int N) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     EnvSmem& S = *reinterpret_cast<EnvSmem*>(smem_raw);
@@ -263,7 +267,7 @@ post_physics_kernel(HgEnvBuffers B, HgEnvNoise Z, uint32_t phases, int64_t commo
     // Table-driven (one rolled loop) to keep the instruction footprint small: a CTA executes this code once,
     // cold, so straight-line code costs an instruction-cache miss per 128 bytes.
     if (tid == 0) {
-        mbar_init(&S.mbar, HG_ENV_THREADS);
+        mbar_init(&S.mbar, T);
         S.cnt = 0;
         S.is_last = 0;
     }
@@ -282,18 +286,23 @@ post_physics_kernel(HgEnvBuffers B, HgEnvNoise Z, uint32_t phases, int64_t commo
 #pragma unroll 1
         for (int t = 0; t < kNumTiles; ++t) {
             int w = kTileWidth[t];
-            tile_load(sbase + kTileSmem[t], fields[kTileField[t]] + (size_t)e0 * w, nE * w, tid, HG_ENV_THREADS);
+            tile_load(sbase + kTileSmem[t], fields[kTileField[t]] + (size_t)e0 * w, nE * w, tid, T);
         }
     }
 #pragma unroll 1
-    for (int i = tid; i < nE * 52; i += HG_ENV_THREADS) {              // feet / knee rows of rigid_state (52-byte runs)
+    for (int i = tid; i < nE * 52; i += T) {              // feet / knee rows of rigid_state (52-byte runs)
         int le = i / 52, r = i - le * 52, b = r / 13, c = r - b * 13;
         int body = (b < 2) ? cP.feet[b] : cP.knees[b - 2];
         cp_async4(S.rg + i, B.rigid_state + ((size_t)(e0 + le) * nb + body) * 13 + c);
     }
+#pragma unroll 1
+    for (int i = tid; i < HG_NUM_REWARDS * E; i += T) {                // episode sums are (22, N): 128-byte runs
+        int le = i % E;
+        if (le < nE) cp_async4(S.sums + i, B.episode_sums + (size_t)(i / E) * N + e0 + le);
+    }
     const int n_slots = 2 + cP.n_term + cP.n_pen;                      // contact-force rows the step reads
 #pragma unroll 1
-    for (int i = tid; i < nE * n_slots * 3; i += HG_ENV_THREADS) {
+    for (int i = tid; i < nE * n_slots * 3; i += T) {
         int le = i / (n_slots * 3), r = i - le * (n_slots * 3), sl = r / 3, c = r - sl * 3;
         int body = sl < 2 ? cP.feet[sl] : (sl < 2 + cP.n_term ? cP.term_bodies[sl - 2] : cP.pen_bodies[sl - 2 - cP.n_term]);
         cp_async4(S.cf + le * (HG_CF_SLOTS * 3) + sl * 3 + c, B.contact_forces + ((size_t)(e0 + le) * nb + body) * 3 + c);
@@ -417,7 +426,7 @@ post_physics_kernel(HgEnvBuffers B, HgEnvNoise Z, uint32_t phases, int64_t commo
                 auto add_term = [&](float rv) {                      // alphabetical accumulation, legged_robot.py:222-230
                     float rk = rv * cP.reward_scales[kk];
                     total += rk;
-                    atomicAdd(B.episode_sums + (size_t)kk * N + e, rk);   // RED: fire-and-forget, no load on the critical path
+                    S.sums[kk * E + le] += rk;
                     if (B.rew_terms) B.rew_terms[(size_t)kk * N + e] = rk;
                     ++kk;
                 };
@@ -585,8 +594,8 @@ post_physics_kernel(HgEnvBuffers B, HgEnvNoise Z, uint32_t phases, int64_t commo
                 ep = 0;
 #pragma unroll 1
                 for (int k = 0; k < HG_NUM_REWARDS; ++k) {          // extras["episode"] :198-202
-                    // read-and-zero in one strongly-ordered op (it follows this thread's REDs to the same address)
-                    atomicAdd(&S.acc[k], atomicExch(B.episode_sums + (size_t)k * N + e, 0.0f));
+                    atomicAdd(&S.acc[k], S.sums[k * E + le]);
+                    S.sums[k * E + le] = 0.0f;
                 }
                 atomicAdd(&S.cnt, 1);
                 B.reset_ids[atomicAdd(&B.scratch[0], 1)] = e;
@@ -676,16 +685,16 @@ post_physics_kernel(HgEnvBuffers B, HgEnvNoise Z, uint32_t phases, int64_t commo
         // They copy every row unconditionally; rows of envs that turn out to reset are zeroed in step 3.
         if (do_obs) {
             stream_history<HG_OBS1, OBS_KEEP, OBS_W, 1>(B.obs_out + (size_t)e0 * opitch, B.obs_buf + (size_t)e0 * opitch, S.reset,
-                                                        nE, warp - 1, 3, lane, opitch);
+                                                        nE, warp - 1, T / 32 - 1, lane, opitch);
             stream_history<HG_PRIV1, PRIV_KEEP, PRIV_W, 5>(B.priv_out + (size_t)e0 * ppitch, B.privileged_obs_buf + (size_t)e0 * ppitch,
-                                                           S.reset, nE, warp - 1, 3, lane, ppitch);
+                                                           S.reset, nE, warp - 1, T / 32 - 1, lane, ppitch);
         }
     }
     __syncthreads();
 
     // ---- 3. newest frame: noise (humanoid_env.py:249-252), +-18 clip (legged_robot.py:104-108), store ---------
     if (do_obs) {
-        for (int i = tid; i < nE * HG_OBS1; i += HG_ENV_THREADS) {
+        for (int i = tid; i < nE * HG_OBS1; i += T) {
             int le = i / HG_OBS1, k = i - le * HG_OBS1;
             float v = S.newobs[i];
             if (cP.add_noise) {
@@ -704,7 +713,7 @@ post_physics_kernel(HgEnvBuffers B, HgEnvNoise Z, uint32_t phases, int64_t commo
             if (do_last) v = clampf(v, -cP.clip_obs, cP.clip_obs);
             B.obs_out[(size_t)(e0 + le) * opitch + OBS_KEEP + k] = v;
         }
-        for (int i = tid; i < nE * HG_PRIV1; i += HG_ENV_THREADS) {
+        for (int i = tid; i < nE * HG_PRIV1; i += T) {
             int le = i / HG_PRIV1, k = i - le * HG_PRIV1;
             float v = S.newpriv[i];
             if (do_last) v = clampf(v, -cP.clip_obs, cP.clip_obs);
@@ -714,29 +723,36 @@ post_physics_kernel(HgEnvBuffers B, HgEnvNoise Z, uint32_t phases, int64_t commo
 #pragma unroll 1
             for (int le = 0; le < nE; ++le) {
                 if (!S.reset[le]) continue;
-                for (int k = tid; k < OBS_KEEP; k += HG_ENV_THREADS) B.obs_out[(size_t)(e0 + le) * opitch + k] = 0.0f;
-                for (int k = tid; k < PRIV_KEEP; k += HG_ENV_THREADS) B.priv_out[(size_t)(e0 + le) * ppitch + k] = 0.0f;
+                for (int k = tid; k < OBS_KEEP; k += T) B.obs_out[(size_t)(e0 + le) * opitch + k] = 0.0f;
+                for (int k = tid; k < PRIV_KEEP; k += T) B.priv_out[(size_t)(e0 + le) * ppitch + k] = 0.0f;
             }
         }
     } else if (do_reset) {
         // stand-alone reset_idx: zero the history rows of the reset envs in place (humanoid_env.py:264-269)
-        for (int i = tid; i < nE * OBS_W; i += HG_ENV_THREADS)
+        for (int i = tid; i < nE * OBS_W; i += T)
             if (S.reset[i / OBS_W]) B.obs_buf[(size_t)(e0 + i / OBS_W) * opitch + i % OBS_W] = 0.0f;
-        for (int i = tid; i < nE * PRIV_W; i += HG_ENV_THREADS)
+        for (int i = tid; i < nE * PRIV_W; i += T)
             if (S.reset[i / PRIV_W]) B.privileged_obs_buf[(size_t)(e0 + i / PRIV_W) * ppitch + i % PRIV_W] = 0.0f;
     }
 
     // ---- 4. coalesced write-back of the tiles the step modified ------------------------------------------------
+    if (phases & (HG_PHASE_REWARD | HG_PHASE_RESET)) {
+#pragma unroll 1
+        for (int i = tid; i < HG_NUM_REWARDS * E; i += T) {
+            int le = i % E;
+            if (le < nE) B.episode_sums[(size_t)(i / E) * N + e0 + le] = S.sums[i];
+        }
+    }
     if (do_reset || (phases & HG_PHASE_CALLBACK)) {
         // root / dof rows change only on push or reset: write back the dirty rows
-        for (int i = tid; i < nE * 13; i += HG_ENV_THREADS)
+        for (int i = tid; i < nE * 13; i += T)
             if (S.root_dirty[i / 13]) B.root_states[(size_t)e0 * 13 + i] = S.root[i];
-        for (int i = tid; i < nE * 24; i += HG_ENV_THREADS)
+        for (int i = tid; i < nE * 24; i += T)
             if (S.reset[i / 24]) B.dof_state[(size_t)e0 * 24 + i] = S.dof[i];
     }
     if (do_last) {                                              // legged_robot.py:147-149 (+ reset zeroing :190-195)
         // last_last <- last (0 if reset); last <- actions (0 if reset); last_dof_vel <- dof_vel
-        for (int i = tid; i < nE * 12; i += HG_ENV_THREADS) {
+        for (int i = tid; i < nE * 12; i += T) {
             int le = i / 12, j = i - le * 12;
             bool rz = S.reset[le];
             size_t gi = (size_t)e0 * 12 + i;
@@ -745,7 +761,7 @@ post_physics_kernel(HgEnvBuffers B, HgEnvNoise Z, uint32_t phases, int64_t commo
             if (rz) B.actions[gi] = 0.0f;
         }
     } else if (do_reset) {
-        for (int i = tid; i < nE * 12; i += HG_ENV_THREADS) {
+        for (int i = tid; i < nE * 12; i += T) {
             if (S.reset[i / 12]) {
                 size_t gi = (size_t)e0 * 12 + i;
                 B.last_last_actions[gi] = 0.0f; B.last_actions[gi] = 0.0f; B.actions[gi] = 0.0f; B.last_dof_vel[gi] = 0.0f;
@@ -777,11 +793,11 @@ post_physics_kernel(HgEnvBuffers B, HgEnvNoise Z, uint32_t phases, int64_t commo
                     uint4* dst = reinterpret_cast<uint4*>(B.extras_time_outs);
                     const int n16 = N >> 4;
 #pragma unroll 4
-                    for (int i = tid; i < n16; i += HG_ENV_THREADS) dst[i] = src[i];
-                    for (int i = (n16 << 4) + tid; i < N; i += HG_ENV_THREADS) B.extras_time_outs[i] = B.time_out_buf[i];
+                    for (int i = tid; i < n16; i += T) dst[i] = src[i];
+                    for (int i = (n16 << 4) + tid; i < N; i += T) B.extras_time_outs[i] = B.time_out_buf[i];
                 } else {
 #pragma unroll 4
-                    for (int i = tid; i < N; i += HG_ENV_THREADS) B.extras_time_outs[i] = B.time_out_buf[i];
+                    for (int i = tid; i < N; i += T) B.extras_time_outs[i] = B.time_out_buf[i];
                 }
             }
             __syncthreads();
@@ -904,13 +920,21 @@ extern "C" int32_t hg_env_post_physics(const HgEnvBuffers* B, const HgEnvParams*
     if (int32_t rc = upload_params(P, st)) return rc;
     static bool attr_set = false;
     if (!attr_set) {
-        cudaFuncSetAttribute(post_physics_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(EnvSmem));
+        cudaFuncSetAttribute(post_physics_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(EnvSmem));
+        cudaFuncSetAttribute(post_physics_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(EnvSmem));
+        cudaFuncSetAttribute(post_physics_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(EnvSmem));
         attr_set = true;
     }
     int grid = (int)((N + HG_ENVS_PER_CTA - 1) / HG_ENVS_PER_CTA);
-    // one CTA per 32-env tile; the kernel body is a tile loop, so a capped (persistent) grid also works, but
-    // measured no gain on B200: the per-tile time is the compute warp's dependent-instruction latency
-    post_physics_kernel<<<grid, HG_ENV_THREADS, sizeof(EnvSmem), st>>>(*B, *Z, phases, common_step_counter, (int)N);
+    // one CTA per 32-env tile (the kernel body is a tile loop, so a capped persistent grid also works, but measured no
+    // gain on B200).  CTA width by grid depth: with <= 1 tile per SM (the 4096-env training configuration) a 16-warp
+    // CTA streams 15 history rows at a time; deep grids use 4-warp CTAs, 7 per SM.
+    static int env_threads = -1;                          // HG_ENV_CTA=128|256|512 pins the width (profiling)
+    if (env_threads < 0) { const char* v = getenv("HG_ENV_CTA"); env_threads = v ? atoi(v) : 0; }
+    const int width = env_threads ? env_threads : (grid <= HG_NUM_SMS ? 512 : (grid <= 3 * HG_NUM_SMS ? 256 : 128));
+    if (width == 512) post_physics_kernel<512><<<grid, 512, sizeof(EnvSmem), st>>>(*B, *Z, phases, common_step_counter, (int)N);
+    else if (width == 256) post_physics_kernel<256><<<grid, 256, sizeof(EnvSmem), st>>>(*B, *Z, phases, common_step_counter, (int)N);
+    else post_physics_kernel<128><<<grid, 128, sizeof(EnvSmem), st>>>(*B, *Z, phases, common_step_counter, (int)N);
     HG_LAUNCHED(1);
     return hg_cuda_status("hg_env_post_physics");
 }

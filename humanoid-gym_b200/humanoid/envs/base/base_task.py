@@ -1,5 +1,7 @@
 """BaseTask: device selection, the VecEnv-facing buffers and getters
 (mirrors reference envs/base/base_task.py:43-145; viewer / camera code is out of scope)."""
+import os
+
 import torch
 
 from humanoid import _native
@@ -31,7 +33,8 @@ class BaseTask:
         # a 128-byte line (the env kernel's warp-wide stores then write whole lines) and TMA can feed the rows to the
         # tensor-core actor / critic; obs_buf / privileged_obs_buf are the (N, 705) / (N, 219) views
         def pitched(width):
-            return torch.zeros(self.num_envs, (width + 31) // 32 * 32, dtype=torch.float, **z)[:, :width]
+            q = int(os.environ.get("HG_OBS_PITCH_ALIGN", "32"))
+            return torch.zeros(self.num_envs, (width + q - 1) // q * q, dtype=torch.float, **z)[:, :width]
         self.obs_buf = pitched(self.num_obs)
         self.rew_buf = torch.zeros(self.num_envs, dtype=torch.float, **z)
         # the reference allocates int64 ones but rebinds a bool tensor on every step
