@@ -143,8 +143,22 @@ def _time_iterations(runner, state, steps, device, world, e2e=False):
     w0 = time.time()
     ev0.record()
     results = []
+    dbg = os.environ.get("HG_BENCH_DEBUG") == "1"
     for _ in range(steps):
-        state, losses = _iterate(runner, state)
+        if dbg:
+            torch.cuda.synchronize(device)
+            t_a = time.time()
+            with torch.inference_mode():
+                o, c = runner.collect(*state)
+                torch.cuda.synchronize(device)
+                t_b = time.time()
+                losses = runner.alg.update()
+                torch.cuda.synchronize(device)
+            state = (o, c)
+            print(f"[bench dbg] rank {os.environ.get('RANK', '0')} e2e={e2e}: collect {1e3 * (t_b - t_a):.1f} ms, update {1e3 * (time.time() - t_b):.1f} ms, "
+                  f"graph={'yes' if getattr(runner, '_graph', None) is not None else 'no'}", file=sys.stderr, flush=True)
+        else:
+            state, losses = _iterate(runner, state)
         if e2e:   # device->host read of the step's result
             results.append((losses, float(runner.env.rew_buf.mean().item())))
     ev1.record()
@@ -311,24 +325,24 @@ def run_product(args):
                               "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms / args.steps, 3), "quick": True,
                               "gpu_launches": int(launches // args.steps)}))
         return
-    _log("value arm done; kernel rooflines")
-    with torch.inference_mode():
-        extra = _kernel_rooflines(runner, device, pk) if rank == 0 else {}
-    _log("rooflines done; e2e arm (host-resident physics frames)")
-    perf = {}
+    _log("value arm done; e2e arm (host-resident physics frames)")
     del runner, env
     torch.cuda.empty_cache()
 
     # ---- end-to-end arm (host-resident physics frames, D2H of results) ---------------------------------
+    # (runs before the rank-0-only kernel rooflines, so that every rank enters its warm-up and timed region together)
     env, runner = _make_runner(N, str(device), "synthetic_host")
     state = (env.get_observations(), env.get_privileged_observations())
     for _ in range(max(1, args.warmup)):
         state, _ = _iterate(runner, state)
     ms_e, _, _, state = _time_iterations(runner, state, args.steps, device, world, e2e=True)
     e2e_value = env_steps / (ms_e * 1e-3)
-    _log("e2e arm done")
+    _log("e2e arm done; kernel rooflines")
     h2d = env.gym.h2d_bytes_per_step() * T_STEPS
     d2h = 8 * 4 + 4
+    with torch.inference_mode():
+        extra = _kernel_rooflines(runner, device, pk) if rank == 0 else {}
+    _log("rooflines done")
     del runner, env
 
     if rank != 0:

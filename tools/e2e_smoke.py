@@ -7,7 +7,9 @@ import bench
 
 N = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
 kind = sys.argv[2] if len(sys.argv) > 2 else "synthetic_host"
-env, runner = bench._make_runner(N, "cuda:0", kind)
+dev = os.environ.get("HG_DEV", "cuda:0")
+torch.cuda.set_device(dev)
+env, runner = bench._make_runner(N, dev, kind)
 state = (env.get_observations(), env.get_privileged_observations())
 for i in range(6):
     torch.cuda.synchronize()
