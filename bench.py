@@ -247,9 +247,10 @@ def _kernel_rooflines(runner, device, pk):
     tf = flops / t / 1e12
     peak_tf32 = pk["bf16_sustained"] / 2.0
     mode = nat.lib.hg_set_gemm_mode(-1)
-    passes = {0: 0, 1: 3, 2: 1}[mode]
+    passes = {0: 0, 1: 3, 2: 1, 3: 3}[mode]
     engine = {0: "gemm_kernel (exact-fp32 CUDA-core path)", 1: "gemm_tc_kernel (tcgen05 kind::tf32, 3xTF32)",
-              2: "gemm_tc_kernel (tcgen05 kind::tf32, 1 pass)"}[mode]
+              2: "gemm_tc_kernel (tcgen05 kind::tf32, 1 pass)",
+              3: "gemm_tc_kernel / gemm_tc_bf16_kernel (experimental bf16x3 on the K-major products)"}[mode]
     out["roofline"] = dict(kernel="ActorCritic fwd+bwd GEMM chain of one 61,440-sample minibatch: " + engine, bound="tensor",
                            achieved=round(tf, 2), peak=round(peak_tf32, 1), unit="TFLOP/s", frac=round(tf / peak_tf32, 4),
                            traffic=None, ms_per_minibatch=round(t * 1e3, 3), flops_per_launch_group=flops,
