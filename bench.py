@@ -345,6 +345,8 @@ def run_product(args):
         extra = _kernel_rooflines(runner, device, pk) if rank == 0 else {}
     _log("rooflines done")
     del runner, env
+    if world > 1:
+        dist.barrier()                       # the other ranks wait here for rank 0's roofline timings: orderly teardown
 
     if rank != 0:
         return
