@@ -341,8 +341,13 @@ def run_product(args):
     _log("e2e arm done; kernel rooflines")
     h2d = env.gym.h2d_bytes_per_step() * T_STEPS
     d2h = 8 * 4 + 4
-    with torch.inference_mode():
-        extra = _kernel_rooflines(runner, device, pk) if rank == 0 else {}
+    extra = {}
+    if rank == 0:
+        try:
+            with torch.inference_mode():
+                extra = _kernel_rooflines(runner, device, pk)
+        except Exception as e:               # never leave the other ranks waiting at the barrier below
+            extra = {"roofline_error": f"{type(e).__name__}: {e}"}
     _log("rooflines done")
     del runner, env
     if world > 1:
