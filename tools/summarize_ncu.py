@@ -3,6 +3,7 @@
 
   launches <launches.csv> <out.md>          per-kernel share of an `ncu --metrics gpu__time_duration.sum` launch list
   kernel   <report.ncu-rep> <out.md>        key metrics of every launch in an `ncu --set full` report
+  hot      <report.ncu-rep> <out.md>        stall reasons + hottest source lines (report taken with --import-source on)
 """
 import collections
 import csv
@@ -57,5 +58,53 @@ def kernel(path, out):
             f.write("\n")
 
 
+def _f(x):
+    try:
+        return float(x)
+    except ValueError:
+        return 0.0
+
+
+def hot(path, out, top=30):
+    """Stall-reason breakdown + hottest CUDA source lines of the (first) kernel in an `ncu --set full
+    --import-source on` report (compile with -lineinfo).  Region rows aggregate 20-line windows of the .cu file."""
+    raw = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(raw.splitlines()))
+    h, v = rows[0], rows[2]
+    stalls = [(n.replace("smsp__pcsamp_warps_issue_stalled_", ""), _f(v[i])) for i, n in enumerate(h)
+              if n.startswith("smsp__pcsamp_warps_issue_stalled_") and "not_issued" not in n]
+    tot_st = sum(x for _, x in stalls) or 1.0
+    src = subprocess.run(["ncu", "-i", path, "--page", "source", "--print-source", "cuda,sass", "--csv"], capture_output=True, text=True).stdout
+    cur, hdr, lines = None, None, []
+    for r in csv.reader(src.splitlines()):
+        if not r:
+            continue
+        if r[0] == "File Path":
+            cur = r[1].split("/")[-1]
+        elif r[0] == "Line No":
+            hdr = r
+        elif hdr and r[0].isdigit():
+            lines.append((cur, int(r[0]), r[1].strip(), _f(r[hdr.index("# Samples")]), _f(r[hdr.index("Instructions Executed")])))
+    ts = sum(l[3] for l in lines) or 1.0
+    ti = sum(l[4] for l in lines) or 1.0
+    region = collections.defaultdict(lambda: [0.0, 0.0])
+    for f, ln, _, s_, i_ in lines:
+        key = f"{f}:{ln // 20 * 20}-{ln // 20 * 20 + 19}"
+        region[key][0] += s_
+        region[key][1] += i_
+    with open(out, "w") as fo:
+        fo.write(f"# ncu source hot spots: {path}\n\n")
+        fo.write(f"kernel: `{v[h.index('Kernel Name')][:100]}`, {v[h.index('gpu__time_duration.sum')]} {rows[1][h.index('gpu__time_duration.sum')]}, "
+                 f"{int(ti)} warp-instructions, {int(ts)} samples\n\n## stall reasons\n\n| reason | share |\n|---|---|\n")
+        for n, x in sorted(stalls, key=lambda t: -t[1])[:10]:
+            fo.write(f"| {n} | {100 * x / tot_st:.1f}% |\n")
+        fo.write("\n## 20-line regions\n\n| region | samples | instructions |\n|---|---|---|\n")
+        for k, (s_, i_) in sorted(region.items(), key=lambda kv: -kv[1][0])[:15]:
+            fo.write(f"| {k} | {100 * s_ / ts:.1f}% | {100 * i_ / ti:.1f}% |\n")
+        fo.write("\n## lines\n\n| file:line | samples | instructions | source |\n|---|---|---|---|\n")
+        for f, ln, text, s_, i_ in sorted(lines, key=lambda l: -l[3])[:top]:
+            fo.write(f"| {f}:{ln} | {100 * s_ / ts:.1f}% | {100 * i_ / ti:.1f}% | `{text[:90].replace('|', '/')}` |\n")
+
+
 if __name__ == "__main__":
-    {"launches": launches, "kernel": kernel}[sys.argv[1]](sys.argv[2], sys.argv[3])
+    {"launches": launches, "kernel": kernel, "hot": hot}[sys.argv[1]](sys.argv[2], sys.argv[3])
