@@ -428,6 +428,12 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo_elem, float hi_elem) { 
     return r;
 }
 
+// MAIN_TF32 = false: pure bf16x3 (1.5 passes; ~9e-6 at network level, enough for the 1e-4 gradient bar).
+// MAIN_TF32 = true : the A_hi B_hi term runs as kind::tf32 on the raw fp32 tiles (the hardware truncates them), only the
+//                    two correction terms use bf16 tiles of (trunc_tf32(x), x - trunc_tf32(x)): 2 passes, ~2.5e-6 at
+//                    network level (tools/experiments/network_precision_study.py) -- the variant for the forward products.
+//                    The raw stage is then released by the splitter warps AND the MMA commit.
+template <bool MAIN_TF32>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_tc_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcArgs g) {
     extern __shared__ unsigned char smem_raw[];
@@ -451,7 +457,7 @@ gemm_tc_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     if (threadIdx.x == 0) {
         for (int s = 0; s < BF_RAW_STAGES; ++s) {
             mbar_init(&full[s], 1);
-            mbar_init(&empty[s], SPLIT_WARPS);
+            mbar_init(&empty[s], SPLIT_WARPS + (MAIN_TF32 ? 1 : 0));
         }
         for (int s = 0; s < BF_STAGES; ++s) {
             mbar_init(&ready[s], 2 * SPLIT_WARPS);
@@ -492,16 +498,28 @@ gemm_tc_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         // ===== MMA issuer: one bf16 stage = 64 k = up to 4 K-steps of 16 =====
         if (lane == 0) {
             const uint32_t idesc = make_idesc_bf16(g.BN);
-            int jt = 0, item = 0;
+            const uint32_t idesc_tf32 = make_idesc(g.BN, false, false);
+            int it = 0, jt = 0, item = 0;
             for (int w = blockIdx.x; w < total_work; w += gridDim.x, ++item) {
                 const Work wk = decode_work(g, w, tiles_n, tiles_mn, num_kb_total);
                 const int acc_stage = item & 1;
                 mbar_wait(&tmem_empty[acc_stage], ((item >> 1) & 1) ^ 1);
                 tc_fence_after();
                 const uint32_t tmem_d = tmem_base + (uint32_t)(acc_stage * 128);
-                const int num_pairs = (wk.num_kb + 1) / 2;
-                for (int j = 0; j < num_pairs; ++j, ++jt) {
-                    const int b = jt % BF_STAGES;
+                for (int kb = 0; kb < wk.num_kb; ++kb, ++it) {
+                    if (MAIN_TF32) {                                            // hi x hi on the raw fp32 pair of this 32-k block
+                        const int s = it % BF_RAW_STAGES;
+                        mbar_wait(&full[s], (it / BF_RAW_STAGES) & 1);
+                        tc_fence_after();
+                        const uint32_t raw = smem_u32(smem + s * PAIR_BYTES);
+#pragma unroll
+                        for (int kk = 0; kk < BK / 8; ++kk)
+                            umma_tf32(tmem_d, make_desc(raw + kk * 32, false), make_desc(raw + TILE_BYTES + kk * 32, false), idesc_tf32,
+                                      (kb > 0 || kk > 0) ? 1u : 0u);
+                        umma_commit(&empty[s]);
+                    }
+                    if ((kb & 1) == 0 && kb != wk.num_kb - 1) continue;         // the quad of this pair is not complete yet
+                    const int b = jt % BF_STAGES, j = kb >> 1;
                     mbar_wait(&ready[b], (jt / BF_STAGES) & 1);
                     tc_fence_after();
                     const uint32_t base = smem_u32(smem_bf + b * BF_QUAD_BYTES);
@@ -511,12 +529,13 @@ gemm_tc_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                         const uint64_t a_lo = make_desc(base + TILE_BYTES + kk * 32, false);
                         const uint64_t b_hi = make_desc(base + 2 * TILE_BYTES + kk * 32, false);
                         const uint64_t b_lo = make_desc(base + 3 * TILE_BYTES + kk * 32, false);
-                        const uint32_t acc = (j > 0 || kk > 0) ? 1u : 0u;
+                        const uint32_t acc = (MAIN_TF32 || j > 0 || kk > 0) ? 1u : 0u;
                         umma_bf16(tmem_d, a_lo, b_hi, idesc, acc);                 // small terms first
                         umma_bf16(tmem_d, a_hi, b_lo, idesc, 1u);
-                        umma_bf16(tmem_d, a_hi, b_hi, idesc, 1u);
+                        if (!MAIN_TF32) umma_bf16(tmem_d, a_hi, b_hi, idesc, 1u);
                     }
                     umma_commit(&bf_empty[b]);
+                    ++jt;
                 }
                 umma_commit(&tmem_full[acc_stage]);
             }
@@ -540,10 +559,20 @@ gemm_tc_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     // i = physical 16-byte chunk of the raw tile: row = i / 8, logical chunk c = (i % 8) ^ (row % 8)
                     const int row = i >> 3, c = (i & 7) ^ (row & 7);
                     const float4 x = raw[i];
-                    const uint32_t h01 = pack_bf16x2(x.x, x.y), h23 = pack_bf16x2(x.z, x.w);
-                    const float r0 = x.x - __uint_as_float(h01 << 16), r1 = x.y - __uint_as_float(h01 & 0xFFFF0000u);
-                    const float r2 = x.z - __uint_as_float(h23 << 16), r3 = x.w - __uint_as_float(h23 & 0xFFFF0000u);
-                    const uint32_t l01 = pack_bf16x2(r0, r1), l23 = pack_bf16x2(r2, r3);
+                    uint32_t h01, h23, l01, l23;
+                    if (MAIN_TF32) {
+                        // correction operands of the 3xTF32 decomposition, each rounded to bf16
+                        const float t0 = __uint_as_float(__float_as_uint(x.x) & 0xFFFFE000u), t1 = __uint_as_float(__float_as_uint(x.y) & 0xFFFFE000u);
+                        const float t2 = __uint_as_float(__float_as_uint(x.z) & 0xFFFFE000u), t3 = __uint_as_float(__float_as_uint(x.w) & 0xFFFFE000u);
+                        h01 = pack_bf16x2(t0, t1); h23 = pack_bf16x2(t2, t3);
+                        l01 = pack_bf16x2(rna_tf32(x.x - t0), rna_tf32(x.y - t1));
+                        l23 = pack_bf16x2(rna_tf32(x.z - t2), rna_tf32(x.w - t3));
+                    } else {
+                        h01 = pack_bf16x2(x.x, x.y); h23 = pack_bf16x2(x.z, x.w);
+                        const float r0 = x.x - __uint_as_float(h01 << 16), r1 = x.y - __uint_as_float(h01 & 0xFFFF0000u);
+                        const float r2 = x.z - __uint_as_float(h23 << 16), r3 = x.w - __uint_as_float(h23 & 0xFFFF0000u);
+                        l01 = pack_bf16x2(r0, r1); l23 = pack_bf16x2(r2, r3);
+                    }
                     // destination: k-elements 32 h + 4 c .. + 3 of the 64-k row -> byte 64 h + 8 c, 16-byte chunks swizzled alike
                     const int off = row * 128 + ((((h << 2) | (c >> 1)) ^ (row & 7)) << 4) + ((c & 1) << 3);
                     *reinterpret_cast<uint2*>(hi_tile + off) = make_uint2(h01, h23);
@@ -670,9 +699,9 @@ int32_t make_map(CUtensorMap* map, const float* base, uint64_t inner, uint64_t o
 extern "C" int32_t hg_gemm_tf32(const HgGemm* d, void* stream) {
     HG_REQUIRE(d); HG_REQUIRE(d->A); HG_REQUIRE(d->B); HG_REQUIRE(d->C);
     if (d->M <= 0 || d->N <= 0 || d->K <= 0) return hg_fail(HG_E_SIZE, "hg_gemm_tf32: bad extents");
-    if (d->passes < 1 || d->passes > 3) return hg_fail(HG_E_ARG, "hg_gemm_tf32: passes must be 1, 2 (bf16x3) or 3");
-    if (d->passes == 2 && (d->a_mn_major || d->b_mn_major))
-        return hg_fail(HG_E_ARG, "hg_gemm_tf32: passes = 2 (bf16x3) handles K-major operands only");
+    if (d->passes < 1 || d->passes > 4) return hg_fail(HG_E_ARG, "hg_gemm_tf32: passes must be 1, 2 (bf16x3), 3 or 4 (TF32 + bf16 corrections)");
+    if ((d->passes == 2 || d->passes == 4) && (d->a_mn_major || d->b_mn_major))
+        return hg_fail(HG_E_ARG, "hg_gemm_tf32: passes = 2 / 4 (bf16 split tiles) handle K-major operands only");
     if ((d->lda & 3) || (d->ldb & 3) || !hg_aligned16(d->A) || !hg_aligned16(d->B))
         return hg_fail(HG_E_ALIGN, "hg_gemm_tf32: operands need 16-byte aligned base and row pitch (TMA)");
     if ((d->epilogue == EPI_BIAS || d->epilogue == EPI_BIAS_ELU) && !d->bias) return hg_fail(HG_E_NULL, "hg_gemm_tf32: bias is NULL");
@@ -716,14 +745,16 @@ extern "C" int32_t hg_gemm_tf32(const HgGemm* d, void* stream) {
     g.splits = splits;
     const int total_work = ((d->N + g.BN - 1) / g.BN) * ((d->M + BM - 1) / BM) * splits;
     const int grid = total_work < HG_NUM_SMS ? total_work : HG_NUM_SMS;       // persistent: one CTA per SM
-    if (d->passes == 2) {
+    if (d->passes == 2 || d->passes == 4) {
         static bool bf_attr_set = false;
         if (!bf_attr_set) {
-            cudaError_t e = cudaFuncSetAttribute(gemm_tc_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BF_SMEM_BYTES);
+            cudaError_t e = cudaFuncSetAttribute(gemm_tc_bf16_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, BF_SMEM_BYTES);
+            if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_tc_bf16_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, BF_SMEM_BYTES);
             if (e != cudaSuccess) return hg_fail((int32_t)e, cudaGetErrorString(e));
             bf_attr_set = true;
         }
-        gemm_tc_bf16_kernel<<<grid, TC_THREADS, BF_SMEM_BYTES, st>>>(tmA, tmB, g);
+        if (d->passes == 4) gemm_tc_bf16_kernel<true><<<grid, TC_THREADS, BF_SMEM_BYTES, st>>>(tmA, tmB, g);
+        else gemm_tc_bf16_kernel<false><<<grid, TC_THREADS, BF_SMEM_BYTES, st>>>(tmA, tmB, g);
     } else {
         gemm_tc_kernel<<<grid, TC_THREADS, SMEM_BYTES, st>>>(tmA, tmB, g);
     }

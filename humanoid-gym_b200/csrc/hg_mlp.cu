@@ -299,7 +299,7 @@ int32_t try_tc(const float* A, int64_t lda, bool a_mn, const float* B, int64_t l
     d.lda = lda; d.ldb = ldb; d.ldc = ldc; d.ldh = ldh;
     d.a_mn_major = a_mn; d.b_mn_major = b_mn;
     d.epilogue = epi; d.passes = (mode == 2) ? 1 : 3; d.split_k = split_k;
-    if (mode == 3 && !a_mn && !b_mn) d.passes = 2;      // bf16x3 on the K-major products, 3xTF32 on the others
+    if (mode == 3 && !a_mn && !b_mn) d.passes = 4;      // TF32 + bf16 corrections on the K-major (forward) products, 3xTF32 on the others
     d.trust_hw_truncation = 1;      // verified on B200: kind::tf32 ignores the low 13 mantissa bits (tests/test_gemm_tc_gpu.py)
     return hg_gemm_tf32(&d, (void*)st);
 }

@@ -211,6 +211,7 @@ int32_t hg_mlp_backward(const HgMlpDesc* net, const float* params, const float* 
  *   b_mn_major = 0: B is (N, K) row-major  (pitch ldb);  1: B is (K, N) row-major
  *   passes     = 3: 3xTF32 split compensation (fp32-class accuracy);  1: plain TF32;
  *                2: EXPERIMENTAL bf16 hi/lo split, three kind::f16 MMAs (K-major operands only, rel. error ~5e-6)
+ *                4: EXPERIMENTAL TF32 main term + two bf16 correction terms (K-major operands only, ~1.5e-6)
  *   epilogue   : 0 store, 1 +bias[N], 2 +bias then ELU, 3 multiply by ELU'(z) recovered from H = ELU(z) (pitch ldh),
  *                4 atomicAdd into C (required when split_k > 1; C must be zeroed by the caller)
  *   trust_hw_truncation: 1 = feed the raw fp32 tile as the "hi" operand (the tensor core drops the low 13
@@ -224,7 +225,7 @@ typedef struct HgGemm {
 } HgGemm;
 int32_t hg_gemm_tf32(const HgGemm* d, void* stream);
 /* GEMM engine of hg_mlp_forward / hg_mlp_backward: 0 = exact-fp32 CUDA-core path, 1 = tcgen05 3xTF32 (default),
- * 2 = tcgen05 plain TF32, 3 = EXPERIMENTAL bf16x3 on the K-major products (forward), 3xTF32 elsewhere.
+ * 2 = tcgen05 plain TF32, 3 = EXPERIMENTAL TF32 + bf16 corrections on the K-major products (forward), 3xTF32 elsewhere.
  * Layers whose operands TMA cannot address fall back to 0.  Returns the previous mode. */
 int32_t hg_set_gemm_mode(int32_t mode);
 

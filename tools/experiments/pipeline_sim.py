@@ -31,16 +31,17 @@ class Bar:
         return (self.phase & 1) != parity
 
 
-def simulate(items, seed):
+def simulate(items, seed, main_tf32=False):
     rng = random.Random(seed)
     full = [Bar(1) for _ in range(RAW)]
-    empty = [Bar(SPLIT_WARPS) for _ in range(RAW)]
+    empty = [Bar(SPLIT_WARPS + (1 if main_tf32 else 0)) for _ in range(RAW)]
     ready = [Bar(2 * SPLIT_WARPS) for _ in range(BF)]
     bf_empty = [Bar(1) for _ in range(BF)]
     tmem_full = [Bar(1) for _ in range(2)]
     tmem_empty = [Bar(4) for _ in range(2)]
     raw_content = [None] * RAW                  # (item, kb) currently held by a raw stage
     raw_reads = [0] * RAW
+    raw_mma = [False] * RAW
     quad = [[None, None] for _ in range(BF)]     # per half: (item, kb) written, by how many warps
     quad_writes = [[0, 0] for _ in range(BF)]
     log = {"mma": [], "epi": []}
@@ -52,7 +53,8 @@ def simulate(items, seed):
                 s = it % RAW
                 yield ("wait", empty[s], ((it // RAW) & 1) ^ 1)
                 assert raw_content[s] is None or raw_reads[s] == SPLIT_WARPS, "raw stage overwritten before all splitter warps read it"
-                raw_content[s], raw_reads[s] = (item, kb), 0
+                assert raw_content[s] is None or not main_tf32 or raw_mma[s], "raw stage overwritten before the tf32 main MMAs read it"
+                raw_content[s], raw_reads[s], raw_mma[s] = (item, kb), 0, False
                 yield ("arrive", full[s])            # models expect_tx + the bytes landing
                 it += 1
 
@@ -79,12 +81,21 @@ def simulate(items, seed):
                 it += 1
 
     def mma():
-        jt = 0
+        it = jt = 0
         for item, nkb in enumerate(items):
             acc = item & 1
             yield ("wait", tmem_empty[acc], ((item >> 1) & 1) ^ 1)
-            for j in range((nkb + 1) // 2):
-                b = jt % BF
+            for kb in range(nkb):
+                if main_tf32:
+                    s = it % RAW
+                    yield ("wait", full[s], (it // RAW) & 1)
+                    assert raw_content[s] == (item, kb), f"tf32 main MMA read raw stage {s} holding {raw_content[s]}, wanted {(item, kb)}"
+                    raw_mma[s] = True
+                    yield ("arrive", empty[s])           # tcgen05.commit
+                it += 1
+                if (kb & 1) == 0 and kb != nkb - 1:
+                    continue
+                b, j = jt % BF, kb >> 1
                 yield ("wait", ready[b], (jt // BF) & 1)
                 halves = min(2, nkb - 2 * j)
                 for h in range(halves):
@@ -93,7 +104,7 @@ def simulate(items, seed):
                 log["mma"].append((item, j, halves))
                 for h in range(2):
                     quad_writes[b][h] = 0
-                yield ("arrive", bf_empty[b])        # tcgen05.commit
+                yield ("arrive", bf_empty[b])            # tcgen05.commit
                 jt += 1
             yield ("arrive", tmem_full[acc])
 
@@ -143,8 +154,9 @@ def main():
     rng = random.Random(0)
     for t in range(trials):
         items = [rng.choice([1, 2, 3, 4, 5, 7, 8, 22, 23]) for _ in range(rng.randint(1, 6))]
-        simulate(items, seed=t)
-    print(f"{trials} random work lists: no deadlock, stage ownership respected")
+        simulate(items, seed=t, main_tf32=False)
+        simulate(items, seed=t, main_tf32=True)
+    print(f"{trials} random work lists x 2 kernel variants: no deadlock, stage ownership respected")
 
 
 if __name__ == "__main__":
