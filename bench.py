@@ -25,9 +25,16 @@ import threading
 import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
-for p in (ROOT, os.path.join(ROOT, "humanoid-gym_b200")):
-    if p not in sys.path:
-        sys.path.insert(0, p)
+PKG = os.path.join(ROOT, "humanoid-gym_b200")
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def _use_product():
+    """Put the product package on sys.path (product arm only: the reference arm must resolve `humanoid` to the
+    reference and must never map libhg_b200.so)."""
+    if PKG not in sys.path:
+        sys.path.insert(0, PKG)
 
 import torch  # noqa: E402
 import torch.distributed as dist  # noqa: E402
@@ -298,6 +305,7 @@ def _make_env_only(num_envs, device, seed=5):
 
 
 def run_product(args):
+    _use_product()
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -376,12 +384,22 @@ def run_product(args):
         _log("env kernel at N=65536 (its bandwidth regime)")
         line["roofline_env_65536"] = env_roofline_large(device, pk)
     if world == 1 and not args.no_cpu_baseline:
+        torch.cuda.empty_cache()
+        if not args.no_ref_gpu:
+            _log("R-GPU: the unmodified reference on cuda:0 (subprocess)")
+            line["reference_gpu"] = reference_gpu(N)
+            if "value" in line["reference_gpu"]:
+                line["vs_reference_gpu"] = {"value_ratio": round(value / line["reference_gpu"]["value"], 2),
+                                            "e2e_ratio": round(e2e_value / line["reference_gpu"]["value"], 2),
+                                            "target": ">= 10 (north_star)"}
+        _log("cpu_baseline: the unmodified reference on the host cores (subprocess)")
         line["cpu_baseline"] = cpu_baseline(N, sample_T=args.cpu_T)
     print(json.dumps(line))
 
 
 # ----------------------------------------------------------------------------------------------
-# reference arm / cpu baseline: the reference's PyTorch path (oracle port) on the host cores
+# reference arm / cpu baseline: the UNMODIFIED reference's PyTorch path (tools/reference_arm.py, a clean subprocess
+# that never imports the product), on the host cores and -- as the ">= 10x" denominator -- on the same B200
 # ----------------------------------------------------------------------------------------------
 def _log(msg):
     print(f"[bench {time.strftime('%H:%M:%S')}] {msg}", file=sys.stderr, flush=True)
@@ -393,25 +411,70 @@ def _cpu_threads():
     return int(os.environ.get("HG_REF_THREADS", min(os.cpu_count() or 1, 32)))
 
 
-def _oracle_trainer(num_envs, T, device="cpu"):
+def _reference_subprocess(device, num_envs, steps, warmup, timeout=1500):
+    """Run tools/reference_arm.py (the unmodified reference over the ring-mode fake gym).  Returns its dict, or
+    {"unavailable": why}."""
+    if os.environ.get("HG_REF_FORCE_PORT") == "1":
+        return {"unavailable": "HG_REF_FORCE_PORT=1"}
+    cmd = [sys.executable, os.path.join(ROOT, "tools", "reference_arm.py"), "--device", device, "--num-envs", str(num_envs),
+           "--steps", str(steps), "--warmup", str(warmup), "--threads", str(_cpu_threads())]
+    env = {k: v for k, v in os.environ.items() if k not in ("RANK", "LOCAL_RANK", "WORLD_SIZE", "MASTER_ADDR", "MASTER_PORT")}
+    env["PYTHONPATH"] = ""
+    try:
+        p = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout, env=env, cwd=ROOT)
+    except subprocess.TimeoutExpired:
+        return {"unavailable": f"reference arm on {device} exceeded {timeout}s"}
+    lines = [ln for ln in p.stdout.strip().splitlines() if ln.startswith("{")]
+    if p.returncode != 0 or not lines:
+        return {"unavailable": f"reference arm on {device} failed (rc {p.returncode}): {p.stderr.strip()[-300:]}"}
+    return json.loads(lines[-1])
+
+
+def _oracle_port(num_envs, T):
+    """Fallback when no reference tree is on the box: the oracle restatement (kind "port")."""
+    _use_product()
     from humanoid.physics import SyntheticPhysics
     from oracle.runner_oracle import OracleTrainer
     from oracle import env_oracle as eo
     torch.set_num_threads(_cpu_threads())
     ranges = {"lin_vel_x": [-0.3, 0.6], "lin_vel_y": [-0.3, 0.3]}
-    ph = SyntheticPhysics(num_envs, device, ranges, eo.grid_origins(num_envs), decimation=10, seed=5)
+    ph = SyntheticPhysics(num_envs, "cpu", ranges, eo.grid_origins(num_envs), decimation=10, seed=5)
     return OracleTrainer(num_envs, ph, T=T)
 
 
+def _ref_sample_text(r, what):
+    return (f"{what}: {r['steps']} learning iteration(s) after {r['warmup']} warm-up of the UNMODIFIED reference "
+            f"(OnPolicyRunner.learn via task_registry, {r['reference_tree']}) over the ring-mode fake isaacgym, "
+            f"N={r['num_envs']}, T={r['num_steps_per_env']}, 2 epochs x 4 minibatches, torch {r['torch']} fp32 on {r['device']}, "
+            f"{r['threads']} host threads; collection {r['collection_s']:.2f}s + learn {r['learn_s']:.2f}s per iteration")
+
+
+def reference_gpu(num_envs, steps=3, warmup=2):
+    """R-GPU: the reference's PyTorch path on the same B200 -- the denominator of north_star's '>= 10x'."""
+    r = _reference_subprocess("cuda:0", num_envs, steps, warmup)
+    if "unavailable" in r:
+        return r
+    return {"value": round(r["env_steps_per_sec"], 1), "unit": "env-steps/s", "device": "cuda:0", "kind": "reference",
+            "ms_per_step": round(r["ms_per_iteration"], 2), "collection_s": round(r["collection_s"], 4),
+            "learn_s": round(r["learn_s"], 4), "loaded_product_so": r["loaded_product_so"],
+            "sample": _ref_sample_text(r, "R-GPU"),
+            "note": "Isaac Gym cannot run on sm_100, so the reference's env+PPO torch code runs over the same synthetic frames "
+                    "as the product (TF32 off); torch_utils helpers are eager here (Isaac Gym ships them torch.jit.script-ed)"}
+
+
 def cpu_baseline(num_envs, sample_T):
-    _log(f"cpu_baseline: oracle port, N={num_envs}, T={sample_T}, {_cpu_threads()} threads")
-    tr = _oracle_trainer(num_envs, sample_T)
+    r = _reference_subprocess("cpu", num_envs, steps=1, warmup=1)
+    if "unavailable" not in r:
+        return {"value": round(r["env_steps_per_sec"], 1), "unit": "env-steps/s", "cores": r["threads"], "kind": "reference",
+                "sample": _ref_sample_text(r, "cpu_baseline"), "collection_s": round(r["collection_s"], 3),
+                "learn_s": round(r["learn_s"], 3), "loaded_product_so": r["loaded_product_so"]}
+    _log(f"cpu_baseline: reference tree unavailable ({r['unavailable']}); oracle port, N={num_envs}, T={sample_T}")
+    tr = _oracle_port(num_envs, sample_T)
     c, l = tr.iteration()
-    _log(f"cpu_baseline done: collection {c:.2f}s learn {l:.2f}s")
     v = num_envs * sample_T / (c + l)
     return {"value": round(v, 1), "unit": "env-steps/s", "cores": torch.get_num_threads(), "kind": "port",
-            "sample": f"1 learning iteration of the oracle port (reference PyTorch path), N={num_envs}, T={sample_T}, "
-                      f"collection {c:.2f}s + learn {l:.2f}s, torch CPU fp32",
+            "sample": f"1 learning iteration of the oracle port (no reference tree on this box: {r['unavailable']}), "
+                      f"N={num_envs}, T={sample_T}, collection {c:.2f}s + learn {l:.2f}s, torch CPU fp32",
             "collection_s": round(c, 3), "learn_s": round(l, 3)}
 
 
@@ -420,30 +483,41 @@ def run_reference(args):
     if rank != 0:
         return
     N = args.num_envs
-    T = args.ref_T
-    tr = _oracle_trainer(N, T)
-    for _ in range(args.warmup):
-        tr.iteration()
-    t0 = time.time()
-    c = l = 0.0
-    for _ in range(args.steps):
-        a, b = tr.iteration()
-        c, l = c + a, l + b
-    dt = time.time() - t0
-    v = N * T * args.steps / dt
-    cores = torch.get_num_threads()
-    sample = (f"each step = one learning iteration of the reference PyTorch path (oracle port) at N={N} with T={T} of the 60 "
-              f"env steps (bounded sample; the metric is a rate: env-steps/s = N*T/(collection+learn)), 2 epochs x 4 "
-              f"minibatches, {cores} host threads")
-    print(json.dumps({
+    r = _reference_subprocess("cpu", N, args.steps, args.warmup)
+    if "unavailable" in r:
+        # no reference tree travelled to this box: time the oracle restatement instead and SAY so
+        T = args.ref_T
+        tr = _oracle_port(N, T)
+        for _ in range(args.warmup):
+            tr.iteration()
+        t0 = time.time()
+        c = l = 0.0
+        for _ in range(args.steps):
+            a, b = tr.iteration()
+            c, l = c + a, l + b
+        dt = time.time() - t0
+        v, ms, cores, kind = N * T * args.steps / dt, dt / args.steps * 1e3, torch.get_num_threads(), "port"
+        c, l = c / args.steps, l / args.steps
+        sample = (f"FALLBACK ({r['unavailable']}): oracle port of the reference PyTorch path, N={N}, T={T} of 60 env steps "
+                  f"per iteration, 2 epochs x 4 minibatches, {cores} host threads")
+        so = None
+    else:
+        v, ms, cores, kind, T = r["env_steps_per_sec"], r["ms_per_iteration"], r["threads"], "reference", r["num_steps_per_env"]
+        c, l, so = r["collection_s"], r["learn_s"], r["loaded_product_so"]
+        sample = _ref_sample_text(r, "each step = one full learning iteration")
+    line = {
         "impl": "reference", "metric": "env_steps_per_sec", "value": round(v, 1), "unit": "env-steps/s",
-        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(dt / args.steps * 1e3, 2),
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms, 2),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "humanoid_ppo XBot-L, %d envs, reference PyTorch path on host CPU" % N, "num_envs_per_gpu": N,
-                   "num_steps_per_env": T},
-        "cpu_baseline": {"value": round(v, 1), "unit": "env-steps/s", "cores": cores, "kind": "port", "sample": sample},
+        "config": {"workload": "humanoid_ppo XBot-L, %d envs x T=%d steps + PPO update (2 epochs x 4 minibatches) per step; "
+                               "reference PyTorch path on the host CPU" % (N, T), "num_envs_per_gpu": N, "num_steps_per_env": T,
+                   "physics": "synthetic tensor source (SURVEY.md 8d), same generator and ring as the product arm"},
+        "cpu_baseline": {"value": round(v, 1), "unit": "env-steps/s", "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": round(v, 1), "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "collection_s": round(c / args.steps, 3), "learn_s": round(l / args.steps, 3)}))
+        "collection_s": round(c, 3), "learn_s": round(l, 3), "loaded_product_so": so}
+    if args.ref_gpu and torch.cuda.is_available():
+        line["reference_gpu"] = reference_gpu(N)
+    print(json.dumps(line))
 
 
 def main():
@@ -453,7 +527,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--num-envs", type=int, default=4096, help="envs per GPU (BASELINE.json configs[1])")
-    ap.add_argument("--ref-T", type=int, default=12, help="env steps per iteration in the reference arm's bounded sample")
+    ap.add_argument("--ref-T", type=int, default=12, help="env steps per iteration of the oracle-port FALLBACK (no reference tree on the box)")
+    ap.add_argument("--ref-gpu", action="store_true", help="reference arm: also time the reference on cuda:0 (R-GPU)")
+    ap.add_argument("--no-ref-gpu", action="store_true", help="product arm: skip the R-GPU measurement")
     ap.add_argument("--cpu-T", type=int, default=12, help="env steps of the cpu_baseline sample (one iteration)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-env-sweep", action="store_true")

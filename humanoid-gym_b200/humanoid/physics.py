@@ -14,11 +14,10 @@ legged_robot.py:96-101,124-126,371-373,395-397,438-457; humanoid_env.py:97-98).
 Nothing here is on the accelerated path; it is the producer of the tensors the fused env kernel
 consumes.
 """
-import math
-
 import torch
 
 from humanoid.envs.custom import xbot_l_model as robot
+from humanoid.synthetic_frames import generate_ring
 
 
 class PhysicsBackend:
@@ -92,72 +91,10 @@ class SyntheticPhysics(PhysicsBackend):
         self.host_resident = host_resident
         N, nb, nd = num_envs, self.num_bodies, self.num_dof
         dev = self.device
-        g = torch.Generator(device=dev)
-        g.manual_seed(seed)
-
-        def randn(*s):
-            return torch.randn(*s, generator=g, device=dev)
-
-        def rand(*s):
-            return torch.rand(*s, generator=g, device=dev)
-
-        origins = torch.zeros(N, 3, device=dev) if env_origins is None else env_origins.to(dev)
-        lo = torch.tensor(robot.DOF_LOWER, device=dev)
-        hi = torch.tensor(robot.DOF_UPPER, device=dev)
         K = ring
-        root = torch.zeros(K, N, 13, device=dev)
-        dof = torch.zeros(K * decimation, N, nd, 2, device=dev)
-        contact = torch.zeros(K, N, nb, 3, device=dev)
-        rigid = torch.zeros(K, N, nb, 13, device=dev)
-        feet, knees = (6, 12), (4, 10)
-        for k in range(K):
-            r = root[k]
-            r[:, 0:2] = origins[:, 0:2] + (2 * rand(N, 2) - 1)
-            r[:, 2] = 0.95 + 0.02 * randn(N)
-            rpy = 0.1 * randn(N, 3)
-            rpy[:, 2] = (2 * rand(N) - 1) * math.pi
-            cr, sr = torch.cos(rpy[:, 0] / 2), torch.sin(rpy[:, 0] / 2)
-            cp, sp = torch.cos(rpy[:, 1] / 2), torch.sin(rpy[:, 1] / 2)
-            cy, sy = torch.cos(rpy[:, 2] / 2), torch.sin(rpy[:, 2] / 2)
-            r[:, 3] = sr * cp * cy - cr * sp * sy
-            r[:, 4] = cr * sp * cy + sr * cp * sy
-            r[:, 5] = cr * cp * sy - sr * sp * cy
-            r[:, 6] = cr * cp * cy + sr * sp * sy
-            cx = cmd_ranges["lin_vel_x"][0] + (cmd_ranges["lin_vel_x"][1] - cmd_ranges["lin_vel_x"][0]) * rand(N)
-            cyv = cmd_ranges["lin_vel_y"][0] + (cmd_ranges["lin_vel_y"][1] - cmd_ranges["lin_vel_y"][0]) * rand(N)
-            yaw = rpy[:, 2]
-            r[:, 7] = torch.cos(yaw) * cx - torch.sin(yaw) * cyv + 0.2 * randn(N)
-            r[:, 8] = torch.sin(yaw) * cx + torch.cos(yaw) * cyv + 0.2 * randn(N)
-            r[:, 9] = 0.2 * randn(N)
-            r[:, 10:13] = 0.3 * randn(N, 3)
-
-            clock = math.sin(2 * math.pi * (k + 0.25) / K)
-            stance = torch.tensor([clock >= 0, clock < 0], device=dev).repeat(N, 1)
-            in_contact = stance ^ (rand(N, 2) < 0.10)
-            c = contact[k]
-            for j, b in enumerate(feet):
-                c[:, b, 2] = (200 + 400 * rand(N)) * in_contact[:, j]
-                c[:, b, 0:2] = 20 * randn(N, 2) * in_contact[:, j:j + 1]
-            hit = rand(N) < p_base_contact
-            c[:, 0, :] = hit.unsqueeze(1) * (2.0 + 5 * rand(N, 3))
-
-            rg = rigid[k]
-            swing = (~in_contact).float()
-            for j, b in enumerate(feet):
-                side = 0.15 if j == 0 else -0.15
-                rg[:, b, 0] = r[:, 0] + 0.05 * randn(N)
-                rg[:, b, 1] = r[:, 1] + side + 0.03 * randn(N)
-                rg[:, b, 2] = 0.05 + 0.06 * swing[:, j] * abs(clock)
-                rg[:, b, 7:9] = 0.3 * randn(N, 2) * swing[:, j:j + 1]
-            for j, b in enumerate(knees):
-                side = 0.12 if j == 0 else -0.12
-                rg[:, b, 0] = r[:, 0] + 0.02 * randn(N)
-                rg[:, b, 1] = r[:, 1] + side + 0.02 * randn(N)
-                rg[:, b, 2] = 0.45
-        for s in range(K * decimation):
-            q = 0.2 * randn(N, nd)
-            dof[s, :, :, 0] = torch.max(torch.min(q, hi), lo)
-            dof[s, :, :, 1] = randn(N, nd)
+        fr = generate_ring(N, dev, cmd_ranges, env_origins, robot.DOF_LOWER, robot.DOF_UPPER, nb, decimation=decimation,
+                           seed=seed, ring=ring, p_base_contact=p_base_contact)
+        root, dof, contact, rigid = fr["root"], fr["dof"], fr["contact"], fr["rigid"]
 
         def place(t):
             return t.cpu().pin_memory() if host_resident else t

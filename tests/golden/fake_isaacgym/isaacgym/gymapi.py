@@ -1,7 +1,18 @@
 """Functional fake of the isaacgym.gymapi surface the reference touches
 (list in SURVEY.md section 8c).  TEST-ONLY.  simulate() writes seeded synthetic
-state tensors; nothing here is physics."""
+state tensors; nothing here is physics.
+
+Two modes (env HG_FAKE_GYM):
+  golden (default) -- CPU, simulate() draws fresh random state every sub-step (tests/golden/make_golden.py).
+  ring             -- bench reference arm: state tensors live on the sim device (cuda:i with the GPU pipeline),
+                      a ring of frames is pre-generated in prepare_sim() by the SAME standalone generator the
+                      product's SyntheticPhysics uses (humanoid-gym_b200/humanoid/synthetic_frames.py, loaded by
+                      file path -- nothing of the product package is imported), simulate() only advances a
+                      counter and refresh_*() copy the current frame: identical per-step "physics" cost in both arms.
+"""
+import importlib.util
 import math
+import os
 import types
 import xml.etree.ElementTree as ET
 
@@ -71,6 +82,28 @@ class _BodyProps:
 _BASE_MASS = 5.0
 
 
+_REPO = os.path.dirname(os.path.dirname(os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))))
+
+
+def _load_by_path(name, rel):
+    spec = importlib.util.spec_from_file_location(name, os.path.join(_REPO, rel))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+class _TableAsset:
+    """XBot-L as Isaac Gym reports it, from the product's constant table (used when the URDF did not travel:
+    `pip install --target baseline/_ref` copies the python packages only, not resources/)."""
+
+    def __init__(self):
+        m = _load_by_path("_hg_xbot_l_model", "humanoid-gym_b200/humanoid/envs/custom/xbot_l_model.py")
+        self.body_names = list(m.BODY_NAMES)
+        self.dof_names = list(m.DOF_NAMES)
+        rows = list(zip(m.DOF_LOWER, m.DOF_UPPER, m.DOF_VELOCITY, m.DOF_EFFORT))
+        self.dof_props = np.array(rows, dtype=[("lower", "f4"), ("upper", "f4"), ("velocity", "f4"), ("effort", "f4")])
+
+
 class _Asset:
     def __init__(self, path, collapse_fixed):
         root = ET.parse(path).getroot()
@@ -103,6 +136,9 @@ class _Sim:
         self.step_count = 0
         self.gen = torch.Generator(device="cpu")
         self.gen.manual_seed(1234)
+        self.mode = os.environ.get("HG_FAKE_GYM", "golden")
+        self.substep = 0
+        self.origins = []
         # knobs for the synthetic writer (set by the golden script)
         self.p_base_contact = 0.02
         self.p_contact_flip = 0.15
@@ -114,14 +150,19 @@ class Gym:
     # ---- construction ----
     def create_sim(self, compute_device, graphics_device, physics_engine, params):
         dev = "cpu"
+        if os.environ.get("HG_FAKE_GYM", "golden") == "ring" and getattr(params, "use_gpu_pipeline", False):
+            dev = f"cuda:{int(compute_device)}"
         return _Sim(params, dev)
 
     def add_ground(self, sim, plane_params):
         pass
 
     def load_asset(self, sim, root, file, options):
-        import os
-        sim.asset = _Asset(os.path.join(root, file), getattr(options, "collapse_fixed_joints", True))
+        path = os.path.join(root, file)
+        if os.path.exists(path):
+            sim.asset = _Asset(path, getattr(options, "collapse_fixed_joints", True))
+        else:
+            sim.asset = _TableAsset()
         return sim.asset
 
     def get_asset_dof_count(self, a):
@@ -152,6 +193,7 @@ class Gym:
 
     def create_actor(self, env, asset, pose, name, group, filt, seg):
         env.body_props = [_BodyProps(_BASE_MASS if i == 0 else 1.0) for i in range(len(asset.body_names))]
+        env.sim.origins.append((pose.p.x, pose.p.y, pose.p.z))
         return 0
 
     def set_actor_dof_properties(self, env, actor, props):
@@ -170,11 +212,23 @@ class Gym:
         n = len(sim.envs)
         nb = len(sim.asset.body_names)
         nd = len(sim.asset.dof_names)
+        dev = sim.device
         sim.tensors = dict(
-            root=torch.zeros(n, 13), dof=torch.zeros(n * nd, 2),
-            contact=torch.zeros(n * nb, 3), rigid=torch.zeros(n * nb, 13))
+            root=torch.zeros(n, 13, device=dev), dof=torch.zeros(n * nd, 2, device=dev),
+            contact=torch.zeros(n * nb, 3, device=dev), rigid=torch.zeros(n * nb, 13, device=dev))
         sim.tensors["root"][:, 6] = 1.0
         sim.tensors["root"][:, 2] = 0.95
+        if sim.mode == "ring":
+            gen = _load_by_path("_hg_synthetic_frames", "humanoid-gym_b200/humanoid/synthetic_frames.py")
+            sim.decimation, sim.ring = 10, 6
+            origins = torch.tensor(sim.origins, dtype=torch.float32)
+            lim = sim.asset.dof_props
+            fr = gen.generate_ring(n, dev, {"lin_vel_x": [-0.3, 0.6], "lin_vel_y": [-0.3, 0.3]}, origins,
+                                   [float(x) for x in lim["lower"]], [float(x) for x in lim["upper"]], nb,
+                                   decimation=sim.decimation, seed=5, ring=sim.ring)
+            K = sim.ring
+            sim.frames = dict(root=fr["root"], dof=fr["dof"].view(K * sim.decimation, n * nd, 2),
+                              contact=fr["contact"].view(K, n * nb, 3), rigid=fr["rigid"].view(K, n * nb, 13))
 
     def create_camera_sensor(self, env, props):
         return 0
@@ -195,17 +249,25 @@ class Gym:
     def acquire_rigid_body_state_tensor(self, sim):
         return sim.tensors["rigid"]
 
+    @staticmethod
+    def _frame(sim):
+        return ((sim.substep - 1) // sim.decimation) % sim.ring if sim.substep > 0 else 0
+
     def refresh_dof_state_tensor(self, sim):
-        pass
+        if sim.mode == "ring":
+            sim.tensors["dof"].copy_(sim.frames["dof"][(sim.substep - 1) % (sim.ring * sim.decimation)], non_blocking=True)
 
     def refresh_actor_root_state_tensor(self, sim):
-        pass
+        if sim.mode == "ring":
+            sim.tensors["root"].copy_(sim.frames["root"][self._frame(sim)], non_blocking=True)
 
     def refresh_net_contact_force_tensor(self, sim):
-        pass
+        if sim.mode == "ring":
+            sim.tensors["contact"].copy_(sim.frames["contact"][self._frame(sim)], non_blocking=True)
 
     def refresh_rigid_body_state_tensor(self, sim):
-        pass
+        if sim.mode == "ring":
+            sim.tensors["rigid"].copy_(sim.frames["rigid"][self._frame(sim)], non_blocking=True)
 
     def set_dof_actuation_force_tensor(self, sim, t):
         sim.last_torques = t
@@ -224,6 +286,9 @@ class Gym:
 
     def simulate(self, sim):
         """Synthetic state writer (in place, like PhysX writing its GPU buffers)."""
+        if sim.mode == "ring":
+            sim.substep += 1
+            return
         sim.step_count += 1
         g = sim.gen
         T = sim.tensors

@@ -1,4 +1,5 @@
-"""bench.py contract, the half that runs without a GPU: the reference arm (`--impl reference`) times the oracle port
+"""bench.py contract, the half that runs without a GPU: the reference arm (`--impl reference`) times the UNMODIFIED
+reference (baseline/_ref or /root/reference over the ring-mode fake isaacgym; oracle port only as the stated fallback)
 on the host cores and prints ONE JSON line with the keys the driver reads."""
 import json
 import os
@@ -25,11 +26,21 @@ def test_reference_arm_prints_one_json_line_with_the_contract_keys():
     assert d["higher_is_better"] is True and d["n_gpus"] == 1 and d["steps"] == 1 and d["warmup"] == 0
     assert d["value"] > 0 and d["ms_per_step"] > 0
     cb = d["cpu_baseline"]
-    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and cb["sample"]
+    have_ref = os.path.isdir(os.path.join(ROOT, "baseline", "_ref", "humanoid")) or os.path.isdir("/root/reference/humanoid")
+    assert cb["kind"] == ("reference" if have_ref else "port") and cb["cores"] >= 1 and cb["value"] == d["value"] and cb["sample"]
+    if have_ref:
+        assert d["config"]["num_steps_per_env"] == 60            # the full configuration, not a shortened sample
+        assert d["loaded_product_so"] is False                    # the reference arm never maps libhg_b200.so
     e2e = d["e2e"]
     assert e2e["value"] == d["value"] and e2e["unit"] == d["unit"]
     assert e2e["h2d_bytes_per_step"] == 0 and e2e["d2h_bytes_per_step"] == 0
     assert "workload" in d["config"]
+
+
+def test_reference_arm_port_fallback_says_so():
+    d = json.loads(_run({"HG_REF_FORCE_PORT": "1"})[0])
+    assert d["cpu_baseline"]["kind"] == "port" and "FALLBACK" in d["cpu_baseline"]["sample"]
+    assert d["config"]["num_steps_per_env"] == 2
 
 
 def test_reference_arm_under_a_multi_rank_launch_runs_on_rank_zero_only():
