@@ -224,20 +224,33 @@ def _kernel_rooflines(runner, device, pk):
     s = alg.storage
     B = (s.num_envs * s.num_transitions_per_env) // alg.num_mini_batches
     idx = torch.randperm(s.num_envs * s.num_transitions_per_env, device=device)[:B]
-    mb = s.gather(idx)
+    split = alg.use_split_path()
+    mb = s.gather(idx, split=split)
     ac = alg.actor_critic
     flat = ac.flat_params()
-    w = alg._scratch(B)
     sp = nat.stream_ptr(device.index)
 
-    def chain():
-        ac.native_forward("actor", mb["obs"], w["mean"], hidden=w["hid_a"])
-        ac.native_forward("critic", mb["priv_obs"], w["value"], hidden=w["hid_c"])
-        g = alg._grad.data_ptr()
-        nat.check(nat.lib.hg_mlp_backward(ac._desc["actor"], flat.data_ptr(), mb["obs"].data_ptr(), mb["obs"].stride(0), w["hid_a"].data_ptr(),
-                                          w["d_mean"].data_ptr(), w["dhid_a"].data_ptr(), g, B, sp))
-        nat.check(nat.lib.hg_mlp_backward(ac._desc["critic"], flat.data_ptr(), mb["priv_obs"].data_ptr(), mb["priv_obs"].stride(0), w["hid_c"].data_ptr(),
-                                          w["d_value"].data_ptr(), w["dhid_c"].data_ptr(), g, B, sp))
+    if split:
+        w = alg._scratch_split(B)
+        ac.refresh_split()
+        xs_a, xs_c = nat.Split.of(mb["obs_split"]), nat.Split.of(mb["priv_split"])
+
+        def chain():
+            ac.native_forward_split("actor", xs_a, w["mean"], w["hid_a"])
+            ac.native_forward_split("critic", xs_c, w["value"], w["hid_c"])
+            ac.native_backward_split("actor", xs_a, w["hid_a"], w["d_mean"], w["dhid_a"], alg._grad)
+            ac.native_backward_split("critic", xs_c, w["hid_c"], w["d_value"], w["dhid_c"], alg._grad)
+    else:
+        w = alg._scratch(B)
+
+        def chain():
+            ac.native_forward("actor", mb["obs"], w["mean"], hidden=w["hid_a"])
+            ac.native_forward("critic", mb["priv_obs"], w["value"], hidden=w["hid_c"])
+            g = alg._grad.data_ptr()
+            nat.check(nat.lib.hg_mlp_backward(ac._desc["actor"], flat.data_ptr(), mb["obs"].data_ptr(), mb["obs"].stride(0), w["hid_a"].data_ptr(),
+                                              w["d_mean"].data_ptr(), w["dhid_a"].data_ptr(), g, B, sp))
+            nat.check(nat.lib.hg_mlp_backward(ac._desc["critic"], flat.data_ptr(), mb["priv_obs"].data_ptr(), mb["priv_obs"].stride(0), w["hid_c"].data_ptr(),
+                                              w["d_value"].data_ptr(), w["dhid_c"].data_ptr(), g, B, sp))
     w["d_mean"].normal_()
     w["d_value"].normal_()
     for _ in range(3):
@@ -252,20 +265,26 @@ def _kernel_rooflines(runner, device, pk):
     t = e0.elapsed_time(e1) / reps * 1e-3
     flops = (FLOPS_FWD + FLOPS_BWD) * B
     tf = flops / t / 1e12
-    peak_tf32 = pk["bf16_sustained"] / 2.0
     mode = nat.lib.hg_set_gemm_mode(-1)
-    passes = {0: 0, 1: 3, 2: 1, 3: 3}[mode]
-    engine = {0: "gemm_kernel (exact-fp32 CUDA-core path)", 1: "gemm_tc_kernel (tcgen05 kind::tf32, 3xTF32)",
-              2: "gemm_tc_kernel (tcgen05 kind::tf32, 1 pass)",
-              3: "gemm_tc_kernel / gemm_tc_bf16_kernel (experimental bf16x3 on the K-major products)"}[mode]
+    # the chain is timed in isolation (5 repetitions, a few ms) -> MEASURED_PEAKS' BURST cuBLAS bf16 figure is the denominator;
+    # kind::tf32 runs at half the bf16 rate
+    if split:
+        peak, passes, kind = pk["bf16"], 3, "bf16"
+        engine = "gemm_bf3_kernel (tcgen05 kind::f16 on pre-split bf16 hi/lo operands, 3 MMAs per product) + head kernels"
+    else:
+        peak = pk["bf16"] / 2.0
+        passes, kind = {0: 0, 1: 3, 2: 1, 4: 3}[mode], "tf32"
+        engine = {0: "gemm_kernel (exact-fp32 CUDA-core path)", 1: "gemm_tc_kernel (tcgen05 kind::tf32, 3xTF32)",
+                  2: "gemm_tc_kernel (tcgen05 kind::tf32, 1 pass)", 4: "gemm_tc_kernel (tcgen05 kind::tf32, 3xTF32)"}[mode]
     out["roofline"] = dict(kernel="ActorCritic fwd+bwd GEMM chain of one 61,440-sample minibatch: " + engine, bound="tensor",
-                           achieved=round(tf, 2), peak=round(peak_tf32, 1), unit="TFLOP/s", frac=round(tf / peak_tf32, 4),
+                           achieved=round(tf, 2), peak=round(peak, 1), unit="TFLOP/s", frac=round(tf / peak, 4),
                            traffic=None, ms_per_minibatch=round(t * 1e3, 3), flops_per_launch_group=flops,
-                           mma_passes=passes, tensor_pipe_tflops=round(tf * max(passes, 1), 2),
-                           tensor_pipe_frac=round(tf * max(passes, 1) / peak_tf32, 4),
-                           note="achieved = ALGORITHMIC fp32 FLOPs (4.486 MFLOP/sample, SURVEY 8d) / time; 3xTF32 issues 3 tensor "
-                                "MMAs per algorithmic product, so the tensor pipe runs at tensor_pipe_tflops",
-                           peak_source=pk["src"] + "; TF32 dense peak taken as bf16_tflops_sustained/2")
+                           mma_passes=passes, mma_kind=kind, tensor_pipe_tflops=round(tf * max(passes, 1), 2),
+                           tensor_pipe_frac=round(tf * max(passes, 1) / peak, 4),
+                           note="achieved = ALGORITHMIC fp32 FLOPs (4.486 MFLOP/sample, SURVEY 8d) / time; the split-precision scheme "
+                                "issues `mma_passes` tensor MMAs of kind `mma_kind` per algorithmic product, so the tensor pipe itself "
+                                "runs at tensor_pipe_tflops; frac is the algorithmic rate over the dense peak of that kind",
+                           peak_source=pk["src"] + f"; burst cuBLAS bf16 figure (chain timed in isolation){'' if split else ' / 2 for kind::tf32'}")
     return out
 
 

@@ -18,6 +18,8 @@ extern "C" int64_t hg_struct_size(int32_t which) {
         case 6: return sizeof(HgMiniBatch);
         case 7: return sizeof(HgPpoLossArgs);
         case 8: return sizeof(HgGemm);
+        case 9: return sizeof(HgSplit);
+        case 10: return sizeof(HgGemmSplit);
         default: return -1;
     }
 }

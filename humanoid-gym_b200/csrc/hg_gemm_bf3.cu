@@ -1,0 +1,519 @@
+// tcgen05 / TMEM / TMA GEMM on PRE-SPLIT bf16 operands ("bf16x3"), sm_100a.
+//
+//     x ~= x_hi + x_lo,   x_hi = bf16(x),   x_lo = bf16(x - x_hi)            (16 significant bits)
+//     D += A_lo B_hi + A_hi B_lo + A_hi B_hi                                   three kind::f16 MMAs, fp32 accumulation in TMEM
+//
+// = 1.5 TF32-equivalent tensor passes (3xTF32 needs 3), relative error ~5e-6 per product, ~9e-6 on the
+// ActorCritic gradients (bar: 1e-4).  Every operand arrives already split -- by the kernel that produced it
+// (previous GEMM epilogue, minibatch gather, dgrad of the output head, the post-Adam weight split) -- as two bf16
+// planes [2][rows][ld], so this kernel has NO splitter warps: TMA loads the four tiles {A_hi, A_lo, B_hi, B_lo}
+// of a 64-k stage straight into 128B-swizzled shared memory and the tensor core reads them from there.
+//
+// One kernel covers the three products of a Linear layer (algo/ppo/actor_critic.py:54-77 and its autograd),
+// without materialising any transpose:
+//     forward  H  = ELU(X W^T + b)   A = X  (K-major)    B = W  (K-major)     epilogue: +bias, ELU, split store
+//     dgrad    dZ' = (dZ W) * ELU'   A = dZ (K-major)    B = W  (MN-major)    epilogue: * ELU'(H), split store, column sums (bias grad)
+//     wgrad    dW = dZ^T X           A = dZ (MN-major)   B = X  (MN-major)    split-K over the batch, fp32 atomics
+//
+// CTA = 128 x BN output tile (BN <= 256), persistent (one CTA per SM), 10 warps:
+//     warps 0-7  epilogue     tcgen05.ld (warp w reads TMEM lanes 32*(w%4).., column half w/4) -> bias/ELU/ELU'/split/atomics
+//     warp  8    TMA producer cp.async.bulk.tensor.3d ({k, rows, plane} boxes; OOB rows / k are zero-filled)
+//     warp  9    MMA issuer   one lane issues 12 tcgen05.mma.kind::f16 (M=128, N=BN, K=16) per stage
+// mbarrier ring of S stages (S = what fits in 227 KB), accumulator double-buffered in TMEM (2 x 256 columns) so the
+// epilogue of tile i overlaps the main loop of tile i+1.
+#include <cuda.h>
+
+#include <mutex>
+#include <unordered_map>
+
+#include "hg_common.cuh"
+#include "hg_tc_ptx.cuh"
+
+using namespace hgtc;
+
+namespace {
+
+constexpr int BM = 128, BK = 64;                     // 64 bf16 = one 128-byte swizzled row
+constexpr int EPI_WARPS = 8;
+constexpr int THREADS = (EPI_WARPS + 2) * 32;
+constexpr int A_PLANE = BM * BK * 2;                 // 16 KB: one bf16 plane of the A tile
+constexpr int A_BYTES = 2 * A_PLANE;                 // hi + lo
+constexpr int SMEM_LIMIT = 227 * 1024;
+constexpr int BAR_BYTES = 256;
+constexpr int MAX_STAGES = 4;
+
+enum { EPI_F32 = 0, EPI_F32_BIAS = 1, EPI_SPLIT_BIAS_ELU = 2, EPI_SPLIT_DELU = 3, EPI_ATOMIC = 4, EPI_SPLIT = 5 };
+
+struct Args {
+    float* C; int64_t ldc;
+    uint16_t* Cs; int64_t ldcs, cs_plane;
+    const float* bias;
+    const uint16_t* Hs; int64_t ldhs, hs_plane;
+    float* colsum;
+    int M, N, K;
+    int BN, a_mn, b_mn, epi;
+    int kb_per_split, splits, stages;
+};
+
+// shared-memory matrix descriptor (sm_100 UMMA, version 1), 16-bit operands, SWIZZLE_128B:
+//   K-major  tile [rows][64 bf16]       : SBO = 1024 B (8 rows x 128 B); LBO unused
+//   MN-major tile blocks of [64 k][64 mn]: SBO = 1024 B (8 k-rows x 128 B), LBO = byte distance between 64-wide MN blocks
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;                          // SWIZZLE_128B
+    return d;
+}
+// instruction descriptor, kind::f16: D = F32, A = B = BF16, M = 128
+__device__ __forceinline__ uint32_t make_idesc(int N, bool a_mn, bool b_mn) {
+    uint32_t d = 0;
+    d |= 1u << 4;                                    // c_format F32
+    d |= 1u << 7;                                    // a_format BF16
+    d |= 1u << 10;                                   // b_format BF16
+    d |= (a_mn ? 1u : 0u) << 15;
+    d |= (b_mn ? 1u : 0u) << 16;
+    d |= (uint32_t)(N >> 3) << 17;
+    d |= (uint32_t)(BM >> 4) << 24;
+    return d;
+}
+
+struct Work { int m0, n0, kb_begin, num_kb; };
+__device__ __forceinline__ Work decode_work(const Args& g, int w, int tiles_n, int tiles_mn, int num_kb_total) {
+    Work r;
+    const int split = w / tiles_mn, t = w - split * tiles_mn;
+    const int tm = t / tiles_n, tn = t - tm * tiles_n;
+    r.m0 = tm * BM;
+    r.n0 = tn * g.BN;
+    r.kb_begin = split * g.kb_per_split;
+    r.num_kb = min(num_kb_total, r.kb_begin + g.kb_per_split) - r.kb_begin;
+    return r;
+}
+
+// (x0 at the lower address)
+__device__ __forceinline__ uint32_t pack_bf16x2(float x0, float x1) {
+    uint32_t r;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(x1), "f"(x0));
+    return r;
+}
+__device__ __forceinline__ float bf_lo(uint32_t p) { return __uint_as_float(p << 16); }
+__device__ __forceinline__ float bf_hi(uint32_t p) { return __uint_as_float(p & 0xFFFF0000u); }
+
+// nn.ELU(alpha=1): expm1 by a short series near 0 (relative error < 1e-7), exp(x) - 1 elsewhere
+__device__ __forceinline__ float elu1(float x) {
+    const float p = x * (1.0f + x * (0.5f + x * (0.16666667f + x * 0.041666668f)));
+    const float e = __expf(x) - 1.0f;
+    return x > 0.0f ? x : (x > -0.06f ? p : e);
+}
+
+__global__ void __launch_bounds__(THREADS, 1)
+gemm_bf3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const Args g) {
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    const int b_plane = g.BN * BK * 2;                          // bytes of one bf16 plane of the B tile
+    const int stage_bytes = A_BYTES + 2 * b_plane;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + g.stages * stage_bytes);
+    uint64_t* full = bars;                          // [S] TMA -> MMA
+    uint64_t* empty = full + MAX_STAGES;            // [S] MMA -> TMA
+    uint64_t* tmem_full = empty + MAX_STAGES;       // [2] MMA -> epilogue
+    uint64_t* tmem_empty = tmem_full + 2;           // [2] epilogue -> MMA
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int num_kb_total = (g.K + BK - 1) / BK;
+    const int tiles_n = (g.N + g.BN - 1) / g.BN, tiles_m = (g.M + BM - 1) / BM;
+    const int tiles_mn = tiles_n * tiles_m;
+    const int total_work = tiles_mn * g.splits;
+    const int S = g.stages;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < S; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(&tmem_full[a], 1);
+            mbar_init(&tmem_empty[a], EPI_WARPS);
+        }
+        fence_barrier_init();
+    }
+    if (warp == EPI_WARPS + 1) tmem_alloc(tmem_slot, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == EPI_WARPS) {
+        // ===== TMA producer =====
+        if (lane == 0) {
+            asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+            asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+            const uint32_t tx = (uint32_t)stage_bytes;
+            int it = 0;
+            for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
+                const Work wk = decode_work(g, w, tiles_n, tiles_mn, num_kb_total);
+                for (int kb = 0; kb < wk.num_kb; ++kb, ++it) {
+                    const int s = it % S, k0 = (wk.kb_begin + kb) * BK;
+                    mbar_wait(&empty[s], ((it / S) & 1) ^ 1);
+                    unsigned char* sa = smem + s * stage_bytes;
+                    unsigned char* sb = sa + A_BYTES;
+                    mbar_expect_tx(&full[s], tx);
+                    if (!g.a_mn) tma_load_3d(sa, &tmA, &full[s], k0, wk.m0, 0);                   // [plane][128][64]
+                    else
+                        for (int j = 0; j < BM / 64; ++j) tma_load_3d(sa + j * 16384, &tmA, &full[s], wk.m0 + 64 * j, k0, 0);   // [plane][64 k][64 mn]
+                    if (!g.b_mn) tma_load_3d(sb, &tmB, &full[s], k0, wk.n0, 0);                   // [plane][BN][64]
+                    else
+                        for (int j = 0; j < g.BN / 64; ++j) tma_load_3d(sb + j * 16384, &tmB, &full[s], wk.n0 + 64 * j, k0, 0);
+                }
+            }
+        }
+    } else if (warp == EPI_WARPS + 1) {
+        // ===== MMA issuer =====
+        if (lane == 0) {
+            const uint32_t idesc = make_idesc(g.BN, g.a_mn, g.b_mn);
+            // byte offsets inside a stage: plane (hi -> lo) and K step (16 bf16)
+            const uint32_t a_lo_off = g.a_mn ? 8192u : (uint32_t)A_PLANE, b_lo_off = g.b_mn ? 8192u : (uint32_t)b_plane;
+            const uint32_t a_kstep = g.a_mn ? 2048u : 32u, b_kstep = g.b_mn ? 2048u : 32u;
+            const uint32_t a_lbo = g.a_mn ? 16384u : 16u, b_lbo = g.b_mn ? 16384u : 16u;
+            int it = 0, item = 0;
+            for (int w = blockIdx.x; w < total_work; w += gridDim.x, ++item) {
+                const Work wk = decode_work(g, w, tiles_n, tiles_mn, num_kb_total);
+                const int acc_stage = item & 1;
+                mbar_wait(&tmem_empty[acc_stage], ((item >> 1) & 1) ^ 1);       // epilogue has drained this accumulator
+                tc_fence_after();
+                const uint32_t tmem_d = tmem_base + (uint32_t)(acc_stage * 256);
+                for (int kb = 0; kb < wk.num_kb; ++kb, ++it) {
+                    const int s = it % S;
+                    mbar_wait(&full[s], (it / S) & 1);
+                    tc_fence_after();
+                    const uint32_t a0 = smem_u32(smem + s * stage_bytes), b0 = a0 + A_BYTES;
+#pragma unroll
+                    for (int kk = 0; kk < BK / 16; ++kk) {
+                        const uint64_t a_hi = make_desc(a0 + kk * a_kstep, a_lbo);
+                        const uint64_t a_lo = make_desc(a0 + a_lo_off + kk * a_kstep, a_lbo);
+                        const uint64_t b_hi = make_desc(b0 + kk * b_kstep, b_lbo);
+                        const uint64_t b_lo = make_desc(b0 + b_lo_off + kk * b_kstep, b_lbo);
+                        umma_bf16(tmem_d, a_lo, b_hi, idesc, (kb > 0 || kk > 0) ? 1u : 0u);      // small terms first
+                        umma_bf16(tmem_d, a_hi, b_lo, idesc, 1u);
+                        umma_bf16(tmem_d, a_hi, b_hi, idesc, 1u);
+                    }
+                    umma_commit(&empty[s]);                                     // stage reusable once these MMAs retire
+                }
+                umma_commit(&tmem_full[acc_stage]);
+            }
+        }
+    } else {
+        // ===== epilogue: warp w <-> TMEM lanes 32*(w%4) .. +31, columns [(w/4) * BN/2, +BN/2) =====
+        const int q = warp & 3, half = warp >> 2;
+        const int c_begin = half * (g.BN >> 1), c_end = c_begin + (g.BN >> 1);
+        int item = 0;
+        for (int w = blockIdx.x; w < total_work; w += gridDim.x, ++item) {
+            const Work wk = decode_work(g, w, tiles_n, tiles_mn, num_kb_total);
+            const int acc_stage = item & 1;
+            mbar_wait(&tmem_full[acc_stage], (item >> 1) & 1);
+            tc_fence_after();
+            const int row = wk.m0 + q * 32 + lane;
+            const bool row_ok = row < g.M;
+            for (int c0 = c_begin; c0 < c_end; c0 += 32) {
+                float v[32];
+                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc_stage * 256 + c0), v);
+                const int col0 = wk.n0 + c0;
+                if (col0 >= g.N) continue;                                  // warp-uniform
+                const int nvalid = min(32, g.N - col0);
+                const bool full_chunk = (nvalid == 32);
+                if (g.epi == EPI_F32_BIAS || g.epi == EPI_SPLIT_BIAS_ELU) {
+                    const float bl = (lane < nvalid) ? __ldg(g.bias + col0 + lane) : 0.0f;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const float x = v[j] + __shfl_sync(0xffffffffu, bl, j);
+                        v[j] = (g.epi == EPI_SPLIT_BIAS_ELU) ? elu1(x) : x;
+                    }
+                } else if (g.epi == EPI_SPLIT_DELU) {
+                    // ELU'(z) recovered from h = ELU(z) ~= h_hi + h_lo:  1 for h > 0, h + 1 otherwise
+                    const uint16_t* hp = g.Hs + (int64_t)row * g.ldhs + col0;
+                    if (row_ok && full_chunk && ((reinterpret_cast<uintptr_t>(hp) & 15u) == 0) && ((g.hs_plane & 7) == 0)) {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 8) {
+                            const uint4 a = __ldg(reinterpret_cast<const uint4*>(hp + j));
+                            const uint4 b = __ldg(reinterpret_cast<const uint4*>(hp + g.hs_plane + j));
+                            const uint32_t ah[4] = {a.x, a.y, a.z, a.w}, bl4[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+                            for (int t = 0; t < 4; ++t) {
+                                const float h0 = bf_lo(ah[t]) + bf_lo(bl4[t]), h1 = bf_hi(ah[t]) + bf_hi(bl4[t]);
+                                v[j + 2 * t] *= (h0 > 0.0f) ? 1.0f : (h0 + 1.0f);
+                                v[j + 2 * t + 1] *= (h1 > 0.0f) ? 1.0f : (h1 + 1.0f);
+                            }
+                        }
+                    } else if (row_ok) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            if (j < nvalid) {
+                                const float h = __uint_as_float((uint32_t)hp[j] << 16) + __uint_as_float((uint32_t)hp[g.hs_plane + j] << 16);
+                                v[j] *= (h > 0.0f) ? 1.0f : (h + 1.0f);
+                            }
+                    }
+                }
+                if (g.epi == EPI_F32 || g.epi == EPI_F32_BIAS || g.epi == EPI_ATOMIC) {
+                    if (!row_ok) continue;
+                    float* dst = g.C + (int64_t)row * g.ldc + col0;
+                    const bool vec = full_chunk && ((reinterpret_cast<uintptr_t>(dst) & 15u) == 0);
+                    if (g.epi == EPI_ATOMIC) {
+                        if (vec) {
+#pragma unroll
+                            for (int j = 0; j < 32; j += 4)
+                                atomicAdd(reinterpret_cast<float4*>(dst + j), make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]));
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j)
+                                if (j < nvalid) atomicAdd(dst + j, v[j]);
+                        }
+                    } else if (vec) {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            if (j < nvalid) dst[j] = v[j];
+                    }
+                    continue;
+                }
+                // ---- split store (hi / lo bf16 planes) ----
+                if (row_ok) {
+                    uint16_t* dp = g.Cs + (int64_t)row * g.ldcs + col0;
+                    uint32_t ph[16], pl[16];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        ph[j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
+                        pl[j] = pack_bf16x2(v[2 * j] - bf_lo(ph[j]), v[2 * j + 1] - bf_hi(ph[j]));
+                    }
+                    if (full_chunk && ((reinterpret_cast<uintptr_t>(dp) & 15u) == 0) && ((g.cs_plane & 7) == 0)) {
+#pragma unroll
+                        for (int j = 0; j < 16; j += 4) {
+                            *reinterpret_cast<uint4*>(dp + 2 * j) = make_uint4(ph[j], ph[j + 1], ph[j + 2], ph[j + 3]);
+                            *reinterpret_cast<uint4*>(dp + g.cs_plane + 2 * j) = make_uint4(pl[j], pl[j + 1], pl[j + 2], pl[j + 3]);
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            if (j < nvalid) {
+                                dp[j] = (uint16_t)((j & 1) ? (ph[j >> 1] >> 16) : (ph[j >> 1] & 0xFFFFu));
+                                dp[g.cs_plane + j] = (uint16_t)((j & 1) ? (pl[j >> 1] >> 16) : (pl[j >> 1] & 0xFFFFu));
+                            }
+                    }
+                }
+                if (g.epi == EPI_SPLIT_DELU && g.colsum != nullptr) {
+                    // bias gradient: column sums of this 32 x 32 block by a butterfly transpose-reduce (31 shuffles),
+                    // lane j ends up with the sum of column j; one atomic per column per warp
+                    if (!row_ok) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] = 0.0f;
+                    }
+#pragma unroll
+                    for (int o = 16; o >= 1; o >>= 1) {
+                        const bool upper = (lane & o) != 0;
+#pragma unroll
+                        for (int i = 0; i < o; ++i) {
+                            const float send = upper ? v[i] : v[i + o];
+                            const float keep = upper ? v[i + o] : v[i];
+                            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+                        }
+                    }
+                    if (lane < nvalid) atomicAdd(g.colsum + col0 + lane, v[0]);
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty[acc_stage]);                 // accumulator free for item + 2
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == EPI_WARPS + 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 512);
+    }
+}
+
+// ---- fp32 -> split planes (weights after every Adam step, test inputs) --------------------------------------------
+__global__ void split_kernel(const float* __restrict__ src, int64_t ld_src, uint16_t* __restrict__ dst, int64_t ld_dst, int64_t plane,
+                             int64_t rows, int64_t cols) {
+    const int64_t pairs_per_row = (cols + 1) >> 1;
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= rows * pairs_per_row) return;
+    const int64_t r = i / pairs_per_row, c = (i - r * pairs_per_row) * 2;
+    const float x0 = src[r * ld_src + c], x1 = (c + 1 < cols) ? src[r * ld_src + c + 1] : 0.0f;
+    const uint32_t h = pack_bf16x2(x0, x1);
+    const uint32_t l = pack_bf16x2(x0 - bf_lo(h), x1 - bf_hi(h));
+    uint16_t* d = dst + r * ld_dst + c;
+    d[0] = (uint16_t)(h & 0xFFFFu);
+    d[plane] = (uint16_t)(l & 0xFFFFu);
+    if (c + 1 < ld_dst) {                                   // the pad column (c + 1 == cols < ld_dst) gets zeros
+        d[1] = (uint16_t)(h >> 16);
+        d[plane + 1] = (uint16_t)(l >> 16);
+    }
+}
+__global__ void unsplit_kernel(const uint16_t* __restrict__ src, int64_t ld_src, int64_t plane, float* __restrict__ dst, int64_t ld_dst,
+                               int64_t rows, int64_t cols) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= rows * cols) return;
+    const int64_t r = i / cols, c = i - r * cols;
+    dst[r * ld_dst + c] = __uint_as_float((uint32_t)src[r * ld_src + c] << 16) + __uint_as_float((uint32_t)src[plane + r * ld_src + c] << 16);
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn g_encode = nullptr;
+
+int32_t load_encode() {
+    if (g_encode) return 0;
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q);
+    if (e != cudaSuccess || q != cudaDriverEntryPointSuccess || !fn) return hg_fail(HG_E_STATE, "cuTensorMapEncodeTiled unavailable");
+    g_encode = reinterpret_cast<EncodeTiledFn>(fn);
+    return 0;
+}
+
+// Tensor maps are pure functions of (base, extents, pitches, box): the update path reuses the same scratch buffers for
+// every minibatch, so each distinct map is encoded once per process and then found in this cache (~176
+// host-side cuTensorMapEncodeTiled calls per update otherwise).
+struct MapKey {
+    const void* base; uint64_t inner, outer, ld, plane; uint32_t box_outer;
+    bool operator==(const MapKey& o) const {
+        return base == o.base && inner == o.inner && outer == o.outer && ld == o.ld && plane == o.plane && box_outer == o.box_outer;
+    }
+};
+struct MapKeyHash {
+    size_t operator()(const MapKey& k) const {
+        uint64_t h = 1469598103934665603ull;
+        const uint64_t v[6] = {(uint64_t)(uintptr_t)k.base, k.inner, k.outer, k.ld, k.plane, k.box_outer};
+        for (uint64_t x : v) { h ^= x; h *= 1099511628211ull; }
+        return (size_t)h;
+    }
+};
+std::unordered_map<MapKey, CUtensorMap, MapKeyHash> g_maps;
+std::mutex g_maps_mu;
+
+// 3-D bf16 map over a split tensor: {inner (contiguous), outer (rows of pitch ld), 2 planes}; box {64, box_outer, 2}
+int32_t get_map(CUtensorMap* out, const uint16_t* base, uint64_t inner, uint64_t outer, uint64_t ld, uint64_t plane, uint32_t box_outer) {
+    MapKey key{base, inner, outer, ld, plane, box_outer};
+    {
+        std::lock_guard<std::mutex> lk(g_maps_mu);
+        auto it = g_maps.find(key);
+        if (it != g_maps.end()) { *out = it->second; return 0; }
+    }
+    cuuint64_t dims[3] = {inner, outer, 2};
+    cuuint64_t strides[2] = {ld * sizeof(uint16_t), plane * sizeof(uint16_t)};
+    cuuint32_t box[3] = {64, box_outer, 2};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = g_encode(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<uint16_t*>(base), dims, strides, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        snprintf(g_hg_err, sizeof(g_hg_err), "cuTensorMapEncodeTiled (bf16 3-D) failed (%d): inner=%llu outer=%llu ld=%llu plane=%llu box=%u",
+                 (int)r, (unsigned long long)inner, (unsigned long long)outer, (unsigned long long)ld, (unsigned long long)plane, box_outer);
+        return HG_E_ARG;
+    }
+    std::lock_guard<std::mutex> lk(g_maps_mu);
+    if (g_maps.size() > 4096) g_maps.clear();            // bounded: callers with ever-changing pointers just re-encode
+    g_maps.emplace(key, *out);
+    return 0;
+}
+
+int32_t check_split(const HgSplit& s, const char* what) {
+    if (!s.p) return hg_fail(HG_E_NULL, what);
+    if ((s.ld & 7) || (s.plane & 7) || !hg_aligned16(s.p)) return hg_fail(HG_E_ALIGN, "hg_gemm_bf16x3: split tensors need a 16-byte aligned base, ld % 8 == 0 and plane % 8 == 0 (TMA)");
+    return 0;
+}
+
+}  // namespace
+
+extern "C" int32_t hg_split_bf16(const float* src, int64_t ld_src, const HgSplit* dst, int64_t rows, int64_t cols, void* stream) {
+    HG_REQUIRE(src); HG_REQUIRE(dst); HG_REQUIRE(dst->p);
+    if (rows <= 0 || cols <= 0 || ld_src < cols || dst->ld < cols) return hg_fail(HG_E_SIZE, "hg_split_bf16: bad extents");
+    const int64_t n = rows * ((cols + 1) / 2);
+    split_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(src, ld_src, dst->p, dst->ld, dst->plane, rows, cols);
+    HG_LAUNCHED(1);
+    return hg_cuda_status("hg_split_bf16");
+}
+
+extern "C" int32_t hg_unsplit_bf16(const HgSplit* src, float* dst, int64_t ld_dst, int64_t rows, int64_t cols, void* stream) {
+    HG_REQUIRE(src); HG_REQUIRE(src->p); HG_REQUIRE(dst);
+    if (rows <= 0 || cols <= 0 || ld_dst < cols || src->ld < cols) return hg_fail(HG_E_SIZE, "hg_unsplit_bf16: bad extents");
+    const int64_t n = rows * cols;
+    unsplit_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(src->p, src->ld, src->plane, dst, ld_dst, rows, cols);
+    HG_LAUNCHED(1);
+    return hg_cuda_status("hg_unsplit_bf16");
+}
+
+// C (M x N) = op(A) op(B) over K on pre-split operands, see HgGemmSplit in hg_b200.h
+extern "C" int32_t hg_gemm_bf16x3(const HgGemmSplit* d, void* stream) {
+    HG_REQUIRE(d);
+    if (int32_t rc = check_split(d->A, "hg_gemm_bf16x3: A is NULL")) return rc;
+    if (int32_t rc = check_split(d->B, "hg_gemm_bf16x3: B is NULL")) return rc;
+    if (d->M <= 0 || d->N <= 0 || d->K <= 0) return hg_fail(HG_E_SIZE, "hg_gemm_bf16x3: bad extents");
+    const int epi = d->epilogue;
+    if (epi < 0 || epi > EPI_SPLIT) return hg_fail(HG_E_ARG, "hg_gemm_bf16x3: bad epilogue");
+    const bool split_out = (epi == EPI_SPLIT_BIAS_ELU || epi == EPI_SPLIT_DELU || epi == EPI_SPLIT);
+    if (split_out) {
+        if (!d->Cs.p) return hg_fail(HG_E_NULL, "hg_gemm_bf16x3: Cs is NULL");
+        if (d->Cs.ld < d->N) return hg_fail(HG_E_SIZE, "hg_gemm_bf16x3: Cs.ld < N");
+    } else if (!d->C) return hg_fail(HG_E_NULL, "hg_gemm_bf16x3: C is NULL");
+    if ((epi == EPI_F32_BIAS || epi == EPI_SPLIT_BIAS_ELU) && !d->bias) return hg_fail(HG_E_NULL, "hg_gemm_bf16x3: bias is NULL");
+    if (epi == EPI_SPLIT_DELU && !d->Hs.p) return hg_fail(HG_E_NULL, "hg_gemm_bf16x3: Hs is NULL");
+    if (int32_t rc = load_encode()) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+
+    Args g{};
+    g.C = d->C; g.ldc = d->ldc;
+    g.Cs = d->Cs.p; g.ldcs = d->Cs.ld; g.cs_plane = d->Cs.plane;
+    g.bias = d->bias;
+    g.Hs = d->Hs.p; g.ldhs = d->Hs.ld; g.hs_plane = d->Hs.plane;
+    g.colsum = d->colsum;
+    g.M = d->M; g.N = d->N; g.K = d->K;
+    g.a_mn = d->a_mn_major ? 1 : 0; g.b_mn = d->b_mn_major ? 1 : 0;
+    g.epi = epi;
+    int bn = ((d->N + 63) / 64) * 64;                    // multiples of 64: MN-major boxes are 64 wide, column halves 32-aligned
+    g.BN = bn > 256 ? 256 : bn;
+    const int stage_bytes = A_BYTES + 2 * g.BN * BK * 2;
+    int stages = (SMEM_LIMIT - 1024 - BAR_BYTES) / stage_bytes;
+    g.stages = stages > MAX_STAGES ? MAX_STAGES : stages;
+    const int smem_bytes = g.stages * stage_bytes + 1024 + BAR_BYTES;
+    const int num_kb = (d->K + BK - 1) / BK;
+    int splits = d->split_k > 0 ? d->split_k : 1;
+    if (splits > num_kb) splits = num_kb;
+    if (splits > 1 && epi != EPI_ATOMIC) return hg_fail(HG_E_ARG, "hg_gemm_bf16x3: split_k needs the atomic epilogue");
+    g.kb_per_split = (num_kb + splits - 1) / splits;
+    splits = (num_kb + g.kb_per_split - 1) / g.kb_per_split;
+    g.splits = splits;
+
+    // K-major operand: map {K, rows, 2}, box {64, tile rows, 2}.  MN-major: map {rows, K, 2}, box {64, 64, 2}.
+    CUtensorMap tmA, tmB;
+    int32_t rc;
+    if (!g.a_mn) rc = get_map(&tmA, d->A.p, d->K, d->M, d->A.ld, d->A.plane, BM);
+    else rc = get_map(&tmA, d->A.p, d->M, d->K, d->A.ld, d->A.plane, BK);
+    if (rc) return rc;
+    if (!g.b_mn) rc = get_map(&tmB, d->B.p, d->K, d->N, d->B.ld, d->B.plane, g.BN);
+    else rc = get_map(&tmB, d->B.p, d->N, d->K, d->B.ld, d->B.plane, BK);
+    if (rc) return rc;
+
+    static bool attr_set[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev >= 0 && dev < 64 && !attr_set[dev]) {
+        cudaError_t e = cudaFuncSetAttribute(gemm_bf3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
+        if (e != cudaSuccess) return hg_fail((int32_t)e, cudaGetErrorString(e));
+        attr_set[dev] = true;
+    }
+    const int total_work = ((d->N + g.BN - 1) / g.BN) * ((d->M + BM - 1) / BM) * splits;
+    const int grid = total_work < HG_NUM_SMS ? total_work : HG_NUM_SMS;       // persistent: one CTA per SM
+    gemm_bf3_kernel<<<grid, THREADS, smem_bytes, st>>>(tmA, tmB, g);
+    HG_LAUNCHED(1);
+    return hg_cuda_status("hg_gemm_bf16x3");
+}

@@ -19,6 +19,7 @@
 #include <cuda.h>
 
 #include "hg_common.cuh"
+#include "hg_tc_ptx.cuh"
 
 namespace {
 
@@ -45,91 +46,7 @@ struct TcArgs {
     int hi_in_place;                 // 1: splitter rewrites the raw tile with its tf32 truncation
 };
 
-// ------------------------------------------------------------------------------------------------
-// PTX wrappers
-// ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "WAIT_%=:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-        "@p bra DONE_%=;\n\t"
-        "bra WAIT_%=;\n\t"
-        "DONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
-}
-__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
-    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
-                     smem_u32(dst)),
-                 "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
-                 : "memory");
-}
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-__device__ __forceinline__ void tmem_alloc(uint32_t* result_in_smem, uint32_t cols) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(result_in_smem)), "r"(cols) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
-}
-// D[tmem] (+)= A[smem] * B[smem], kind::tf32, issued by ONE thread
-__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
-        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-// same, kind::f16 with bf16 operands (K = 16 per instruction)
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
-        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-// all previously issued MMAs of this thread arrive on `bar` when complete (implies fence::before_thread_sync)
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
-    uint32_t r[32];
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
-          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
-          "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
-          "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-        : "r"(taddr)
-        : "memory");
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-}
-
-__device__ __forceinline__ float rna_tf32(float x) {
-    uint32_t r;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-    return __uint_as_float(r);
-}
+using namespace hgtc;
 
 // UMMA shared-memory matrix descriptor, descriptor version 1 (sm_100).
 //   K-major  tile [rows][32 fp32], SWIZZLE_128B (type 2)          : SBO = 1024 B (8 rows x 128 B), LBO unused (1)
@@ -152,17 +69,6 @@ __device__ __forceinline__ uint32_t make_idesc(int N, bool a_mn, bool b_mn) {
     d |= 2u << 10;                      // b_format TF32
     d |= (a_mn ? 1u : 0u) << 15;
     d |= (b_mn ? 1u : 0u) << 16;
-    d |= (uint32_t)(N >> 3) << 17;
-    d |= (uint32_t)(BM >> 4) << 24;
-    return d;
-}
-
-// instruction descriptor: D = F32, A = B = BF16 (kind::f16 format code 1), both K-major, M = 128
-__device__ __forceinline__ uint32_t make_idesc_bf16(int N) {
-    uint32_t d = 0;
-    d |= 1u << 4;                       // c_format F32
-    d |= 1u << 7;                       // a_format BF16
-    d |= 1u << 10;                      // b_format BF16
     d |= (uint32_t)(N >> 3) << 17;
     d |= (uint32_t)(BM >> 4) << 24;
     return d;
@@ -405,258 +311,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 }
 
 // ------------------------------------------------------------------------------------------------
-// bf16x3 variant (EXPERIMENTAL, selected with passes = 2 / HG_GEMM=bf16x3; K-major operands only).
-//
-//     x ~= x_hi + x_lo,  x_hi = bf16(x),  x_lo = bf16(x - x_hi)        (16 significant bits)
-//     D += A_lo B_hi + A_hi B_lo + A_hi B_hi                             three kind::f16 MMAs, fp32 accumulation
-//
-// = 1.5 TF32-equivalent tensor passes instead of 3, relative error 4.6e-6 on the layer shapes
-// (tools/experiments/split_precision_study.py).  A K-major bf16 tile of 64 k-elements is byte for byte the
-// 128-byte-row SWIZZLE_128B tile used for 32 fp32 k-elements (same shared-memory descriptor, same 32-byte K step
-// per MMA), so only the instruction descriptor differs on the MMA side.  The splitter converts each raw fp32
-// stage (32 k) into one half (64 bytes of every row) of the {A_hi, A_lo, B_hi, B_lo} tiles of a 64-k stage; the
-// tensor core never reads the raw tiles, so the splitter (not the MMA warp) releases them to the TMA producer.
-// ------------------------------------------------------------------------------------------------
-constexpr int BF_RAW_STAGES = 3;                       // raw {A, B} fp32 pairs of 32 k
-constexpr int BF_STAGES = 2;                           // {A_hi, A_lo, B_hi, B_lo} bf16 quads of 64 k
-constexpr int BF_QUAD_BYTES = 4 * TILE_BYTES;
-constexpr int BF_SMEM_BYTES = BF_RAW_STAGES * PAIR_BYTES + BF_STAGES * BF_QUAD_BYTES + 1024 /*align*/ + 256 /*barriers*/;
-
-__device__ __forceinline__ uint32_t pack_bf16x2(float lo_elem, float hi_elem) {   // lo_elem at the lower address
-    uint32_t r;
-    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi_elem), "f"(lo_elem));
-    return r;
-}
-
-// MAIN_TF32 = false: pure bf16x3 (1.5 passes; ~9e-6 at network level, enough for the 1e-4 gradient bar).
-// MAIN_TF32 = true : the A_hi B_hi term runs as kind::tf32 on the raw fp32 tiles (the hardware truncates them), only the
-//                    two correction terms use bf16 tiles of (trunc_tf32(x), x - trunc_tf32(x)): 2 passes, ~2.5e-6 at
-//                    network level (tools/experiments/network_precision_study.py) -- the variant for the forward products.
-//                    The raw stage is then released by the splitter warps AND the MMA commit.
-template <bool MAIN_TF32>
-__global__ void __launch_bounds__(TC_THREADS, 1)
-gemm_tc_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcArgs g) {
-    extern __shared__ unsigned char smem_raw[];
-    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    unsigned char* smem_bf = smem + BF_RAW_STAGES * PAIR_BYTES;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_bf + BF_STAGES * BF_QUAD_BYTES);
-    uint64_t* full = bars;                          // [RAW] TMA -> splitter
-    uint64_t* empty = full + BF_RAW_STAGES;         // [RAW] splitter -> TMA
-    uint64_t* ready = empty + BF_RAW_STAGES;        // [BF]  splitter -> MMA (both halves)
-    uint64_t* bf_empty = ready + BF_STAGES;         // [BF]  MMA -> splitter
-    uint64_t* tmem_full = bf_empty + BF_STAGES;     // [2]   MMA -> epilogue
-    uint64_t* tmem_empty = tmem_full + 2;           // [2]   epilogue -> MMA
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
-
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int num_kb_total = (g.K + BK - 1) / BK;
-    const int tiles_n = (g.N + g.BN - 1) / g.BN, tiles_m = (g.M + BM - 1) / BM;
-    const int tiles_mn = tiles_n * tiles_m;
-    const int total_work = tiles_mn * g.splits;
-
-    if (threadIdx.x == 0) {
-        for (int s = 0; s < BF_RAW_STAGES; ++s) {
-            mbar_init(&full[s], 1);
-            mbar_init(&empty[s], SPLIT_WARPS + (MAIN_TF32 ? 1 : 0));
-        }
-        for (int s = 0; s < BF_STAGES; ++s) {
-            mbar_init(&ready[s], 2 * SPLIT_WARPS);
-            mbar_init(&bf_empty[s], 1);
-        }
-        for (int a = 0; a < 2; ++a) {
-            mbar_init(&tmem_full[a], 1);
-            mbar_init(&tmem_empty[a], 4);
-        }
-        fence_barrier_init();
-    }
-    if (warp == 5) tmem_alloc(tmem_slot, 256);
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
-
-    if (warp == 4) {
-        // ===== TMA producer (K-major boxes only) =====
-        if (lane == 0) {
-            asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
-            asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
-            const uint32_t tx = TILE_BYTES + (uint32_t)g.BN * BK * 4;
-            int it = 0;
-            for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
-                const Work wk = decode_work(g, w, tiles_n, tiles_mn, num_kb_total);
-                for (int kb = 0; kb < wk.num_kb; ++kb, ++it) {
-                    const int s = it % BF_RAW_STAGES, k0 = (wk.kb_begin + kb) * BK;
-                    mbar_wait(&empty[s], ((it / BF_RAW_STAGES) & 1) ^ 1);
-                    unsigned char* st = smem + s * PAIR_BYTES;
-                    mbar_expect_tx(&full[s], tx);
-                    tma_load_2d(st, &tmA, &full[s], k0, wk.m0);
-                    tma_load_2d(st + TILE_BYTES, &tmB, &full[s], k0, wk.n0);
-                }
-            }
-        }
-    } else if (warp == 5) {
-        // ===== MMA issuer: one bf16 stage = 64 k = up to 4 K-steps of 16 =====
-        if (lane == 0) {
-            const uint32_t idesc = make_idesc_bf16(g.BN);
-            const uint32_t idesc_tf32 = make_idesc(g.BN, false, false);
-            int it = 0, jt = 0, item = 0;
-            for (int w = blockIdx.x; w < total_work; w += gridDim.x, ++item) {
-                const Work wk = decode_work(g, w, tiles_n, tiles_mn, num_kb_total);
-                const int acc_stage = item & 1;
-                mbar_wait(&tmem_empty[acc_stage], ((item >> 1) & 1) ^ 1);
-                tc_fence_after();
-                const uint32_t tmem_d = tmem_base + (uint32_t)(acc_stage * 128);
-                for (int kb = 0; kb < wk.num_kb; ++kb, ++it) {
-                    if (MAIN_TF32) {                                            // hi x hi on the raw fp32 pair of this 32-k block
-                        const int s = it % BF_RAW_STAGES;
-                        mbar_wait(&full[s], (it / BF_RAW_STAGES) & 1);
-                        tc_fence_after();
-                        const uint32_t raw = smem_u32(smem + s * PAIR_BYTES);
-#pragma unroll
-                        for (int kk = 0; kk < BK / 8; ++kk)
-                            umma_tf32(tmem_d, make_desc(raw + kk * 32, false), make_desc(raw + TILE_BYTES + kk * 32, false), idesc_tf32,
-                                      (kb > 0 || kk > 0) ? 1u : 0u);
-                        umma_commit(&empty[s]);
-                    }
-                    if ((kb & 1) == 0 && kb != wk.num_kb - 1) continue;         // the quad of this pair is not complete yet
-                    const int b = jt % BF_STAGES, j = kb >> 1;
-                    mbar_wait(&ready[b], (jt / BF_STAGES) & 1);
-                    tc_fence_after();
-                    const uint32_t base = smem_u32(smem_bf + b * BF_QUAD_BYTES);
-                    const int ksteps = 2 * min(2, wk.num_kb - 2 * j);               // a trailing half stage holds 32 k only
-                    for (int kk = 0; kk < ksteps; ++kk) {
-                        const uint64_t a_hi = make_desc(base + kk * 32, false);
-                        const uint64_t a_lo = make_desc(base + TILE_BYTES + kk * 32, false);
-                        const uint64_t b_hi = make_desc(base + 2 * TILE_BYTES + kk * 32, false);
-                        const uint64_t b_lo = make_desc(base + 3 * TILE_BYTES + kk * 32, false);
-                        const uint32_t acc = (MAIN_TF32 || j > 0 || kk > 0) ? 1u : 0u;
-                        umma_bf16(tmem_d, a_lo, b_hi, idesc, acc);                 // small terms first
-                        umma_bf16(tmem_d, a_hi, b_lo, idesc, 1u);
-                        if (!MAIN_TF32) umma_bf16(tmem_d, a_hi, b_hi, idesc, 1u);
-                    }
-                    umma_commit(&bf_empty[b]);
-                    ++jt;
-                }
-                umma_commit(&tmem_full[acc_stage]);
-            }
-        }
-    } else if (warp >= 6) {
-        // ===== splitter: raw fp32 (32 k, 128-byte rows) -> bf16 hi / lo halves (64 bytes of the 64-k rows) =====
-        const int t = threadIdx.x - 6 * 32;
-        constexpr int NT = 32 * SPLIT_WARPS;
-        const int nB4 = g.BN * BK / 4;
-        int it = 0, jt = 0;
-        for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
-            const Work wk = decode_work(g, w, tiles_n, tiles_mn, num_kb_total);
-            for (int kb = 0; kb < wk.num_kb; ++kb, ++it) {
-                const int s = it % BF_RAW_STAGES, b = jt % BF_STAGES, h = kb & 1;
-                if (h == 0) mbar_wait(&bf_empty[b], ((jt / BF_STAGES) & 1) ^ 1);    // MMA is done with this quad
-                mbar_wait(&full[s], (it / BF_RAW_STAGES) & 1);
-                const float4* a = reinterpret_cast<const float4*>(smem + s * PAIR_BYTES);
-                const float4* bsrc = a + TILE_BYTES / 16;
-                unsigned char* quad = smem_bf + b * BF_QUAD_BYTES;
-                auto convert = [&](const float4* raw, unsigned char* hi_tile, unsigned char* lo_tile, int i) {
-                    // i = physical 16-byte chunk of the raw tile: row = i / 8, logical chunk c = (i % 8) ^ (row % 8)
-                    const int row = i >> 3, c = (i & 7) ^ (row & 7);
-                    const float4 x = raw[i];
-                    uint32_t h01, h23, l01, l23;
-                    if (MAIN_TF32) {
-                        // correction operands of the 3xTF32 decomposition, each rounded to bf16
-                        const float t0 = __uint_as_float(__float_as_uint(x.x) & 0xFFFFE000u), t1 = __uint_as_float(__float_as_uint(x.y) & 0xFFFFE000u);
-                        const float t2 = __uint_as_float(__float_as_uint(x.z) & 0xFFFFE000u), t3 = __uint_as_float(__float_as_uint(x.w) & 0xFFFFE000u);
-                        h01 = pack_bf16x2(t0, t1); h23 = pack_bf16x2(t2, t3);
-                        l01 = pack_bf16x2(rna_tf32(x.x - t0), rna_tf32(x.y - t1));
-                        l23 = pack_bf16x2(rna_tf32(x.z - t2), rna_tf32(x.w - t3));
-                    } else {
-                        h01 = pack_bf16x2(x.x, x.y); h23 = pack_bf16x2(x.z, x.w);
-                        const float r0 = x.x - __uint_as_float(h01 << 16), r1 = x.y - __uint_as_float(h01 & 0xFFFF0000u);
-                        const float r2 = x.z - __uint_as_float(h23 << 16), r3 = x.w - __uint_as_float(h23 & 0xFFFF0000u);
-                        l01 = pack_bf16x2(r0, r1); l23 = pack_bf16x2(r2, r3);
-                    }
-                    // destination: k-elements 32 h + 4 c .. + 3 of the 64-k row -> byte 64 h + 8 c, 16-byte chunks swizzled alike
-                    const int off = row * 128 + ((((h << 2) | (c >> 1)) ^ (row & 7)) << 4) + ((c & 1) << 3);
-                    *reinterpret_cast<uint2*>(hi_tile + off) = make_uint2(h01, h23);
-                    *reinterpret_cast<uint2*>(lo_tile + off) = make_uint2(l01, l23);
-                };
-#pragma unroll 4
-                for (int i = t; i < TILE_BYTES / 16; i += NT) convert(a, quad, quad + TILE_BYTES, i);
-#pragma unroll 4
-                for (int i = t; i < nB4; i += NT) convert(bsrc, quad + 2 * TILE_BYTES, quad + 3 * TILE_BYTES, i);
-                fence_proxy_async();                                            // generic-proxy writes -> tensor-core reads
-                __syncwarp();
-                const bool last = (kb == wk.num_kb - 1);
-                if (lane == 0) {
-                    mbar_arrive(&empty[s]);                                     // raw pair back to the TMA producer
-                    mbar_arrive(&ready[b]);
-                    if (last && h == 0) mbar_arrive(&ready[b]);                 // no second half in this quad
-                }
-                if (h == 1 || last) ++jt;
-            }
-        }
-    } else {
-        // ===== epilogue (identical to gemm_tc_kernel) =====
-        int item = 0;
-        for (int w = blockIdx.x; w < total_work; w += gridDim.x, ++item) {
-            const Work wk = decode_work(g, w, tiles_n, tiles_mn, num_kb_total);
-            const int acc_stage = item & 1;
-            mbar_wait(&tmem_full[acc_stage], (item >> 1) & 1);
-            tc_fence_after();
-            const int row = wk.m0 + warp * 32 + lane;
-            const bool row_ok = row < g.M;
-            for (int c0 = 0; c0 < g.BN; c0 += 32) {
-                float v[32];
-                tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(acc_stage * 128 + c0), v);
-                const int col0 = wk.n0 + c0;
-                if (col0 >= g.N) continue;
-                float* dst = g.C + (int64_t)row * g.ldc + col0;
-                const int nvalid = min(32, g.N - col0);
-                const bool vec_ok = (nvalid == 32);
-                if (g.epi == EPI_BIAS || g.epi == EPI_BIAS_ELU) {
-                    const float bl = (lane < nvalid) ? __ldg(g.bias + col0 + lane) : 0.0f;
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        float x = v[j] + __shfl_sync(0xffffffffu, bl, j);
-                        v[j] = (g.epi == EPI_BIAS_ELU) ? (x > 0.0f ? x : __expf(x) - 1.0f) : x;
-                    }
-                } else if (g.epi == EPI_MUL_DELU) {
-                    const float* hp = g.H + (int64_t)row * g.ldh + col0;
-                    if (row_ok) {
-#pragma unroll
-                        for (int j = 0; j < 32; ++j)
-                            if (j < nvalid) {
-                                float hv = __ldg(hp + j);
-                                v[j] *= (hv > 0.0f) ? 1.0f : (hv + 1.0f);
-                            }
-                    }
-                }
-                if (!row_ok) continue;
-                if (g.epi == EPI_ATOMIC) {
-#pragma unroll
-                    for (int j = 0; j < 32; ++j)
-                        if (j < nvalid) atomicAdd(dst + j, v[j]);
-                } else if (vec_ok && ((reinterpret_cast<uintptr_t>(dst) & 15u) == 0)) {
-#pragma unroll
-                    for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-                } else {
-#pragma unroll
-                    for (int j = 0; j < 32; ++j)
-                        if (j < nvalid) dst[j] = v[j];
-                }
-            }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&tmem_empty[acc_stage]);
-        }
-    }
-    tc_fence_before();
-    __syncthreads();
-    if (warp == 5) {
-        tc_fence_after();
-        tmem_dealloc(tmem_base, 256);
-    }
-}
-
-// ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -699,9 +353,7 @@ int32_t make_map(CUtensorMap* map, const float* base, uint64_t inner, uint64_t o
 extern "C" int32_t hg_gemm_tf32(const HgGemm* d, void* stream) {
     HG_REQUIRE(d); HG_REQUIRE(d->A); HG_REQUIRE(d->B); HG_REQUIRE(d->C);
     if (d->M <= 0 || d->N <= 0 || d->K <= 0) return hg_fail(HG_E_SIZE, "hg_gemm_tf32: bad extents");
-    if (d->passes < 1 || d->passes > 4) return hg_fail(HG_E_ARG, "hg_gemm_tf32: passes must be 1, 2 (bf16x3), 3 or 4 (TF32 + bf16 corrections)");
-    if ((d->passes == 2 || d->passes == 4) && (d->a_mn_major || d->b_mn_major))
-        return hg_fail(HG_E_ARG, "hg_gemm_tf32: passes = 2 / 4 (bf16 split tiles) handle K-major operands only");
+    if (d->passes != 1 && d->passes != 3) return hg_fail(HG_E_ARG, "hg_gemm_tf32: passes must be 1 (plain TF32) or 3 (3xTF32)");
     if ((d->lda & 3) || (d->ldb & 3) || !hg_aligned16(d->A) || !hg_aligned16(d->B))
         return hg_fail(HG_E_ALIGN, "hg_gemm_tf32: operands need 16-byte aligned base and row pitch (TMA)");
     if ((d->epilogue == EPI_BIAS || d->epilogue == EPI_BIAS_ELU) && !d->bias) return hg_fail(HG_E_NULL, "hg_gemm_tf32: bias is NULL");
@@ -745,19 +397,7 @@ extern "C" int32_t hg_gemm_tf32(const HgGemm* d, void* stream) {
     g.splits = splits;
     const int total_work = ((d->N + g.BN - 1) / g.BN) * ((d->M + BM - 1) / BM) * splits;
     const int grid = total_work < HG_NUM_SMS ? total_work : HG_NUM_SMS;       // persistent: one CTA per SM
-    if (d->passes == 2 || d->passes == 4) {
-        static bool bf_attr_set = false;
-        if (!bf_attr_set) {
-            cudaError_t e = cudaFuncSetAttribute(gemm_tc_bf16_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, BF_SMEM_BYTES);
-            if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_tc_bf16_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, BF_SMEM_BYTES);
-            if (e != cudaSuccess) return hg_fail((int32_t)e, cudaGetErrorString(e));
-            bf_attr_set = true;
-        }
-        if (d->passes == 4) gemm_tc_bf16_kernel<true><<<grid, TC_THREADS, BF_SMEM_BYTES, st>>>(tmA, tmB, g);
-        else gemm_tc_bf16_kernel<false><<<grid, TC_THREADS, BF_SMEM_BYTES, st>>>(tmA, tmB, g);
-    } else {
-        gemm_tc_kernel<<<grid, TC_THREADS, SMEM_BYTES, st>>>(tmA, tmB, g);
-    }
+    gemm_tc_kernel<<<grid, TC_THREADS, SMEM_BYTES, st>>>(tmA, tmB, g);
     HG_LAUNCHED(1);
     return hg_cuda_status("hg_gemm_tf32");
 }

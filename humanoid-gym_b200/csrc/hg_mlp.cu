@@ -278,10 +278,10 @@ int g_gemm_mode = -1;   // -1: read HG_GEMM on first use
 int gemm_mode() {
     if (g_gemm_mode < 0) {
         const char* e = getenv("HG_GEMM");
-        g_gemm_mode = 1;
+        g_gemm_mode = 4;                                                         // bf16x3 update + 3xTF32 rollout (hg_b200.h)
         if (e && (!strcmp(e, "simt") || !strcmp(e, "0"))) g_gemm_mode = 0;
+        if (e && (!strcmp(e, "3xtf32") || !strcmp(e, "1"))) g_gemm_mode = 1;
         if (e && (!strcmp(e, "tf32") || !strcmp(e, "2"))) g_gemm_mode = 2;
-        if (e && (!strcmp(e, "bf16x3") || !strcmp(e, "3"))) g_gemm_mode = 3;     // experimental, see hg_gemm_tc.cu
     }
     return g_gemm_mode;
 }
@@ -299,7 +299,6 @@ int32_t try_tc(const float* A, int64_t lda, bool a_mn, const float* B, int64_t l
     d.lda = lda; d.ldb = ldb; d.ldc = ldc; d.ldh = ldh;
     d.a_mn_major = a_mn; d.b_mn_major = b_mn;
     d.epilogue = epi; d.passes = (mode == 2) ? 1 : 3; d.split_k = split_k;
-    if (mode == 3 && !a_mn && !b_mn) d.passes = 4;      // TF32 + bf16 corrections on the K-major (forward) products, 3xTF32 on the others
     d.trust_hw_truncation = 1;      // verified on B200: kind::tf32 ignores the low 13 mantissa bits (tests/test_gemm_tc_gpu.py)
     return hg_gemm_tf32(&d, (void*)st);
 }
@@ -318,7 +317,7 @@ int32_t check_net(const HgMlpDesc* net) {
 
 extern "C" int32_t hg_set_gemm_mode(int32_t mode) {
     int prev = gemm_mode();
-    if (mode >= 0 && mode <= 3) g_gemm_mode = mode;      // any other value: query only
+    if (mode == 0 || mode == 1 || mode == 2 || mode == 4) g_gemm_mode = mode;      // any other value: query only
     return prev;
 }
 

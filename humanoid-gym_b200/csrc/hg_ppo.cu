@@ -160,19 +160,39 @@ __global__ void adv_normalise_kernel(HgStorage S, const double* __restrict__ sta
 // ---------------------------------------------------------------------------------------------
 // minibatch gather: one warp per row
 // ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t gather_pack_bf16x2(float x0, float x1) {      // x0 at the lower address
+    uint32_t r;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(x1), "f"(x0));
+    return r;
+}
+// one row of `width` floats -> dense fp32 copy (dst may be NULL) and/or split bf16 planes (sp.p may be NULL);
+// a lane owns element pairs (2 lane + 64 i, +1): 128-byte warp stores into each plane
+__device__ __forceinline__ void gather_row(const float* __restrict__ src, int width, float* dst, const HgSplit& sp, size_t row, int lane) {
+    uint16_t* sh = sp.p ? sp.p + row * sp.ld : nullptr;
+    for (int k = 2 * lane; k < width; k += 64) {
+        const float x0 = __ldg(src + k), x1 = (k + 1 < width) ? __ldg(src + k + 1) : 0.0f;
+        if (dst) {
+            dst[k] = x0;
+            if (k + 1 < width) dst[k + 1] = x1;
+        }
+        if (sh) {
+            const uint32_t h = gather_pack_bf16x2(x0, x1);
+            const uint32_t l = gather_pack_bf16x2(x0 - __uint_as_float(h << 16), x1 - __uint_as_float(h & 0xFFFF0000u));
+            *reinterpret_cast<uint32_t*>(sh + k) = h;                     // ld is even (multiple of 8): pair stays inside the row pitch
+            *reinterpret_cast<uint32_t*>(sh + sp.plane + k) = l;
+        }
+    }
+}
 __global__ void gather_kernel(HgStorage S, const int64_t* __restrict__ idx, HgMiniBatch mb, int B) {
     int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     int lane = threadIdx.x & 31;
     if (row >= B) return;
     size_t src = (size_t)idx[row];
-    const float* o = S.observations + src * S.num_obs;
-    float* od = mb.obs + (size_t)row * (mb.ld_obs ? mb.ld_obs : S.num_obs);
-    for (int k = lane; k < S.num_obs; k += 32) od[k] = __ldg(o + k);
-    if (S.privileged_observations) {
-        const float* p = S.privileged_observations + src * S.num_priv;
-        float* pd = mb.priv_obs + (size_t)row * (mb.ld_priv ? mb.ld_priv : S.num_priv);
-        for (int k = lane; k < S.num_priv; k += 32) pd[k] = __ldg(p + k);
-    }
+    gather_row(S.observations + src * S.num_obs, S.num_obs,
+               mb.obs ? mb.obs + (size_t)row * (mb.ld_obs ? mb.ld_obs : S.num_obs) : nullptr, mb.obs_split, (size_t)row, lane);
+    if (S.privileged_observations)
+        gather_row(S.privileged_observations + src * S.num_priv, S.num_priv,
+                   mb.priv_obs ? mb.priv_obs + (size_t)row * (mb.ld_priv ? mb.ld_priv : S.num_priv) : nullptr, mb.priv_split, (size_t)row, lane);
     int A = S.num_actions;
     for (int k = lane; k < A; k += 32) {
         mb.actions[(size_t)row * A + k] = S.actions[src * A + k];
@@ -386,9 +406,13 @@ extern "C" int32_t hg_gae(const HgStorage* S, const float* last_values, float ga
 
 extern "C" int32_t hg_minibatch_gather(const HgStorage* S, const int64_t* idx, const HgMiniBatch* mb, int64_t B, void* stream) {
     HG_REQUIRE(S); HG_REQUIRE(idx); HG_REQUIRE(mb);
-    HG_REQUIRE(mb->obs); HG_REQUIRE(mb->actions); HG_REQUIRE(mb->values); HG_REQUIRE(mb->advantages); HG_REQUIRE(mb->returns);
+    HG_REQUIRE(mb->actions); HG_REQUIRE(mb->values); HG_REQUIRE(mb->advantages); HG_REQUIRE(mb->returns);
     HG_REQUIRE(mb->old_log_prob); HG_REQUIRE(mb->old_mu); HG_REQUIRE(mb->old_sigma);
-    if (S->privileged_observations) HG_REQUIRE(mb->priv_obs);
+    if (!mb->obs && !mb->obs_split.p) return hg_fail(HG_E_NULL, "hg_minibatch_gather: neither obs nor obs_split given");
+    if (S->privileged_observations && !mb->priv_obs && !mb->priv_split.p) return hg_fail(HG_E_NULL, "hg_minibatch_gather: neither priv_obs nor priv_split given");
+    if ((mb->obs_split.p && ((mb->obs_split.ld & 7) || mb->obs_split.ld < S->num_obs + (S->num_obs & 1))) ||
+        (mb->priv_split.p && ((mb->priv_split.ld & 7) || mb->priv_split.ld < S->num_priv + (S->num_priv & 1))))
+        return hg_fail(HG_E_ALIGN, "hg_minibatch_gather: split row pitch must be a multiple of 8 and cover the row");
     if (B <= 0) return hg_fail(HG_E_SIZE, "hg_minibatch_gather: bad B");
     gather_kernel<<<(unsigned)((B + 7) / 8), 256, 0, (cudaStream_t)stream>>>(*S, idx, *mb, (int)B);
     HG_LAUNCHED(1);

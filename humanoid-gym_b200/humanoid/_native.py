@@ -87,9 +87,21 @@ class Storage(C.Structure):
                [("T", i32), ("num_obs", i32), ("num_priv", i32), ("num_actions", i32)]
 
 
+class Split(C.Structure):
+    """x ~= hi + lo as two bf16 planes: element (r, c) of plane k at p[k * plane + r * ld + c] (include/hg_b200.h)."""
+    _fields_ = [("p", PF), ("ld", i64), ("plane", i64)]
+
+    @classmethod
+    def of(cls, t):
+        """t: (2, rows, ld) int16/uint16/bfloat16 CUDA tensor, planes contiguous."""
+        assert t.is_cuda and t.dim() == 3 and t.shape[0] == 2 and t.element_size() == 2 and t.stride(2) == 1
+        return cls(t.data_ptr(), t.stride(1), t.stride(0))
+
+
 class MiniBatch(C.Structure):
     _fields_ = [(n, PF) for n in ("obs", "priv_obs", "actions", "values", "advantages", "returns",
-                                  "old_log_prob", "old_mu", "old_sigma")] + [("ld_obs", i64), ("ld_priv", i64)]
+                                  "old_log_prob", "old_mu", "old_sigma")] + [("ld_obs", i64), ("ld_priv", i64),
+                                                                             ("obs_split", Split), ("priv_split", Split)]
 
 
 class PpoLossArgs(C.Structure):
@@ -106,7 +118,13 @@ class Gemm(C.Structure):
                 ("epilogue", i32), ("passes", i32), ("split_k", i32), ("trust_hw_truncation", i32)]
 
 
-_STRUCTS = (EnvParams, EnvBuffers, EnvNoise, MlpDesc, Transition, Storage, MiniBatch, PpoLossArgs, Gemm)
+class GemmSplit(C.Structure):
+    _fields_ = [("A", Split), ("B", Split), ("C", PF), ("ldc", i64), ("Cs", Split), ("bias", PF), ("Hs", Split),
+                ("colsum", PF), ("M", i32), ("N", i32), ("K", i32), ("a_mn_major", i32), ("b_mn_major", i32),
+                ("epilogue", i32), ("split_k", i32)]
+
+
+_STRUCTS = (EnvParams, EnvBuffers, EnvNoise, MlpDesc, Transition, Storage, MiniBatch, PpoLossArgs, Gemm, Split, GemmSplit)
 
 
 class NativeError(RuntimeError):
@@ -132,6 +150,11 @@ def _load():
         "hg_mlp_backward": (i32, [P(MlpDesc), PF, PF, i64, PF, PF, PF, PF, i64, PF]),
         "hg_gemm_tf32": (i32, [P(Gemm), PF]),
         "hg_set_gemm_mode": (i32, [i32]),
+        "hg_split_bf16": (i32, [PF, i64, P(Split), i64, i64, PF]),
+        "hg_unsplit_bf16": (i32, [P(Split), PF, i64, i64, i64, PF]),
+        "hg_gemm_bf16x3": (i32, [P(GemmSplit), PF]),
+        "hg_mlp_forward_split": (i32, [P(MlpDesc), PF, PF, i64, P(Split), PF, PF, i64, PF]),
+        "hg_mlp_backward_split": (i32, [P(MlpDesc), PF, PF, i64, P(Split), PF, PF, PF, PF, i64, PF]),
         "hg_policy_sample": (i32, [PF, PF, PF, u64, u64, PF, PF, PF, PF, i64, i32, PF]),
         "hg_storage_add": (i32, [P(Storage), P(Transition), i32, f32, i64, PF]),
         "hg_gae": (i32, [P(Storage), PF, f32, f32, PF, i32, i64, PF]),

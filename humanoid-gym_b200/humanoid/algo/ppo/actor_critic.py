@@ -48,9 +48,10 @@ class ActorCritic(nn.Module):
     def _flatten(self):
         """(Re)alias every parameter into one contiguous buffer on its current device.
 
-        Weight rows are laid out with a pitch rounded up to 4 floats and every block starts on a 16-byte
-        boundary, so that TMA can address each matrix directly (tensor-core path); the parameters themselves
-        are (out, in) views of that storage, the pad floats stay zero for ever (zero gradient)."""
+        Weight rows are laid out with a pitch rounded up to 8 elements and every block starts on a multiple of 8
+        elements, so that TMA can address each matrix directly both in the fp32 buffer (3xTF32 path) and in its
+        split bf16 image `_wsplit` (same element offsets; bf16x3 update path); the parameters themselves are
+        (out, in) views of that storage, the pad floats stay zero for ever (zero gradient)."""
         params = list(self.parameters())
         dev = params[0].device
         if dev.type != "cuda":
@@ -60,12 +61,12 @@ class ActorCritic(nn.Module):
         for name, p in self.named_parameters():
             if p.dim() == 2:
                 rows, cols = p.shape
-                ld = (cols + 3) // 4 * 4
+                ld = (cols + 7) // 8 * 8
                 self._layout[name] = (off, (rows, cols), ld)
                 off += rows * ld
             else:
                 self._layout[name] = (off, tuple(p.shape), None)
-                off += (p.numel() + 3) // 4 * 4
+                off += (p.numel() + 7) // 8 * 8
         n = off
         flat = torch.zeros(n, dtype=torch.float32, device=dev)
         for name, p in self.named_parameters():
@@ -74,6 +75,8 @@ class ActorCritic(nn.Module):
             p.data = v
         self._offsets = {k: v[0] for k, v in self._layout.items()}
         self._flat = flat
+        self._wsplit = torch.zeros(2, 1, n, dtype=torch.int16, device=dev)     # split bf16 image of the flat buffer (hi, lo planes)
+        self._wsplit_dirty = True
         self.num_params = n                       # allocated floats (incl. pads) == length of every flat buffer
         self.num_real_params = sum(p.numel() for p in params)
         self._desc = {}
@@ -104,6 +107,42 @@ class ActorCritic(nn.Module):
         if self._flat is None or first.data_ptr() != self._flat.data_ptr() or self._flat.device != first.device:
             self._flatten()
         return self._flat
+
+    # ---- split-precision (bf16x3) update path -----------------------------------------------------
+    def split_eligible(self):
+        """hg_mlp_*_split needs >= 2 layers, hidden widths % 8 == 0 and an output layer <= 16 wide."""
+        self.flat_params()
+        ok = True
+        for dims in (self._actor_dims, self._critic_dims):
+            ok = ok and len(dims) >= 3 and dims[-1] <= 16 and all(w % 8 == 0 for w in dims[1:-1])
+        return ok
+
+    def refresh_split(self):
+        """Re-split the whole flat parameter buffer into its bf16 hi / lo image (one launch, 3.7 MB): after every
+        optimizer step, a checkpoint load or any direct write to the parameters."""
+        flat = self.flat_params()
+        sp = nat.Split.of(self._wsplit)
+        nat.check(nat.lib.hg_split_bf16(flat.data_ptr(), flat.numel(), sp, 1, flat.numel(), nat.stream_ptr(flat.device.index)),
+                  "hg_split_bf16(params)")
+        self._wsplit_dirty = False
+
+    def native_forward_split(self, which, x_split, out, hidden):
+        """out (M, dims[-1]) fp32 <- MLP_which(x) on split tensors; x_split: nat.Split of the (M, K) input;
+        hidden: int16 scratch of 2 * M * hidden_width(which) elements (every hidden activation, split)."""
+        flat = self.flat_params()
+        if self._wsplit_dirty:
+            self.refresh_split()
+        M = out.shape[0]
+        nat.check(nat.lib.hg_mlp_forward_split(self._desc[which], flat.data_ptr(), self._wsplit.data_ptr(), self._wsplit.stride(0),
+                                               x_split, hidden.data_ptr(), out.data_ptr(), M, nat.stream_ptr(flat.device.index)),
+                  "hg_mlp_forward_split")
+
+    def native_backward_split(self, which, x_split, hidden, d_out, dhidden, grads):
+        flat = self.flat_params()
+        M = d_out.shape[0]
+        nat.check(nat.lib.hg_mlp_backward_split(self._desc[which], flat.data_ptr(), self._wsplit.data_ptr(), self._wsplit.stride(0),
+                                                x_split, hidden.data_ptr(), d_out.data_ptr(), dhidden.data_ptr(), grads.data_ptr(),
+                                                M, nat.stream_ptr(flat.device.index)), "hg_mlp_backward_split")
 
     def hidden_width(self, which):
         dims = self._actor_dims if which == "actor" else self._critic_dims

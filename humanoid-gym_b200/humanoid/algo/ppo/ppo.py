@@ -191,20 +191,51 @@ class PPO:
                 hid_c=torch.empty(B * ac.hidden_width("critic"), **z), dhid_c=torch.empty(B * ac.hidden_width("critic"), **z))}
         return self._mb_scratch[B]
 
+    def use_split_path(self):
+        """PPO.update runs on the split-precision (bf16x3) tensor-core path when the GEMM engine is 4 (default) and the
+        architecture is eligible; the fp32-operand engines (0 exact CUDA-core, 1 3xTF32, 2 TF32) stay selectable."""
+        return nat.lib.hg_set_gemm_mode(-1) == 4 and self.actor_critic.split_eligible()
+
+    def _scratch_split(self, B):
+        key = ("split", B)
+        if key not in self._mb_scratch:
+            ac, z = self.actor_critic, dict(dtype=torch.float32, device=self.device)
+            A = ac.num_actions
+            h = dict(dtype=torch.int16, device=self.device)
+            self._mb_scratch = {key: dict(
+                mean=torch.empty(B, A, **z), value=torch.empty(B, 1, **z), d_mean=torch.empty(B, A, **z),
+                d_value=torch.empty(B, 1, **z),
+                hid_a=torch.empty(2 * B * ac.hidden_width("actor"), **h), dhid_a=torch.empty(2 * B * ac.hidden_width("actor"), **h),
+                hid_c=torch.empty(2 * B * ac.hidden_width("critic"), **h), dhid_c=torch.empty(2 * B * ac.hidden_width("critic"), **h))}
+        return self._mb_scratch[key]
+
     def minibatch_step(self, mb, world=1):
         """Loss forward/backward + gradient (all-reduce) + lr rule + clip + Adam for one minibatch."""
         ac = self.actor_critic
         flat = ac.flat_params()
         st = nat.stream_ptr(self._dev_index)
-        obs = mb["obs"]
-        cobs = mb["priv_obs"] if mb["priv_obs"] is not None else obs
-        B = obs.shape[0]
-        w = self._scratch(B)
+        split = mb.get("obs_split") is not None and self.use_split_path()
         cur = torch.cuda.current_stream(self._dev_index)
-        self._side.wait_stream(cur)
-        with torch.cuda.stream(self._side):               # critic chain overlaps the actor chain
-            ac.native_forward("critic", cobs, w["value"], hidden=w["hid_c"])
-        ac.native_forward("actor", obs, w["mean"], hidden=w["hid_a"])
+        if split:
+            xs_a = nat.Split.of(mb["obs_split"])
+            xs_c = nat.Split.of(mb["priv_split"]) if mb.get("priv_split") is not None else xs_a
+            B = mb["obs_split"].shape[1]
+            w = self._scratch_split(B)
+            if ac._wsplit_dirty:
+                ac.refresh_split()
+            self._side.wait_stream(cur)
+            with torch.cuda.stream(self._side):               # critic chain overlaps the actor chain
+                ac.native_forward_split("critic", xs_c, w["value"], w["hid_c"])
+            ac.native_forward_split("actor", xs_a, w["mean"], w["hid_a"])
+        else:
+            obs = mb["obs"]
+            cobs = mb["priv_obs"] if mb["priv_obs"] is not None else obs
+            B = obs.shape[0]
+            w = self._scratch(B)
+            self._side.wait_stream(cur)
+            with torch.cuda.stream(self._side):               # critic chain overlaps the actor chain
+                ac.native_forward("critic", cobs, w["value"], hidden=w["hid_c"])
+            ac.native_forward("actor", obs, w["mean"], hidden=w["hid_a"])
         cur.wait_stream(self._side)
         a = nat.PpoLossArgs()
         a.mean, a.value, a.std = w["mean"].data_ptr(), w["value"].data_ptr(), ac.std.data_ptr()
@@ -220,12 +251,17 @@ class PPO:
         nat.check(nat.lib.hg_ppo_loss_fwd_bwd(a, B, st), "hg_ppo_loss_fwd_bwd")
         g = self._grad.data_ptr()
         self._side.wait_stream(cur)
-        with torch.cuda.stream(self._side):               # the two backward chains write disjoint gradient ranges
-            nat.check(nat.lib.hg_mlp_backward(ac._desc["critic"], flat.data_ptr(), cobs.data_ptr(), cobs.stride(0), w["hid_c"].data_ptr(),
-                                              w["d_value"].data_ptr(), w["dhid_c"].data_ptr(), g, B,
-                                              nat.stream_ptr(self._dev_index)), "hg_mlp_backward(critic)")
-        nat.check(nat.lib.hg_mlp_backward(ac._desc["actor"], flat.data_ptr(), obs.data_ptr(), obs.stride(0), w["hid_a"].data_ptr(),
-                                          w["d_mean"].data_ptr(), w["dhid_a"].data_ptr(), g, B, st), "hg_mlp_backward(actor)")
+        if split:
+            with torch.cuda.stream(self._side):           # the two backward chains write disjoint gradient ranges
+                ac.native_backward_split("critic", xs_c, w["hid_c"], w["d_value"], w["dhid_c"], self._grad)
+            ac.native_backward_split("actor", xs_a, w["hid_a"], w["d_mean"], w["dhid_a"], self._grad)
+        else:
+            with torch.cuda.stream(self._side):
+                nat.check(nat.lib.hg_mlp_backward(ac._desc["critic"], flat.data_ptr(), cobs.data_ptr(), cobs.stride(0), w["hid_c"].data_ptr(),
+                                                  w["d_value"].data_ptr(), w["dhid_c"].data_ptr(), g, B,
+                                                  nat.stream_ptr(self._dev_index)), "hg_mlp_backward(critic)")
+            nat.check(nat.lib.hg_mlp_backward(ac._desc["actor"], flat.data_ptr(), obs.data_ptr(), obs.stride(0), w["hid_a"].data_ptr(),
+                                              w["d_mean"].data_ptr(), w["dhid_a"].data_ptr(), g, B, st), "hg_mlp_backward(actor)")
         cur.wait_stream(self._side)
         if world > 1:
             dist.all_reduce(self._grad)                         # the ONE collective of the update path
@@ -236,6 +272,9 @@ class PPO:
         nat.check(nat.lib.hg_clip_adam_step(flat.data_ptr(), g, self._exp_avg.data_ptr(), self._exp_avg_sq.data_ptr(),
                                             self._sqnorm.data_ptr(), float(self.max_grad_norm), self._lr.data_ptr(),
                                             self._adam_step.data_ptr(), 0.9, 0.999, 1e-8, 1.0, n, st), "hg_clip_adam_step")
+        ac._wsplit_dirty = True
+        if split:
+            ac.refresh_split()                             # the next minibatch's GEMMs read the split image of the new weights
         self._loss_sums.add_(self._scalars)
 
     def update(self):
@@ -246,9 +285,12 @@ class PPO:
         mini = batch_size // self.num_mini_batches
         indices = torch.randperm(self.num_mini_batches * mini, requires_grad=False, device=self.device)
         self._loss_sums.zero_()
+        split = self.use_split_path()
+        if split:
+            self.actor_critic.refresh_split()              # parameters may have been written from outside (load, tests)
         for _ in range(self.num_learning_epochs):
             for i in range(self.num_mini_batches):
-                mb = s.gather(indices[i * mini:(i + 1) * mini])
+                mb = s.gather(indices[i * mini:(i + 1) * mini], split=split)
                 self.minibatch_step(mb, world)
         num_updates = self.num_learning_epochs * self.num_mini_batches
         sums = self._loss_sums.tolist()                          # the only device->host read of the update

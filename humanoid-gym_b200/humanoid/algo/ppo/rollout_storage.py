@@ -139,13 +139,35 @@ class RolloutStorage:
             m.ld_obs = self._mb["obs"].stride(0)
             m.ld_priv = self._mb["priv_obs"].stride(0) if self._mb["priv_obs"] is not None else 0
             self._mbs = m
+            self._mbs_split = None
         return self._mb
 
-    def gather(self, batch_idx):
-        """Rows `batch_idx` of the flattened (T*N, .) storage -> contiguous minibatch tensors."""
-        B = batch_idx.numel()
+    def _split_buffers(self, B):
+        """Split (bf16 hi / lo planes, row pitch % 8) images of the minibatch observations for the bf16x3 update path;
+        the fp32 copies are then not written at all (same bytes, no extra traffic)."""
         mb = self._minibatch_buffers(B)
-        nat.check(nat.lib.hg_minibatch_gather(self._native(), batch_idx.data_ptr(), self._mbs, B,
+        if self._mbs_split is None:
+            def planes(width):
+                return torch.zeros(2, B, (width + 7) // 8 * 8, dtype=torch.int16, device=self.device)
+            self._split_t = dict(obs_split=planes(self.obs_shape[0]),
+                                 priv_split=planes(self.privileged_obs_shape[0]) if self.privileged_observations is not None else None)
+            m = nat.MiniBatch()
+            for k in ("actions", "values", "advantages", "returns", "old_log_prob", "old_mu", "old_sigma"):
+                setattr(m, k, mb[k].data_ptr())
+            m.obs = None
+            m.priv_obs = None
+            m.obs_split = nat.Split.of(self._split_t["obs_split"])
+            if self._split_t["priv_split"] is not None:
+                m.priv_split = nat.Split.of(self._split_t["priv_split"])
+            self._mbs_split = m
+        return dict(mb, obs=None, priv_obs=None, **self._split_t)
+
+    def gather(self, batch_idx, split=False):
+        """Rows `batch_idx` of the flattened (T*N, .) storage -> contiguous minibatch tensors (split=True: the
+        observations come out as split bf16 planes `obs_split` / `priv_split` instead of fp32)."""
+        B = batch_idx.numel()
+        mb = self._split_buffers(B) if split else self._minibatch_buffers(B)
+        nat.check(nat.lib.hg_minibatch_gather(self._native(), batch_idx.data_ptr(), self._mbs_split if split else self._mbs, B,
                                               nat.stream_ptr(self._dev_index)), "hg_minibatch_gather")
         return mb
 

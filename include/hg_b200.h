@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define HG_VERSION 100
+#define HG_VERSION 200
 #define HG_NUM_DOF 12
 #define HG_NUM_REWARDS 22
 #define HG_OBS1 47          /* single-frame observation width   */
@@ -209,9 +209,7 @@ int32_t hg_mlp_backward(const HgMlpDesc* net, const float* params, const float* 
  * in TMEM, operands by TMA):  C (M x N, pitch ldc) = A x B reduced over K, fp32 in / fp32 out.
  *   a_mn_major = 0: A is (M, K) row-major  (pitch lda);  1: A is (K, M) row-major, i.e. the M index is contiguous
  *   b_mn_major = 0: B is (N, K) row-major  (pitch ldb);  1: B is (K, N) row-major
- *   passes     = 3: 3xTF32 split compensation (fp32-class accuracy);  1: plain TF32;
- *                2: EXPERIMENTAL bf16 hi/lo split, three kind::f16 MMAs (K-major operands only, rel. error ~5e-6)
- *                4: EXPERIMENTAL TF32 main term + two bf16 correction terms (K-major operands only, ~1.5e-6)
+ *   passes     = 3: 3xTF32 split compensation (fp32-class accuracy);  1: plain TF32
  *   epilogue   : 0 store, 1 +bias[N], 2 +bias then ELU, 3 multiply by ELU'(z) recovered from H = ELU(z) (pitch ldh),
  *                4 atomicAdd into C (required when split_k > 1; C must be zeroed by the caller)
  *   trust_hw_truncation: 1 = feed the raw fp32 tile as the "hi" operand (the tensor core drops the low 13
@@ -224,10 +222,55 @@ typedef struct HgGemm {
     int32_t a_mn_major, b_mn_major, epilogue, passes, split_k, trust_hw_truncation;
 } HgGemm;
 int32_t hg_gemm_tf32(const HgGemm* d, void* stream);
-/* GEMM engine of hg_mlp_forward / hg_mlp_backward: 0 = exact-fp32 CUDA-core path, 1 = tcgen05 3xTF32 (default),
- * 2 = tcgen05 plain TF32, 3 = EXPERIMENTAL TF32 + bf16 corrections on the K-major products (forward), 3xTF32 elsewhere.
+/* GEMM engine of hg_mlp_forward / hg_mlp_backward: 0 = exact-fp32 CUDA-core path, 1 = tcgen05 3xTF32,
+ * 2 = tcgen05 plain TF32, 4 (default) = 3xTF32 for this fp32 API (rollout forward, 1e-5 bar) AND a hint to the host
+ * layer to run PPO.update on the split-precision API below (hg_mlp_*_split, 1e-4 gradient bar).
  * Layers whose operands TMA cannot address fall back to 0.  Returns the previous mode. */
 int32_t hg_set_gemm_mode(int32_t mode);
+
+/* ---- split-precision ("bf16x3") learning path -------------------------------------------------------------
+ * A split tensor stores x ~= hi + lo with hi = bf16(x), lo = bf16(x - hi) (16 significant bits) as two bf16
+ * planes: element (r, c) of plane k (0 = hi, 1 = lo) is p[k * plane + r * ld + c].  ld and plane are multiples
+ * of 8 elements and p is 16-byte aligned (TMA).  Every producer on the update path (minibatch gather, GEMM
+ * epilogues, output-head backward, the post-Adam weight split) writes this format directly, so the tensor-core
+ * GEMM needs no conversion pass: D += A_lo B_hi + A_hi B_lo + A_hi B_hi as three tcgen05 kind::f16 MMAs with
+ * fp32 accumulation (relative error ~5e-6 per product; gradients ~1e-5 against the 1e-4 bar). */
+typedef struct HgSplit { uint16_t* p; int64_t ld; int64_t plane; } HgSplit;
+int32_t hg_split_bf16(const float* src, int64_t ld_src, const HgSplit* dst, int64_t rows, int64_t cols, void* stream);
+int32_t hg_unsplit_bf16(const HgSplit* src, float* dst, int64_t ld_dst, int64_t rows, int64_t cols, void* stream);
+
+/* C (M x N) = op(A) op(B) reduced over K on split operands (tcgen05.mma kind::f16, TMEM accumulators, TMA).
+ *   a_mn_major = 0: A is (M, K) row-major;  1: A is (K, M) row-major.   b_mn_major likewise with N.
+ *   epilogue 0: C fp32 store            1: C fp32 = acc + bias[N]
+ *            2: Cs split = ELU(acc + bias)                         (forward of a hidden Linear layer)
+ *            3: Cs split = acc * ELU'(h), h = Hs ~= ELU(z); colsum[N] += column sums of the result (bias gradient; may be NULL)
+ *            4: atomicAdd into C fp32 (required for split_k > 1; caller zeroes C)      (weight gradient)
+ *            5: Cs split = acc */
+typedef struct HgGemmSplit {
+    HgSplit A, B;
+    float* C; int64_t ldc;
+    HgSplit Cs;
+    const float* bias;
+    HgSplit Hs;
+    float* colsum;
+    int32_t M, N, K;
+    int32_t a_mn_major, b_mn_major, epilogue, split_k;
+} HgGemmSplit;
+int32_t hg_gemm_bf16x3(const HgGemmSplit* d, void* stream);
+
+/* The MLP of hg_mlp_forward / hg_mlp_backward on split tensors (PPO.update path).  `wsplit` is the split image of
+ * the flat parameter buffer (same element offsets: w_off / ldw of HgMlpDesc, ldw % 8 == 0 required), `w_plane` its
+ * plane distance.  hidden / dhidden: split scratch, hidden layer l (1 <= l < n_layers) at element offset
+ * 2 * M * sum(dims[1..l-1]) as planes (M, dims[l]), ld = dims[l], plane = M * dims[l]; every hidden width must be a
+ * multiple of 8.  The output layer (<= 16 wide) runs on CUDA cores straight from the last hidden split tensor; in
+ * the backward pass one kernel produces its weight / bias gradients, the previous layer's dZ (split) and that
+ * layer's bias gradient in a single pass over the activations.  Bias gradients of the hidden layers come out of
+ * the dgrad epilogues (no separate column-sum pass).  Returns HG_E_ALIGN when the net is not eligible. */
+int32_t hg_mlp_forward_split(const HgMlpDesc* net, const float* params, const uint16_t* wsplit, int64_t w_plane,
+                             const HgSplit* X, uint16_t* hidden, float* out, int64_t M, void* stream);
+int32_t hg_mlp_backward_split(const HgMlpDesc* net, const float* params, const uint16_t* wsplit, int64_t w_plane,
+                              const HgSplit* X, const uint16_t* hidden, const float* dY, uint16_t* dhidden,
+                              float* grads, int64_t M, void* stream);
 
 /* PPO.act epilogue (ppo.py:91-101, actor_critic.py:111-120): actions =
  * mean + std*eps, log-prob summed over actions, sigma broadcast.
@@ -272,6 +315,8 @@ typedef struct HgMiniBatch {
     float* old_log_prob; float* old_mu; float* old_sigma;
     int64_t ld_obs, ld_priv;            /* row pitch of obs / priv_obs in elements (0 = dense); a multiple of 4
                                            makes the rows TMA-addressable for the tensor-core MLP path        */
+    HgSplit obs_split, priv_split;      /* optional (p may be NULL): the observations are ALSO / INSTEAD (obs == NULL)
+                                           written as split bf16 planes for the bf16x3 update path              */
 } HgMiniBatch;
 int32_t hg_minibatch_gather(const HgStorage* S, const int64_t* idx, const HgMiniBatch* mb, int64_t B, void* stream);
 
@@ -314,7 +359,8 @@ int32_t hg_adapt_lr(const float* kl_mean_dev, double desired_kl, double* lr_dev,
 /* ------------------------------------------------------------------------ */
 int32_t hg_version(void);
 /* sizeof() of the ABI structs, for binding self-checks: 0 HgEnvParams, 1 HgEnvBuffers,
- * 2 HgEnvNoise, 3 HgMlpDesc, 4 HgTransition, 5 HgStorage, 6 HgMiniBatch, 7 HgPpoLossArgs, 8 HgGemm */
+ * 2 HgEnvNoise, 3 HgMlpDesc, 4 HgTransition, 5 HgStorage, 6 HgMiniBatch, 7 HgPpoLossArgs, 8 HgGemm, 9 HgSplit,
+ * 10 HgGemmSplit */
 int64_t hg_struct_size(int32_t which);
 const char* hg_last_error(void);
 /* number of kernel launches issued by this library in the calling process */

@@ -8,7 +8,8 @@ import pytest
 import torch
 
 from golden_io import Golden, oracle_state_from_golden
-from parity_utils import (make_env, random_state, random_noise, load_state, oracle_step, compare_step, env_value)
+from parity_utils import (make_env, random_state, random_noise, load_state, oracle_step, compare_step, env_value,
+                          near_threshold_envs)
 
 pytestmark = pytest.mark.gpu
 RTOL, ATOL = 1e-5, 1e-6
@@ -90,9 +91,11 @@ def test_golden_rollout_step_by_step():
     assert not problems, problems[:3]
 
 
-@pytest.mark.parametrize("N,seed", [(4096, 1), (1000, 2), (7, 3)])
+@pytest.mark.parametrize("N,seed", [(4096, 1), (8192, 4), (1000, 2), (7, 3)])
 def test_random_state_vs_oracle(N, seed):
-    """All phases, with pushes (counter 399 -> 400), time-outs, resampling, resets; ragged N included."""
+    """All phases, with pushes (counter 399 -> 400), time-outs, resampling, resets; ragged N included; 8192 envs is
+    BASELINE.json configs[2] (domain randomisation + observation-history stack on).  Out-of-tolerance elements are
+    accepted ONLY in envs the oracle flags as sitting on a discontinuity (near_threshold_envs): no blanket allowance."""
     g = torch.Generator().manual_seed(seed)
     env = make_env(N, physics="external")
     S, noise = random_state(N, g), random_noise(N, g)
@@ -104,7 +107,9 @@ def test_random_state_vs_oracle(N, seed):
     torch.cuda.synchronize()
     ref = oracle_step(S, noise, actions)
     assert int(ref["reset_buf"].sum()) > 0 or N < 64
-    bad = compare_step(env, ref, RTOL, ATOL, max_outlier_frac=2e-3)
+    near = near_threshold_envs(S, ref, noise)
+    assert int(near.sum()) <= max(2, N // 500), int(near.sum())      # the mask must stay a handful of envs
+    bad = compare_step(env, ref, RTOL, ATOL, near=near)
     assert not bad, bad
     # reset_ids: the compacted list holds exactly the reset envs
     cnt = env.last_reset_count
@@ -135,11 +140,13 @@ def test_stage_entry_points_match_oracle():
     env.inject_noise(z_obs=noise["z_obs"])
     env.compute_observations()
     eo.compute_observations(R, P, noise["z_obs"])
-    bad = compare_step(env, R, RTOL, ATOL, max_outlier_frac=2e-3, keys=("obs_buf", "privileged_obs_buf", "ref_dof_pos"))
+    Rn = dict(R, reset_buf=torch.zeros(N, dtype=torch.bool))
+    near = near_threshold_envs(dict(S, episode_length_buf=R["episode_length_buf"] - 1), Rn)
+    bad = compare_step(env, R, RTOL, ATOL, near=near, keys=("obs_buf", "privileged_obs_buf", "ref_dof_pos"))
     assert not bad, bad
 
 
-@pytest.mark.parametrize("N", [4096, 65536])
+@pytest.mark.parametrize("N", [1024, 4096, 8192, 16384, 65536])
 def test_properties_at_benchmark_sizes(N):
     """Size-independent invariants with in-kernel Philox noise on the synthetic physics source."""
     env = make_env(N, physics="synthetic")

@@ -103,21 +103,3 @@ def test_alignment_errors():
     W = torch.randn(32, 705, device="cuda")
     with pytest.raises(nat.NativeError, match="16-byte"):
         _run(X, W, 64, 32, 705, 0, 0, 3)
-
-
-@pytest.mark.skipif(__import__("os").environ.get("HG_TEST_BF16X3") != "1",
-                    reason="experimental bf16x3 kernel (passes = 2): opt in with HG_TEST_BF16X3=1")
-@pytest.mark.parametrize("M,N,K", [(256, 128, 64), (256, 128, 96), (384, 512, 705), (4096, 768, 219), (300, 12, 128)])
-@pytest.mark.parametrize("passes,tol", [(2, 2e-5), (4, 6e-6)])
-def test_bf16x3_forward_layout(M, N, K, passes, tol):
-    """passes = 2: bf16 hi/lo split, three kind::f16 MMAs (~5e-6); passes = 4: TF32 main term + two bf16 correction terms
-    (~1.5e-6) -- tools/experiments/split_precision_study.py.  K = 96 and K = 705 end on a half-filled 64-k stage."""
-    g = torch.Generator(device="cuda").manual_seed(M + N + K)
-    X = _pad4(torch.randn(M, K, device="cuda", generator=g))
-    W = _pad4(torch.randn(N, K, device="cuda", generator=g) / K ** 0.5)
-    b = torch.randn(N, device="cuda", generator=g)
-    ref = X.double() @ W.double().t()
-    C = _run(X, W, M, N, K, 0, 0, passes)
-    assert _rel(C, ref) < tol, _rel(C, ref)
-    C2 = _run(X, W, M, N, K, 0, 0, passes, epilogue=2, bias=b)
-    assert _rel(C2, torch.nn.functional.elu(ref + b.double())) < 2 * tol

@@ -72,7 +72,7 @@ def main():
     perm = torch.randperm(N * T, device=dev)
     ts = []
     for r in range(a.reps + 1):
-        mb = s.gather(perm[:B])
+        mb = s.gather(perm[:B], split=alg.use_split_path())
         e0.record()
         alg.minibatch_step(mb)
         e1.record()
