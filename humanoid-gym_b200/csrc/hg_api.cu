@@ -20,6 +20,7 @@ extern "C" int64_t hg_struct_size(int32_t which) {
         case 8: return sizeof(HgGemm);
         case 9: return sizeof(HgSplit);
         case 10: return sizeof(HgGemmSplit);
+        case 11: return sizeof(HgMlpFwdOpts);
         default: return -1;
     }
 }

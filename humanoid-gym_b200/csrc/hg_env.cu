@@ -847,6 +847,43 @@ __global__ void compute_torques_kernel(HgEnvBuffers B, int N) {
     B.torques[i] = clampf(t, -cP.torque_limits[j], cP.torque_limits[j]);
 }
 
+// Synthetic-physics fast path of the decimation loop (legged_robot.py:94-101): with an open-loop frame source the
+// `decimation` x {PD torque, set forces, simulate, refresh dof} sub-steps and the three state refreshes of
+// post_physics_step (:124-126) are ONE launch instead of ~23 graph nodes.  Every sub-step's PD law is still
+// evaluated against the dof state the previous sub-step left (the first one against the live state, which carries the
+// reset rewrites); only the last torque and the last dof frame are observable downstream, exactly as in the loop.
+__global__ void synth_decimation_kernel(HgEnvBuffers B, const float2* __restrict__ dof_frames, int decimation,
+                                        const float* __restrict__ root_f, const float* __restrict__ contact_f,
+                                        const float* __restrict__ rigid_f, int N, int nb) {
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x, nt = gridDim.x * blockDim.x;
+    const int nd = N * 12;
+    float2* live = reinterpret_cast<float2*>(B.dof_state);
+    for (int i = tid; i < nd; i += nt) {
+        const int j = i % 12;
+        float2 s = live[i];
+        const float scaled = B.actions[i] * cP.action_scale;
+        float t = 0.0f;
+        for (int d = 0; d < decimation; ++d) {
+            t = cP.p_gains[j] * (scaled + cP.default_dof_pos[j] - s.x) - cP.d_gains[j] * s.y;
+            t = clampf(t, -cP.torque_limits[j], cP.torque_limits[j]);
+            s = __ldg(dof_frames + (size_t)d * nd + i);
+        }
+        B.torques[i] = t;
+        live[i] = s;
+    }
+    float* contact = const_cast<float*>(B.contact_forces);
+    float* rigid = const_cast<float*>(B.rigid_state);
+    for (int i = tid; i < N * 13; i += nt) B.root_states[i] = __ldg(root_f + i);
+    for (int i = tid; i < N * nb * 3; i += nt) contact[i] = __ldg(contact_f + i);
+    const int nr4 = (N * nb * 13) >> 2;
+    if ((((uintptr_t)rigid | (uintptr_t)rigid_f) & 15u) == 0) {
+        for (int i = tid; i < nr4; i += nt) reinterpret_cast<float4*>(rigid)[i] = __ldg(reinterpret_cast<const float4*>(rigid_f) + i);
+        for (int i = (nr4 << 2) + tid; i < N * nb * 13; i += nt) rigid[i] = __ldg(rigid_f + i);
+    } else {
+        for (int i = tid; i < N * nb * 13; i += nt) rigid[i] = __ldg(rigid_f + i);
+    }
+}
+
 // The params live in __constant__ memory; re-upload only when they change.
 HgEnvParams g_params_host;
 bool g_params_valid = false;
@@ -901,6 +938,26 @@ extern "C" int32_t hg_env_compute_torques(const HgEnvBuffers* B, const HgEnvPara
     compute_torques_kernel<<<(total + 255) / 256, 256, 0, st>>>(*B, (int)N);
     HG_LAUNCHED(1);
     return hg_cuda_status("hg_env_compute_torques");
+}
+
+extern "C" int32_t hg_env_synth_decimation(const HgEnvBuffers* B, const HgEnvParams* P, const float* dof_frames, int32_t decimation,
+                                           const float* root_frame, const float* contact_frame, const float* rigid_frame,
+                                           int64_t N, void* stream) {
+    HG_REQUIRE(B); HG_REQUIRE(P); HG_REQUIRE(B->actions); HG_REQUIRE(B->dof_state); HG_REQUIRE(B->torques);
+    HG_REQUIRE(B->root_states); HG_REQUIRE(B->contact_forces); HG_REQUIRE(B->rigid_state);
+    HG_REQUIRE(dof_frames); HG_REQUIRE(root_frame); HG_REQUIRE(contact_frame); HG_REQUIRE(rigid_frame);
+    if (N <= 0 || N > (1 << 22) || decimation < 1) return hg_fail(HG_E_SIZE, "hg_env_synth_decimation: bad N / decimation");
+    if (!hg_aligned16(B->dof_state) || (reinterpret_cast<uintptr_t>(dof_frames) & 7u)) return hg_fail(HG_E_ALIGN, "hg_env_synth_decimation: dof tensors must be 8-byte aligned");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (int32_t rc = upload_params(P, st)) return rc;
+    const int64_t work = N * P->num_bodies * 13 / 4;
+    int grid = (int)((work + 255) / 256);
+    if (grid > 4 * HG_NUM_SMS) grid = 4 * HG_NUM_SMS;
+    if (grid < 1) grid = 1;
+    synth_decimation_kernel<<<grid, 256, 0, st>>>(*B, reinterpret_cast<const float2*>(dof_frames), decimation, root_frame, contact_frame,
+                                                  rigid_frame, (int)N, P->num_bodies);
+    HG_LAUNCHED(1);
+    return hg_cuda_status("hg_env_synth_decimation");
 }
 
 extern "C" int32_t hg_env_post_physics(const HgEnvBuffers* B, const HgEnvParams* P, const HgEnvNoise* Z,

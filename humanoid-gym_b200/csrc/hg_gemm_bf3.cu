@@ -101,12 +101,10 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float x0, float x1) {
 __device__ __forceinline__ float bf_lo(uint32_t p) { return __uint_as_float(p << 16); }
 __device__ __forceinline__ float bf_hi(uint32_t p) { return __uint_as_float(p & 0xFFFF0000u); }
 
-// nn.ELU(alpha=1): expm1 by a short series near 0 (relative error < 1e-7), exp(x) - 1 elsewhere
-__device__ __forceinline__ float elu1(float x) {
-    const float p = x * (1.0f + x * (0.5f + x * (0.16666667f + x * 0.041666668f)));
-    const float e = __expf(x) - 1.0f;
-    return x > 0.0f ? x : (x > -0.06f ? p : e);
-}
+// nn.ELU(alpha=1) as exp(x) - 1 for x <= 0: ABSOLUTE error ~1e-7 (same form as torch's CUDA kernel).  The consumers are
+// matrix products and ELU' = h + 1, for which only the absolute error matters; the epilogue is issue-bound, so the
+// series that would restore relative accuracy near 0 is not spent here (the 3xTF32 rollout path keeps expm1).
+__device__ __forceinline__ float elu1(float x) { return x > 0.0f ? x : __expf(x) - 1.0f; }
 
 __global__ void __launch_bounds__(THREADS, 1)
 gemm_bf3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const Args g) {
@@ -206,47 +204,81 @@ gemm_bf3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         }
     } else {
         // ===== epilogue: warp w <-> TMEM lanes 32*(w%4) .. +31, columns [(w/4) * BN/2, +BN/2) =====
+        // With only 8 epilogue warps every exposed latency costs: the H rows a dgrad chunk needs (ELU') are prefetched one
+        // chunk ahead -- the first chunk's before the accumulator is even complete -- and bias values come as warp-uniform
+        // 128-bit loads (one L1 broadcast each) instead of 32 shuffles.
         const int q = warp & 3, half = warp >> 2;
         const int c_begin = half * (g.BN >> 1), c_end = c_begin + (g.BN >> 1);
+        const bool h_fast = (g.epi == EPI_SPLIT_DELU) && ((g.ldhs & 7) == 0) && ((g.hs_plane & 7) == 0) && ((reinterpret_cast<uintptr_t>(g.Hs) & 15u) == 0);
+        const bool bias_fast = (g.epi == EPI_F32_BIAS || g.epi == EPI_SPLIT_BIAS_ELU) && ((reinterpret_cast<uintptr_t>(g.bias) & 15u) == 0);
         int item = 0;
         for (int w = blockIdx.x; w < total_work; w += gridDim.x, ++item) {
             const Work wk = decode_work(g, w, tiles_n, tiles_mn, num_kb_total);
             const int acc_stage = item & 1;
-            mbar_wait(&tmem_full[acc_stage], (item >> 1) & 1);
-            tc_fence_after();
             const int row = wk.m0 + q * 32 + lane;
             const bool row_ok = row < g.M;
+            uint4 hn[8];                                                    // prefetched H (4 x hi, 4 x lo) of the NEXT chunk
+            auto prefetch_h = [&](int c0) {
+                const int col0 = wk.n0 + c0;
+                if (h_fast && row_ok && col0 + 32 <= g.N) {
+                    const uint16_t* hp = g.Hs + (int64_t)row * g.ldhs + col0;
+#pragma unroll
+                    for (int t = 0; t < 4; ++t) {
+                        hn[t] = __ldg(reinterpret_cast<const uint4*>(hp) + t);
+                        hn[4 + t] = __ldg(reinterpret_cast<const uint4*>(hp + g.hs_plane) + t);
+                    }
+                }
+            };
+            if (g.epi == EPI_SPLIT_DELU) prefetch_h(c_begin);
+            mbar_wait(&tmem_full[acc_stage], (item >> 1) & 1);
+            tc_fence_after();
             for (int c0 = c_begin; c0 < c_end; c0 += 32) {
                 float v[32];
                 tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc_stage * 256 + c0), v);
                 const int col0 = wk.n0 + c0;
+                uint4 hc[8];
+                if (g.epi == EPI_SPLIT_DELU) {
+#pragma unroll
+                    for (int t = 0; t < 8; ++t) hc[t] = hn[t];
+                    if (c0 + 32 < c_end) prefetch_h(c0 + 32);
+                }
                 if (col0 >= g.N) continue;                                  // warp-uniform
                 const int nvalid = min(32, g.N - col0);
                 const bool full_chunk = (nvalid == 32);
                 if (g.epi == EPI_F32_BIAS || g.epi == EPI_SPLIT_BIAS_ELU) {
-                    const float bl = (lane < nvalid) ? __ldg(g.bias + col0 + lane) : 0.0f;
+                    if (bias_fast && full_chunk && ((col0 & 3) == 0)) {
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        const float x = v[j] + __shfl_sync(0xffffffffu, bl, j);
-                        v[j] = (g.epi == EPI_SPLIT_BIAS_ELU) ? elu1(x) : x;
+                        for (int j = 0; j < 32; j += 4) {
+                            const float4 b4 = __ldg(reinterpret_cast<const float4*>(g.bias + col0 + j));     // same address in every lane
+                            v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
+                        }
+                    } else {
+                        const float bl = (lane < nvalid) ? __ldg(g.bias + col0 + lane) : 0.0f;
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] += __shfl_sync(0xffffffffu, bl, j);
+                    }
+                    if (g.epi == EPI_SPLIT_BIAS_ELU) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] = elu1(v[j]);
                     }
                 } else if (g.epi == EPI_SPLIT_DELU) {
                     // ELU'(z) recovered from h = ELU(z) ~= h_hi + h_lo:  1 for h > 0, h + 1 otherwise
-                    const uint16_t* hp = g.Hs + (int64_t)row * g.ldhs + col0;
-                    if (row_ok && full_chunk && ((reinterpret_cast<uintptr_t>(hp) & 15u) == 0) && ((g.hs_plane & 7) == 0)) {
-#pragma unroll
-                        for (int j = 0; j < 32; j += 8) {
-                            const uint4 a = __ldg(reinterpret_cast<const uint4*>(hp + j));
-                            const uint4 b = __ldg(reinterpret_cast<const uint4*>(hp + g.hs_plane + j));
-                            const uint32_t ah[4] = {a.x, a.y, a.z, a.w}, bl4[4] = {b.x, b.y, b.z, b.w};
+                    if (h_fast && full_chunk) {
+                        if (row_ok) {
 #pragma unroll
                             for (int t = 0; t < 4; ++t) {
-                                const float h0 = bf_lo(ah[t]) + bf_lo(bl4[t]), h1 = bf_hi(ah[t]) + bf_hi(bl4[t]);
-                                v[j + 2 * t] *= (h0 > 0.0f) ? 1.0f : (h0 + 1.0f);
-                                v[j + 2 * t + 1] *= (h1 > 0.0f) ? 1.0f : (h1 + 1.0f);
+                                const uint32_t ah[4] = {hc[t].x, hc[t].y, hc[t].z, hc[t].w};
+                                const uint32_t al[4] = {hc[4 + t].x, hc[4 + t].y, hc[4 + t].z, hc[4 + t].w};
+#pragma unroll
+                                for (int u = 0; u < 4; ++u) {
+                                    const float h0 = bf_lo(ah[u]) + bf_lo(al[u]), h1 = bf_hi(ah[u]) + bf_hi(al[u]);
+                                    v[8 * t + 2 * u] *= (h0 > 0.0f) ? 1.0f : (h0 + 1.0f);
+                                    v[8 * t + 2 * u + 1] *= (h1 > 0.0f) ? 1.0f : (h1 + 1.0f);
+                                }
                             }
                         }
                     } else if (row_ok) {
+                        const uint16_t* hp = g.Hs + (int64_t)row * g.ldhs + col0;
 #pragma unroll
                         for (int j = 0; j < 32; ++j)
                             if (j < nvalid) {

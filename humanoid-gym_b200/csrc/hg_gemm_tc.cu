@@ -18,6 +18,9 @@
 // persistent (one per SM) and the accumulator is double-buffered in TMEM so that epilogue and main loop overlap.
 #include <cuda.h>
 
+#include <mutex>
+#include <unordered_map>
+
 #include "hg_common.cuh"
 #include "hg_tc_ptx.cuh"
 
@@ -30,9 +33,10 @@ constexpr int TILE_BYTES = BM * BK * 4;              // 16 KB: 128 rows (or 4 MN
 constexpr int PAIR_BYTES = 2 * TILE_BYTES;           // one {A, B} pair
 constexpr int SPLIT_WARPS = 8;
 constexpr int TC_THREADS = (6 + SPLIT_WARPS) * 32;   // 4 epilogue + TMA + MMA + splitters
-constexpr int SMEM_BYTES = (RAW_STAGES + LO_STAGES) * PAIR_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+constexpr int SMEM_BYTES = (RAW_STAGES + LO_STAGES) * PAIR_BYTES + 1024 /*align*/ + 256 /*barriers*/;      // upper bound over all configurations
 
-enum { EPI_STORE = 0, EPI_BIAS = 1, EPI_BIAS_ELU = 2, EPI_MUL_DELU = 3, EPI_ATOMIC = 4 };
+enum { EPI_STORE = 0, EPI_BIAS = 1, EPI_BIAS_ELU = 2, EPI_MUL_DELU = 3, EPI_ATOMIC = 4, EPI_BIAS_SAMPLE = 5 };
+constexpr float kLogSqrt2Pi = 0.9189385332046727f;
 
 struct TcArgs {
     float* C; const float* bias; const float* H;
@@ -44,6 +48,10 @@ struct TcArgs {
     int kb_per_split;                // k-blocks (of 32) per split
     int splits;
     int hi_in_place;                 // 1: splitter rewrites the raw tile with its tf32 truncation
+    int b_lo_tma;                    // 1: B_lo (pre-split weights) arrives by TMA inside the raw stage; the splitter handles A only
+    // EPI_BIAS_SAMPLE (PPO.act fused into the output layer, ppo.py:91-101): C receives the mean
+    const float* stdv; const float* eps; float* actions; float* logp; float* sigma;
+    uint64_t seed, step; const uint64_t* step_dev;
 };
 
 using namespace hgtc;
@@ -90,11 +98,16 @@ __device__ __forceinline__ Work decode_work(const TcArgs& g, int w, int tiles_n,
 }
 
 __global__ void __launch_bounds__(TC_THREADS, 1)
-gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcArgs g) {
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmBlo,
+               const TcArgs g) {
     extern __shared__ unsigned char smem_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    unsigned char* smem_lo = smem + RAW_STAGES * PAIR_BYTES;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_lo + LO_STAGES * PAIR_BYTES);
+    // raw stage = {A, B [, B_lo]}, lo stage = {A_lo [, B_lo]}: with pre-split weights (b_lo_tma) B_lo rides in the raw stage
+    const int b_bytes = g.BN * BK * 4;
+    const int raw_stride = TILE_BYTES + b_bytes + (g.b_lo_tma ? b_bytes : 0);
+    const int lo_stride = TILE_BYTES + (g.b_lo_tma ? 0 : b_bytes);
+    unsigned char* smem_lo = smem + RAW_STAGES * raw_stride;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_lo + LO_STAGES * lo_stride);
     uint64_t* full = bars;                          // [RAW] TMA -> splitter (and MMA)
     uint64_t* empty = full + RAW_STAGES;            // [RAW] MMA -> TMA
     uint64_t* ready = empty + RAW_STAGES;           // [LO]  splitter -> MMA
@@ -135,15 +148,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (lane == 0) {
             asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
             asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
-            const uint32_t tx = TILE_BYTES + (uint32_t)g.BN * BK * 4;
+            if (g.b_lo_tma) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmBlo) : "memory");
+            const uint32_t tx = TILE_BYTES + (uint32_t)b_bytes * (g.b_lo_tma ? 2u : 1u);
             int it = 0;
             for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
                 const Work wk = decode_work(g, w, tiles_n, tiles_mn, num_kb_total);
                 for (int kb = 0; kb < wk.num_kb; ++kb, ++it) {
                     const int s = it % RAW_STAGES, k0 = (wk.kb_begin + kb) * BK;
                     mbar_wait(&empty[s], ((it / RAW_STAGES) & 1) ^ 1);
-                    unsigned char* st = smem + s * PAIR_BYTES;
+                    unsigned char* st = smem + s * raw_stride;
                     mbar_expect_tx(&full[s], tx);
+                    if (g.b_lo_tma) tma_load_2d(st + TILE_BYTES + b_bytes, &tmBlo, &full[s], k0, wk.n0);      // K-major weights only
                     if (!g.a_mn) tma_load_2d(st, &tmA, &full[s], k0, wk.m0);
                     else
                         for (int j = 0; j < BM / 32; ++j) tma_load_2d(st + j * 4096, &tmA, &full[s], wk.m0 + 32 * j, k0);
@@ -170,7 +185,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     mbar_wait(&ready[l], (it / LO_STAGES) & 1);                   // lo tiles written (raw tiles landed before that)
                     mbar_wait(&full[s], (it / RAW_STAGES) & 1);
                     tc_fence_after();
-                    const uint32_t base = smem_u32(smem + s * PAIR_BYTES), base_lo = smem_u32(smem_lo + l * PAIR_BYTES);
+                    const uint32_t base = smem_u32(smem + s * raw_stride), base_lo = smem_u32(smem_lo + l * lo_stride);
+                    const uint32_t b_lo_base = g.b_lo_tma ? base + TILE_BYTES + b_bytes : base_lo + TILE_BYTES;
 #pragma unroll
                     for (int kk = 0; kk < BK / 8; ++kk) {
                         const uint64_t a_hi = make_desc(base + kk * kstep_a, g.a_mn);
@@ -178,7 +194,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         const uint32_t acc = (kb > 0 || kk > 0) ? 1u : 0u;
                         if (g.passes == 3) {
                             const uint64_t a_lo = make_desc(base_lo + kk * kstep_a, g.a_mn);
-                            const uint64_t b_lo = make_desc(base_lo + TILE_BYTES + kk * kstep_b, g.b_mn);
+                            const uint64_t b_lo = make_desc(b_lo_base + kk * kstep_b, g.b_mn);
                             umma_tf32(tmem_d, a_lo, b_hi, idesc, acc);          // small terms first
                             umma_tf32(tmem_d, a_hi, b_lo, idesc, 1u);
                             umma_tf32(tmem_d, a_hi, b_hi, idesc, 1u);
@@ -205,9 +221,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 mbar_wait(&lo_empty[l], ((it / LO_STAGES) & 1) ^ 1);            // MMA is done with this lo pair
                 mbar_wait(&full[s], (it / RAW_STAGES) & 1);
                 if (g.passes == 3) {
-                    float4* a = reinterpret_cast<float4*>(smem + s * PAIR_BYTES);
+                    float4* a = reinterpret_cast<float4*>(smem + s * raw_stride);
                     float4* b = a + TILE_BYTES / 16;
-                    float4* alo = reinterpret_cast<float4*>(smem_lo + l * PAIR_BYTES);
+                    float4* alo = reinterpret_cast<float4*>(smem_lo + l * lo_stride);
                     float4* blo = alo + TILE_BYTES / 16;
                     auto split = [&](float4* raw, float4* lo, int i) {
                         // hi = truncation (what the tensor core does to a raw fp32 operand anyway);
@@ -222,8 +238,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     };
 #pragma unroll 4
                     for (int i = t; i < TILE_BYTES / 16; i += NT) split(a, alo, i);
+                    if (!g.b_lo_tma) {
 #pragma unroll 4
-                    for (int i = t; i < nB4; i += NT) split(b, blo, i);
+                        for (int i = t; i < nB4; i += NT) split(b, blo, i);
+                    }
                     fence_proxy_async();                                        // generic-proxy writes -> tensor-core reads
                 }
                 __syncwarp();
@@ -248,14 +266,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 float* dst = g.C + (int64_t)row * g.ldc + col0;
                 const int nvalid = min(32, g.N - col0);
                 const bool vec_ok = (nvalid == 32);
-                if (g.epi == EPI_BIAS || g.epi == EPI_BIAS_ELU) {
+                if (g.epi == EPI_BIAS || g.epi == EPI_BIAS_ELU || g.epi == EPI_BIAS_SAMPLE) {
                     // one coalesced load of the 32 bias values of this chunk, then warp shuffles
                     const float bl = (lane < nvalid) ? __ldg(g.bias + col0 + lane) : 0.0f;
 #pragma unroll
                     for (int j = 0; j < 32; ++j) {
                         float x = v[j] + __shfl_sync(0xffffffffu, bl, j);
                         // nn.ELU(alpha=1): exp(x) - 1 for x <= 0 (absolute error ~1e-7, same form as torch's CUDA kernel)
-                        v[j] = (g.epi == EPI_BIAS_ELU) ? (x > 0.0f ? x : __expf(x) - 1.0f) : x;
+                        v[j] = (g.epi == EPI_BIAS_ELU) ? (x > 0.0f ? x : expm1f(x)) : x;                     // nn.ELU(alpha=1)
                     }
                 } else if (g.epi == EPI_MUL_DELU) {
                     const float* h = g.H + (int64_t)row * g.ldh + col0;
@@ -278,6 +296,32 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     }
                 }
                 if (!row_ok) continue;
+                if (g.epi == EPI_BIAS_SAMPLE) {
+                    // ActorCritic.act + get_actions_log_prob (actor_critic.py:111-120) on the row this thread owns:
+                    // a = mu + sigma z, log-prob summed over the actions, sigma broadcast (same arithmetic as policy_sample_kernel)
+                    uint64_t stp = g.step_dev ? *g.step_dev : g.step;
+                    float lp = 0.0f;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j)
+                        if (j < nvalid) {
+                            const float mu = v[j];
+                            const float sg = mu * 0.0f + __ldg(g.stdv + j);
+                            float z;
+                            if (g.eps) z = g.eps[(size_t)row * g.N + j];
+                            else {
+                                HgPhilox r = hg_philox(g.seed, (uint32_t)row, (uint32_t)stp, HG_RNG_SAMPLE | ((uint32_t)(stp >> 32) << 8), j);
+                                z = hg_normal(r.c[0], r.c[1]);
+                            }
+                            const float a = mu + sg * z;
+                            const float d = a - mu;
+                            lp += -(d * d) / (2.0f * (sg * sg)) - logf(sg) - kLogSqrt2Pi;
+                            dst[j] = mu;
+                            g.actions[(size_t)row * g.N + j] = a;
+                            g.sigma[(size_t)row * g.N + j] = sg;
+                        }
+                    g.logp[row] = lp;
+                    continue;
+                }
                 if (g.epi == EPI_ATOMIC) {
                     if (vec_ok && ((reinterpret_cast<uintptr_t>(dst) & 15u) == 0)) {
 #pragma unroll
@@ -347,6 +391,38 @@ int32_t make_map(CUtensorMap* map, const float* base, uint64_t inner, uint64_t o
     return 0;
 }
 
+// Tensor maps are pure functions of (base, extents, pitch, box): encode each distinct one once per process.
+struct MapKey {
+    const void* base; uint64_t inner, outer, ld; uint32_t box_inner, box_outer; int mn;
+    bool operator==(const MapKey& o) const {
+        return base == o.base && inner == o.inner && outer == o.outer && ld == o.ld && box_inner == o.box_inner && box_outer == o.box_outer && mn == o.mn;
+    }
+};
+struct MapKeyHash {
+    size_t operator()(const MapKey& k) const {
+        uint64_t h = 1469598103934665603ull;
+        const uint64_t v[7] = {(uint64_t)(uintptr_t)k.base, k.inner, k.outer, k.ld, k.box_inner, k.box_outer, (uint64_t)k.mn};
+        for (uint64_t x : v) { h ^= x; h *= 1099511628211ull; }
+        return (size_t)h;
+    }
+};
+std::unordered_map<MapKey, CUtensorMap, MapKeyHash> g_maps;
+std::mutex g_maps_mu;
+
+int32_t get_map(CUtensorMap* map, const float* base, uint64_t inner, uint64_t outer, uint64_t ld, uint32_t box_inner, uint32_t box_outer, bool mn) {
+    MapKey key{base, inner, outer, ld, box_inner, box_outer, mn ? 1 : 0};
+    {
+        std::lock_guard<std::mutex> lk(g_maps_mu);
+        auto it = g_maps.find(key);
+        if (it != g_maps.end()) { *map = it->second; return 0; }
+    }
+    if (int32_t rc = make_map(map, base, inner, outer, ld, box_inner, box_outer, mn)) return rc;
+    std::lock_guard<std::mutex> lk(g_maps_mu);
+    if (g_maps.size() > 4096) g_maps.clear();
+    g_maps.emplace(key, *map);
+    return 0;
+}
+
 }  // namespace
 
 // C (M x N) = op(A) op(B) over K, see HgGemm in hg_b200.h
@@ -356,9 +432,16 @@ extern "C" int32_t hg_gemm_tf32(const HgGemm* d, void* stream) {
     if (d->passes != 1 && d->passes != 3) return hg_fail(HG_E_ARG, "hg_gemm_tf32: passes must be 1 (plain TF32) or 3 (3xTF32)");
     if ((d->lda & 3) || (d->ldb & 3) || !hg_aligned16(d->A) || !hg_aligned16(d->B))
         return hg_fail(HG_E_ALIGN, "hg_gemm_tf32: operands need 16-byte aligned base and row pitch (TMA)");
-    if ((d->epilogue == EPI_BIAS || d->epilogue == EPI_BIAS_ELU) && !d->bias) return hg_fail(HG_E_NULL, "hg_gemm_tf32: bias is NULL");
-    if (d->epilogue == EPI_MUL_DELU && !d->H) return hg_fail(HG_E_NULL, "hg_gemm_tf32: H is NULL");
-    if (d->epilogue < 0 || d->epilogue > EPI_ATOMIC) return hg_fail(HG_E_ARG, "hg_gemm_tf32: bad epilogue");
+    const int epi = d->epilogue;
+    if (epi < 0 || epi > EPI_BIAS_SAMPLE) return hg_fail(HG_E_ARG, "hg_gemm_tf32: bad epilogue");
+    if ((epi == EPI_BIAS || epi == EPI_BIAS_ELU || epi == EPI_BIAS_SAMPLE) && !d->bias) return hg_fail(HG_E_NULL, "hg_gemm_tf32: bias is NULL");
+    if (epi == EPI_MUL_DELU && !d->H) return hg_fail(HG_E_NULL, "hg_gemm_tf32: H is NULL");
+    if (epi == EPI_BIAS_SAMPLE) {
+        if (d->N > 32) return hg_fail(HG_E_SIZE, "hg_gemm_tf32: the fused sampling epilogue needs N <= 32");
+        if (!d->sample_std || !d->sample_actions || !d->sample_log_prob || !d->sample_sigma) return hg_fail(HG_E_NULL, "hg_gemm_tf32: sampling outputs are NULL");
+    }
+    const bool b_lo = d->B_lo != nullptr && d->passes == 3 && !d->b_mn_major;
+    if (d->B_lo && !hg_aligned16(d->B_lo)) return hg_fail(HG_E_ALIGN, "hg_gemm_tf32: B_lo must be 16-byte aligned");
     if (int32_t rc = load_encode()) return rc;
     cudaStream_t st = (cudaStream_t)stream;
 
@@ -367,10 +450,21 @@ extern "C" int32_t hg_gemm_tf32(const HgGemm* d, void* stream) {
     g.M = d->M; g.N = d->N; g.K = d->K;
     g.ldc = d->ldc; g.ldh = d->ldh;
     g.a_mn = d->a_mn_major ? 1 : 0; g.b_mn = d->b_mn_major ? 1 : 0;
-    g.epi = d->epilogue; g.passes = d->passes;
+    g.epi = epi; g.passes = d->passes;
     g.hi_in_place = d->trust_hw_truncation ? 0 : 1;
+    g.b_lo_tma = b_lo ? 1 : 0;
+    g.stdv = d->sample_std; g.eps = d->sample_eps; g.actions = d->sample_actions; g.logp = d->sample_log_prob; g.sigma = d->sample_sigma;
+    g.seed = d->sample_seed; g.step = d->sample_step; g.step_dev = d->sample_step_dev;
+    // Tile width: 128 columns when there are enough row tiles to fill the chip, narrower for skinny batches (the
+    // rollout's M = 4096 gives only 32 row tiles: BN = 64 / 32 spreads a layer over 4x more SMs and the per-CTA
+    // main loop -- which is what such a launch waits for -- shrinks with it)
+    const int tiles_m = (d->M + BM - 1) / BM;
     int bn = ((d->N + 31) / 32) * 32;
-    g.BN = bn > 128 ? 128 : bn;
+    if (bn > 128) bn = 128;
+    if (epi != EPI_ATOMIC && d->split_k <= 1)
+        while (bn > 32 && tiles_m * ((d->N + bn - 1) / bn) < HG_NUM_SMS * 3 / 4 && (bn / 2) % 32 == 0) bn /= 2;
+    if (epi == EPI_BIAS_SAMPLE) bn = 32;
+    g.BN = bn;
     const int num_kb = (d->K + BK - 1) / BK;
     int splits = d->split_k > 0 ? d->split_k : 1;
     if (splits > num_kb) splits = num_kb;
@@ -379,25 +473,32 @@ extern "C" int32_t hg_gemm_tf32(const HgGemm* d, void* stream) {
     splits = (num_kb + g.kb_per_split - 1) / g.kb_per_split;
 
     // K-major operand: tensor (inner = K, outer = rows), box {32, rows}.  MN-major: (inner = rows, outer = K), box {32, 32}.
-    CUtensorMap tmA, tmB;
+    CUtensorMap tmA, tmB, tmBlo;
     int32_t rc;
-    if (!g.a_mn) rc = make_map(&tmA, d->A, d->K, d->M, d->lda, BK, BM, false);
-    else rc = make_map(&tmA, d->A, d->M, d->K, d->lda, 32, BK, true);
+    if (!g.a_mn) rc = get_map(&tmA, d->A, d->K, d->M, d->lda, BK, BM, false);
+    else rc = get_map(&tmA, d->A, d->M, d->K, d->lda, 32, BK, true);
     if (rc) return rc;
-    if (!g.b_mn) rc = make_map(&tmB, d->B, d->K, d->N, d->ldb, BK, g.BN, false);
-    else rc = make_map(&tmB, d->B, d->N, d->K, d->ldb, 32, BK, true);
+    if (!g.b_mn) rc = get_map(&tmB, d->B, d->K, d->N, d->ldb, BK, g.BN, false);
+    else rc = get_map(&tmB, d->B, d->N, d->K, d->ldb, 32, BK, true);
     if (rc) return rc;
+    if (b_lo) {
+        if (int32_t rc2 = get_map(&tmBlo, d->B_lo, d->K, d->N, d->ldb, BK, g.BN, false)) return rc2;
+    } else tmBlo = tmB;
 
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    static bool attr_set[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev >= 0 && dev < 64 && !attr_set[dev]) {
+        cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e != cudaSuccess) return hg_fail((int32_t)e, cudaGetErrorString(e));
-        attr_set = true;
+        attr_set[dev] = true;
     }
     g.splits = splits;
-    const int total_work = ((d->N + g.BN - 1) / g.BN) * ((d->M + BM - 1) / BM) * splits;
+    const int total_work = ((d->N + g.BN - 1) / g.BN) * tiles_m * splits;
     const int grid = total_work < HG_NUM_SMS ? total_work : HG_NUM_SMS;       // persistent: one CTA per SM
-    gemm_tc_kernel<<<grid, TC_THREADS, SMEM_BYTES, st>>>(tmA, tmB, g);
+    const int b_bytes = g.BN * BK * 4;
+    const int smem_bytes = RAW_STAGES * (TILE_BYTES + b_bytes * (b_lo ? 2 : 1)) + LO_STAGES * (TILE_BYTES + (b_lo ? 0 : b_bytes)) + 1024 + 256;
+    gemm_tc_kernel<<<grid, TC_THREADS, smem_bytes, st>>>(tmA, tmB, tmBlo, g);
     HG_LAUNCHED(1);
     return hg_cuda_status("hg_gemm_tf32");
 }

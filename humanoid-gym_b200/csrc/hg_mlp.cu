@@ -289,7 +289,8 @@ int gemm_mode() {
 // Try the tensor-core kernel for C = A x B; returns HG_E_ALIGN-style "not eligible" as 1 so the caller falls back.
 // a_mn / b_mn: operand is stored with its M / N index contiguous (see HgGemm).
 int32_t try_tc(const float* A, int64_t lda, bool a_mn, const float* B, int64_t ldb, bool b_mn, float* C, int64_t ldc, int M, int N,
-               int K, int epi, const float* bias, const float* H, int64_t ldh, int split_k, cudaStream_t st) {
+               int K, int epi, const float* bias, const float* H, int64_t ldh, int split_k, cudaStream_t st,
+               const float* B_lo = nullptr, const HgMlpFwdOpts* sample = nullptr) {
     const int mode = gemm_mode();
     if (mode == 0) return 1;
     if ((lda & 3) || (ldb & 3) || !hg_aligned16(A) || !hg_aligned16(B)) return 1;
@@ -300,6 +301,13 @@ int32_t try_tc(const float* A, int64_t lda, bool a_mn, const float* B, int64_t l
     d.a_mn_major = a_mn; d.b_mn_major = b_mn;
     d.epilogue = epi; d.passes = (mode == 2) ? 1 : 3; d.split_k = split_k;
     d.trust_hw_truncation = 1;      // verified on B200: kind::tf32 ignores the low 13 mantissa bits (tests/test_gemm_tc_gpu.py)
+    d.B_lo = (d.passes == 3) ? B_lo : nullptr;
+    if (sample) {                   // output layer of the actor during the rollout: PPO.act fused into the epilogue
+        d.epilogue = 5;
+        d.sample_std = sample->std; d.sample_eps = sample->eps; d.sample_actions = sample->actions;
+        d.sample_log_prob = sample->log_prob; d.sample_sigma = sample->sigma;
+        d.sample_seed = sample->seed; d.sample_step = sample->step; d.sample_step_dev = sample->step_dev;
+    }
     return hg_gemm_tf32(&d, (void*)st);
 }
 
@@ -321,9 +329,34 @@ extern "C" int32_t hg_set_gemm_mode(int32_t mode) {
     return prev;
 }
 
+__global__ void tf32_residual_kernel(const float* __restrict__ src, float* __restrict__ dst, int64_t n) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float x = src[i];
+    const float h = __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x - h));
+    dst[i] = __uint_as_float(r);
+}
+extern "C" int32_t hg_tf32_residual(const float* src, float* dst, int64_t n, void* stream) {
+    HG_REQUIRE(src); HG_REQUIRE(dst);
+    if (n <= 0) return hg_fail(HG_E_SIZE, "hg_tf32_residual: bad n");
+    tf32_residual_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(src, dst, n);
+    HG_LAUNCHED(1);
+    return hg_cuda_status("hg_tf32_residual");
+}
+
 extern "C" int32_t hg_mlp_forward(const HgMlpDesc* net, const float* params, const float* X, int64_t ldx,
                                   float* hidden, float* out, int64_t M, void* stream) {
+    return hg_mlp_forward_ex(net, params, X, ldx, hidden, out, M, nullptr, stream);
+}
+
+extern "C" int32_t hg_mlp_forward_ex(const HgMlpDesc* net, const float* params, const float* X, int64_t ldx,
+                                     float* hidden, float* out, int64_t M, const HgMlpFwdOpts* opts, void* stream) {
     if (int32_t rc = check_net(net)) return rc;
+    const float* params_lo = opts ? opts->params_lo : nullptr;
+    const bool want_sample = opts && opts->actions;
+    if (want_sample && (!opts->std || !opts->log_prob || !opts->sigma)) return hg_fail(HG_E_NULL, "hg_mlp_forward_ex: sampling outputs are NULL");
     HG_REQUIRE(params); HG_REQUIRE(X); HG_REQUIRE(out);
     if (net->n_layers > 1) HG_REQUIRE(hidden);
     if (M <= 0 || M > (1 << 28) || ldx < net->dims[0]) return hg_fail(HG_E_SIZE, "hg_mlp_forward: bad M/ldx");
@@ -331,13 +364,17 @@ extern "C" int32_t hg_mlp_forward(const HgMlpDesc* net, const float* params, con
     const float* in = X;
     int64_t ld_in = ldx;
     float* h = hidden;
+    bool sampled = false;
     for (int l = 0; l < net->n_layers; ++l) {
         const int K = net->dims[l], N = net->dims[l + 1];
         const bool last = (l + 1 == net->n_layers);
         const float* W = params + net->w_off[l];
         const int64_t ldw = net->ldw[l];
         float* dst = last ? out : h;
-        int32_t rc = try_tc(in, ld_in, false, W, ldw, false, dst, N, (int)M, N, K, last ? 1 : 2, params + net->b_off[l], nullptr, 0, 1, st);
+        const bool fuse_sample = last && want_sample && N <= 32 && gemm_mode() != 0;
+        int32_t rc = try_tc(in, ld_in, false, W, ldw, false, dst, N, (int)M, N, K, last ? 1 : 2, params + net->b_off[l], nullptr, 0, 1, st,
+                            params_lo ? params_lo + net->w_off[l] : nullptr, fuse_sample ? opts : nullptr);
+        if (rc == 0 && fuse_sample) sampled = true;
         if (rc == 1) {
             GemmArgs g{};
             g.A = in; g.sai = ld_in; g.sap = 1;
@@ -350,6 +387,11 @@ extern "C" int32_t hg_mlp_forward(const HgMlpDesc* net, const float* params, con
         if (rc) return rc;
         in = h; ld_in = N;
         h += M * N;
+    }
+    if (want_sample && !sampled) {       // engines without the fused epilogue: the stand-alone kernel on the mean just written
+        const int A = net->dims[net->n_layers];
+        return hg_policy_sample(out, opts->std, opts->eps, opts->seed, opts->step, opts->step_dev, opts->actions, opts->log_prob,
+                                opts->sigma, M, A, stream);
     }
     return 0;
 }

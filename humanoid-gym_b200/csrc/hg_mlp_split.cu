@@ -59,20 +59,23 @@ __global__ void __launch_bounds__(128) head_forward_kernel(const uint16_t* __res
         if (n < N) out[(int64_t)m * N + n] = acc[n];
 }
 
-// One pass over ROWS rows of h (split, width K): thread t owns the column pair (2t, 2t+1) of the block's 256-column slab.
+// One pass over HB_ROWS rows of h (split, width K).  Block = 256 threads = (256-column slab, as 128 column pairs) x 2 row
+// groups (a slab narrower than 256 columns packs more row groups: K = 128 -> 64 pairs x 4 groups), so every thread
+// is busy; the row groups' partial sums meet in shared memory, then one set of atomics per block.
 //   dW[n][k]  += sum_m dY[m][n] h[m][k]                       (head weight gradient)
 //   db[n]     += sum_m dY[m][n]                               (head bias gradient; blockIdx.x == 0 only)
 //   dZ[m][k]   = (sum_n dY[m][n] W[n][k]) * ELU'(h[m][k])     -> split store
 //   dbp[k]    += sum_m dZ[m][k]                               (bias gradient of the layer that produced h)
-constexpr int HB_ROWS = 128;
+constexpr int HB_ROWS = 64, HB_THREADS = 256;
 template <int NO>
-__global__ void __launch_bounds__(128) head_backward_kernel(const float* __restrict__ dY, const uint16_t* __restrict__ hs, int64_t ldh,
-                                                            int64_t hplane, const float* __restrict__ W, int64_t ldw,
-                                                            float* __restrict__ dW, float* __restrict__ db, uint16_t* __restrict__ dzs,
-                                                            int64_t dzplane, float* __restrict__ dbp, int M, int N, int K) {
+__global__ void __launch_bounds__(HB_THREADS) head_backward_kernel(const float* __restrict__ dY, const uint16_t* __restrict__ hs, int64_t ldh,
+                                                                   int64_t hplane, const float* __restrict__ W, int64_t ldw,
+                                                                   float* __restrict__ dW, float* __restrict__ db, uint16_t* __restrict__ dzs,
+                                                                   int64_t dzplane, float* __restrict__ dbp, int M, int N, int K) {
     __shared__ float dy[HB_ROWS][NO];
+    __shared__ float red[HB_THREADS][2 * NO + 2 + 1];        // +1: odd pitch, conflict-free column walks
     const int m0 = blockIdx.y * HB_ROWS, rows = min(HB_ROWS, M - m0);
-    for (int i = threadIdx.x; i < HB_ROWS * NO; i += 128) {
+    for (int i = threadIdx.x; i < HB_ROWS * NO; i += HB_THREADS) {
         const int r = i / NO, n = i - r * NO;
         dy[r][n] = (r < rows && n < N) ? dY[(int64_t)(m0 + r) * N + n] : 0.0f;
     }
@@ -82,45 +85,65 @@ __global__ void __launch_bounds__(128) head_backward_kernel(const float* __restr
         for (int r = 0; r < rows; ++r) s += dy[r][threadIdx.x];
         atomicAdd(db + threadIdx.x, s);
     }
-    const int k = blockIdx.x * 256 + 2 * threadIdx.x;
-    if (k >= K) return;
-    float w0[NO], w1[NO], a0[NO], a1[NO];
-#pragma unroll
-    for (int n = 0; n < NO; ++n) {
-        w0[n] = (n < N) ? W[(int64_t)n * ldw + k] : 0.0f;
-        w1[n] = (n < N) ? W[(int64_t)n * ldw + k + 1] : 0.0f;
-        a0[n] = 0.0f; a1[n] = 0.0f;
-    }
+    const int slab = min(256, K - blockIdx.x * 256);          // columns of this block (even)
+    const int pairs = slab >> 1, groups = HB_THREADS / pairs;  // pairs in {4 .. 128}: K % 8 == 0
+    const int pi = threadIdx.x % pairs, gi = threadIdx.x / pairs;
+    const int k = blockIdx.x * 256 + 2 * pi;
+    float a0[NO], a1[NO];
     float s0 = 0.0f, s1 = 0.0f;
-    const uint16_t* hp = hs + (int64_t)m0 * ldh + k;
-    uint16_t* zp = dzs + (int64_t)m0 * ldh + k;
-    for (int r = 0; r < rows; ++r) {
-        const uint32_t ph = __ldg(reinterpret_cast<const uint32_t*>(hp + (int64_t)r * ldh));
-        const uint32_t pl = __ldg(reinterpret_cast<const uint32_t*>(hp + hplane + (int64_t)r * ldh));
-        const float h0 = bf_lo(ph) + bf_lo(pl), h1 = bf_hi(ph) + bf_hi(pl);
-        float z0 = 0.0f, z1 = 0.0f;
+#pragma unroll
+    for (int n = 0; n < NO; ++n) { a0[n] = 0.0f; a1[n] = 0.0f; }
+    if (gi < groups) {
+        float w0[NO], w1[NO];
 #pragma unroll
         for (int n = 0; n < NO; ++n) {
-            const float d = dy[r][n];
-            a0[n] = fmaf(d, h0, a0[n]); a1[n] = fmaf(d, h1, a1[n]);
-            z0 = fmaf(d, w0[n], z0); z1 = fmaf(d, w1[n], z1);
+            w0[n] = (n < N) ? W[(int64_t)n * ldw + k] : 0.0f;
+            w1[n] = (n < N) ? W[(int64_t)n * ldw + k + 1] : 0.0f;
         }
-        z0 *= (h0 > 0.0f) ? 1.0f : (h0 + 1.0f);
-        z1 *= (h1 > 0.0f) ? 1.0f : (h1 + 1.0f);
-        const uint32_t zh = pack_bf16x2(z0, z1);
-        const uint32_t zl = pack_bf16x2(z0 - bf_lo(zh), z1 - bf_hi(zh));
-        *reinterpret_cast<uint32_t*>(zp + (int64_t)r * ldh) = zh;
-        *reinterpret_cast<uint32_t*>(zp + dzplane + (int64_t)r * ldh) = zl;
-        s0 += z0; s1 += z1;
-    }
+        const uint16_t* hp = hs + (int64_t)m0 * ldh + k;
+        uint16_t* zp = dzs + (int64_t)m0 * ldh + k;
+#pragma unroll 4
+        for (int r = gi; r < rows; r += groups) {
+            const uint32_t ph = __ldg(reinterpret_cast<const uint32_t*>(hp + (int64_t)r * ldh));
+            const uint32_t pl = __ldg(reinterpret_cast<const uint32_t*>(hp + hplane + (int64_t)r * ldh));
+            const float h0 = bf_lo(ph) + bf_lo(pl), h1 = bf_hi(ph) + bf_hi(pl);
+            float z0 = 0.0f, z1 = 0.0f;
 #pragma unroll
-    for (int n = 0; n < NO; ++n)
-        if (n < N) {
-            atomicAdd(dW + (int64_t)n * ldw + k, a0[n]);
-            atomicAdd(dW + (int64_t)n * ldw + k + 1, a1[n]);
+            for (int n = 0; n < NO; ++n) {
+                const float d = dy[r][n];
+                a0[n] = fmaf(d, h0, a0[n]); a1[n] = fmaf(d, h1, a1[n]);
+                z0 = fmaf(d, w0[n], z0); z1 = fmaf(d, w1[n], z1);
+            }
+            z0 *= (h0 > 0.0f) ? 1.0f : (h0 + 1.0f);
+            z1 *= (h1 > 0.0f) ? 1.0f : (h1 + 1.0f);
+            const uint32_t zh = pack_bf16x2(z0, z1);
+            const uint32_t zl = pack_bf16x2(z0 - bf_lo(zh), z1 - bf_hi(zh));
+            *reinterpret_cast<uint32_t*>(zp + (int64_t)r * ldh) = zh;
+            *reinterpret_cast<uint32_t*>(zp + dzplane + (int64_t)r * ldh) = zl;
+            s0 += z0; s1 += z1;
         }
-    atomicAdd(dbp + k, s0);
-    atomicAdd(dbp + k + 1, s1);
+    }
+    // meet the row groups' partial sums: thread (pi, gi) parks its 2 NO + 2 values, group 0 adds them up
+    float* mine = red[threadIdx.x];
+#pragma unroll
+    for (int n = 0; n < NO; ++n) { mine[2 * n] = a0[n]; mine[2 * n + 1] = a1[n]; }
+    mine[2 * NO] = s0; mine[2 * NO + 1] = s1;
+    __syncthreads();
+    if (gi == 0) {
+#pragma unroll
+        for (int n = 0; n < NO; ++n) {
+            float t0 = 0.0f, t1 = 0.0f;
+            for (int g2 = 0; g2 < groups; ++g2) { t0 += red[g2 * pairs + pi][2 * n]; t1 += red[g2 * pairs + pi][2 * n + 1]; }
+            if (n < N) {
+                atomicAdd(dW + (int64_t)n * ldw + k, t0);
+                atomicAdd(dW + (int64_t)n * ldw + k + 1, t1);
+            }
+        }
+        float t0 = 0.0f, t1 = 0.0f;
+        for (int g2 = 0; g2 < groups; ++g2) { t0 += red[g2 * pairs + pi][2 * NO]; t1 += red[g2 * pairs + pi][2 * NO + 1]; }
+        atomicAdd(dbp + k, t0);
+        atomicAdd(dbp + k + 1, t1);
+    }
 }
 
 int32_t check_net_split(const HgMlpDesc* net, const HgSplit* X) {
@@ -198,7 +221,7 @@ extern "C" int32_t hg_mlp_backward_split(const HgMlpDesc* net, const float* para
         const HgSplit h = hidden_slot(hid, net, L - 1, M), dz = hidden_slot(dhidden, net, L - 1, M);
         const float* W = params + net->w_off[L - 1];
         dim3 grid((K + 255) / 256, (unsigned)((M + HB_ROWS - 1) / HB_ROWS));
-#define HEAD_BWD(NO) head_backward_kernel<NO><<<grid, 128, 0, st>>>(dY, h.p, h.ld, h.plane, W, net->ldw[L - 1], grads + net->w_off[L - 1], \
+#define HEAD_BWD(NO) head_backward_kernel<NO><<<grid, HB_THREADS, 0, st>>>(dY, h.p, h.ld, h.plane, W, net->ldw[L - 1], grads + net->w_off[L - 1], \
         grads + net->b_off[L - 1], dz.p, dz.plane, grads + net->b_off[L - 2], (int)M, N, K)
         if (N == 1) HEAD_BWD(1); else if (N <= 4) HEAD_BWD(4); else if (N <= 8) HEAD_BWD(8); else if (N <= 12) HEAD_BWD(12); else HEAD_BWD(16);
 #undef HEAD_BWD

@@ -115,7 +115,14 @@ class PpoLossArgs(C.Structure):
 class Gemm(C.Structure):
     _fields_ = [("A", PF), ("B", PF), ("C", PF), ("bias", PF), ("H", PF), ("M", i32), ("N", i32), ("K", i32),
                 ("lda", i64), ("ldb", i64), ("ldc", i64), ("ldh", i64), ("a_mn_major", i32), ("b_mn_major", i32),
-                ("epilogue", i32), ("passes", i32), ("split_k", i32), ("trust_hw_truncation", i32)]
+                ("epilogue", i32), ("passes", i32), ("split_k", i32), ("trust_hw_truncation", i32),
+                ("B_lo", PF), ("sample_std", PF), ("sample_eps", PF), ("sample_actions", PF), ("sample_log_prob", PF),
+                ("sample_sigma", PF), ("sample_seed", u64), ("sample_step", u64), ("sample_step_dev", PF)]
+
+
+class MlpFwdOpts(C.Structure):
+    _fields_ = [("params_lo", PF), ("std", PF), ("eps", PF), ("actions", PF), ("log_prob", PF), ("sigma", PF),
+                ("seed", u64), ("step", u64), ("step_dev", PF)]
 
 
 class GemmSplit(C.Structure):
@@ -124,7 +131,7 @@ class GemmSplit(C.Structure):
                 ("epilogue", i32), ("split_k", i32)]
 
 
-_STRUCTS = (EnvParams, EnvBuffers, EnvNoise, MlpDesc, Transition, Storage, MiniBatch, PpoLossArgs, Gemm, Split, GemmSplit)
+_STRUCTS = (EnvParams, EnvBuffers, EnvNoise, MlpDesc, Transition, Storage, MiniBatch, PpoLossArgs, Gemm, Split, GemmSplit, MlpFwdOpts)
 
 
 class NativeError(RuntimeError):
@@ -145,8 +152,11 @@ def _load():
         "hg_struct_size": (i64, [i32]),
         "hg_env_pre_physics": (i32, [P(EnvBuffers), P(EnvParams), PF, PF, PF, u64, u64, i64, PF]),
         "hg_env_compute_torques": (i32, [P(EnvBuffers), P(EnvParams), i64, PF]),
+        "hg_env_synth_decimation": (i32, [P(EnvBuffers), P(EnvParams), PF, i32, PF, PF, PF, i64, PF]),
         "hg_env_post_physics": (i32, [P(EnvBuffers), P(EnvParams), P(EnvNoise), C.c_uint32, i64, i64, PF]),
         "hg_mlp_forward": (i32, [P(MlpDesc), PF, PF, i64, PF, PF, i64, PF]),
+        "hg_mlp_forward_ex": (i32, [P(MlpDesc), PF, PF, i64, PF, PF, i64, P(MlpFwdOpts), PF]),
+        "hg_tf32_residual": (i32, [PF, PF, i64, PF]),
         "hg_mlp_backward": (i32, [P(MlpDesc), PF, PF, i64, PF, PF, PF, PF, i64, PF]),
         "hg_gemm_tf32": (i32, [P(Gemm), PF]),
         "hg_set_gemm_mode": (i32, [i32]),

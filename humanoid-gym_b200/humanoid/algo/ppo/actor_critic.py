@@ -77,6 +77,8 @@ class ActorCritic(nn.Module):
         self._flat = flat
         self._wsplit = torch.zeros(2, 1, n, dtype=torch.int16, device=dev)     # split bf16 image of the flat buffer (hi, lo planes)
         self._wsplit_dirty = True
+        self._wlo = torch.zeros(n, dtype=torch.float32, device=dev)            # tf32 residuals of the flat buffer (3xTF32 "lo" operand)
+        self._wlo_dirty = True
         self.num_params = n                       # allocated floats (incl. pads) == length of every flat buffer
         self.num_real_params = sum(p.numel() for p in params)
         self._desc = {}
@@ -154,16 +156,45 @@ class ActorCritic(nn.Module):
             self._scratch[key] = torch.empty(M * self.hidden_width(which), dtype=torch.float32, device=self._flat.device)
         return self._scratch[key]
 
-    def native_forward(self, which, x, out, hidden=None):
-        """out (M, dims[-1]) <- MLP_which(x); returns the hidden-activation scratch."""
+    def invalidate_derived(self):
+        """Call after writing parameters behind this module's back (p.data.copy_, optimizer steps of your own): the
+        split images of the weights (bf16 hi / lo planes, tf32 residuals) are recomputed on next use."""
+        self._wsplit_dirty = True
+        self._wlo_dirty = True
+
+    def load_state_dict(self, *a, **k):
+        r = super().load_state_dict(*a, **k)
+        self.invalidate_derived()
+        return r
+
+    def refresh_lo(self):
+        """tf32 residuals of the whole flat buffer (one launch, 3.7 MB): the rollout's GEMMs then load weight-lo tiles by
+        TMA and their splitter warps handle the activations only."""
+        flat = self.flat_params()
+        nat.check(nat.lib.hg_tf32_residual(flat.data_ptr(), self._wlo.data_ptr(), flat.numel(), nat.stream_ptr(flat.device.index)),
+                  "hg_tf32_residual")
+        self._wlo_dirty = False
+
+    def native_forward(self, which, x, out, hidden=None, sample=None):
+        """out (M, dims[-1]) <- MLP_which(x); returns the hidden-activation scratch.
+        sample: optional dict(std, eps, actions, log_prob, sigma, seed, step, step_dev) -> PPO.act fused into the output
+        layer's epilogue (out receives the mean)."""
         flat = self.flat_params()
         M = x.shape[0]
         assert x.dtype == torch.float32 and x.stride(1) == 1
         if hidden is None:
             hidden = self._hidden_scratch(which, M)
-        nat.check(nat.lib.hg_mlp_forward(self._desc[which], flat.data_ptr(), x.data_ptr(), x.stride(0),
-                                         hidden.data_ptr(), out.data_ptr(), M, nat.stream_ptr(flat.device.index)),
-                  "hg_mlp_forward")
+        if self._wlo_dirty and not torch.cuda.is_current_stream_capturing():
+            self.refresh_lo()
+        o = nat.MlpFwdOpts()
+        o.params_lo = None if self._wlo_dirty else self._wlo.data_ptr()
+        if sample is not None:
+            o.std, o.eps = sample["std"].data_ptr(), nat.ptr(sample.get("eps"))
+            o.actions, o.log_prob, o.sigma = sample["actions"].data_ptr(), sample["log_prob"].data_ptr(), sample["sigma"].data_ptr()
+            o.seed, o.step, o.step_dev = sample["seed"], sample["step"], sample.get("step_dev")
+        nat.check(nat.lib.hg_mlp_forward_ex(self._desc[which], flat.data_ptr(), x.data_ptr(), x.stride(0),
+                                            hidden.data_ptr(), out.data_ptr(), M, o, nat.stream_ptr(flat.device.index)),
+                  "hg_mlp_forward_ex")
         return hidden
 
     # ------------------------------------------------------------------------------------------

@@ -63,7 +63,9 @@ class OnPolicyRunner:
         if begin is not None:
             begin(self.num_steps_per_env)                 # host-resident frames: a self-contained prefetch schedule
         for t in range(self.num_steps_per_env):
-            actions = alg.act(obs, critic_obs, step_dev=step_dev)
+            # the Philox step of the action noise is the env's noise-step counter: its device copy when the launches must
+            # be graph-replayable, the host mirror otherwise -- the same value either way, so replay == eager bit for bit
+            actions = alg.act(obs, critic_obs, step_dev=step_dev, step=getattr(env, "_noise_step", None))
             obs, privileged_obs, rewards, dones, infos = env.step(actions)
             critic_obs = privileged_obs if privileged_obs is not None else obs
             alg.process_env_step(rewards, dones, infos)

@@ -53,9 +53,22 @@ class PPO:
         self._loss_sums = torch.zeros(_TAIL, dtype=torch.float32, device=dev)
         self._sample_step = 0
         self._seed = (torch.initial_seed() * 0x9E3779B97F4A7C15 + 12345) % (1 << 64)
+        # env-sharded data parallelism: every rank seeds torch identically (set_seed), and the Philox counter of
+        # hg_policy_sample is (seed, LOCAL env index, step) -- without the rank in the key all shards would draw the
+        # same exploration noise
+        rank = dist.get_rank() if dist.is_available() and dist.is_initialized() else int(__import__("os").environ.get("RANK", "0"))
+        self._seed = self.rank_seed(self._seed, rank)
         self._alias_grads_and_state()
         self._mb_scratch = {}
         self._side = torch.cuda.Stream(dev)
+
+    @staticmethod
+    def rank_seed(seed, rank):
+        """splitmix64 of the rank folded into the Philox key (rank 0 keeps a non-trivial offset too)."""
+        z = (rank + 1) * 0x9E3779B97F4A7C15 % (1 << 64)
+        z = ((z ^ (z >> 30)) * 0xBF58476D1CE4E5B9) % (1 << 64)
+        z = ((z ^ (z >> 27)) * 0x94D049BB133111EB) % (1 << 64)
+        return (seed ^ z ^ (z >> 31)) % (1 << 64)
 
     # ------------------------------------------------------------------------------------------
     def _alias_grads_and_state(self):
@@ -110,7 +123,7 @@ class PPO:
     # ------------------------------------------------------------------------------------------
     # rollout
     # ------------------------------------------------------------------------------------------
-    def act(self, obs, critic_obs, eps=None, step_dev=None):
+    def act(self, obs, critic_obs, eps=None, step_dev=None, step=None):
         """ppo.py:91-101.  Everything lands directly in slab t of the storage: actor mean -> mu[t],
         value -> values[t], sampled actions / log-prob / sigma -> actions[t] / actions_log_prob[t] / sigma[t];
         obs and critic obs are copied now, because env.step() overwrites the env's buffers in place."""
@@ -128,12 +141,10 @@ class PPO:
             # the 15 MB observation copy into slab t rides on the side stream too: nothing before the update reads it
             s.add_native(t, obs=obs, priv_obs=critic_obs if s.privileged_observations is not None else None)
         self._critic_pending = True
-        st = nat.stream_ptr(self._dev_index)
-        ac.native_forward("actor", obs, s.mu[t])
-        nat.check(nat.lib.hg_policy_sample(
-            s.mu[t].data_ptr(), ac.std.data_ptr(), nat.ptr(eps), self._seed, self._sample_step, step_dev,
-            s.actions[t].data_ptr(), s.actions_log_prob[t].data_ptr(), s.sigma[t].data_ptr(),
-            s.num_envs, s.actions_shape[0], st), "hg_policy_sample")
+        # actor forward with ActorCritic.act + get_actions_log_prob fused into the output layer's epilogue
+        ac.native_forward("actor", obs, s.mu[t], sample=dict(
+            std=ac.std, eps=eps, actions=s.actions[t], log_prob=s.actions_log_prob[t], sigma=s.sigma[t], seed=self._seed,
+            step=self._sample_step if step is None else int(step), step_dev=step_dev))
         self._sample_step += 1
         # The value estimate is not needed before process_env_step (r += gamma * V * time_out), so the critic chain is
         # joined there: it overlaps the whole env step instead of sitting on the act -> step critical path.  The env
@@ -272,7 +283,7 @@ class PPO:
         nat.check(nat.lib.hg_clip_adam_step(flat.data_ptr(), g, self._exp_avg.data_ptr(), self._exp_avg_sq.data_ptr(),
                                             self._sqnorm.data_ptr(), float(self.max_grad_norm), self._lr.data_ptr(),
                                             self._adam_step.data_ptr(), 0.9, 0.999, 1e-8, 1.0, n, st), "hg_clip_adam_step")
-        ac._wsplit_dirty = True
+        ac.invalidate_derived()
         if split:
             ac.refresh_split()                             # the next minibatch's GEMMs read the split image of the new weights
         self._loss_sums.add_(self._scalars)
@@ -292,6 +303,7 @@ class PPO:
             for i in range(self.num_mini_batches):
                 mb = s.gather(indices[i * mini:(i + 1) * mini], split=split)
                 self.minibatch_step(mb, world)
+        self.actor_critic.refresh_lo()                       # the next rollout's GEMMs load weight-lo tiles by TMA
         num_updates = self.num_learning_epochs * self.num_mini_batches
         sums = self._loss_sums.tolist()                          # the only device->host read of the update
         s.clear()

@@ -303,11 +303,13 @@ class LeggedRobot(BaseTask):
             self.actions.copy_(torch.clip(actions, -clip, clip))
         g = self.gym
         st = nat.stream_ptr(self._dev_index)
-        for _ in range(self.cfg.control.decimation):
-            nat.check(nat.lib.hg_env_compute_torques(self._B, self._P, self.num_envs, st), "hg_env_compute_torques")
-            g.set_dof_actuation_force_tensor(self.torques)
-            g.simulate()
-            g.refresh_dof_state_tensor()
+        self._refreshed = bool(g.fused_decimation(self))          # synthetic source: the whole loop + refreshes, one launch
+        if not self._refreshed:
+            for _ in range(self.cfg.control.decimation):
+                nat.check(nat.lib.hg_env_compute_torques(self._B, self._P, self.num_envs, st), "hg_env_compute_torques")
+                g.set_dof_actuation_force_tensor(self.torques)
+                g.simulate()
+                g.refresh_dof_state_tensor()
         self.post_physics_step()
         return self.obs_buf, self.privileged_obs_buf, self.rew_buf, self.reset_buf, self.extras
 
@@ -320,9 +322,11 @@ class LeggedRobot(BaseTask):
 
     def post_physics_step(self):                                  # :119-154 + the clip of :104-108
         g = self.gym
-        g.refresh_actor_root_state_tensor()
-        g.refresh_net_contact_force_tensor()
-        g.refresh_rigid_body_state_tensor()
+        if not getattr(self, "_refreshed", False):
+            g.refresh_actor_root_state_tensor()
+            g.refresh_net_contact_force_tensor()
+            g.refresh_rigid_body_state_tensor()
+        self._refreshed = False
         self.common_step_counter += 1
         self._launch_post_physics(nat.PHASE_STEP_ALL)
         self._injected = {}

@@ -165,6 +165,16 @@ int32_t hg_env_pre_physics(const HgEnvBuffers* B, const HgEnvParams* P, const fl
  * decimation sub-step.  Reads B->actions, B->dof_state; writes B->torques. */
 int32_t hg_env_compute_torques(const HgEnvBuffers* B, const HgEnvParams* P, int64_t N, void* stream);
 
+/* Synthetic-physics fast path of the decimation loop (legged_robot.py:94-101) + the three state refreshes of
+ * post_physics_step (:124-126): with an open-loop frame source the `decimation` x {PD torque, set forces, simulate,
+ * refresh dof} sub-steps collapse into ONE launch.  dof_frames: (decimation, N*12, 2) the dof state after each
+ * sub-step; root / contact / rigid frame: the state after the last one.  Sub-step d's PD law is evaluated against
+ * the state sub-step d-1 left (d = 0: the live B->dof_state); B->torques receives the last torque, B->dof_state the
+ * last frame -- exactly what the loop leaves behind.  A real simulator keeps the loop (hg_env_compute_torques). */
+int32_t hg_env_synth_decimation(const HgEnvBuffers* B, const HgEnvParams* P, const float* dof_frames, int32_t decimation,
+                                const float* root_frame, const float* contact_frame, const float* rigid_frame,
+                                int64_t N, void* stream);
+
 /* LeggedRobot.post_physics_step (legged_robot.py:119-154) with everything it
  * calls, fused into one launch; `phases` selects sub-sequences so that
  * reset_idx() / compute_observations() stay callable on their own.
@@ -211,7 +221,8 @@ int32_t hg_mlp_backward(const HgMlpDesc* net, const float* params, const float* 
  *   b_mn_major = 0: B is (N, K) row-major  (pitch ldb);  1: B is (K, N) row-major
  *   passes     = 3: 3xTF32 split compensation (fp32-class accuracy);  1: plain TF32
  *   epilogue   : 0 store, 1 +bias[N], 2 +bias then ELU, 3 multiply by ELU'(z) recovered from H = ELU(z) (pitch ldh),
- *                4 atomicAdd into C (required when split_k > 1; C must be zeroed by the caller)
+ *                4 atomicAdd into C (required when split_k > 1; C must be zeroed by the caller),
+ *                5 +bias then the fused PPO.act sampling epilogue (sample_* fields)
  *   trust_hw_truncation: 1 = feed the raw fp32 tile as the "hi" operand (the tensor core drops the low 13
  *                mantissa bits itself); 0 = rewrite it with an explicit truncation first
  * Requirements: A, B 16-byte aligned with lda, ldb multiples of 4 (TMA); violations return HG_E_ALIGN. */
@@ -220,8 +231,26 @@ typedef struct HgGemm {
     int32_t M, N, K;
     int64_t lda, ldb, ldc, ldh;
     int32_t a_mn_major, b_mn_major, epilogue, passes, split_k, trust_hw_truncation;
+    const float* B_lo;              /* optional, K-major B with passes = 3: rna_tf32(B - trunc_tf32(B)) in the same layout
+                                       (hg_tf32_residual): the tile arrives by TMA and the kernel splits A only         */
+    /* epilogue 5 (N <= 32): + bias, then PPO.act on the row -- C receives the mean, see hg_policy_sample */
+    const float* sample_std; const float* sample_eps; float* sample_actions; float* sample_log_prob; float* sample_sigma;
+    uint64_t sample_seed, sample_step; const uint64_t* sample_step_dev;
 } HgGemm;
 int32_t hg_gemm_tf32(const HgGemm* d, void* stream);
+/* dst[i] = rna_tf32(src[i] - trunc_tf32(src[i])): the "lo" operand of the 3xTF32 scheme for a whole buffer (weights). */
+int32_t hg_tf32_residual(const float* src, float* dst, int64_t n, void* stream);
+
+/* hg_mlp_forward with options for the rollout (PPO.act, ppo.py:91-101): params_lo = hg_tf32_residual(params) lets
+ * every layer load its weight residuals by TMA (the in-kernel splitter then handles the activations only); when
+ * `actions` is set the output layer's epilogue also samples a = mu + sigma z, log-prob and sigma (out receives mu). */
+typedef struct HgMlpFwdOpts {
+    const float* params_lo;
+    const float* std; const float* eps; float* actions; float* log_prob; float* sigma;
+    uint64_t seed, step; const uint64_t* step_dev;
+} HgMlpFwdOpts;
+int32_t hg_mlp_forward_ex(const HgMlpDesc* net, const float* params, const float* X, int64_t ldx, float* hidden, float* out,
+                          int64_t M, const HgMlpFwdOpts* opts, void* stream);
 /* GEMM engine of hg_mlp_forward / hg_mlp_backward: 0 = exact-fp32 CUDA-core path, 1 = tcgen05 3xTF32,
  * 2 = tcgen05 plain TF32, 4 (default) = 3xTF32 for this fp32 API (rollout forward, 1e-5 bar) AND a hint to the host
  * layer to run PPO.update on the split-precision API below (hg_mlp_*_split, 1e-4 gradient bar).
@@ -360,7 +389,7 @@ int32_t hg_adapt_lr(const float* kl_mean_dev, double desired_kl, double* lr_dev,
 int32_t hg_version(void);
 /* sizeof() of the ABI structs, for binding self-checks: 0 HgEnvParams, 1 HgEnvBuffers,
  * 2 HgEnvNoise, 3 HgMlpDesc, 4 HgTransition, 5 HgStorage, 6 HgMiniBatch, 7 HgPpoLossArgs, 8 HgGemm, 9 HgSplit,
- * 10 HgGemmSplit */
+ * 10 HgGemmSplit, 11 HgMlpFwdOpts */
 int64_t hg_struct_size(int32_t which);
 const char* hg_last_error(void);
 /* number of kernel launches issued by this library in the calling process */

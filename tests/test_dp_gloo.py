@@ -98,3 +98,18 @@ def test_sharded_gradient_equals_single_process():
     want = (full - full.mean()) / (full.std() + 1e-8)
     got = torch.cat([a0, a1])
     assert torch.allclose(got, want, atol=1e-6)
+
+
+def test_policy_sample_seed_differs_per_rank():
+    """the Philox key of hg_policy_sample must include the rank, or every env shard draws the same
+    exploration noise.  (Host-side check of the seed derivation; the draw itself is keyed (seed, env, step).)"""
+    import importlib.util
+    import os
+    import re
+    src = open(os.path.join(ROOT, "humanoid-gym_b200", "humanoid", "algo", "ppo", "ppo.py")).read()
+    body = re.search(r"    def rank_seed\(seed, rank\):\n((?:        .*\n)+)", src).group(1)
+    ns = {}
+    exec("def rank_seed(seed, rank):\n" + body.replace("        ", "    ", 1).replace("\n        ", "\n    "), ns)
+    seeds = {ns["rank_seed"](123456789, r) for r in range(8)}
+    assert len(seeds) == 8
+    assert all(0 <= s < (1 << 64) for s in seeds)

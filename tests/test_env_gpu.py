@@ -187,7 +187,7 @@ def test_properties_at_benchmark_sizes(N):
     clean = env2.obs_buf[:, -47:]
     d = (noisy - clean)
     want = env2.noise_scale_vec * 0.6
-    assert torch.allclose(d.std(dim=0), want, rtol=0.03, atol=1e-6)
+    assert torch.allclose(d.std(dim=0), want, rtol=max(0.03, 4.0 / np.sqrt(2 * N)), atol=1e-6)      # std of a std estimate: 1/sqrt(2N)
     assert d.mean(dim=0).abs().max() < 4 * float(want.max()) / np.sqrt(N)
 
 
@@ -227,3 +227,27 @@ def test_host_resident_frames_match_device_resident():
         assert torch.equal(ra, rb) and torch.equal(da, db), t
     torch.cuda.synchronize()
     assert b.gym.h2d_bytes_per_step() > 0 and a.gym.h2d_bytes_per_step() == 0
+
+
+def test_fused_decimation_matches_the_loop():
+    """SyntheticPhysics.fused_decimation (one launch for the 10 sub-steps + refreshes) leaves exactly what the
+    reference-shaped loop (10 x {hg_env_compute_torques, simulate, refresh_dof} + 3 refreshes) leaves: bit-identical
+    torques, states, observations and rewards over a ring wrap."""
+    N, steps = 512, 14
+    torch.manual_seed(0)
+    np.random.seed(0)
+    a = make_env(N, physics="synthetic")
+    torch.manual_seed(0)
+    np.random.seed(0)
+    b = make_env(N, physics="synthetic")
+    b.gym.fused = False
+    assert a.gym.fused
+    g = torch.Generator(device="cuda").manual_seed(4)
+    for t in range(steps):
+        act = torch.randn(N, 12, device="cuda", generator=g)
+        oa, pa, ra, da, _ = a.step(act.clone())
+        ob, pb, rb, db, _ = b.step(act.clone())
+        for k in ("torques", "dof_state", "root_states", "contact_forces", "rigid_state"):
+            assert torch.equal(getattr(a, k), getattr(b, k)), (t, k)
+        assert torch.equal(oa, ob) and torch.equal(pa, pb) and torch.equal(ra, rb) and torch.equal(da, db), t
+    assert a.gym.substep == b.gym.substep == steps * 10

@@ -1,7 +1,7 @@
 """tcgen05 bf16x3 GEMM on pre-split operands (hg_gemm_bf16x3) against an fp64 torch reference: every operand layout and
 epilogue the split-precision MLP path uses, ragged extents included.  Two error budgets are checked separately:
-  * exactness of the kernel on the operands it is given (reference = fp64 product of the SAME hi + lo values): ~1e-6,
-    i.e. only the dropped lo*lo term and fp32 accumulation;
+  * exactness of the kernel on the operands it is given (reference = fp64 product of the SAME hi + lo values): < 5e-6,
+    i.e. only the dropped lo*lo term (2^-18 relative per element at worst) and fp32 accumulation;
   * accuracy against the original fp32 operands (what the gradient bar sees): ~5e-6 per product."""
 import pytest
 import torch
@@ -77,7 +77,7 @@ def test_forward_layout_k_major(M, N, K):
     Xs, Xv = _split(X)
     Ws, Wv = _split(W)
     C = _gemm(Xs, Ws, M, N, K, 0, 0, 0)
-    assert _rel(C, Xv.double() @ Wv.double().t()) < 2e-6, _rel(C, Xv.double() @ Wv.double().t())
+    assert _rel(C, Xv.double() @ Wv.double().t()) < 5e-6, _rel(C, Xv.double() @ Wv.double().t())
     ref = X.double() @ W.double().t()
     assert _rel(C, ref) < 1e-5, _rel(C, ref)
     C1 = _gemm(Xs, Ws, M, N, K, 0, 0, 1, bias=b)
@@ -117,7 +117,7 @@ def test_wgrad_layout(Nout, Kin, batch, split):
     Xs, xv = _split(X)
     C = _gemm(dZs, Xs, Nout, Kin, batch, 1, 1, 4, split_k=split)
     exact = dv.double().t() @ xv.double()
-    assert _rel(C, exact) < max(2e-6, 2e-7 * batch ** 0.5), _rel(C, exact)
+    assert _rel(C, exact) < max(5e-6, 2e-7 * batch ** 0.5), _rel(C, exact)
     ref = dZ.double().t() @ X.double()
     assert _rel(C, ref) < max(1e-5, 2e-7 * batch ** 0.5), _rel(C, ref)
 

@@ -5,7 +5,7 @@ import torch
 pytestmark = pytest.mark.gpu
 
 
-def _run(A, B, M, N, K, a_mn, b_mn, passes, epilogue=0, bias=None, H=None, split_k=1, trust=0, C=None):
+def _run(A, B, M, N, K, a_mn, b_mn, passes, epilogue=0, bias=None, H=None, split_k=1, trust=0, C=None, B_lo=None):
     from humanoid import _native as nat
     if C is None:
         C = torch.zeros(M, N, device="cuda")
@@ -16,6 +16,7 @@ def _run(A, B, M, N, K, a_mn, b_mn, passes, epilogue=0, bias=None, H=None, split
     d.M, d.N, d.K = M, N, K
     d.lda, d.ldb, d.ldc = A.stride(0), B.stride(0), C.stride(0)
     d.ldh = H.stride(0) if H is not None else 0
+    d.B_lo = B_lo.data_ptr() if B_lo is not None else None
     d.a_mn_major, d.b_mn_major, d.epilogue, d.passes, d.split_k, d.trust_hw_truncation = a_mn, b_mn, epilogue, passes, split_k, trust
     nat.check(nat.lib.hg_gemm_tf32(d, torch.cuda.current_stream().cuda_stream), "hg_gemm_tf32")
     torch.cuda.synchronize()
@@ -103,3 +104,24 @@ def test_alignment_errors():
     W = torch.randn(32, 705, device="cuda")
     with pytest.raises(nat.NativeError, match="16-byte"):
         _run(X, W, 64, 32, 705, 0, 0, 3)
+
+
+@pytest.mark.parametrize("M,N,K", [(4096, 512, 705), (4096, 256, 512), (4096, 128, 256), (300, 768, 219), (4096, 12, 128)])
+def test_presplit_weight_residuals(M, N, K):
+    """B_lo = hg_tf32_residual(B) loaded by TMA (the rollout path: splitter handles A only) must reproduce the in-kernel
+    split bit for bit -- same residual formula, same MMA order -- for every tile width the skinny-batch heuristic picks."""
+    from humanoid import _native as nat
+    g = torch.Generator(device="cuda").manual_seed(M + N + K)
+    X = _pad4(torch.randn(M, K, device="cuda", generator=g))
+    W = _pad4(torch.randn(N, K, device="cuda", generator=g) / K ** 0.5)
+    b = torch.randn(N, device="cuda", generator=g)
+    Wbuf = torch.zeros(N, W.stride(0), device="cuda")
+    Wbuf[:, :K] = W
+    lo = torch.empty_like(Wbuf)
+    nat.check(nat.lib.hg_tf32_residual(Wbuf.data_ptr(), lo.data_ptr(), Wbuf.numel(), 0), "hg_tf32_residual")
+    Wv = Wbuf[:, :K]
+    a = _run(X, Wv, M, N, K, 0, 0, 3, epilogue=2, bias=b, trust=1)
+    c = _run(X, Wv, M, N, K, 0, 0, 3, epilogue=2, bias=b, trust=1, B_lo=lo[:, :K])
+    assert torch.equal(a, c), float((a - c).abs().max())
+    ref = torch.nn.functional.elu(X.double() @ W.double().t() + b.double())
+    assert _rel(c, ref) < 2e-5, _rel(c, ref)

@@ -112,6 +112,36 @@ def test_forward_sample_logprob_vs_golden():
     assert abs(float((a2 ** 4).mean()) - 3) < 0.1
 
 
+def test_act_fused_sampling_matches_standalone_kernel():
+    """PPO.act samples inside the actor's output-layer epilogue on the tensor-core engines; the stand-alone
+    hg_policy_sample kernel on the same mean must give bit-identical actions / log-prob / sigma (Philox and injected eps)."""
+    from humanoid.algo import PPO
+    from humanoid import _native as nat
+    ac = _make_ac(705, 219, 12, [512, 256, 128], [768, 256, 128])
+    with torch.no_grad():
+        ac.std.copy_(0.5 + torch.rand(12, device="cuda"))
+    alg = PPO(ac, num_learning_epochs=1, num_mini_batches=1, device="cuda:0")
+    N = 1000
+    alg.init_storage(N, 4, [705], [219], [12])
+    s = alg.storage
+    g = torch.Generator(device="cuda").manual_seed(2)
+    for t, eps in enumerate((None, torch.randn(N, 12, device="cuda", generator=g))):
+        obs = _pad4(torch.randn(N, 705, device="cuda", generator=g))
+        cobs = _pad4(torch.randn(N, 219, device="cuda", generator=g))
+        alg.act(obs, cobs, eps=eps, step=77 + t)
+        torch.cuda.synchronize()
+        mu = s.mu[t].contiguous()
+        a, lp, sg = torch.empty(N, 12, device="cuda"), torch.empty(N, device="cuda"), torch.empty(N, 12, device="cuda")
+        nat.check(nat.lib.hg_policy_sample(mu.data_ptr(), ac.std.data_ptr(), nat.ptr(eps), alg._seed, 77 + t, None, a.data_ptr(),
+                                           lp.data_ptr(), sg.data_ptr(), N, 12, 0))
+        torch.cuda.synchronize()
+        assert torch.equal(a, s.actions[t]) and torch.equal(sg, s.sigma[t]), t
+        assert torch.equal(lp, s.actions_log_prob[t].view(-1)), float((lp - s.actions_log_prob[t].view(-1)).abs().max())
+        ref_mu = po.mlp(obs.cpu(), {k: v.detach().cpu() for k, v in ac.state_dict().items()}, "actor")
+        assert _rel(mu.cpu(), ref_mu) < 1e-5
+        s.step += 1
+
+
 def test_gae_vs_golden_and_large():
     from humanoid.algo import RolloutStorage
     g = Golden("ppo_learning.npz")
@@ -337,3 +367,47 @@ def test_runner_end_to_end_small():
     assert torch.isfinite(runner.alg.actor_critic.flat_params()).all()
     assert not torch.equal(w0, runner.alg.actor_critic.flat_params())
     assert runner.last_perf["fps"] > 0
+
+
+def test_graph_replay_matches_eager_rollout():
+    """The CUDA-graph rollout (default) must reproduce the eager rollout bit for bit: same storage slabs, same final
+    observations / env state, for two consecutive collection phases (capture happens on the second)."""
+    from parity_utils import make_args
+    from humanoid.envs import XBotLCfg  # noqa: F401
+    from humanoid.utils import task_registry
+    import os
+
+    def build():
+        torch.manual_seed(0)
+        np.random.seed(0)
+        args = make_args(256)
+        env, _ = task_registry.make_env("humanoid_ppo", args=args)
+        runner, _ = task_registry.make_alg_runner(env, name="humanoid_ppo", args=args, log_root=None)
+        return env, runner
+
+    def run(runner, env, phases):
+        obs, cobs = env.get_observations(), env.get_privileged_observations()
+        out = []
+        with torch.inference_mode():
+            for _ in range(phases):
+                obs, cobs = runner.collect(obs, cobs)
+                torch.cuda.synchronize()
+                s = runner.alg.storage
+                out.append({k: getattr(s, k).clone() for k in ("observations", "privileged_observations", "actions", "rewards", "dones",
+                                                               "values", "actions_log_prob", "mu", "sigma", "returns", "advantages")})
+                out[-1]["obs"], out[-1]["rew"] = obs.clone(), env.rew_buf.clone()
+                s.clear()
+        return out
+
+    os.environ["HG_CUDA_GRAPH"] = "0"
+    try:
+        env_e, run_e = build()
+        eager = run(run_e, env_e, 3)
+    finally:
+        os.environ["HG_CUDA_GRAPH"] = "1"
+    env_g, run_g = build()
+    graph = run(run_g, env_g, 3)
+    assert getattr(run_g, "_graph", None) is not None, "the graph path did not engage"
+    for ph, (a, b) in enumerate(zip(eager, graph)):
+        for k in a:
+            assert torch.equal(a[k], b[k]), (ph, k, float((a[k].float() - b[k].float()).abs().max()))
