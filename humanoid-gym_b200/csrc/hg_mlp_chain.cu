@@ -1,0 +1,464 @@
+// PPO.act in ONE launch: actor AND critic MLPs (actor_critic.py:54-77,111-128; ppo.py:91-101), every Linear layer of both
+// as tcgen05 3xTF32 tiles of one persistent kernel, with the layer-to-layer dependencies resolved inside the kernel.
+//
+// Why: at rollout batch sizes (M = num_envs = 4096 -> 32 row tiles) each layer is a 1-9 us main loop wrapped in ~8 us of
+// launch / TMEM-allocation / pipeline-fill / drain overhead, and the 200 KB shared-memory footprint of a tensor-core CTA
+// means the eight per-layer kernels of actor and critic cannot share an SM: they serialise (~100 us per env step,
+// measured).  Here the fixed costs are paid once, actor and critic tiles interleave on all 148 SMs, and a layer's tiles
+// start as soon as the row tile they consume is complete.
+//
+// Work list (same in every warp role): for layer l = 0 .. L-1 (actor and critic layers interleaved, inputs first):
+// items (row tile tm, column tile tn), CTA c takes items c' = (c + rot_l) mod G, c' + G, ...  Dependencies: layer l reads
+// the activations its `dep` layer wrote to global memory (L2-resident: 128 x N x 4 B per row tile); the epilogue
+// publishes a finished tile with  __threadfence + barrier + atomicAdd(counters[l][tm]),  the TMA producer spins on
+// counters[dep][tm] == tiles_n(dep) (acquire) and issues a cross-proxy fence before the first load of the item.  All CTAs
+// are co-resident (grid <= #SMs, one CTA per SM) and walk the layers in the same order, so the waits cannot cycle.  The
+// last CTA to finish re-zeroes the counters: the launch is self-contained and CUDA-graph replayable.
+//
+// Tile pipeline = gemm_tc_kernel's (hg_gemm_tc.cu): 14 warps (4 epilogue, TMA producer, MMA issuer, 8 splitter warps),
+// 4-deep ring of raw {A, B, B_lo} stages (weight residuals pre-split by hg_tf32_residual, loaded by TMA), 2-deep ring of
+// A_lo tiles written by the splitter, accumulator double-buffered in TMEM.  The actor's output layer samples the action
+// in its epilogue (same arithmetic as policy_sample_kernel).
+#include <cuda.h>
+
+#include <mutex>
+#include <unordered_map>
+
+#include "hg_common.cuh"
+#include "hg_tc_ptx.cuh"
+
+using namespace hgtc;
+
+namespace {
+
+constexpr int BM = 128, BK = 32, BN_MAX = 128;
+constexpr int RAW_STAGES = 4, LO_STAGES = 2;
+constexpr int TILE_BYTES = BM * BK * 4;                         // 16 KB
+constexpr int RAW_STRIDE = TILE_BYTES + 2 * BN_MAX * BK * 4;    // A + B + B_lo = 48 KB
+constexpr int LO_STRIDE = TILE_BYTES;                           // A_lo
+constexpr int SPLIT_WARPS = 8;
+constexpr int THREADS = (6 + SPLIT_WARPS) * 32;
+constexpr int SMEM_BYTES = RAW_STAGES * RAW_STRIDE + LO_STAGES * LO_STRIDE + 1024 + 256;
+constexpr int MAX_CHAIN = 8;
+constexpr float kLogSqrt2Pi = 0.9189385332046727f;
+
+enum { CH_BIAS = 1, CH_BIAS_ELU = 2, CH_BIAS_SAMPLE = 5 };
+
+struct ChainLayer {
+    float* C; const float* bias; int64_t ldc;
+    int N, K, BN, epi, tiles_n, dep, rot;
+};
+struct ChainArgs {
+    int M, tiles_m, n_layers;
+    int* counters;                       // [MAX_CHAIN][tiles_m] tile counters + [MAX_CHAIN * tiles_m] "CTAs done"
+    ChainLayer L[MAX_CHAIN];
+    const float* stdv; const float* eps; float* actions; float* logp; float* sigma;
+    uint64_t seed, step; const uint64_t* step_dev;
+};
+struct alignas(64) ChainMaps { CUtensorMap a[MAX_CHAIN], b[MAX_CHAIN], blo[MAX_CHAIN]; };
+
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {         // K-major [rows][32 fp32], SWIZZLE_128B
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+__device__ __forceinline__ uint32_t make_idesc(int N) {                 // D = F32, A = B = TF32, K-major, M = 128
+    uint32_t d = 0;
+    d |= 1u << 4;
+    d |= 2u << 7;
+    d |= 2u << 10;
+    d |= (uint32_t)(N >> 3) << 17;
+    d |= (uint32_t)(BM >> 4) << 24;
+    return d;
+}
+__device__ __forceinline__ int ld_acquire(const int* p) {
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+__global__ void __launch_bounds__(THREADS, 1) mlp_chain_kernel(const __grid_constant__ ChainMaps maps, const ChainArgs g) {
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    unsigned char* smem_lo = smem + RAW_STAGES * RAW_STRIDE;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_lo + LO_STAGES * LO_STRIDE);
+    uint64_t* full = bars;                          // [RAW] TMA -> splitter (and MMA)
+    uint64_t* empty = full + RAW_STAGES;            // [RAW] MMA -> TMA
+    uint64_t* ready = empty + RAW_STAGES;           // [LO]  splitter -> MMA
+    uint64_t* lo_empty = ready + LO_STAGES;         // [LO]  MMA -> splitter
+    uint64_t* tmem_full = lo_empty + LO_STAGES;     // [2]   MMA -> epilogue
+    uint64_t* tmem_empty = tmem_full + 2;           // [2]   epilogue -> MMA
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int G = gridDim.x;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < RAW_STAGES; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], 1);
+        }
+        for (int s = 0; s < LO_STAGES; ++s) {
+            mbar_init(&ready[s], SPLIT_WARPS);
+            mbar_init(&lo_empty[s], 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(&tmem_full[a], 1);
+            mbar_init(&tmem_empty[a], 4);
+        }
+        fence_barrier_init();
+    }
+    if (warp == 5) tmem_alloc(tmem_slot, 256);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 4) {
+        // ===== TMA producer =====
+        if (lane == 0) {
+            for (int l = 0; l < g.n_layers; ++l) {
+                asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.a[l]) : "memory");
+                asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.b[l]) : "memory");
+                asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.blo[l]) : "memory");
+            }
+            int it = 0;
+            for (int l = 0; l < g.n_layers; ++l) {
+                const ChainLayer& Ly = g.L[l];
+                const int items = g.tiles_m * Ly.tiles_n, num_kb = (Ly.K + BK - 1) / BK;
+                const uint32_t b_bytes = (uint32_t)Ly.BN * BK * 4, tx = TILE_BYTES + 2 * b_bytes;
+                for (int w = (blockIdx.x + Ly.rot) % G; w < items; w += G) {
+                    const int tm = w / Ly.tiles_n, tn = w - tm * Ly.tiles_n;
+                    if (Ly.dep >= 0) {                   // wait until every column tile of the producing layer has published row tile tm
+                        const int need = g.L[Ly.dep].tiles_n;
+                        const int* c = g.counters + Ly.dep * g.tiles_m + tm;
+                        while (ld_acquire(c) < need) __nanosleep(64);
+                        asm volatile("fence.proxy.async;" ::: "memory");    // generic-proxy acquire -> async-proxy (TMA) reads
+                    }
+                    for (int kb = 0; kb < num_kb; ++kb, ++it) {
+                        const int s = it % RAW_STAGES, k0 = kb * BK;
+                        mbar_wait(&empty[s], ((it / RAW_STAGES) & 1) ^ 1);
+                        unsigned char* st = smem + s * RAW_STRIDE;
+                        mbar_expect_tx(&full[s], tx);
+                        tma_load_2d(st, &maps.a[l], &full[s], k0, tm * BM);
+                        tma_load_2d(st + TILE_BYTES, &maps.b[l], &full[s], k0, tn * Ly.BN);
+                        tma_load_2d(st + TILE_BYTES + BN_MAX * BK * 4, &maps.blo[l], &full[s], k0, tn * Ly.BN);
+                    }
+                }
+            }
+        }
+    } else if (warp == 5) {
+        // ===== MMA issuer =====
+        if (lane == 0) {
+            int it = 0, item = 0;
+            for (int l = 0; l < g.n_layers; ++l) {
+                const ChainLayer& Ly = g.L[l];
+                const int items = g.tiles_m * Ly.tiles_n, num_kb = (Ly.K + BK - 1) / BK;
+                const uint32_t idesc = make_idesc(Ly.BN);
+                for (int w = (blockIdx.x + Ly.rot) % G; w < items; w += G, ++item) {
+                    const int acc_stage = item & 1;
+                    mbar_wait(&tmem_empty[acc_stage], ((item >> 1) & 1) ^ 1);
+                    tc_fence_after();
+                    const uint32_t tmem_d = tmem_base + (uint32_t)(acc_stage * 128);
+                    for (int kb = 0; kb < num_kb; ++kb, ++it) {
+                        const int s = it % RAW_STAGES, lo = it % LO_STAGES;
+                        mbar_wait(&ready[lo], (it / LO_STAGES) & 1);              // A_lo written (the raw stage landed before that)
+                        mbar_wait(&full[s], (it / RAW_STAGES) & 1);
+                        tc_fence_after();
+                        const uint32_t base = smem_u32(smem + s * RAW_STRIDE), base_lo = smem_u32(smem_lo + lo * LO_STRIDE);
+#pragma unroll
+                        for (int kk = 0; kk < BK / 8; ++kk) {
+                            const uint64_t a_hi = make_desc(base + kk * 32);
+                            const uint64_t b_hi = make_desc(base + TILE_BYTES + kk * 32);
+                            const uint64_t a_lo = make_desc(base_lo + kk * 32);
+                            const uint64_t b_lo = make_desc(base + TILE_BYTES + BN_MAX * BK * 4 + kk * 32);
+                            umma_tf32(tmem_d, a_lo, b_hi, idesc, (kb > 0 || kk > 0) ? 1u : 0u);   // small terms first
+                            umma_tf32(tmem_d, a_hi, b_lo, idesc, 1u);
+                            umma_tf32(tmem_d, a_hi, b_hi, idesc, 1u);
+                        }
+                        umma_commit(&empty[s]);
+                        umma_commit(&lo_empty[lo]);
+                    }
+                    umma_commit(&tmem_full[acc_stage]);
+                }
+            }
+        }
+    } else if (warp >= 6) {
+        // ===== splitter: A -> A_lo = rna_tf32(x - trunc_tf32(x)) (elementwise, swizzle-agnostic); the tensor core truncates raw A itself =====
+        const int t = threadIdx.x - 6 * 32;
+        constexpr int NT = 32 * SPLIT_WARPS;
+        int it = 0;
+        for (int l = 0; l < g.n_layers; ++l) {
+            const ChainLayer& Ly = g.L[l];
+            const int items = g.tiles_m * Ly.tiles_n, num_kb = (Ly.K + BK - 1) / BK;
+            for (int w = (blockIdx.x + Ly.rot) % G; w < items; w += G) {
+                for (int kb = 0; kb < num_kb; ++kb, ++it) {
+                    const int s = it % RAW_STAGES, lo = it % LO_STAGES;
+                    mbar_wait(&lo_empty[lo], ((it / LO_STAGES) & 1) ^ 1);
+                    mbar_wait(&full[s], (it / RAW_STAGES) & 1);
+                    const float4* a = reinterpret_cast<const float4*>(smem + s * RAW_STRIDE);
+                    float4* alo = reinterpret_cast<float4*>(smem_lo + lo * LO_STRIDE);
+#pragma unroll 4
+                    for (int i = t; i < TILE_BYTES / 16; i += NT) {
+                        const float4 x = a[i];
+                        float4 r;
+                        r.x = rna_tf32(x.x - __uint_as_float(__float_as_uint(x.x) & 0xFFFFE000u));
+                        r.y = rna_tf32(x.y - __uint_as_float(__float_as_uint(x.y) & 0xFFFFE000u));
+                        r.z = rna_tf32(x.z - __uint_as_float(__float_as_uint(x.z) & 0xFFFFE000u));
+                        r.w = rna_tf32(x.w - __uint_as_float(__float_as_uint(x.w) & 0xFFFFE000u));
+                        alo[i] = r;
+                    }
+                    fence_proxy_async();                                        // generic-proxy writes -> tensor-core reads
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&ready[lo]);
+                }
+            }
+        }
+    } else {
+        // ===== epilogue (warps 0-3 <-> TMEM lanes 32*warp .. +31) =====
+        int item = 0;
+        for (int l = 0; l < g.n_layers; ++l) {
+            const ChainLayer& Ly = g.L[l];
+            const int items = g.tiles_m * Ly.tiles_n;
+            for (int w = (blockIdx.x + Ly.rot) % G; w < items; w += G, ++item) {
+                const int tm = w / Ly.tiles_n, tn = w - tm * Ly.tiles_n;
+                const int acc_stage = item & 1;
+                mbar_wait(&tmem_full[acc_stage], (item >> 1) & 1);
+                tc_fence_after();
+                const int row = tm * BM + warp * 32 + lane;
+                const bool row_ok = row < g.M;
+                for (int c0 = 0; c0 < Ly.BN; c0 += 32) {
+                    float v[32];
+                    tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(acc_stage * 128 + c0), v);
+                    const int col0 = tn * Ly.BN + c0;
+                    if (col0 >= Ly.N) continue;                                 // warp-uniform
+                    const int nvalid = min(32, Ly.N - col0);
+                    const float bl = (lane < nvalid) ? __ldg(Ly.bias + col0 + lane) : 0.0f;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const float x = v[j] + __shfl_sync(0xffffffffu, bl, j);
+                        v[j] = (Ly.epi == CH_BIAS_ELU) ? (x > 0.0f ? x : expm1f(x)) : x;        // nn.ELU(alpha=1)
+                    }
+                    if (!row_ok) continue;
+                    float* dst = Ly.C + (int64_t)row * Ly.ldc + col0;
+                    if (Ly.epi == CH_BIAS_SAMPLE) {
+                        // ActorCritic.act + get_actions_log_prob (actor_critic.py:111-120) on the row this thread owns
+                        const uint64_t stp = g.step_dev ? *g.step_dev : g.step;
+                        float lp = 0.0f;
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            if (j < nvalid) {
+                                const float mu = v[j];
+                                const float sg = mu * 0.0f + __ldg(g.stdv + j);
+                                float z;
+                                if (g.eps) z = g.eps[(size_t)row * Ly.N + j];
+                                else {
+                                    HgPhilox r = hg_philox(g.seed, (uint32_t)row, (uint32_t)stp, HG_RNG_SAMPLE | ((uint32_t)(stp >> 32) << 8), j);
+                                    z = hg_normal(r.c[0], r.c[1]);
+                                }
+                                const float a = mu + sg * z;
+                                const float d = a - mu;
+                                lp += -(d * d) / (2.0f * (sg * sg)) - logf(sg) - kLogSqrt2Pi;
+                                dst[j] = mu;
+                                g.actions[(size_t)row * Ly.N + j] = a;
+                                g.sigma[(size_t)row * Ly.N + j] = sg;
+                            }
+                        g.logp[row] = lp;
+                    } else if (nvalid == 32 && ((reinterpret_cast<uintptr_t>(dst) & 15u) == 0)) {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            if (j < nvalid) dst[j] = v[j];
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tmem_empty[acc_stage]);             // accumulator free for item + 2
+                // publish the tile: every epilogue thread's stores are device-visible before the counter moves
+                __threadfence();
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                if (threadIdx.x == 0) atomicAdd(g.counters + l * g.tiles_m + tm, 1);
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 5) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 256);
+    }
+    // the last CTA to get here re-zeroes the counters (every wait of this launch has been satisfied by then)
+    if (threadIdx.x == 0) {
+        __threadfence();
+        int* done = g.counters + MAX_CHAIN * g.tiles_m;
+        if (atomicAdd(done, 1) == G - 1) {
+            for (int i = 0; i < g.n_layers * g.tiles_m; ++i) g.counters[i] = 0;
+            *done = 0;
+            __threadfence();
+        }
+    }
+}
+
+// ---- host ----------------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn g_encode = nullptr;
+int32_t load_encode() {
+    if (g_encode) return 0;
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q);
+    if (e != cudaSuccess || q != cudaDriverEntryPointSuccess || !fn) return hg_fail(HG_E_STATE, "cuTensorMapEncodeTiled unavailable");
+    g_encode = reinterpret_cast<EncodeTiledFn>(fn);
+    return 0;
+}
+int32_t make_map(CUtensorMap* map, const float* base, uint64_t inner, uint64_t outer, uint64_t ld, uint32_t box_outer) {
+    cuuint64_t dims[2] = {inner, outer};
+    cuuint64_t strides[1] = {ld * sizeof(float)};
+    cuuint32_t box[2] = {BK, box_outer};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = g_encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                          CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        snprintf(g_hg_err, sizeof(g_hg_err), "hg_actor_critic_forward: cuTensorMapEncodeTiled failed (%d): inner=%llu outer=%llu ld=%llu", (int)r,
+                 (unsigned long long)inner, (unsigned long long)outer, (unsigned long long)ld);
+        return HG_E_ARG;
+    }
+    return 0;
+}
+
+// the (maps, args) pair of a call is a pure function of its pointer / shape arguments: built once, replayed afterwards
+struct ChainKey {
+    const void* p[10]; int64_t v[4];
+    bool operator==(const ChainKey& o) const { return memcmp(this, &o, sizeof(ChainKey)) == 0; }
+};
+struct ChainKeyHash {
+    size_t operator()(const ChainKey& k) const {
+        uint64_t h = 1469598103934665603ull;
+        const unsigned char* b = reinterpret_cast<const unsigned char*>(&k);
+        for (size_t i = 0; i < sizeof(ChainKey); ++i) { h ^= b[i]; h *= 1099511628211ull; }
+        return (size_t)h;
+    }
+};
+struct ChainPlan { ChainMaps maps; ChainArgs args; int grid; };
+std::unordered_map<ChainKey, ChainPlan, ChainKeyHash> g_plans;
+std::mutex g_plans_mu;
+
+bool tma_ok(const void* p, int64_t ld) { return hg_aligned16(p) && (ld & 3) == 0; }
+
+}  // namespace
+
+extern "C" int64_t hg_actor_critic_counters_size(int64_t M) { return (int64_t)MAX_CHAIN * ((M + BM - 1) / BM) + 1; }
+
+extern "C" int32_t hg_actor_critic_forward(const HgMlpDesc* actor, const HgMlpDesc* critic, const float* params, const float* params_lo,
+                                           const float* obs, int64_t ld_obs, const float* cobs, int64_t ld_cobs, float* hidden_a,
+                                           float* hidden_c, float* mu, float* value, const HgMlpFwdOpts* sample, int32_t* counters,
+                                           int64_t M, void* stream) {
+    HG_REQUIRE(actor); HG_REQUIRE(critic); HG_REQUIRE(params); HG_REQUIRE(params_lo); HG_REQUIRE(obs); HG_REQUIRE(cobs);
+    HG_REQUIRE(hidden_a); HG_REQUIRE(hidden_c); HG_REQUIRE(mu); HG_REQUIRE(value); HG_REQUIRE(counters);
+    if (M <= 0 || M > (1 << 24)) return hg_fail(HG_E_SIZE, "hg_actor_critic_forward: bad M");
+    const int La = actor->n_layers, Lc = critic->n_layers;
+    if (La < 1 || Lc < 1 || La + Lc > MAX_CHAIN) return hg_fail(HG_E_ALIGN, "hg_actor_critic_forward: more than 8 layers in total");
+    const bool want_sample = sample && sample->actions;
+    if (want_sample && (!sample->std || !sample->log_prob || !sample->sigma)) return hg_fail(HG_E_NULL, "hg_actor_critic_forward: sampling outputs are NULL");
+    if (want_sample && actor->dims[La] > 32) return hg_fail(HG_E_ALIGN, "hg_actor_critic_forward: more than 32 actions");
+    if (int32_t rc = load_encode()) return rc;
+
+    ChainKey key{};
+    const void* ptrs[10] = {actor, critic, params, params_lo, obs, cobs, hidden_a, hidden_c, mu, value};
+    memcpy(key.p, ptrs, sizeof(ptrs));
+    key.v[0] = ld_obs; key.v[1] = ld_cobs; key.v[2] = M; key.v[3] = (int64_t)(uintptr_t)counters;
+    ChainPlan plan;
+    bool have = false;
+    {
+        std::lock_guard<std::mutex> lk(g_plans_mu);
+        auto it = g_plans.find(key);
+        if (it != g_plans.end()) { plan = it->second; have = true; }
+    }
+    if (!have) {
+        ChainArgs& g = plan.args;
+        memset(&plan, 0, sizeof(plan));
+        g.M = (int)M; g.tiles_m = (int)((M + BM - 1) / BM); g.counters = counters;
+        const HgMlpDesc* nets[2] = {actor, critic};
+        const float* X[2] = {obs, cobs};
+        const int64_t ldx[2] = {ld_obs, ld_cobs};
+        float* hid[2] = {hidden_a, hidden_c};
+        float* out[2] = {mu, value};
+        const int Lmax = La > Lc ? La : Lc;
+        int prev[2] = {-1, -1};
+        int64_t hoff[2] = {0, 0};
+        int n = 0, rot = 0, max_items = 0;
+        for (int l = 0; l < Lmax; ++l)
+            for (int which = 0; which < 2; ++which) {
+                const HgMlpDesc* net = nets[which];
+                if (l >= net->n_layers) continue;
+                const int K = net->dims[l], N = net->dims[l + 1];
+                const bool last = (l + 1 == net->n_layers);
+                const float* in = (l == 0) ? X[which] : hid[which] + hoff[which] - M * K;
+                const int64_t ld_in = (l == 0) ? ldx[which] : K;
+                const float* W = params + net->w_off[l];
+                const float* Wlo = params_lo + net->w_off[l];
+                if (!tma_ok(in, ld_in) || !tma_ok(W, net->ldw[l]) || !tma_ok(Wlo, net->ldw[l]))
+                    return hg_fail(HG_E_ALIGN, "hg_actor_critic_forward: an operand is not TMA-addressable (16-byte base, pitch % 4)");
+                ChainLayer& Ly = g.L[n];
+                Ly.N = N; Ly.K = K;
+                // tile width: enough column tiles that a layer's items cover the chip (see hg_gemm_tf32)
+                int bn = ((N + 31) / 32) * 32;
+                if (bn > BN_MAX) bn = BN_MAX;
+                while (bn > 32 && g.tiles_m * ((N + bn - 1) / bn) < HG_NUM_SMS * 3 / 4 && (bn / 2) % 32 == 0) bn /= 2;
+                Ly.BN = bn; Ly.tiles_n = (N + bn - 1) / bn;
+                Ly.bias = params + net->b_off[l];
+                Ly.C = last ? out[which] : hid[which] + hoff[which];
+                Ly.ldc = N;
+                // the actor's output layer CAN sample when it is a single column tile; whether it does is decided per call
+                Ly.epi = last ? ((which == 0 && N <= 32 && Ly.tiles_n == 1) ? CH_BIAS_SAMPLE : CH_BIAS) : CH_BIAS_ELU;
+                Ly.dep = prev[which];
+                Ly.rot = rot;
+                const int items = g.tiles_m * Ly.tiles_n;
+                rot = (rot + items) % HG_NUM_SMS;
+                if (items > max_items) max_items = items;
+                if (int32_t rc = make_map(&plan.maps.a[n], in, K, M, ld_in, BM)) return rc;
+                if (int32_t rc = make_map(&plan.maps.b[n], W, K, N, net->ldw[l], bn)) return rc;
+                if (int32_t rc = make_map(&plan.maps.blo[n], Wlo, K, N, net->ldw[l], bn)) return rc;
+                prev[which] = n;
+                if (!last) hoff[which] += M * N;
+                ++n;
+            }
+        g.n_layers = n;
+        plan.grid = max_items < HG_NUM_SMS ? max_items : HG_NUM_SMS;
+        // rotations were computed modulo the SM count; with a smaller grid fold them again
+        for (int i = 0; i < n; ++i) g.L[i].rot %= plan.grid;
+        std::lock_guard<std::mutex> lk(g_plans_mu);
+        if (g_plans.size() > 256) g_plans.clear();
+        g_plans.emplace(key, plan);
+    }
+    ChainArgs& g = plan.args;
+    if (want_sample) {
+        bool can = false;
+        for (int i = 0; i < g.n_layers; ++i) can = can || g.L[i].epi == CH_BIAS_SAMPLE;
+        if (!can) return hg_fail(HG_E_ALIGN, "hg_actor_critic_forward: the actor's output layer cannot host the sampling epilogue");
+        g.stdv = sample->std; g.eps = sample->eps; g.actions = sample->actions; g.logp = sample->log_prob; g.sigma = sample->sigma;
+        g.seed = sample->seed; g.step = sample->step; g.step_dev = sample->step_dev;
+    } else {
+        for (int i = 0; i < g.n_layers; ++i)
+            if (g.L[i].epi == CH_BIAS_SAMPLE) g.L[i].epi = CH_BIAS;
+    }
+    static bool attr_set[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev >= 0 && dev < 64 && !attr_set[dev]) {
+        cudaError_t e = cudaFuncSetAttribute(mlp_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+        if (e != cudaSuccess) return hg_fail((int32_t)e, cudaGetErrorString(e));
+        attr_set[dev] = true;
+    }
+    mlp_chain_kernel<<<plan.grid, THREADS, SMEM_BYTES, (cudaStream_t)stream>>>(plan.maps, g);
+    HG_LAUNCHED(1);
+    return hg_cuda_status("hg_actor_critic_forward");
+}

@@ -6,6 +6,8 @@ critic.*) so that the gradient all-reduce, the norm clip and Adam each touch a s
 `self.actor` / `self.critic` stay real nn.Sequential(Linear, ELU, ...) modules: checkpoints
 (`model_state_dict`) and export_policy_as_jit keep working unchanged.
 """
+import os
+
 import torch
 import torch.nn as nn
 from torch.distributions import Normal
@@ -196,6 +198,39 @@ class ActorCritic(nn.Module):
                                             hidden.data_ptr(), out.data_ptr(), M, o, nat.stream_ptr(flat.device.index)),
                   "hg_mlp_forward_ex")
         return hidden
+
+    def native_act(self, obs, critic_obs, mu, value, sample=None):
+        """PPO.act in one launch (hg_actor_critic_forward): mu (M, A) and value (M, 1) <- actor(obs), critic(critic_obs),
+        optionally with the sampling epilogue (see native_forward).  Returns False when the fused kernel is not eligible
+        (exact-fp32 engine selected, operands not TMA-addressable): the caller then runs the two chains separately."""
+        if nat.lib.hg_set_gemm_mode(-1) not in (1, 4) or os.environ.get("HG_FUSED_ACT", "1") == "0":
+            return False
+        flat = self.flat_params()
+        M = obs.shape[0]
+        for x in (obs, critic_obs):
+            if x.dtype != torch.float32 or x.stride(1) != 1 or x.stride(0) % 4 or x.data_ptr() % 16:
+                return False
+        if len(self._actor_dims) + len(self._critic_dims) - 2 > 8 or self.num_actions > 32:
+            return False
+        if self._wlo_dirty:
+            if torch.cuda.is_current_stream_capturing():
+                return False
+            self.refresh_lo()
+        key = ("act_counters", M)
+        if key not in self._scratch:
+            self._scratch[key] = torch.zeros(int(nat.lib.hg_actor_critic_counters_size(M)), dtype=torch.int32, device=flat.device)
+        o = nat.MlpFwdOpts()
+        if sample is not None:
+            o.std, o.eps = sample["std"].data_ptr(), nat.ptr(sample.get("eps"))
+            o.actions, o.log_prob, o.sigma = sample["actions"].data_ptr(), sample["log_prob"].data_ptr(), sample["sigma"].data_ptr()
+            o.seed, o.step, o.step_dev = sample["seed"], sample["step"], sample.get("step_dev")
+        ha, hc = self._hidden_scratch("actor", M), self._hidden_scratch("critic", M)
+        nat.check(nat.lib.hg_actor_critic_forward(self._desc["actor"], self._desc["critic"], flat.data_ptr(), self._wlo.data_ptr(),
+                                                  obs.data_ptr(), obs.stride(0), critic_obs.data_ptr(), critic_obs.stride(0),
+                                                  ha.data_ptr(), hc.data_ptr(), mu.data_ptr(), value.data_ptr(), o,
+                                                  self._scratch[key].data_ptr(), M, nat.stream_ptr(flat.device.index)),
+                  "hg_actor_critic_forward")
+        return True
 
     # ------------------------------------------------------------------------------------------
     # reference API

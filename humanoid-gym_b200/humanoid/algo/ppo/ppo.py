@@ -131,20 +131,22 @@ class PPO:
         t = s.step
         if t >= s.num_transitions_per_env:
             raise AssertionError("Rollout buffer overflow")
-        # actor and critic are independent chains of small GEMMs (M = num_envs): run them on two streams so that
-        # the tail layers of one (32-64 CTAs) overlap the other instead of leaving most of the 148 SMs idle
         cur = torch.cuda.current_stream(self._dev_index)
         self._join_critic(cur)                             # (only if the caller skipped process_env_step)
+        sample = dict(std=ac.std, eps=eps, actions=s.actions[t], log_prob=s.actions_log_prob[t], sigma=s.sigma[t], seed=self._seed,
+                      step=self._sample_step if step is None else int(step), step_dev=step_dev)
         self._side.wait_stream(cur)
+        # ONE launch for both nets incl. the sampling epilogue (hg_actor_critic_forward); the 15 MB observation copy into
+        # slab t rides on the side stream: nothing before the update reads it
+        fused = ac.native_act(obs, critic_obs, s.mu[t], s.values[t], sample)
         with torch.cuda.stream(self._side):
-            ac.native_forward("critic", critic_obs, s.values[t])
-            # the 15 MB observation copy into slab t rides on the side stream too: nothing before the update reads it
+            if not fused:
+                # fallback: actor and critic as independent chains of small GEMMs on two streams
+                ac.native_forward("critic", critic_obs, s.values[t])
             s.add_native(t, obs=obs, priv_obs=critic_obs if s.privileged_observations is not None else None)
         self._critic_pending = True
-        # actor forward with ActorCritic.act + get_actions_log_prob fused into the output layer's epilogue
-        ac.native_forward("actor", obs, s.mu[t], sample=dict(
-            std=ac.std, eps=eps, actions=s.actions[t], log_prob=s.actions_log_prob[t], sigma=s.sigma[t], seed=self._seed,
-            step=self._sample_step if step is None else int(step), step_dev=step_dev))
+        if not fused:
+            ac.native_forward("actor", obs, s.mu[t], sample=sample)
         self._sample_step += 1
         # The value estimate is not needed before process_env_step (r += gamma * V * time_out), so the critic chain is
         # joined there: it overlaps the whole env step instead of sitting on the act -> step critical path.  The env

@@ -142,6 +142,46 @@ def test_act_fused_sampling_matches_standalone_kernel():
         s.step += 1
 
 
+@pytest.mark.parametrize("N", [4096, 1000, 16384])
+def test_fused_act_matches_separate_chains(N, gemm_engine):
+    """hg_actor_critic_forward (both nets, all layers, one persistent launch with on-device layer dependencies) against
+    the per-layer launches: same tile shapes and MMA order -> bit-identical mean / value / actions / log-prob, over
+    several calls (the tile counters must come back to zero) and with a ragged last row tile."""
+    import os
+    from humanoid.algo import PPO
+    if gemm_engine == "simt_fp32":
+        pytest.skip("the fused kernel is a tensor-core path")
+    ac = _make_ac(705, 219, 12, [512, 256, 128], [768, 256, 128])
+    with torch.no_grad():
+        ac.std.copy_(0.5 + torch.rand(12, device="cuda"))
+    alg = PPO(ac, num_learning_epochs=1, num_mini_batches=1, device="cuda:0")
+    alg.init_storage(N, 6, [705], [219], [12])
+    s = alg.storage
+    g = torch.Generator(device="cuda").manual_seed(N)
+    obs = [_pad4(torch.randn(N, 705, device="cuda", generator=g)) for _ in range(3)]
+    cobs = [_pad4(torch.randn(N, 219, device="cuda", generator=g)) for _ in range(3)]
+    for t in range(3):                                   # fused (default)
+        alg.act(obs[t], cobs[t], step=100 + t)
+        s.step += 1
+    torch.cuda.synchronize()
+    assert ac._scratch[("act_counters", N)].abs().sum() == 0, "tile counters were not re-zeroed"
+    os.environ["HG_FUSED_ACT"] = "0"
+    try:
+        for t in range(3):
+            alg.act(obs[t], cobs[t], step=100 + t)
+            s.step += 1
+    finally:
+        os.environ["HG_FUSED_ACT"] = "1"
+    torch.cuda.synchronize()
+    for t in range(3):
+        for k in ("mu", "values", "actions", "actions_log_prob", "sigma"):
+            a, b = getattr(s, k)[t], getattr(s, k)[t + 3]
+            assert torch.equal(a, b), (t, k, float((a - b).abs().max()))
+    p = {k: v.detach().cpu() for k, v in ac.state_dict().items()}
+    assert _rel(s.mu[0].cpu(), po.mlp(obs[0].cpu(), p, "actor")) < 1e-5
+    assert _rel(s.values[0].cpu(), po.mlp(cobs[0].cpu(), p, "critic")) < 1e-5
+
+
 def test_gae_vs_golden_and_large():
     from humanoid.algo import RolloutStorage
     g = Golden("ppo_learning.npz")
