@@ -273,7 +273,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     for (int j = 0; j < 32; ++j) {
                         float x = v[j] + __shfl_sync(0xffffffffu, bl, j);
                         // nn.ELU(alpha=1): exp(x) - 1 for x <= 0 (absolute error ~1e-7, same form as torch's CUDA kernel)
-                        v[j] = (g.epi == EPI_BIAS_ELU) ? (x > 0.0f ? x : expm1f(x)) : x;                     // nn.ELU(alpha=1)
+                        v[j] = (g.epi == EPI_BIAS_ELU) ? elu_fp32(x) : x;                                   // nn.ELU(alpha=1)
                     }
                 } else if (g.epi == EPI_MUL_DELU) {
                     const float* h = g.H + (int64_t)row * g.ldh + col0;

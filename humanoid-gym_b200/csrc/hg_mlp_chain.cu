@@ -15,10 +15,14 @@
 // are co-resident (grid <= #SMs, one CTA per SM) and walk the layers in the same order, so the waits cannot cycle.  The
 // last CTA to finish re-zeroes the counters: the launch is self-contained and CUDA-graph replayable.
 //
-// Tile pipeline = gemm_tc_kernel's (hg_gemm_tc.cu): 14 warps (4 epilogue, TMA producer, MMA issuer, 8 splitter warps),
-// 4-deep ring of raw {A, B, B_lo} stages (weight residuals pre-split by hg_tf32_residual, loaded by TMA), 2-deep ring of
-// A_lo tiles written by the splitter, accumulator double-buffered in TMEM.  The actor's output layer samples the action
-// in its epilogue (same arithmetic as policy_sample_kernel).
+// Tile pipeline: 14 warps (4 epilogue, TMA producer, MMA issuer, 8 splitter warps), ONE 3-deep ring of 64 KB stages
+// {A, A_lo, B, B_lo}, accumulator double-buffered in TMEM.  Weight residuals are pre-split (hg_tf32_residual) and every
+// hidden layer's epilogue stores the residual of its activations next to them, so for all layers but the first all four
+// tiles of a stage arrive by TMA and the MMA warp starts the moment they land; only the network inputs (observations,
+// written by the env kernel) go through the splitter warps, which fill the stage's A_lo slot in place.  (Measured on the
+// per-layer kernel: a separate 2-deep A_lo ring costs a TMA -> splitter -> MMA -> commit -> splitter round trip of ~3.8 k
+// cycles per two k-blocks, i.e. 40 % tensor-pipe at best.)  The actor's output layer samples the action in its epilogue
+// (same arithmetic as policy_sample_kernel).
 #include <cuda.h>
 
 #include <mutex>
@@ -32,21 +36,21 @@ using namespace hgtc;
 namespace {
 
 constexpr int BM = 128, BK = 32, BN_MAX = 128;
-constexpr int RAW_STAGES = 4, LO_STAGES = 2;
+constexpr int STAGES = 3;
 constexpr int TILE_BYTES = BM * BK * 4;                         // 16 KB
-constexpr int RAW_STRIDE = TILE_BYTES + 2 * BN_MAX * BK * 4;    // A + B + B_lo = 48 KB
-constexpr int LO_STRIDE = TILE_BYTES;                           // A_lo
+constexpr int OFF_ALO = TILE_BYTES, OFF_B = 2 * TILE_BYTES, OFF_BLO = 2 * TILE_BYTES + BN_MAX * BK * 4;
+constexpr int STAGE_BYTES = 2 * TILE_BYTES + 2 * BN_MAX * BK * 4;   // A + A_lo + B + B_lo = 64 KB
 constexpr int SPLIT_WARPS = 8;
 constexpr int THREADS = (6 + SPLIT_WARPS) * 32;
-constexpr int SMEM_BYTES = RAW_STAGES * RAW_STRIDE + LO_STAGES * LO_STRIDE + 1024 + 256;
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
 constexpr int MAX_CHAIN = 8;
 constexpr float kLogSqrt2Pi = 0.9189385332046727f;
 
 enum { CH_BIAS = 1, CH_BIAS_ELU = 2, CH_BIAS_SAMPLE = 5 };
 
 struct ChainLayer {
-    float* C; const float* bias; int64_t ldc;
-    int N, K, BN, epi, tiles_n, dep, rot;
+    float* C; float* C_lo; const float* bias; int64_t ldc;      // C_lo: residual of the stored activations (hidden layers), may be NULL
+    int N, K, BN, epi, tiles_n, dep, rot, has_alo;              // has_alo: A_lo comes by TMA (maps.alo) instead of the splitter
 };
 struct ChainArgs {
     int M, tiles_m, n_layers;
@@ -55,7 +59,7 @@ struct ChainArgs {
     const float* stdv; const float* eps; float* actions; float* logp; float* sigma;
     uint64_t seed, step; const uint64_t* step_dev;
 };
-struct alignas(64) ChainMaps { CUtensorMap a[MAX_CHAIN], b[MAX_CHAIN], blo[MAX_CHAIN]; };
+struct alignas(64) ChainMaps { CUtensorMap a[MAX_CHAIN], alo[MAX_CHAIN], b[MAX_CHAIN], blo[MAX_CHAIN]; };
 
 __device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {         // K-major [rows][32 fp32], SWIZZLE_128B
     uint64_t d = 0;
@@ -75,6 +79,7 @@ __device__ __forceinline__ uint32_t make_idesc(int N) {                 // D = F
     d |= (uint32_t)(BM >> 4) << 24;
     return d;
 }
+__device__ __forceinline__ float tf32_residual(float x) { return rna_tf32(x - __uint_as_float(__float_as_uint(x) & 0xFFFFE000u)); }
 __device__ __forceinline__ int ld_acquire(const int* p) {
     int v;
     asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
@@ -84,27 +89,22 @@ __device__ __forceinline__ int ld_acquire(const int* p) {
 __global__ void __launch_bounds__(THREADS, 1) mlp_chain_kernel(const __grid_constant__ ChainMaps maps, const ChainArgs g) {
     extern __shared__ unsigned char smem_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    unsigned char* smem_lo = smem + RAW_STAGES * RAW_STRIDE;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_lo + LO_STAGES * LO_STRIDE);
-    uint64_t* full = bars;                          // [RAW] TMA -> splitter (and MMA)
-    uint64_t* empty = full + RAW_STAGES;            // [RAW] MMA -> TMA
-    uint64_t* ready = empty + RAW_STAGES;           // [LO]  splitter -> MMA
-    uint64_t* lo_empty = ready + LO_STAGES;         // [LO]  MMA -> splitter
-    uint64_t* tmem_full = lo_empty + LO_STAGES;     // [2]   MMA -> epilogue
-    uint64_t* tmem_empty = tmem_full + 2;           // [2]   epilogue -> MMA
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+    uint64_t* full = bars;                          // [S] TMA -> splitter / MMA
+    uint64_t* empty = full + STAGES;                // [S] MMA -> TMA
+    uint64_t* ready = empty + STAGES;               // [S] splitter -> MMA (layers whose A_lo is made in-kernel)
+    uint64_t* tmem_full = ready + STAGES;           // [2] MMA -> epilogue
+    uint64_t* tmem_empty = tmem_full + 2;           // [2] epilogue -> MMA
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int G = gridDim.x;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < RAW_STAGES; ++s) {
+        for (int s = 0; s < STAGES; ++s) {
             mbar_init(&full[s], 1);
             mbar_init(&empty[s], 1);
-        }
-        for (int s = 0; s < LO_STAGES; ++s) {
             mbar_init(&ready[s], SPLIT_WARPS);
-            mbar_init(&lo_empty[s], 1);
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(&tmem_full[a], 1);
@@ -125,28 +125,30 @@ __global__ void __launch_bounds__(THREADS, 1) mlp_chain_kernel(const __grid_cons
                 asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.a[l]) : "memory");
                 asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.b[l]) : "memory");
                 asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.blo[l]) : "memory");
+                if (g.L[l].has_alo) asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.alo[l]) : "memory");
             }
             int it = 0;
             for (int l = 0; l < g.n_layers; ++l) {
                 const ChainLayer& Ly = g.L[l];
                 const int items = g.tiles_m * Ly.tiles_n, num_kb = (Ly.K + BK - 1) / BK;
-                const uint32_t b_bytes = (uint32_t)Ly.BN * BK * 4, tx = TILE_BYTES + 2 * b_bytes;
+                const uint32_t b_bytes = (uint32_t)Ly.BN * BK * 4, tx = TILE_BYTES * (Ly.has_alo ? 2u : 1u) + 2 * b_bytes;
                 for (int w = (blockIdx.x + Ly.rot) % G; w < items; w += G) {
                     const int tm = w / Ly.tiles_n, tn = w - tm * Ly.tiles_n;
                     if (Ly.dep >= 0) {                   // wait until every column tile of the producing layer has published row tile tm
                         const int need = g.L[Ly.dep].tiles_n;
                         const int* c = g.counters + Ly.dep * g.tiles_m + tm;
-                        while (ld_acquire(c) < need) __nanosleep(64);
+                        while (ld_acquire(c) < need) __nanosleep(32);
                         asm volatile("fence.proxy.async;" ::: "memory");    // generic-proxy acquire -> async-proxy (TMA) reads
                     }
                     for (int kb = 0; kb < num_kb; ++kb, ++it) {
-                        const int s = it % RAW_STAGES, k0 = kb * BK;
-                        mbar_wait(&empty[s], ((it / RAW_STAGES) & 1) ^ 1);
-                        unsigned char* st = smem + s * RAW_STRIDE;
+                        const int s = it % STAGES, k0 = kb * BK;
+                        mbar_wait(&empty[s], ((it / STAGES) & 1) ^ 1);
+                        unsigned char* st = smem + s * STAGE_BYTES;
                         mbar_expect_tx(&full[s], tx);
                         tma_load_2d(st, &maps.a[l], &full[s], k0, tm * BM);
-                        tma_load_2d(st + TILE_BYTES, &maps.b[l], &full[s], k0, tn * Ly.BN);
-                        tma_load_2d(st + TILE_BYTES + BN_MAX * BK * 4, &maps.blo[l], &full[s], k0, tn * Ly.BN);
+                        if (Ly.has_alo) tma_load_2d(st + OFF_ALO, &maps.alo[l], &full[s], k0, tm * BM);
+                        tma_load_2d(st + OFF_B, &maps.b[l], &full[s], k0, tn * Ly.BN);
+                        tma_load_2d(st + OFF_BLO, &maps.blo[l], &full[s], k0, tn * Ly.BN);
                     }
                 }
             }
@@ -155,6 +157,7 @@ __global__ void __launch_bounds__(THREADS, 1) mlp_chain_kernel(const __grid_cons
         // ===== MMA issuer =====
         if (lane == 0) {
             int it = 0, item = 0;
+            uint32_t ready_phase = 0;                    // per-stage phase bits of ready[]: only split iterations complete a phase
             for (int l = 0; l < g.n_layers; ++l) {
                 const ChainLayer& Ly = g.L[l];
                 const int items = g.tiles_m * Ly.tiles_n, num_kb = (Ly.K + BK - 1) / BK;
@@ -165,30 +168,33 @@ __global__ void __launch_bounds__(THREADS, 1) mlp_chain_kernel(const __grid_cons
                     tc_fence_after();
                     const uint32_t tmem_d = tmem_base + (uint32_t)(acc_stage * 128);
                     for (int kb = 0; kb < num_kb; ++kb, ++it) {
-                        const int s = it % RAW_STAGES, lo = it % LO_STAGES;
-                        mbar_wait(&ready[lo], (it / LO_STAGES) & 1);              // A_lo written (the raw stage landed before that)
-                        mbar_wait(&full[s], (it / RAW_STAGES) & 1);
+                        const int s = it % STAGES;
+                        mbar_wait(&full[s], (it / STAGES) & 1);
+                        if (!Ly.has_alo) {                                      // A_lo is written by the splitter warps
+                            mbar_wait(&ready[s], (ready_phase >> s) & 1u);
+                            ready_phase ^= 1u << s;
+                        }
                         tc_fence_after();
-                        const uint32_t base = smem_u32(smem + s * RAW_STRIDE), base_lo = smem_u32(smem_lo + lo * LO_STRIDE);
+                        const uint32_t base = smem_u32(smem + s * STAGE_BYTES);
 #pragma unroll
                         for (int kk = 0; kk < BK / 8; ++kk) {
                             const uint64_t a_hi = make_desc(base + kk * 32);
-                            const uint64_t b_hi = make_desc(base + TILE_BYTES + kk * 32);
-                            const uint64_t a_lo = make_desc(base_lo + kk * 32);
-                            const uint64_t b_lo = make_desc(base + TILE_BYTES + BN_MAX * BK * 4 + kk * 32);
+                            const uint64_t a_lo = make_desc(base + OFF_ALO + kk * 32);
+                            const uint64_t b_hi = make_desc(base + OFF_B + kk * 32);
+                            const uint64_t b_lo = make_desc(base + OFF_BLO + kk * 32);
                             umma_tf32(tmem_d, a_lo, b_hi, idesc, (kb > 0 || kk > 0) ? 1u : 0u);   // small terms first
                             umma_tf32(tmem_d, a_hi, b_lo, idesc, 1u);
                             umma_tf32(tmem_d, a_hi, b_hi, idesc, 1u);
                         }
                         umma_commit(&empty[s]);
-                        umma_commit(&lo_empty[lo]);
                     }
                     umma_commit(&tmem_full[acc_stage]);
                 }
             }
         }
     } else if (warp >= 6) {
-        // ===== splitter: A -> A_lo = rna_tf32(x - trunc_tf32(x)) (elementwise, swizzle-agnostic); the tensor core truncates raw A itself =====
+        // ===== splitter (network inputs only): A -> A_lo = rna_tf32(x - trunc_tf32(x)) into the stage's A_lo slot; the tensor core
+        //       truncates the raw A tile itself.  Elementwise, so the 128B swizzle is untouched. =====
         const int t = threadIdx.x - 6 * 32;
         constexpr int NT = 32 * SPLIT_WARPS;
         int it = 0;
@@ -196,13 +202,13 @@ __global__ void __launch_bounds__(THREADS, 1) mlp_chain_kernel(const __grid_cons
             const ChainLayer& Ly = g.L[l];
             const int items = g.tiles_m * Ly.tiles_n, num_kb = (Ly.K + BK - 1) / BK;
             for (int w = (blockIdx.x + Ly.rot) % G; w < items; w += G) {
+                if (Ly.has_alo) { it += num_kb; continue; }
                 for (int kb = 0; kb < num_kb; ++kb, ++it) {
-                    const int s = it % RAW_STAGES, lo = it % LO_STAGES;
-                    mbar_wait(&lo_empty[lo], ((it / LO_STAGES) & 1) ^ 1);
-                    mbar_wait(&full[s], (it / RAW_STAGES) & 1);
-                    const float4* a = reinterpret_cast<const float4*>(smem + s * RAW_STRIDE);
-                    float4* alo = reinterpret_cast<float4*>(smem_lo + lo * LO_STRIDE);
-#pragma unroll 4
+                    const int s = it % STAGES;
+                    mbar_wait(&full[s], (it / STAGES) & 1);
+                    const float4* a = reinterpret_cast<const float4*>(smem + s * STAGE_BYTES);
+                    float4* alo = reinterpret_cast<float4*>(smem + s * STAGE_BYTES + OFF_ALO);
+#pragma unroll
                     for (int i = t; i < TILE_BYTES / 16; i += NT) {
                         const float4 x = a[i];
                         float4 r;
@@ -214,7 +220,7 @@ __global__ void __launch_bounds__(THREADS, 1) mlp_chain_kernel(const __grid_cons
                     }
                     fence_proxy_async();                                        // generic-proxy writes -> tensor-core reads
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(&ready[lo]);
+                    if (lane == 0) mbar_arrive(&ready[s]);
                 }
             }
         }
@@ -241,7 +247,7 @@ __global__ void __launch_bounds__(THREADS, 1) mlp_chain_kernel(const __grid_cons
 #pragma unroll
                     for (int j = 0; j < 32; ++j) {
                         const float x = v[j] + __shfl_sync(0xffffffffu, bl, j);
-                        v[j] = (Ly.epi == CH_BIAS_ELU) ? (x > 0.0f ? x : expm1f(x)) : x;        // nn.ELU(alpha=1)
+                        v[j] = (Ly.epi == CH_BIAS_ELU) ? elu_fp32(x) : x;
                     }
                     if (!row_ok) continue;
                     float* dst = Ly.C + (int64_t)row * Ly.ldc + col0;
@@ -271,10 +277,20 @@ __global__ void __launch_bounds__(THREADS, 1) mlp_chain_kernel(const __grid_cons
                     } else if (nvalid == 32 && ((reinterpret_cast<uintptr_t>(dst) & 15u) == 0)) {
 #pragma unroll
                         for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                        if (Ly.C_lo) {                                          // the consumer layer's A_lo, ready-made
+                            float* dlo = Ly.C_lo + (int64_t)row * Ly.ldc + col0;
+#pragma unroll
+                            for (int j = 0; j < 32; j += 4)
+                                *reinterpret_cast<float4*>(dlo + j) = make_float4(tf32_residual(v[j]), tf32_residual(v[j + 1]),
+                                                                                  tf32_residual(v[j + 2]), tf32_residual(v[j + 3]));
+                        }
                     } else {
 #pragma unroll
                         for (int j = 0; j < 32; ++j)
-                            if (j < nvalid) dst[j] = v[j];
+                            if (j < nvalid) {
+                                dst[j] = v[j];
+                                if (Ly.C_lo) Ly.C_lo[(int64_t)row * Ly.ldc + col0 + j] = tf32_residual(v[j]);
+                            }
                     }
                 }
                 tc_fence_before();
@@ -336,7 +352,7 @@ int32_t make_map(CUtensorMap* map, const float* base, uint64_t inner, uint64_t o
 
 // the (maps, args) pair of a call is a pure function of its pointer / shape arguments: built once, replayed afterwards
 struct ChainKey {
-    const void* p[10]; int64_t v[4];
+    const void* p[12]; int64_t v[4];
     bool operator==(const ChainKey& o) const { return memcmp(this, &o, sizeof(ChainKey)) == 0; }
 };
 struct ChainKeyHash {
@@ -359,8 +375,8 @@ extern "C" int64_t hg_actor_critic_counters_size(int64_t M) { return (int64_t)MA
 
 extern "C" int32_t hg_actor_critic_forward(const HgMlpDesc* actor, const HgMlpDesc* critic, const float* params, const float* params_lo,
                                            const float* obs, int64_t ld_obs, const float* cobs, int64_t ld_cobs, float* hidden_a,
-                                           float* hidden_c, float* mu, float* value, const HgMlpFwdOpts* sample, int32_t* counters,
-                                           int64_t M, void* stream) {
+                                           float* hidden_c, float* hidden_lo_a, float* hidden_lo_c, float* mu, float* value,
+                                           const HgMlpFwdOpts* sample, int32_t* counters, int64_t M, void* stream) {
     HG_REQUIRE(actor); HG_REQUIRE(critic); HG_REQUIRE(params); HG_REQUIRE(params_lo); HG_REQUIRE(obs); HG_REQUIRE(cobs);
     HG_REQUIRE(hidden_a); HG_REQUIRE(hidden_c); HG_REQUIRE(mu); HG_REQUIRE(value); HG_REQUIRE(counters);
     if (M <= 0 || M > (1 << 24)) return hg_fail(HG_E_SIZE, "hg_actor_critic_forward: bad M");
@@ -371,8 +387,9 @@ extern "C" int32_t hg_actor_critic_forward(const HgMlpDesc* actor, const HgMlpDe
     if (want_sample && actor->dims[La] > 32) return hg_fail(HG_E_ALIGN, "hg_actor_critic_forward: more than 32 actions");
     if (int32_t rc = load_encode()) return rc;
 
+    HG_REQUIRE(hidden_lo_a); HG_REQUIRE(hidden_lo_c);
     ChainKey key{};
-    const void* ptrs[10] = {actor, critic, params, params_lo, obs, cobs, hidden_a, hidden_c, mu, value};
+    const void* ptrs[12] = {actor, critic, params, params_lo, obs, cobs, hidden_a, hidden_c, mu, value, hidden_lo_a, hidden_lo_c};
     memcpy(key.p, ptrs, sizeof(ptrs));
     key.v[0] = ld_obs; key.v[1] = ld_cobs; key.v[2] = M; key.v[3] = (int64_t)(uintptr_t)counters;
     ChainPlan plan;
@@ -390,6 +407,7 @@ extern "C" int32_t hg_actor_critic_forward(const HgMlpDesc* actor, const HgMlpDe
         const float* X[2] = {obs, cobs};
         const int64_t ldx[2] = {ld_obs, ld_cobs};
         float* hid[2] = {hidden_a, hidden_c};
+        float* hid_lo[2] = {hidden_lo_a, hidden_lo_c};
         float* out[2] = {mu, value};
         const int Lmax = La > Lc ? La : Lc;
         int prev[2] = {-1, -1};
@@ -416,6 +434,8 @@ extern "C" int32_t hg_actor_critic_forward(const HgMlpDesc* actor, const HgMlpDe
                 Ly.BN = bn; Ly.tiles_n = (N + bn - 1) / bn;
                 Ly.bias = params + net->b_off[l];
                 Ly.C = last ? out[which] : hid[which] + hoff[which];
+                Ly.C_lo = last ? nullptr : hid_lo[which] + hoff[which];
+                Ly.has_alo = (l > 0) ? 1 : 0;
                 Ly.ldc = N;
                 // the actor's output layer CAN sample when it is a single column tile; whether it does is decided per call
                 Ly.epi = last ? ((which == 0 && N <= 32 && Ly.tiles_n == 1) ? CH_BIAS_SAMPLE : CH_BIAS) : CH_BIAS_ELU;
@@ -425,6 +445,9 @@ extern "C" int32_t hg_actor_critic_forward(const HgMlpDesc* actor, const HgMlpDe
                 rot = (rot + items) % HG_NUM_SMS;
                 if (items > max_items) max_items = items;
                 if (int32_t rc = make_map(&plan.maps.a[n], in, K, M, ld_in, BM)) return rc;
+                if (l > 0) {
+                    if (int32_t rc = make_map(&plan.maps.alo[n], hid_lo[which] + hoff[which] - M * K, K, M, ld_in, BM)) return rc;
+                } else plan.maps.alo[n] = plan.maps.a[n];
                 if (int32_t rc = make_map(&plan.maps.b[n], W, K, N, net->ldw[l], bn)) return rc;
                 if (int32_t rc = make_map(&plan.maps.blo[n], Wlo, K, N, net->ldw[l], bn)) return rc;
                 prev[which] = n;

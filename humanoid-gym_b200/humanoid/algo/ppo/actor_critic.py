@@ -149,7 +149,7 @@ class ActorCritic(nn.Module):
                                                 M, nat.stream_ptr(flat.device.index)), "hg_mlp_backward_split")
 
     def hidden_width(self, which):
-        dims = self._actor_dims if which == "actor" else self._critic_dims
+        dims = self._actor_dims if which.startswith("actor") else self._critic_dims
         return sum(dims[1:-1])
 
     def _hidden_scratch(self, which, M):
@@ -225,9 +225,10 @@ class ActorCritic(nn.Module):
             o.actions, o.log_prob, o.sigma = sample["actions"].data_ptr(), sample["log_prob"].data_ptr(), sample["sigma"].data_ptr()
             o.seed, o.step, o.step_dev = sample["seed"], sample["step"], sample.get("step_dev")
         ha, hc = self._hidden_scratch("actor", M), self._hidden_scratch("critic", M)
+        la, lc = self._hidden_scratch("actor_lo", M), self._hidden_scratch("critic_lo", M)
         nat.check(nat.lib.hg_actor_critic_forward(self._desc["actor"], self._desc["critic"], flat.data_ptr(), self._wlo.data_ptr(),
                                                   obs.data_ptr(), obs.stride(0), critic_obs.data_ptr(), critic_obs.stride(0),
-                                                  ha.data_ptr(), hc.data_ptr(), mu.data_ptr(), value.data_ptr(), o,
+                                                  ha.data_ptr(), hc.data_ptr(), la.data_ptr(), lc.data_ptr(), mu.data_ptr(), value.data_ptr(), o,
                                                   self._scratch[key].data_ptr(), M, nat.stream_ptr(flat.device.index)),
                   "hg_actor_critic_forward")
         return True

@@ -257,14 +257,16 @@ int32_t hg_mlp_forward_ex(const HgMlpDesc* net, const float* params, const float
  * in `counters`, hg_actor_critic_counters_size(M) int32, zero-initialised once by the caller; the kernel leaves them
  * zero).  Same arithmetic, tile shapes and results as two hg_mlp_forward_ex calls; ~3x less wall time at rollout
  * batch sizes, where each layer is a few microseconds of tensor work behind ~8 us of per-launch fixed cost and the
- * shared-memory footprint forbids two GEMM kernels per SM.  hidden_a / hidden_c as `hidden` of hg_mlp_forward.
+ * shared-memory footprint forbids two GEMM kernels per SM.  hidden_a / hidden_c as `hidden` of hg_mlp_forward;
+ * hidden_lo_a / hidden_lo_c: scratch of the same size receiving the tf32 residuals of the hidden activations (the
+ * next layer's A_lo tiles then arrive by TMA: no in-kernel splitting except for the network inputs).
  * sample (may be NULL / actions == NULL): the actor's output epilogue samples as in hg_policy_sample.
  * Returns HG_E_ALIGN when an operand is not TMA-addressable or the nets have more than 8 layers in total. */
 int64_t hg_actor_critic_counters_size(int64_t M);
 int32_t hg_actor_critic_forward(const HgMlpDesc* actor, const HgMlpDesc* critic, const float* params, const float* params_lo,
                                 const float* obs, int64_t ld_obs, const float* cobs, int64_t ld_cobs, float* hidden_a,
-                                float* hidden_c, float* mu, float* value, const HgMlpFwdOpts* sample, int32_t* counters,
-                                int64_t M, void* stream);
+                                float* hidden_c, float* hidden_lo_a, float* hidden_lo_c, float* mu, float* value,
+                                const HgMlpFwdOpts* sample, int32_t* counters, int64_t M, void* stream);
 
 /* GEMM engine of hg_mlp_forward / hg_mlp_backward: 0 = exact-fp32 CUDA-core path, 1 = tcgen05 3xTF32,
  * 2 = tcgen05 plain TF32, 4 (default) = 3xTF32 for this fp32 API (rollout forward, 1e-5 bar) AND a hint to the host
