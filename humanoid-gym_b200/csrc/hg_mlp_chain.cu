@@ -24,6 +24,7 @@
 // cycles per two k-blocks, i.e. 40 % tensor-pipe at best.)  The actor's output layer samples the action in its epilogue
 // (same arithmetic as policy_sample_kernel).
 #include <cuda.h>
+#include <stdlib.h>
 
 #include <mutex>
 #include <unordered_map>
@@ -54,6 +55,7 @@ struct ChainLayer {
 };
 struct ChainArgs {
     int M, tiles_m, n_layers;
+    int tma_lo;                          // 1: A_lo (hidden layers) and B_lo tiles come by TMA; 0: the splitter warps make both in the stage
     int* counters;                       // [MAX_CHAIN][tiles_m] tile counters + [MAX_CHAIN * tiles_m] "CTAs done"
     ChainLayer L[MAX_CHAIN];
     const float* stdv; const float* eps; float* actions; float* logp; float* sigma;
@@ -131,7 +133,9 @@ __global__ void __launch_bounds__(THREADS, 1) mlp_chain_kernel(const __grid_cons
             for (int l = 0; l < g.n_layers; ++l) {
                 const ChainLayer& Ly = g.L[l];
                 const int items = g.tiles_m * Ly.tiles_n, num_kb = (Ly.K + BK - 1) / BK;
-                const uint32_t b_bytes = (uint32_t)Ly.BN * BK * 4, tx = TILE_BYTES * (Ly.has_alo ? 2u : 1u) + 2 * b_bytes;
+                const bool alo_tma = g.tma_lo && Ly.has_alo;
+                const uint32_t b_bytes = (uint32_t)Ly.BN * BK * 4;
+                const uint32_t tx = TILE_BYTES * (alo_tma ? 2u : 1u) + b_bytes * (g.tma_lo ? 2u : 1u);
                 for (int w = (blockIdx.x + Ly.rot) % G; w < items; w += G) {
                     const int tm = w / Ly.tiles_n, tn = w - tm * Ly.tiles_n;
                     if (Ly.dep >= 0) {                   // wait until every column tile of the producing layer has published row tile tm
@@ -146,9 +150,9 @@ __global__ void __launch_bounds__(THREADS, 1) mlp_chain_kernel(const __grid_cons
                         unsigned char* st = smem + s * STAGE_BYTES;
                         mbar_expect_tx(&full[s], tx);
                         tma_load_2d(st, &maps.a[l], &full[s], k0, tm * BM);
-                        if (Ly.has_alo) tma_load_2d(st + OFF_ALO, &maps.alo[l], &full[s], k0, tm * BM);
+                        if (alo_tma) tma_load_2d(st + OFF_ALO, &maps.alo[l], &full[s], k0, tm * BM);
                         tma_load_2d(st + OFF_B, &maps.b[l], &full[s], k0, tn * Ly.BN);
-                        tma_load_2d(st + OFF_BLO, &maps.blo[l], &full[s], k0, tn * Ly.BN);
+                        if (g.tma_lo) tma_load_2d(st + OFF_BLO, &maps.blo[l], &full[s], k0, tn * Ly.BN);
                     }
                 }
             }
@@ -170,7 +174,7 @@ __global__ void __launch_bounds__(THREADS, 1) mlp_chain_kernel(const __grid_cons
                     for (int kb = 0; kb < num_kb; ++kb, ++it) {
                         const int s = it % STAGES;
                         mbar_wait(&full[s], (it / STAGES) & 1);
-                        if (!Ly.has_alo) {                                      // A_lo is written by the splitter warps
+                        if (!(g.tma_lo && Ly.has_alo)) {                        // lo tiles are written by the splitter warps
                             mbar_wait(&ready[s], (ready_phase >> s) & 1u);
                             ready_phase ^= 1u << s;
                         }
@@ -202,21 +206,25 @@ __global__ void __launch_bounds__(THREADS, 1) mlp_chain_kernel(const __grid_cons
             const ChainLayer& Ly = g.L[l];
             const int items = g.tiles_m * Ly.tiles_n, num_kb = (Ly.K + BK - 1) / BK;
             for (int w = (blockIdx.x + Ly.rot) % G; w < items; w += G) {
-                if (Ly.has_alo) { it += num_kb; continue; }
+                if (g.tma_lo && Ly.has_alo) { it += num_kb; continue; }
+                const int nB4 = Ly.BN * BK / 4;
                 for (int kb = 0; kb < num_kb; ++kb, ++it) {
                     const int s = it % STAGES;
                     mbar_wait(&full[s], (it / STAGES) & 1);
                     const float4* a = reinterpret_cast<const float4*>(smem + s * STAGE_BYTES);
                     float4* alo = reinterpret_cast<float4*>(smem + s * STAGE_BYTES + OFF_ALO);
-#pragma unroll
-                    for (int i = t; i < TILE_BYTES / 16; i += NT) {
-                        const float4 x = a[i];
+                    auto residual4 = [](const float4& x) {
                         float4 r;
-                        r.x = rna_tf32(x.x - __uint_as_float(__float_as_uint(x.x) & 0xFFFFE000u));
-                        r.y = rna_tf32(x.y - __uint_as_float(__float_as_uint(x.y) & 0xFFFFE000u));
-                        r.z = rna_tf32(x.z - __uint_as_float(__float_as_uint(x.z) & 0xFFFFE000u));
-                        r.w = rna_tf32(x.w - __uint_as_float(__float_as_uint(x.w) & 0xFFFFE000u));
-                        alo[i] = r;
+                        r.x = tf32_residual(x.x); r.y = tf32_residual(x.y); r.z = tf32_residual(x.z); r.w = tf32_residual(x.w);
+                        return r;
+                    };
+#pragma unroll
+                    for (int i = t; i < TILE_BYTES / 16; i += NT) alo[i] = residual4(a[i]);
+                    if (!g.tma_lo) {
+                        const float4* b = reinterpret_cast<const float4*>(smem + s * STAGE_BYTES + OFF_B);
+                        float4* blo = reinterpret_cast<float4*>(smem + s * STAGE_BYTES + OFF_BLO);
+#pragma unroll 4
+                        for (int i = t; i < nB4; i += NT) blo[i] = residual4(b[i]);
                     }
                     fence_proxy_async();                                        // generic-proxy writes -> tensor-core reads
                     __syncwarp();
@@ -277,7 +285,7 @@ __global__ void __launch_bounds__(THREADS, 1) mlp_chain_kernel(const __grid_cons
                     } else if (nvalid == 32 && ((reinterpret_cast<uintptr_t>(dst) & 15u) == 0)) {
 #pragma unroll
                         for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-                        if (Ly.C_lo) {                                          // the consumer layer's A_lo, ready-made
+                        if (g.tma_lo && Ly.C_lo) {                              // the consumer layer's A_lo, ready-made
                             float* dlo = Ly.C_lo + (int64_t)row * Ly.ldc + col0;
 #pragma unroll
                             for (int j = 0; j < 32; j += 4)
@@ -289,7 +297,7 @@ __global__ void __launch_bounds__(THREADS, 1) mlp_chain_kernel(const __grid_cons
                         for (int j = 0; j < 32; ++j)
                             if (j < nvalid) {
                                 dst[j] = v[j];
-                                if (Ly.C_lo) Ly.C_lo[(int64_t)row * Ly.ldc + col0 + j] = tf32_residual(v[j]);
+                                if (g.tma_lo && Ly.C_lo) Ly.C_lo[(int64_t)row * Ly.ldc + col0 + j] = tf32_residual(v[j]);
                             }
                     }
                 }
@@ -455,6 +463,11 @@ extern "C" int32_t hg_actor_critic_forward(const HgMlpDesc* actor, const HgMlpDe
                 ++n;
             }
         g.n_layers = n;
+        {   // HG_CHAIN_TMA_LO=1: residual tiles by TMA (64 KB per k-block over L2 -> SM); default 0: the splitter warps make them in the
+            // stage (32 KB per k-block: the L2 -> SM feed of ~42 B/clk/SM, not the tensor pipe, is what bounds these kernels)
+            const char* e = getenv("HG_CHAIN_TMA_LO");
+            g.tma_lo = (e && e[0] == '1') ? 1 : 0;
+        }
         plan.grid = max_items < HG_NUM_SMS ? max_items : HG_NUM_SMS;
         // rotations were computed modulo the SM count; with a smaller grid fold them again
         for (int i = 0; i < n; ++i) g.L[i].rot %= plan.grid;
