@@ -267,13 +267,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 const int nvalid = min(32, g.N - col0);
                 const bool vec_ok = (nvalid == 32);
                 if (g.epi == EPI_BIAS || g.epi == EPI_BIAS_ELU || g.epi == EPI_BIAS_SAMPLE) {
-                    // one coalesced load of the 32 bias values of this chunk, then warp shuffles
-                    const float bl = (lane < nvalid) ? __ldg(g.bias + col0 + lane) : 0.0f;
+                    // bias: warp-uniform loads (L1 broadcast), not shuffles -- the MIO pipe is saturated by tensor-core operand reads
+                    if (vec_ok && ((reinterpret_cast<uintptr_t>(g.bias + col0) & 15u) == 0)) {
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        float x = v[j] + __shfl_sync(0xffffffffu, bl, j);
-                        // nn.ELU(alpha=1): exp(x) - 1 for x <= 0 (absolute error ~1e-7, same form as torch's CUDA kernel)
-                        v[j] = (g.epi == EPI_BIAS_ELU) ? elu_fp32(x) : x;                                   // nn.ELU(alpha=1)
+                        for (int j = 0; j < 32; j += 4) {
+                            const float4 b4 = __ldg(reinterpret_cast<const float4*>(g.bias + col0 + j));
+                            v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            if (j < nvalid) v[j] += __ldg(g.bias + col0 + j);
+                    }
+                    if (g.epi == EPI_BIAS_ELU) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] = elu_fp32(v[j]);                                  // nn.ELU(alpha=1)
                     }
                 } else if (g.epi == EPI_MUL_DELU) {
                     const float* h = g.H + (int64_t)row * g.ldh + col0;

@@ -55,6 +55,7 @@ struct ChainLayer {
 };
 struct ChainArgs {
     int M, tiles_m, n_layers;
+    long long* trace;                    // optional (HG_CHAIN_TRACE): [grid][16 items][16] globaltimer stamps, see tools/chain_trace.py
     int tma_lo;                          // 1: A_lo (hidden layers) and B_lo tiles come by TMA; 0: the splitter warps make both in the stage
     int* counters;                       // [MAX_CHAIN][tiles_m] tile counters + [MAX_CHAIN * tiles_m] "CTAs done"
     ChainLayer L[MAX_CHAIN];
@@ -82,6 +83,12 @@ __device__ __forceinline__ uint32_t make_idesc(int N) {                 // D = F
     return d;
 }
 __device__ __forceinline__ float tf32_residual(float x) { return rna_tf32(x - __uint_as_float(__float_as_uint(x) & 0xFFFFE000u)); }
+__device__ __forceinline__ long long gtime() {
+    long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+#define TRACE(item_, slot_) do { if (g.trace && (item_) < 16) g.trace[((size_t)blockIdx.x * 16 + (item_)) * 16 + (slot_)] = gtime(); } while (0)
 __device__ __forceinline__ int ld_acquire(const int* p) {
     int v;
     asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
@@ -129,21 +136,24 @@ __global__ void __launch_bounds__(THREADS, 1) mlp_chain_kernel(const __grid_cons
                 asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.blo[l]) : "memory");
                 if (g.L[l].has_alo) asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.alo[l]) : "memory");
             }
-            int it = 0;
+            int it = 0, pitem = 0;
             for (int l = 0; l < g.n_layers; ++l) {
                 const ChainLayer& Ly = g.L[l];
                 const int items = g.tiles_m * Ly.tiles_n, num_kb = (Ly.K + BK - 1) / BK;
                 const bool alo_tma = g.tma_lo && Ly.has_alo;
                 const uint32_t b_bytes = (uint32_t)Ly.BN * BK * 4;
                 const uint32_t tx = TILE_BYTES * (alo_tma ? 2u : 1u) + b_bytes * (g.tma_lo ? 2u : 1u);
-                for (int w = (blockIdx.x + Ly.rot) % G; w < items; w += G) {
+                for (int w = (blockIdx.x + Ly.rot) % G; w < items; w += G, ++pitem) {
                     const int tm = w / Ly.tiles_n, tn = w - tm * Ly.tiles_n;
+                    TRACE(pitem, 0);
+                    if (g.trace && pitem < 16) g.trace[((size_t)blockIdx.x * 16 + pitem) * 16 + 7] = ((long long)l << 32) | (unsigned)w;
                     if (Ly.dep >= 0) {                   // wait until every column tile of the producing layer has published row tile tm
                         const int need = g.L[Ly.dep].tiles_n;
                         const int* c = g.counters + Ly.dep * g.tiles_m + tm;
                         while (ld_acquire(c) < need) __nanosleep(32);
                         asm volatile("fence.proxy.async;" ::: "memory");    // generic-proxy acquire -> async-proxy (TMA) reads
                     }
+                    TRACE(pitem, 1);
                     for (int kb = 0; kb < num_kb; ++kb, ++it) {
                         const int s = it % STAGES, k0 = kb * BK;
                         mbar_wait(&empty[s], ((it / STAGES) & 1) ^ 1);
@@ -154,6 +164,7 @@ __global__ void __launch_bounds__(THREADS, 1) mlp_chain_kernel(const __grid_cons
                         tma_load_2d(st + OFF_B, &maps.b[l], &full[s], k0, tn * Ly.BN);
                         if (g.tma_lo) tma_load_2d(st + OFF_BLO, &maps.blo[l], &full[s], k0, tn * Ly.BN);
                     }
+                    TRACE(pitem, 2);
                 }
             }
         }
@@ -171,6 +182,7 @@ __global__ void __launch_bounds__(THREADS, 1) mlp_chain_kernel(const __grid_cons
                     mbar_wait(&tmem_empty[acc_stage], ((item >> 1) & 1) ^ 1);
                     tc_fence_after();
                     const uint32_t tmem_d = tmem_base + (uint32_t)(acc_stage * 128);
+                    TRACE(item, 3);
                     for (int kb = 0; kb < num_kb; ++kb, ++it) {
                         const int s = it % STAGES;
                         mbar_wait(&full[s], (it / STAGES) & 1);
@@ -193,6 +205,7 @@ __global__ void __launch_bounds__(THREADS, 1) mlp_chain_kernel(const __grid_cons
                         umma_commit(&empty[s]);
                     }
                     umma_commit(&tmem_full[acc_stage]);
+                    TRACE(item, 4);
                 }
             }
         }
@@ -243,20 +256,36 @@ __global__ void __launch_bounds__(THREADS, 1) mlp_chain_kernel(const __grid_cons
                 const int acc_stage = item & 1;
                 mbar_wait(&tmem_full[acc_stage], (item >> 1) & 1);
                 tc_fence_after();
+                if (threadIdx.x == 0) TRACE(item, 5);
                 const int row = tm * BM + warp * 32 + lane;
                 const bool row_ok = row < g.M;
                 for (int c0 = 0; c0 < Ly.BN; c0 += 32) {
                     float v[32];
+                    if (threadIdx.x == 0 && c0 == 0) TRACE(item, 8);
                     tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(acc_stage * 128 + c0), v);
+                    if (threadIdx.x == 0 && c0 == 0) TRACE(item, 9);
                     const int col0 = tn * Ly.BN + c0;
                     if (col0 >= Ly.N) continue;                                 // warp-uniform
                     const int nvalid = min(32, Ly.N - col0);
-                    const float bl = (lane < nvalid) ? __ldg(Ly.bias + col0 + lane) : 0.0f;
+                    // bias: warp-uniform 128-bit loads (one L1 broadcast each).  NOT shuffles: the shared-memory / MIO pipe is
+                    // saturated by the tensor core's operand reads during the next item's main loop, and 32 dependent SHFLs
+                    // queued behind it cost ~5 k cycles per chunk (measured with %globaltimer stamps, tools/chain_trace.py)
+                    if (nvalid == 32 && ((reinterpret_cast<uintptr_t>(Ly.bias + col0) & 15u) == 0)) {
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        const float x = v[j] + __shfl_sync(0xffffffffu, bl, j);
-                        v[j] = (Ly.epi == CH_BIAS_ELU) ? elu_fp32(x) : x;
+                        for (int j = 0; j < 32; j += 4) {
+                            const float4 b4 = __ldg(reinterpret_cast<const float4*>(Ly.bias + col0 + j));
+                            v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            if (j < nvalid) v[j] += __ldg(Ly.bias + col0 + j);
                     }
+                    if (Ly.epi == CH_BIAS_ELU) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] = elu_fp32(v[j]);
+                    }
+                    if (threadIdx.x == 0 && c0 == 0) TRACE(item, 10);
                     if (!row_ok) continue;
                     float* dst = Ly.C + (int64_t)row * Ly.ldc + col0;
                     if (Ly.epi == CH_BIAS_SAMPLE) {
@@ -301,13 +330,18 @@ __global__ void __launch_bounds__(THREADS, 1) mlp_chain_kernel(const __grid_cons
                             }
                     }
                 }
+                if (threadIdx.x == 0) TRACE(item, 11);
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&tmem_empty[acc_stage]);             // accumulator free for item + 2
                 // publish the tile: every epilogue thread's stores are device-visible before the counter moves
                 __threadfence();
+                if (threadIdx.x == 0) TRACE(item, 12);
                 asm volatile("bar.sync 1, 128;" ::: "memory");
-                if (threadIdx.x == 0) atomicAdd(g.counters + l * g.tiles_m + tm, 1);
+                if (threadIdx.x == 0) {
+                    atomicAdd(g.counters + l * g.tiles_m + tm, 1);
+                    TRACE(item, 6);
+                }
             }
         }
     }
@@ -375,9 +409,14 @@ struct ChainPlan { ChainMaps maps; ChainArgs args; int grid; };
 std::unordered_map<ChainKey, ChainPlan, ChainKeyHash> g_plans;
 std::mutex g_plans_mu;
 
+long long* g_chain_trace = nullptr;
+
 bool tma_ok(const void* p, int64_t ld) { return hg_aligned16(p) && (ld & 3) == 0; }
 
 }  // namespace
+
+// debug: per-item globaltimer stamps of the next launches are written to `buf` ([148][16][16] int64, device memory); NULL = off
+extern "C" void hg_actor_critic_set_trace(long long* buf) { g_chain_trace = buf; }
 
 extern "C" int64_t hg_actor_critic_counters_size(int64_t M) { return (int64_t)MAX_CHAIN * ((M + BM - 1) / BM) + 1; }
 
@@ -385,17 +424,18 @@ extern "C" int32_t hg_actor_critic_forward(const HgMlpDesc* actor, const HgMlpDe
                                            const float* obs, int64_t ld_obs, const float* cobs, int64_t ld_cobs, float* hidden_a,
                                            float* hidden_c, float* hidden_lo_a, float* hidden_lo_c, float* mu, float* value,
                                            const HgMlpFwdOpts* sample, int32_t* counters, int64_t M, void* stream) {
-    HG_REQUIRE(actor); HG_REQUIRE(critic); HG_REQUIRE(params); HG_REQUIRE(params_lo); HG_REQUIRE(obs); HG_REQUIRE(cobs);
-    HG_REQUIRE(hidden_a); HG_REQUIRE(hidden_c); HG_REQUIRE(mu); HG_REQUIRE(value); HG_REQUIRE(counters);
+    HG_REQUIRE(params); HG_REQUIRE(params_lo); HG_REQUIRE(counters);
+    if (!actor && !critic) return hg_fail(HG_E_NULL, "hg_actor_critic_forward: actor and critic are both NULL");
+    if (actor) { HG_REQUIRE(obs); HG_REQUIRE(hidden_a); HG_REQUIRE(hidden_lo_a); HG_REQUIRE(mu); }
+    if (critic) { HG_REQUIRE(cobs); HG_REQUIRE(hidden_c); HG_REQUIRE(hidden_lo_c); HG_REQUIRE(value); }
     if (M <= 0 || M > (1 << 24)) return hg_fail(HG_E_SIZE, "hg_actor_critic_forward: bad M");
-    const int La = actor->n_layers, Lc = critic->n_layers;
-    if (La < 1 || Lc < 1 || La + Lc > MAX_CHAIN) return hg_fail(HG_E_ALIGN, "hg_actor_critic_forward: more than 8 layers in total");
+    const int La = actor ? actor->n_layers : 0, Lc = critic ? critic->n_layers : 0;
+    if ((actor && La < 1) || (critic && Lc < 1) || La + Lc > MAX_CHAIN) return hg_fail(HG_E_ALIGN, "hg_actor_critic_forward: more than 8 layers in total");
     const bool want_sample = sample && sample->actions;
     if (want_sample && (!sample->std || !sample->log_prob || !sample->sigma)) return hg_fail(HG_E_NULL, "hg_actor_critic_forward: sampling outputs are NULL");
-    if (want_sample && actor->dims[La] > 32) return hg_fail(HG_E_ALIGN, "hg_actor_critic_forward: more than 32 actions");
+    if (want_sample && (!actor || actor->dims[La] > 32)) return hg_fail(HG_E_ALIGN, "hg_actor_critic_forward: sampling needs an actor with <= 32 actions");
     if (int32_t rc = load_encode()) return rc;
 
-    HG_REQUIRE(hidden_lo_a); HG_REQUIRE(hidden_lo_c);
     ChainKey key{};
     const void* ptrs[12] = {actor, critic, params, params_lo, obs, cobs, hidden_a, hidden_c, mu, value, hidden_lo_a, hidden_lo_c};
     memcpy(key.p, ptrs, sizeof(ptrs));
@@ -424,7 +464,7 @@ extern "C" int32_t hg_actor_critic_forward(const HgMlpDesc* actor, const HgMlpDe
         for (int l = 0; l < Lmax; ++l)
             for (int which = 0; which < 2; ++which) {
                 const HgMlpDesc* net = nets[which];
-                if (l >= net->n_layers) continue;
+                if (!net || l >= net->n_layers) continue;
                 const int K = net->dims[l], N = net->dims[l + 1];
                 const bool last = (l + 1 == net->n_layers);
                 const float* in = (l == 0) ? X[which] : hid[which] + hoff[which] - M * K;
@@ -494,6 +534,7 @@ extern "C" int32_t hg_actor_critic_forward(const HgMlpDesc* actor, const HgMlpDe
         if (e != cudaSuccess) return hg_fail((int32_t)e, cudaGetErrorString(e));
         attr_set[dev] = true;
     }
+    g.trace = g_chain_trace;
     mlp_chain_kernel<<<plan.grid, THREADS, SMEM_BYTES, (cudaStream_t)stream>>>(plan.maps, g);
     HG_LAUNCHED(1);
     return hg_cuda_status("hg_actor_critic_forward");

@@ -158,6 +158,7 @@ def _load():
         "hg_mlp_forward_ex": (i32, [P(MlpDesc), PF, PF, i64, PF, PF, i64, P(MlpFwdOpts), PF]),
         "hg_tf32_residual": (i32, [PF, PF, i64, PF]),
         "hg_actor_critic_counters_size": (i64, [i64]),
+        "hg_actor_critic_set_trace": (None, [PF]),
         "hg_actor_critic_forward": (i32, [P(MlpDesc), P(MlpDesc), PF, PF, PF, i64, PF, i64, PF, PF, PF, PF, PF, PF, P(MlpFwdOpts), PF, i64, PF]),
         "hg_mlp_backward": (i32, [P(MlpDesc), PF, PF, i64, PF, PF, PF, PF, i64, PF]),
         "hg_gemm_tf32": (i32, [P(Gemm), PF]),

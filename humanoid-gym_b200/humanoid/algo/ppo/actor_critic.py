@@ -199,15 +199,11 @@ class ActorCritic(nn.Module):
                   "hg_mlp_forward_ex")
         return hidden
 
-    def native_act(self, obs, critic_obs, mu, value, sample=None):
-        """PPO.act in one launch (hg_actor_critic_forward): mu (M, A) and value (M, 1) <- actor(obs), critic(critic_obs),
-        optionally with the sampling epilogue (see native_forward).  Returns False when the fused kernel is not eligible
-        (exact-fp32 engine selected, operands not TMA-addressable): the caller then runs the two chains separately."""
+    def chain_eligible(self, *inputs):
+        """hg_actor_critic_forward applies: a tensor-core engine is selected, <= 8 layers, TMA-addressable inputs."""
         if nat.lib.hg_set_gemm_mode(-1) not in (1, 4) or os.environ.get("HG_FUSED_ACT", "1") == "0":
             return False
-        flat = self.flat_params()
-        M = obs.shape[0]
-        for x in (obs, critic_obs):
+        for x in inputs:
             if x.dtype != torch.float32 or x.stride(1) != 1 or x.stride(0) % 4 or x.data_ptr() % 16:
                 return False
         if len(self._actor_dims) + len(self._critic_dims) - 2 > 8 or self.num_actions > 32:
@@ -216,7 +212,17 @@ class ActorCritic(nn.Module):
             if torch.cuda.is_current_stream_capturing():
                 return False
             self.refresh_lo()
-        key = ("act_counters", M)
+        return True
+
+    def native_chain(self, which, x, out, sample=None):
+        """One persistent multi-layer launch (hg_actor_critic_forward) for the actor ("actor": out = mean, optional sampling
+        epilogue, see native_forward), the critic ("critic": out = value) or both ("both": x = (obs, critic_obs),
+        out = (mean, value)).  The caller checks chain_eligible() first."""
+        flat = self.flat_params()
+        obs, cobs = (x if which == "both" else ((x, None) if which == "actor" else (None, x)))
+        mu, value = (out if which == "both" else ((out, None) if which == "actor" else (None, out)))
+        M = (obs if obs is not None else cobs).shape[0]
+        key = ("chain_counters", which, M)
         if key not in self._scratch:
             self._scratch[key] = torch.zeros(int(nat.lib.hg_actor_critic_counters_size(M)), dtype=torch.int32, device=flat.device)
         o = nat.MlpFwdOpts()
@@ -224,13 +230,25 @@ class ActorCritic(nn.Module):
             o.std, o.eps = sample["std"].data_ptr(), nat.ptr(sample.get("eps"))
             o.actions, o.log_prob, o.sigma = sample["actions"].data_ptr(), sample["log_prob"].data_ptr(), sample["sigma"].data_ptr()
             o.seed, o.step, o.step_dev = sample["seed"], sample["step"], sample.get("step_dev")
-        ha, hc = self._hidden_scratch("actor", M), self._hidden_scratch("critic", M)
-        la, lc = self._hidden_scratch("actor_lo", M), self._hidden_scratch("critic_lo", M)
-        nat.check(nat.lib.hg_actor_critic_forward(self._desc["actor"], self._desc["critic"], flat.data_ptr(), self._wlo.data_ptr(),
-                                                  obs.data_ptr(), obs.stride(0), critic_obs.data_ptr(), critic_obs.stride(0),
-                                                  ha.data_ptr(), hc.data_ptr(), la.data_ptr(), lc.data_ptr(), mu.data_ptr(), value.data_ptr(), o,
-                                                  self._scratch[key].data_ptr(), M, nat.stream_ptr(flat.device.index)),
-                  "hg_actor_critic_forward")
+        a_on, c_on = obs is not None, cobs is not None
+        ha = self._hidden_scratch("actor", M) if a_on else None
+        la = self._hidden_scratch("actor_lo", M) if a_on else None
+        hc = self._hidden_scratch("critic", M) if c_on else None
+        lc = self._hidden_scratch("critic_lo", M) if c_on else None
+        P = nat.ptr
+        nat.check(nat.lib.hg_actor_critic_forward(self._desc["actor"] if a_on else None, self._desc["critic"] if c_on else None,
+                                                  flat.data_ptr(), self._wlo.data_ptr(),
+                                                  obs.data_ptr() if a_on else None, obs.stride(0) if a_on else 0,
+                                                  cobs.data_ptr() if c_on else None, cobs.stride(0) if c_on else 0,
+                                                  P(ha), P(hc), P(la), P(lc), mu.data_ptr() if a_on else None,
+                                                  value.data_ptr() if c_on else None, o, self._scratch[key].data_ptr(), M,
+                                                  nat.stream_ptr(flat.device.index)), "hg_actor_critic_forward")
+
+    def native_act(self, obs, critic_obs, mu, value, sample=None):
+        """Both nets in one launch (kept for tests / callers without a side stream)."""
+        if not self.chain_eligible(obs, critic_obs):
+            return False
+        self.native_chain("both", (obs, critic_obs), (mu, value), sample)
         return True
 
     # ------------------------------------------------------------------------------------------

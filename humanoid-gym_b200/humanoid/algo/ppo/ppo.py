@@ -7,6 +7,8 @@ gradient buffer -- whose tail carries [surrogate, value loss, entropy, KL] parti
 all-reduced (SUM) once per optimizer step; every mean already uses 1/B_global, so the summed buffer is
 exactly the single-process gradient of the G*B-sample minibatch and all ranks take the same lr decision.
 """
+import os
+
 import torch
 import torch.distributed as dist
 import torch.optim as optim
@@ -136,16 +138,24 @@ class PPO:
         sample = dict(std=ac.std, eps=eps, actions=s.actions[t], log_prob=s.actions_log_prob[t], sigma=s.sigma[t], seed=self._seed,
                       step=self._sample_step if step is None else int(step), step_dev=step_dev)
         self._side.wait_stream(cur)
-        # ONE launch for both nets incl. the sampling epilogue (hg_actor_critic_forward); the 15 MB observation copy into
-        # slab t rides on the side stream: nothing before the update reads it
-        fused = ac.native_act(obs, critic_obs, s.mu[t], s.values[t], sample)
+        # Actor + critic, all layers, with the sampling epilogue: ONE persistent launch (hg_actor_critic_forward).  The 15 MB
+        # observation copy into slab t rides on the side stream: nothing before the update reads it.  (HG_ACT_STREAMS=2 puts
+        # the critic into its own launch on the side stream; measured slower -- 184 vs 158 us per step -- because two
+        # 200 KB-shared-memory grids fight for the same SMs.)
+        fused = ac.chain_eligible(obs, critic_obs)
+        split_streams = os.environ.get("HG_ACT_STREAMS", "1") == "2"
+        if fused and not split_streams:
+            ac.native_chain("both", (obs, critic_obs), (s.mu[t], s.values[t]), sample)
         with torch.cuda.stream(self._side):
-            if not fused:
-                # fallback: actor and critic as independent chains of small GEMMs on two streams
-                ac.native_forward("critic", critic_obs, s.values[t])
+            if fused and split_streams:
+                ac.native_chain("critic", critic_obs, s.values[t])
+            elif not fused:
+                ac.native_forward("critic", critic_obs, s.values[t])       # fallback: per-layer launches
             s.add_native(t, obs=obs, priv_obs=critic_obs if s.privileged_observations is not None else None)
         self._critic_pending = True
-        if not fused:
+        if fused and split_streams:
+            ac.native_chain("actor", obs, s.mu[t], sample)
+        elif not fused:
             ac.native_forward("actor", obs, s.mu[t], sample=sample)
         self._sample_step += 1
         # The value estimate is not needed before process_env_step (r += gamma * V * time_out), so the critic chain is

@@ -261,8 +261,12 @@ int32_t hg_mlp_forward_ex(const HgMlpDesc* net, const float* params, const float
  * hidden_lo_a / hidden_lo_c: scratch of the same size receiving the tf32 residuals of the hidden activations (the
  * next layer's A_lo tiles then arrive by TMA: no in-kernel splitting except for the network inputs).
  * sample (may be NULL / actions == NULL): the actor's output epilogue samples as in hg_policy_sample.
+ * Either net may be NULL (its arguments are then ignored): the runner launches the actor alone on the critical path and the
+ * critic alone on a side stream, where it overlaps the env step.
  * Returns HG_E_ALIGN when an operand is not TMA-addressable or the nets have more than 8 layers in total. */
 int64_t hg_actor_critic_counters_size(int64_t M);
+/* debug aid: per-item %globaltimer stamps of the following launches go to buf ([148][16][16] int64, device); NULL = off */
+void hg_actor_critic_set_trace(long long* buf);
 int32_t hg_actor_critic_forward(const HgMlpDesc* actor, const HgMlpDesc* critic, const float* params, const float* params_lo,
                                 const float* obs, int64_t ld_obs, const float* cobs, int64_t ld_cobs, float* hidden_a,
                                 float* hidden_c, float* hidden_lo_a, float* hidden_lo_c, float* mu, float* value,
