@@ -131,15 +131,15 @@ def _make_runner(num_envs, device, physics, seed=5):
     return env, runner
 
 
-def _iterate(runner, state):
+def _iterate(runner, state, book=None):
     obs, cobs = state
     with torch.inference_mode():
-        obs, cobs = runner.collect(obs, cobs)       # CUDA-graph replay of the 60-step rollout when the physics allows
+        obs, cobs = runner.collect(obs, cobs, book)  # CUDA-graph replay of the 60-step rollout when the physics allows
         vl, sl = runner.alg.update()
     return (obs, cobs), (vl, sl)
 
 
-def _time_iterations(runner, state, steps, device, world, e2e=False):
+def _time_iterations(runner, state, steps, device, world, e2e=False, book=None):
     """CUDA-event time of exactly `steps` iterations, barrier + synchronize on both sides, max over ranks."""
     from humanoid import _native as nat
     if world > 1:
@@ -165,9 +165,10 @@ def _time_iterations(runner, state, steps, device, world, e2e=False):
             print(f"[bench dbg] rank {os.environ.get('RANK', '0')} e2e={e2e}: collect {1e3 * (t_b - t_a):.1f} ms, update {1e3 * (time.time() - t_b):.1f} ms, "
                   f"graph={'yes' if getattr(runner, '_graph', None) is not None else 'no'}", file=sys.stderr, flush=True)
         else:
-            state, losses = _iterate(runner, state)
-        if e2e:   # device->host read of the step's result
-            results.append((losses, float(runner.env.rew_buf.mean().item())))
+            state, losses = _iterate(runner, state, book)
+        if e2e:   # device->host read of the step's result: losses, mean reward, and what train.py's logger reads every iteration
+            ep = book.drain_infos() if book is not None else None
+            results.append((losses, float(runner.env.rew_buf.mean().item()), ep))
     ev1.record()
     torch.cuda.synchronize(device)
     if world > 1:
@@ -361,13 +362,20 @@ def run_product(args):
     # (runs before the rank-0-only kernel rooflines, so that every rank enters its warm-up and timed region together)
     env, runner = _make_runner(N, str(device), "synthetic_host")
     state = (env.get_observations(), env.get_privileged_observations())
+    # the e2e arm runs what `scripts/train.py` runs with a log dir: per-step episode bookkeeping (one native launch per env
+    # step, inside the rollout graph) and the per-iteration read-back of finished episodes + the 22 reward-term means
+    from humanoid.algo.ppo.on_policy_runner import _EpisodeBook
+    book = _EpisodeBook(env.num_envs, T_STEPS, len(env.extras.get("episode", {})), str(device))
     for _ in range(max(1, args.warmup)):
-        state, _ = _iterate(runner, state)
-    ms_e, _, _, state = _time_iterations(runner, state, args.steps, device, world, e2e=True)
+        state, _ = _iterate(runner, state, book)
+        book.drain_infos()
+    n_done0 = len(book.rewbuffer)
+    ms_e, _, _, state = _time_iterations(runner, state, args.steps, device, world, e2e=True, book=book)
     e2e_value = env_steps / (ms_e * 1e-3)
     _log("e2e arm done; kernel rooflines")
     h2d = env.gym.h2d_bytes_per_step() * T_STEPS
-    d2h = 8 * 4 + 4
+    finished = float(torch.isfinite(book.done_rew).sum().item())          # finished episodes of the last iteration
+    d2h = 8 * 4 + 4 + int(2 * 4 * finished) + 4 * len(env.extras.get("episode", {}))
     extra = {}
     if rank == 0:
         try:
@@ -393,7 +401,7 @@ def run_product(args):
                    "l2": "per-step working set (rollout storage 947 MB + minibatch 237 MB) exceeds the 126 MB L2"},
         "e2e": {"value": round(e2e_value, 1), "unit": "env-steps/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": d2h,
                 "ms_per_step": round(ms_e / args.steps, 3),
-                "note": "physics frames staged from pinned host memory every env step through a double buffer (the H2D of step s+1 overlaps step s; memcpy nodes of the rollout graph); losses + mean reward read back"},
+                "note": "physics frames staged from pinned host memory every env step through a double buffer (the H2D of step s+1 overlaps step s; memcpy nodes of the rollout graph); per-step episode bookkeeping on (the log_dir path of train.py); losses, mean reward, finished-episode rewards / lengths and the 22 reward-term means read back every iteration"},
         "gpu_launches": int(launches // args.steps),
         "clocks": clocks.summary(),
         "host_wall_ms_per_step": round(wall_ms / args.steps, 3),
@@ -413,6 +421,10 @@ def run_product(args):
                                             "target": ">= 10 (north_star)"}
         _log("cpu_baseline: the unmodified reference on the host cores (subprocess)")
         line["cpu_baseline"] = cpu_baseline(N, sample_T=args.cpu_T)
+        try:
+            line["cpu_baseline_sim2sim"] = sim2sim_cpu()
+        except Exception as e:
+            line["cpu_baseline_sim2sim"] = {"unavailable": f"{type(e).__name__}: {e}"}
     print(json.dumps(line))
 
 
@@ -495,6 +507,36 @@ def cpu_baseline(num_envs, sample_T):
             "sample": f"1 learning iteration of the oracle port (no reference tree on this box: {r['unavailable']}), "
                       f"N={num_envs}, T={sample_T}, collection {c:.2f}s + learn {l:.2f}s, torch CPU fp32",
             "collection_s": round(c, 3), "learn_s": round(l, 3)}
+
+
+def sim2sim_cpu(calls=6000):
+    """BASELINE.json configs[0] (C1): the reference's sim2sim deployment loop on the host -- 100 Hz observation assembly,
+    15-frame stack, TorchScript actor, PD law at 1 kHz (reference scripts/sim2sim.py:113-160) -- with the reference's
+    shipped policy (weights from the committed KAT fixture).  MuJoCo is not installable here: mj_step is not run."""
+    import importlib.util
+    import numpy as np
+    spec = importlib.util.spec_from_file_location("hg_sim2sim", os.path.join(PKG, "humanoid", "scripts", "sim2sim.py"))
+    s2s = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(s2s)
+    k = np.load(os.path.join(ROOT, "tests", "golden", "policy_example_kat.npz"))
+    layers = []
+    for i in (0, 2, 4, 6):
+        w, b = torch.from_numpy(k[f"w.{i}.weight"]), torch.from_numpy(k[f"w.{i}.bias"])
+        lin = torch.nn.Linear(w.shape[1], w.shape[0])
+        lin.weight.data.copy_(w), lin.bias.data.copy_(b)
+        layers += [lin] + ([torch.nn.ELU()] if i < 6 else [])
+    policy = torch.jit.script(torch.nn.Sequential(*layers))
+    threads = torch.get_num_threads()
+    torch.set_num_threads(1)                             # a batch-1 MLP: one core, like the robot's control thread
+    try:
+        s2s.run(policy, low_level_steps=500)             # warm-up
+        n, sec = s2s.run(policy, low_level_steps=calls * 10)
+    finally:
+        torch.set_num_threads(threads)
+    return {"value": round(n / sec, 1), "unit": "policy calls/s (1 env)", "cores": 1, "kind": "reference-shaped loop",
+            "ms_per_call": round(1e3 * sec / n, 4), "calls": n,
+            "sample": f"{n} policy calls (60 s of 100 Hz control): obs assembly + 15-frame stack + TorchScript actor + PD law "
+                      f"at 1 kHz; MuJoCo unavailable (mujoco==2.3.6 not installable): mj_step was not run"}
 
 
 def run_reference(args):

@@ -347,6 +347,25 @@ __global__ void clip_adam_kernel(AdamArgs a) {
 }
 __global__ void adam_finish_kernel(int32_t* step, double* sqnorm) { *step += 1; *sqnorm = 0.0; }
 
+// OnPolicyRunner.learn's per-step bookkeeping (on_policy_runner.py:140-154) for one env step: running reward / length of the
+// current episode per env; where the env finished, the totals go to row t of (T, N) result slabs (NaN elsewhere) and the
+// running values restart; the step's extras["episode"] means are filed into row t of a (T, n_infos) slab.
+__global__ void episode_book_kernel(const float* __restrict__ rewards, const uint8_t* __restrict__ dones, float* __restrict__ cur_rew,
+                                    float* __restrict__ cur_len, float* __restrict__ done_rew, float* __restrict__ done_len,
+                                    const float* __restrict__ infos_in, float* __restrict__ infos_out, int n_infos, int N) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e < n_infos && infos_in) infos_out[e] = infos_in[e];
+    if (e >= N) return;
+    const float r = cur_rew[e] + rewards[e];                    // cur_reward_sum += rewards
+    const float l = cur_len[e] + 1.0f;                          // cur_episode_length += 1
+    const bool d = dones[e] != 0;
+    const float nanv = __int_as_float(0x7fc00000);
+    done_rew[e] = d ? r : nanv;
+    done_len[e] = d ? l : nanv;
+    cur_rew[e] = d ? 0.0f : r;
+    cur_len[e] = d ? 0.0f : l;
+}
+
 __global__ void adapt_lr_kernel(const float* kl_mean, double desired_kl, double* lr) {
     float kl = *kl_mean;                                         // ppo.py:142-145 (fp32 tensor vs python scalar)
     double v = *lr;
@@ -458,6 +477,18 @@ extern "C" int32_t hg_clip_adam_step(float* params, const float* grads, float* e
     adam_finish_kernel<<<1, 1, 0, st>>>(step_dev, sqnorm);
     HG_LAUNCHED(2);
     return hg_cuda_status("hg_clip_adam_step");
+}
+
+extern "C" int32_t hg_episode_book_step(const float* rewards, const uint8_t* dones, float* cur_reward_sum, float* cur_episode_length,
+                                        float* done_rew_t, float* done_len_t, const float* infos_in, float* infos_out_t,
+                                        int32_t n_infos, int64_t N, void* stream) {
+    HG_REQUIRE(rewards); HG_REQUIRE(dones); HG_REQUIRE(cur_reward_sum); HG_REQUIRE(cur_episode_length); HG_REQUIRE(done_rew_t); HG_REQUIRE(done_len_t);
+    if (N <= 0 || n_infos < 0 || (n_infos > 0 && infos_in && !infos_out_t)) return hg_fail(HG_E_SIZE, "hg_episode_book_step: bad N / infos");
+    const int64_t work = N > n_infos ? N : n_infos;
+    episode_book_kernel<<<(unsigned)((work + 255) / 256), 256, 0, (cudaStream_t)stream>>>(rewards, dones, cur_reward_sum, cur_episode_length,
+                                                                                         done_rew_t, done_len_t, infos_in, infos_out_t, n_infos, (int)N);
+    HG_LAUNCHED(1);
+    return hg_cuda_status("hg_episode_book_step");
 }
 
 extern "C" int32_t hg_adapt_lr(const float* kl_mean_dev, double desired_kl, double* lr_dev, void* stream) {

@@ -177,6 +177,7 @@ def _load():
         "hg_grad_sqnorm": (i32, [PF, i64, PF, PF]),
         "hg_clip_adam_step": (i32, [PF, PF, PF, PF, PF, f32, PF, PF, f32, f32, f32, f32, i64, PF]),
         "hg_adapt_lr": (i32, [PF, C.c_double, PF, PF]),
+        "hg_episode_book_step": (i32, [PF, PF, PF, PF, PF, PF, PF, PF, i32, i64, PF]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)          # AttributeError here == the library does not export the ABI

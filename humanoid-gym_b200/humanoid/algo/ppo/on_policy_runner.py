@@ -227,32 +227,40 @@ class OnPolicyRunner:
 
 
 class _EpisodeBook:
-    """Per-episode reward / length bookkeeping of on_policy_runner.py:140-154, kept on the device in
-    preallocated (T, N) buffers (so the per-step updates are CUDA-graph capturable); finished-episode statistics
-    are read back once per iteration instead of once per step."""
+    """Per-episode reward / length bookkeeping of on_policy_runner.py:140-154: ONE native launch per env step
+    (hg_episode_book_step) into preallocated (T, N) slabs, CUDA-graph capturable; finished-episode statistics are read
+    back once per iteration instead of once per step."""
 
     def __init__(self, n, T, n_infos, device):
         z = dict(dtype=torch.float, device=device)
+        self.n, self.n_infos = n, n_infos
         self.cur_reward_sum = torch.zeros(n, **z)
         self.cur_episode_length = torch.zeros(n, **z)
         self.done_rew = torch.full((T, n), float("nan"), **z)
         self.done_len = torch.full((T, n), float("nan"), **z)
         self.infos = torch.zeros(T, max(n_infos, 1), **z)
-        self.nan = torch.full((n,), float("nan"), **z)
         self.rewbuffer, self.lenbuffer = deque(maxlen=100), deque(maxlen=100)
         self._info_keys = []
+        self._dev_index = torch.device(device).index
 
     def step(self, t, rewards, dones, infos):
-        if "episode" in infos and infos["episode"]:
+        from humanoid import _native as nat
+        means = None
+        if isinstance(infos, dict) and infos.get("episode"):
             self._info_keys = list(infos["episode"].keys())
-            self.infos[t, :len(self._info_keys)].copy_(torch.stack(list(infos["episode"].values())))
-        self.cur_reward_sum += rewards
-        self.cur_episode_length += 1
-        d = dones > 0
-        torch.where(d, self.cur_reward_sum, self.nan, out=self.done_rew[t])
-        torch.where(d, self.cur_episode_length, self.nan, out=self.done_len[t])
-        self.cur_reward_sum.masked_fill_(d, 0)
-        self.cur_episode_length.masked_fill_(d, 0)
+            vals = list(infos["episode"].values())
+            base = getattr(vals[0], "_base", None)
+            # the env publishes the 22 means as views of ONE (22,) tensor: pass it straight through; anything else is stacked
+            if base is not None and base.is_contiguous() and base.numel() == len(vals) and all(getattr(v, "_base", None) is base for v in vals):
+                means = base
+            else:
+                means = torch.stack([v.reshape(()) for v in vals]).contiguous()
+        d = dones if dones.dtype in (torch.bool, torch.uint8) else (dones > 0)
+        nat.check(nat.lib.hg_episode_book_step(
+            rewards.contiguous().data_ptr(), d.contiguous().data_ptr(), self.cur_reward_sum.data_ptr(), self.cur_episode_length.data_ptr(),
+            self.done_rew[t].data_ptr(), self.done_len[t].data_ptr(), None if means is None else means.data_ptr(), self.infos[t].data_ptr(),
+            0 if means is None else min(len(self._info_keys), self.infos.shape[1]), self.n, nat.stream_ptr(self._dev_index)),
+            "hg_episode_book_step")
 
     def drain_infos(self):
         r, ln = self.done_rew.flatten(), self.done_len.flatten()

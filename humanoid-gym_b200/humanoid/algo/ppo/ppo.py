@@ -274,20 +274,31 @@ class PPO:
         nat.check(nat.lib.hg_ppo_loss_fwd_bwd(a, B, st), "hg_ppo_loss_fwd_bwd")
         g = self._grad.data_ptr()
         self._side.wait_stream(cur)
-        if split:
-            with torch.cuda.stream(self._side):           # the two backward chains write disjoint gradient ranges
+        # The flat gradient buffer is [std | actor.* | critic.* | 8 loss statistics]; the critic's backward chain runs on the side
+        # stream, and its range (+ the statistics, complete since the loss kernel) starts its all-reduce the moment that chain
+        # ends -- behind the actor's backward -- while the actor's range follows its own chain: ONE logical reduction of the
+        # buffer per optimizer step in two pieces, only the second of which is exposed.
+        c0 = ac._offsets[next(k for k in ac._layout if k.startswith("critic."))]
+        works = []
+        with torch.cuda.stream(self._side):               # the two backward chains write disjoint gradient ranges
+            if split:
                 ac.native_backward_split("critic", xs_c, w["hid_c"], w["d_value"], w["dhid_c"], self._grad)
-            ac.native_backward_split("actor", xs_a, w["hid_a"], w["d_mean"], w["dhid_a"], self._grad)
-        else:
-            with torch.cuda.stream(self._side):
+            else:
                 nat.check(nat.lib.hg_mlp_backward(ac._desc["critic"], flat.data_ptr(), cobs.data_ptr(), cobs.stride(0), w["hid_c"].data_ptr(),
                                                   w["d_value"].data_ptr(), w["dhid_c"].data_ptr(), g, B,
                                                   nat.stream_ptr(self._dev_index)), "hg_mlp_backward(critic)")
+            if world > 1:
+                works.append(dist.all_reduce(self._grad[c0:], async_op=True))
+        if split:
+            ac.native_backward_split("actor", xs_a, w["hid_a"], w["d_mean"], w["dhid_a"], self._grad)
+        else:
             nat.check(nat.lib.hg_mlp_backward(ac._desc["actor"], flat.data_ptr(), obs.data_ptr(), obs.stride(0), w["hid_a"].data_ptr(),
                                               w["d_mean"].data_ptr(), w["dhid_a"].data_ptr(), g, B, st), "hg_mlp_backward(actor)")
-        cur.wait_stream(self._side)
         if world > 1:
-            dist.all_reduce(self._grad)                         # the ONE collective of the update path
+            works.append(dist.all_reduce(self._grad[:c0], async_op=True))
+        cur.wait_stream(self._side)
+        for wk in works:
+            wk.wait()                                           # stream-side wait (no host block)
         if self.desired_kl is not None and self.schedule == "adaptive":
             nat.check(nat.lib.hg_adapt_lr(self._scalars.data_ptr() + 12, float(self.desired_kl), self._lr.data_ptr(), st), "hg_adapt_lr")
         n = ac.num_params

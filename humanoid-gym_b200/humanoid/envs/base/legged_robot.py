@@ -183,7 +183,11 @@ class LeggedRobot(BaseTask):
                 self.reward_scales.pop(key)
             else:
                 self.reward_scales[key] *= self.dt
-        self.reward_names = [k for k in self.reward_scales.keys() if k != "termination"]
+        if "termination" in self.reward_scales:
+            # reference legged_robot.py:231-235 adds a post-clip termination reward; the fused kernel has no such term
+            # (XBotLCfg: scale -0.0, filtered above).  Refuse rather than silently drop it.
+            raise NotImplementedError("rewards.scales.termination != 0 is not supported by the fused env kernel")
+        self.reward_names = list(self.reward_scales.keys())
         K = len(self.reward_names)
         self._episode_sums = torch.zeros(K, self.num_envs, dtype=torch.float, device=self.device)
         self._episode_means = torch.zeros(K, dtype=torch.float, device=self.device)

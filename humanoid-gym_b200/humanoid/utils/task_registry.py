@@ -66,7 +66,10 @@ class TaskRegistry:
         runner_class = getattr(algo, all_cfg["runner_class_name"])
         runner = runner_class(env, all_cfg, log_dir, device=args.rl_device)
         if train_cfg.runner.resume:
-            resume_path = get_load_path(log_root, load_run=train_cfg.runner.load_run,
+            # resolve the checkpoint from the experiment's log root on EVERY rank: ranks > 0 run with log_root=None (no
+            # logging), and os.listdir(None) would silently pick a checkpoint out of the CWD or fail -> diverging replicas
+            load_root = log_root if log_root is not None else os.path.join(LEGGED_GYM_ROOT_DIR, "logs", train_cfg.runner.experiment_name)
+            resume_path = get_load_path(load_root, load_run=train_cfg.runner.load_run,
                                         checkpoint=train_cfg.runner.checkpoint)
             print(f"Loading model from: {resume_path}")
             runner.load(resume_path, load_optimizer=False)

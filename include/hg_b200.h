@@ -400,6 +400,15 @@ int32_t hg_clip_adam_step(float* params, const float* grads, float* exp_avg, flo
                           double* sqnorm, float max_grad_norm, const double* lr_dev, int32_t* step_dev,
                           float beta1, float beta2, float eps, float grad_scale, int64_t n, void* stream);
 
+/* OnPolicyRunner.learn's per-step episode bookkeeping (on_policy_runner.py:140-154), one launch, no host sync:
+ * cur_reward_sum += rewards; cur_episode_length += 1; for finished envs (dones != 0) the totals are written to
+ * done_rew_t / done_len_t (row t of (T, N) slabs; NaN where the env did not finish) and the running values restart at 0;
+ * the n_infos extras["episode"] scalars of this step (infos_in, may be NULL) are copied to infos_out_t (row t of (T, n_infos)).
+ * The runner reads the slabs back once per iteration instead of `.cpu()`-ing every step. */
+int32_t hg_episode_book_step(const float* rewards, const uint8_t* dones, float* cur_reward_sum, float* cur_episode_length,
+                             float* done_rew_t, float* done_len_t, const float* infos_in, float* infos_out_t,
+                             int32_t n_infos, int64_t N, void* stream);
+
 /* Adaptive-KL learning-rate rule (ppo.py:142-148) evaluated on the device:
  * reads kl_mean_dev[0] (fp32 KL mean of the minibatch), updates lr_dev[0]. */
 int32_t hg_adapt_lr(const float* kl_mean_dev, double desired_kl, double* lr_dev, void* stream);

@@ -85,3 +85,16 @@ class OracleTrainer:
         self.learner.update({k: v.clone() for k, v in st.items()}, perm)
         t2 = time.time()
         return t1 - t0, t2 - t1
+
+
+def episode_book_step(cur_reward_sum, cur_episode_length, rewards, dones):
+    """ORACLE restatement of the runner's per-step episode bookkeeping (reference on_policy_runner.py:140-154):
+    returns (finished episode rewards, finished episode lengths) of this step; mutates the two running tensors."""
+    cur_reward_sum += rewards
+    cur_episode_length += 1
+    new_ids = (dones > 0).nonzero(as_tuple=False)
+    rew = cur_reward_sum[new_ids][:, 0].clone()
+    ln = cur_episode_length[new_ids][:, 0].clone()
+    cur_reward_sum[new_ids] = 0
+    cur_episode_length[new_ids] = 0
+    return rew, ln

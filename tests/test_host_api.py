@@ -5,6 +5,7 @@ import os
 import pytest
 
 HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
 
 
 def _norm(x):
@@ -81,3 +82,38 @@ def test_wrap_to_pi_and_quat_helpers():
     q = torch.tensor([[0.0, 0.0, math.sin(math.pi / 4), math.cos(math.pi / 4)]])
     v = quat_apply_yaw(q, torch.tensor([[1.0, 0.0, 0.0]]))
     assert torch.allclose(v, torch.tensor([[0.0, 1.0, 0.0]]), atol=1e-6)
+
+
+def test_sim2sim_plumbing_matches_a_direct_restatement():
+    """scripts/sim2sim.py (reference scripts/sim2sim.py:113-160): the policy input at every 100 Hz tick is the 15-frame
+    stack of clipped 47-wide frames, oldest first; actions are clipped and scaled into PD targets.  Runs on CPU with the
+    reference's shipped actor (weights from the committed KAT fixture)."""
+    import importlib.util
+    import numpy as np
+    import torch
+    from golden_io import Golden
+    spec = importlib.util.spec_from_file_location("hg_sim2sim", os.path.join(ROOT, "humanoid-gym_b200", "humanoid", "scripts", "sim2sim.py"))
+    s2s = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(s2s)
+    k = Golden("policy_example_kat.npz")
+    w = k.group("w.")
+    layers = []
+    for i in (0, 2, 4, 6):
+        lin = torch.nn.Linear(w[f"{i}.weight"].shape[1], w[f"{i}.weight"].shape[0])
+        lin.weight.data.copy_(w[f"{i}.weight"]), lin.bias.data.copy_(w[f"{i}.bias"])
+        layers += [lin] + ([torch.nn.ELU()] if i < 6 else [])
+    policy = torch.jit.script(torch.nn.Sequential(*layers))
+    rec = []
+    calls, sec = s2s.run(policy, low_level_steps=400, record=rec)
+    assert calls == 40 and len(rec) == 40 and sec > 0
+    x, a = rec[-1]
+    assert x.shape == (1, 705) and np.isfinite(x).all() and np.abs(x).max() <= 18 and np.abs(a).max() <= 18
+    # frame i of call n is frame i+1 of call n-1 (history shift), the newest frame carries the gait clock of its tick
+    assert np.array_equal(rec[-1][0][0, :658], rec[-2][0][0, 47:])
+    t = 390 * 0.001
+    assert abs(x[0, 658] - np.sin(2 * np.pi * t / 0.64)) < 1e-6 and abs(x[0, 659] - np.cos(2 * np.pi * t / 0.64)) < 1e-6
+    assert x[0, 660] == np.float32(0.4 * 2.0)                       # cmd.vx * obs_scales.lin_vel
+    assert np.allclose(x[0, 658 + 29:658 + 41], rec[-2][1])          # last action
+    # the first call sees an all-zero history except its own frame, and the actor's known answer on zeros is reproduced
+    y0 = policy(torch.zeros(1, 705))[0].detach().numpy()
+    np.testing.assert_allclose(y0, [0.0847, -0.0234, 0.0057, 0.2348, 0.6382, -0.2275, -0.1129, -0.1501, 0.2042, 0.3535, 0.0077, -0.4530], atol=5e-5)

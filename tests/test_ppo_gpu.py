@@ -453,3 +453,54 @@ def test_graph_replay_matches_eager_rollout():
     for ph, (a, b) in enumerate(zip(eager, graph)):
         for k in a:
             assert torch.equal(a[k], b[k]), (ph, k, float((a[k].float() - b[k].float()).abs().max()))
+
+
+def test_episode_book_kernel_vs_oracle():
+    """hg_episode_book_step (one launch per env step, no host sync) against the oracle restatement of the reference's
+    per-step bookkeeping (on_policy_runner.py:140-154): same finished-episode rewards / lengths in the same order."""
+    from humanoid.algo.ppo.on_policy_runner import _EpisodeBook
+    from oracle.runner_oracle import episode_book_step
+    N, T = 1000, 24
+    g = torch.Generator().manual_seed(3)
+    book = _EpisodeBook(N, T, 22, "cuda:0")
+    cur_r, cur_l = torch.zeros(N), torch.zeros(N)
+    means_buf = torch.zeros(22, device="cuda")
+    want_r, want_l, want_infos = [], [], []
+    for t in range(T):
+        rew = torch.rand(N, generator=g)
+        dones = torch.rand(N, generator=g) < 0.07
+        means = torch.rand(22, generator=g)
+        means_buf.copy_(means)
+        infos = {"episode": {f"rew_{k}": means_buf[k] for k in range(22)}, "time_outs": dones.cuda()}
+        book.step(t, rew.cuda(), dones.cuda(), infos)
+        r, ln = episode_book_step(cur_r, cur_l, rew, dones)
+        want_r += r.tolist()
+        want_l += ln.tolist()
+        want_infos.append(means)
+    torch.cuda.synchronize()
+    out = book.drain_infos()
+    assert list(book.lenbuffer) == want_l[-100:]
+    np.testing.assert_allclose(list(book.rewbuffer), want_r[-100:], rtol=1e-6)
+    np.testing.assert_allclose([out[f"rew_{k}"] for k in range(22)], torch.stack(want_infos).mean(0).numpy(), rtol=1e-5)
+    assert torch.equal(book.cur_reward_sum.cpu(), cur_r) and torch.equal(book.cur_episode_length.cpu(), cur_l)
+
+
+def test_export_policy_as_jit_roundtrip(tmp_path):
+    """export_policy_as_jit (reference utils/helpers.py:248-253): the TorchScript actor written from the product's
+    ActorCritic reproduces the reference's shipped policy_example.pt answers on CPU and agrees with the native forward."""
+    from humanoid.utils import export_policy_as_jit
+    k = Golden("policy_example_kat.npz")
+    ac = _make_ac(705, 219, 12, [512, 256, 128], [768, 256, 128])
+    sd = ac.state_dict()
+    for n, v in k.group("w.").items():
+        sd["actor." + n] = v.cuda()
+    ac.load_state_dict(sd)
+    export_policy_as_jit(ac, str(tmp_path))
+    pol = torch.jit.load(str(tmp_path / "policy_1.pt"), map_location="cpu")
+    x = k.t("x")
+    with torch.no_grad():
+        y = pol(x)
+    np.testing.assert_allclose(y.numpy(), k["y"], rtol=1e-5, atol=1e-6)
+    y_native = ac.act_inference(x.cuda()).cpu()
+    assert _rel(y_native, y) < 1e-5
+    assert ac.actor[0].weight.is_cuda                      # exporting must not move the live module off the GPU
