@@ -152,6 +152,7 @@ def _load():
         "hg_struct_size": (i64, [i32]),
         "hg_env_pre_physics": (i32, [P(EnvBuffers), P(EnvParams), PF, PF, PF, u64, u64, i64, PF]),
         "hg_env_compute_torques": (i32, [P(EnvBuffers), P(EnvParams), i64, PF]),
+        "hg_env_set_trace": (None, [PF]),
         "hg_env_synth_decimation": (i32, [P(EnvBuffers), P(EnvParams), PF, i32, PF, PF, PF, i64, PF]),
         "hg_env_post_physics": (i32, [P(EnvBuffers), P(EnvParams), P(EnvNoise), C.c_uint32, i64, i64, PF]),
         "hg_mlp_forward": (i32, [P(MlpDesc), PF, PF, i64, PF, PF, i64, PF]),

@@ -165,6 +165,9 @@ int32_t hg_env_pre_physics(const HgEnvBuffers* B, const HgEnvParams* P, const fl
  * decimation sub-step.  Reads B->actions, B->dof_state; writes B->torques. */
 int32_t hg_env_compute_torques(const HgEnvBuffers* B, const HgEnvParams* P, int64_t N, void* stream);
 
+/* debug aid: the following hg_env_post_physics launches stamp %globaltimer at their phase boundaries, buf = [grid][12] int64 */
+void hg_env_set_trace(long long* buf);
+
 /* Synthetic-physics fast path of the decimation loop (legged_robot.py:94-101) + the three state refreshes of
  * post_physics_step (:124-126): with an open-loop frame source the `decimation` x {PD torque, set forces, simulate,
  * refresh dof} sub-steps collapse into ONE launch.  dof_frames: (decimation, N*12, 2) the dof state after each
