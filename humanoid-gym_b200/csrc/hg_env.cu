@@ -259,10 +259,16 @@ __device__ __forceinline__ void stream_history(float* __restrict__ out, const fl
 
 // T = threads per CTA: 4 compute warps (4 lanes per env, 8 envs per warp) that join the history shift when done, plus T/32 - 4
 // pure streaming warps: 128 (no extra warps) when the grid is several waves deep, 512 when there is at most one tile per SM
+#ifndef HIST_OBS_ROWS
+#define HIST_OBS_ROWS 2
+#endif
+#ifndef HIST_CTAS_128
+#define HIST_CTAS_128 4
+#endif
 // debug timeline (hg_env_set_trace): thread 0 of every CTA stamps %globaltimer at the phase boundaries, [grid][12] int64
 #define ETRACE(slot_) do { if (trace && threadIdx.x == 0) { long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); trace[(size_t)blockIdx.x * 12 + (slot_)] = t_; } } while (0)
 template <int T>
-__global__ void __launch_bounds__(T, (T == 128 ? 5 : (T == 256 ? 2 : 1)))
+__global__ void __launch_bounds__(T, (T == 128 ? HIST_CTAS_128 : (T == 256 ? 2 : 1)))
 post_physics_kernel(HgEnvBuffers B, HgEnvNoise Z, uint32_t phases, int64_t common_step, int N, long long* trace) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     EnvSmem& S = *reinterpret_cast<EnvSmem*>(smem_raw);
@@ -775,7 +781,7 @@ post_physics_kernel(HgEnvBuffers B, HgEnvNoise Z, uint32_t phases, int64_t commo
     // ---- 2b. history shift: every warp pulls rows off a per-tile queue (the compute warps join when they are done), overlapped
     // with staging and the reward / observation math.  Rows are copied unconditionally; those of envs that reset are zeroed in step 3.
     if (do_obs) {
-        stream_history<HG_OBS1, OBS_KEEP, 1>(B.obs_out + (size_t)e0 * opitch, B.obs_buf + (size_t)e0 * opitch, &S.next_row[0], nE, lane, opitch);
+        stream_history<HG_OBS1, OBS_KEEP, HIST_OBS_ROWS>(B.obs_out + (size_t)e0 * opitch, B.obs_buf + (size_t)e0 * opitch, &S.next_row[0], nE, lane, opitch);
         stream_history<HG_PRIV1, PRIV_KEEP, 4>(B.priv_out + (size_t)e0 * ppitch, B.privileged_obs_buf + (size_t)e0 * ppitch, &S.next_row[1],
                                                nE, lane, ppitch);
     }
