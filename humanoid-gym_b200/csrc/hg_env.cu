@@ -1113,13 +1113,13 @@ extern "C" int32_t hg_env_post_physics(const HgEnvBuffers* B, const HgEnvParams*
     }
     int grid = (int)((N + HG_ENVS_PER_CTA - 1) / HG_ENVS_PER_CTA);
     // one CTA per 32-env tile (the kernel body is a tile loop, so a capped persistent grid also works, but measured no
-    // gain on B200).  CTA width by grid depth: with <= 1 tile per SM (the 4096-env training configuration) a 16-warp
-    // CTA streams 15 history rows at a time; deeper grids use 4-warp CTAs, 7 per SM.
+    // gain on B200).  CTA width by grid depth: 4 role warps + 12 streaming warps with <= 1 tile per SM (the 4096-env training
+    // configuration), 4 + 4 warps (2 CTAs per SM) for deeper grids (measured at N = 65536: 172 us vs 186 us for 4 + 0).
     static int env_threads = -1;                          // HG_ENV_CTA=128|256|512 pins the width (profiling)
     if (env_threads < 0) { const char* v = getenv("HG_ENV_CTA"); env_threads = v ? atoi(v) : 0; }
     // (the 8-warp variant measured no better than either neighbour -- 49 us at N=4096, 84 vs 72 us at N=16384 -- so it
     // is only reachable through HG_ENV_CTA)
-    const int width = env_threads ? env_threads : (grid <= HG_NUM_SMS ? 512 : 128);
+    const int width = env_threads ? env_threads : (grid <= HG_NUM_SMS ? 512 : 256);
     if (width == 512) post_physics_kernel<512><<<grid, 512, sizeof(EnvSmem), st>>>(*B, *Z, phases, common_step_counter, (int)N, g_env_trace);
     else if (width == 256) post_physics_kernel<256><<<grid, 256, sizeof(EnvSmem), st>>>(*B, *Z, phases, common_step_counter, (int)N, g_env_trace);
     else post_physics_kernel<128><<<grid, 128, sizeof(EnvSmem), st>>>(*B, *Z, phases, common_step_counter, (int)N, g_env_trace);

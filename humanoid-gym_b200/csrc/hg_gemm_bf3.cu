@@ -22,6 +22,7 @@
 // mbarrier ring of S stages (S = what fits in 227 KB), accumulator double-buffered in TMEM (2 x 256 columns) so the
 // epilogue of tile i overlaps the main loop of tile i+1.
 #include <cuda.h>
+#include <stdlib.h>
 
 #include <mutex>
 #include <unordered_map>
@@ -42,7 +43,7 @@ constexpr int SMEM_LIMIT = 227 * 1024;
 constexpr int BAR_BYTES = 256;
 constexpr int MAX_STAGES = 4;
 
-enum { EPI_F32 = 0, EPI_F32_BIAS = 1, EPI_SPLIT_BIAS_ELU = 2, EPI_SPLIT_DELU = 3, EPI_ATOMIC = 4, EPI_SPLIT = 5 };
+enum { EPI_F32 = 0, EPI_F32_BIAS = 1, EPI_SPLIT_BIAS_ELU = 2, EPI_SPLIT_DELU = 3, EPI_ATOMIC = 4, EPI_SPLIT = 5, EPI_DISCARD = 6 /* profiling: bias + ELU + split math, no stores */ };
 
 struct Args {
     float* C; int64_t ldc;
@@ -68,7 +69,7 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes
     return d;
 }
 // instruction descriptor, kind::f16: D = F32, A = B = BF16, M = 128
-__device__ __forceinline__ uint32_t make_idesc(int N, bool a_mn, bool b_mn) {
+__device__ __forceinline__ uint32_t make_idesc(int M, int N, bool a_mn, bool b_mn) {
     uint32_t d = 0;
     d |= 1u << 4;                                    // c_format F32
     d |= 1u << 7;                                    // a_format BF16
@@ -76,16 +77,16 @@ __device__ __forceinline__ uint32_t make_idesc(int N, bool a_mn, bool b_mn) {
     d |= (a_mn ? 1u : 0u) << 15;
     d |= (b_mn ? 1u : 0u) << 16;
     d |= (uint32_t)(N >> 3) << 17;
-    d |= (uint32_t)(BM >> 4) << 24;
+    d |= (uint32_t)(M >> 4) << 24;
     return d;
 }
 
 struct Work { int m0, n0, kb_begin, num_kb; };
-__device__ __forceinline__ Work decode_work(const Args& g, int w, int tiles_n, int tiles_mn, int num_kb_total) {
+__device__ __forceinline__ Work decode_work(const Args& g, int w, int tiles_n, int tiles_mn, int num_kb_total, int tile_m = BM) {
     Work r;
     const int split = w / tiles_mn, t = w - split * tiles_mn;
     const int tm = t / tiles_n, tn = t - tm * tiles_n;
-    r.m0 = tm * BM;
+    r.m0 = tm * tile_m;
     r.n0 = tn * g.BN;
     r.kb_begin = split * g.kb_per_split;
     r.num_kb = min(num_kb_total, r.kb_begin + g.kb_per_split) - r.kb_begin;
@@ -106,11 +107,19 @@ __device__ __forceinline__ float bf_hi(uint32_t p) { return __uint_as_float(p & 
 // series that would restore relative accuracy near 0 is not spent here (the 3xTF32 rollout path keeps expm1).
 __device__ __forceinline__ float elu1(float x) { return x > 0.0f ? x : __expf(x) - 1.0f; }
 
+// PAIR = true: the CTA-pair form (cluster of 2 on one TPC, tcgen05 cta_group::2).  The pair owns a 256 x BN tile: each CTA loads
+// its own 128 rows of A and HALF of the B tile, the leader's single MMA thread issues M = 256 instructions that read B from
+// both CTAs' shared memory, each CTA's TMEM receives its 128 rows and each CTA's epilogue warps drain them.  Per SM that halves
+// the B bytes fetched over L2 -> SM and read from shared memory per MMA -- the two feeds that bound the single-CTA form
+// (64 KB instead of 96 KB per 64-k stage at BN = 256, so three stages fit instead of two).
+template <bool PAIR>
 __global__ void __launch_bounds__(THREADS, 1)
 gemm_bf3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const Args g) {
     extern __shared__ unsigned char smem_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    const int b_plane = g.BN * BK * 2;                          // bytes of one bf16 plane of the B tile
+    const uint32_t rank = PAIR ? cluster_ctarank() : 0u;        // 0 = leader
+    const int bn_cta = PAIR ? (g.BN >> 1) : g.BN;               // B rows this CTA holds
+    const int b_plane = bn_cta * BK * 2;                        // bytes of one bf16 plane of this CTA's share of the B tile
     const int stage_bytes = A_BYTES + 2 * b_plane;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + g.stages * stage_bytes);
     uint64_t* full = bars;                          // [S] TMA -> MMA
@@ -121,25 +130,29 @@ gemm_bf3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int num_kb_total = (g.K + BK - 1) / BK;
-    const int tiles_n = (g.N + g.BN - 1) / g.BN, tiles_m = (g.M + BM - 1) / BM;
+    constexpr int TILE_M = PAIR ? 2 * BM : BM;
+    const int tiles_n = (g.N + g.BN - 1) / g.BN, tiles_m = (g.M + TILE_M - 1) / TILE_M;
     const int tiles_mn = tiles_n * tiles_m;
     const int total_work = tiles_mn * g.splits;
     const int S = g.stages;
+    const int w_begin = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x, w_step = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < S; ++s) {
-            mbar_init(&full[s], 1);
+            mbar_init(&full[s], PAIR ? 2 : 1);                  // pair: the leader's expect_tx arrival + the peer's remote arrival
             mbar_init(&empty[s], 1);
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(&tmem_full[a], 1);
-            mbar_init(&tmem_empty[a], EPI_WARPS);
+            mbar_init(&tmem_empty[a], PAIR ? 2 * EPI_WARPS : EPI_WARPS);
         }
         fence_barrier_init();
     }
-    if (warp == EPI_WARPS + 1) tmem_alloc(tmem_slot, 512);
+    if (warp == EPI_WARPS + 1) {
+        if (PAIR) tmem_alloc_2sm(tmem_slot, 512); else tmem_alloc(tmem_slot, 512);
+    }
     tc_fence_before();
-    __syncthreads();
+    if (PAIR) cluster_sync(); else __syncthreads();             // barriers initialised in BOTH CTAs before any remote arrival
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
@@ -148,38 +161,44 @@ gemm_bf3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         if (lane == 0) {
             asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
             asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
-            const uint32_t tx = (uint32_t)stage_bytes;
+            const uint32_t tx = (uint32_t)stage_bytes * (PAIR ? 2u : 1u);      // pair: both CTAs' loads are credited to the leader's barrier
+            const uint32_t full0_remote = PAIR ? mapa_u32(&full[0], 0) : 0u;
+            auto load = [&](void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+                if (PAIR) tma_load_3d_2sm(dst, map, bar, c0, c1, 0); else tma_load_3d(dst, map, bar, c0, c1, 0);
+            };
             int it = 0;
-            for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
-                const Work wk = decode_work(g, w, tiles_n, tiles_mn, num_kb_total);
+            for (int w = w_begin; w < total_work; w += w_step) {
+                const Work wk = decode_work(g, w, tiles_n, tiles_mn, num_kb_total, TILE_M);
+                const int m0 = wk.m0 + (int)rank * BM, n0 = wk.n0 + (int)rank * bn_cta;       // this CTA's rows of A / rows of B
                 for (int kb = 0; kb < wk.num_kb; ++kb, ++it) {
                     const int s = it % S, k0 = (wk.kb_begin + kb) * BK;
                     mbar_wait(&empty[s], ((it / S) & 1) ^ 1);
                     unsigned char* sa = smem + s * stage_bytes;
                     unsigned char* sb = sa + A_BYTES;
-                    mbar_expect_tx(&full[s], tx);
-                    if (!g.a_mn) tma_load_3d(sa, &tmA, &full[s], k0, wk.m0, 0);                   // [plane][128][64]
+                    if (!PAIR || rank == 0) mbar_expect_tx(&full[s], tx);
+                    else mbar_arrive_remote(full0_remote + (uint32_t)(s * sizeof(uint64_t)));
+                    if (!g.a_mn) load(sa, &tmA, &full[s], k0, m0);                                // [plane][128][64]
                     else
-                        for (int j = 0; j < BM / 64; ++j) tma_load_3d(sa + j * 16384, &tmA, &full[s], wk.m0 + 64 * j, k0, 0);   // [plane][64 k][64 mn]
-                    if (!g.b_mn) tma_load_3d(sb, &tmB, &full[s], k0, wk.n0, 0);                   // [plane][BN][64]
+                        for (int j = 0; j < BM / 64; ++j) load(sa + j * 16384, &tmA, &full[s], m0 + 64 * j, k0);   // [plane][64 k][64 mn]
+                    if (!g.b_mn) load(sb, &tmB, &full[s], k0, n0);                                // [plane][bn_cta][64]
                     else
-                        for (int j = 0; j < g.BN / 64; ++j) tma_load_3d(sb + j * 16384, &tmB, &full[s], wk.n0 + 64 * j, k0, 0);
+                        for (int j = 0; j < bn_cta / 64; ++j) load(sb + j * 16384, &tmB, &full[s], n0 + 64 * j, k0);
                 }
             }
         }
     } else if (warp == EPI_WARPS + 1) {
         // ===== MMA issuer =====
-        if (lane == 0) {
-            const uint32_t idesc = make_idesc(g.BN, g.a_mn, g.b_mn);
+        if (lane == 0 && rank == 0) {                           // pair: the leader issues for both CTAs
+            const uint32_t idesc = make_idesc(TILE_M, g.BN, g.a_mn, g.b_mn);
             // byte offsets inside a stage: plane (hi -> lo) and K step (16 bf16)
             const uint32_t a_lo_off = g.a_mn ? 8192u : (uint32_t)A_PLANE, b_lo_off = g.b_mn ? 8192u : (uint32_t)b_plane;
             const uint32_t a_kstep = g.a_mn ? 2048u : 32u, b_kstep = g.b_mn ? 2048u : 32u;
             const uint32_t a_lbo = g.a_mn ? 16384u : 16u, b_lbo = g.b_mn ? 16384u : 16u;
             int it = 0, item = 0;
-            for (int w = blockIdx.x; w < total_work; w += gridDim.x, ++item) {
-                const Work wk = decode_work(g, w, tiles_n, tiles_mn, num_kb_total);
+            for (int w = w_begin; w < total_work; w += w_step, ++item) {
+                const Work wk = decode_work(g, w, tiles_n, tiles_mn, num_kb_total, TILE_M);
                 const int acc_stage = item & 1;
-                mbar_wait(&tmem_empty[acc_stage], ((item >> 1) & 1) ^ 1);       // epilogue has drained this accumulator
+                mbar_wait(&tmem_empty[acc_stage], ((item >> 1) & 1) ^ 1);       // epilogue(s) have drained this accumulator
                 tc_fence_after();
                 const uint32_t tmem_d = tmem_base + (uint32_t)(acc_stage * 256);
                 for (int kb = 0; kb < wk.num_kb; ++kb, ++it) {
@@ -193,13 +212,19 @@ gemm_bf3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                         const uint64_t a_lo = make_desc(a0 + a_lo_off + kk * a_kstep, a_lbo);
                         const uint64_t b_hi = make_desc(b0 + kk * b_kstep, b_lbo);
                         const uint64_t b_lo = make_desc(b0 + b_lo_off + kk * b_kstep, b_lbo);
-                        umma_bf16(tmem_d, a_lo, b_hi, idesc, (kb > 0 || kk > 0) ? 1u : 0u);      // small terms first
-                        umma_bf16(tmem_d, a_hi, b_lo, idesc, 1u);
-                        umma_bf16(tmem_d, a_hi, b_hi, idesc, 1u);
+                        if (PAIR) {
+                            umma_bf16_2sm(tmem_d, a_lo, b_hi, idesc, (kb > 0 || kk > 0) ? 1u : 0u);
+                            umma_bf16_2sm(tmem_d, a_hi, b_lo, idesc, 1u);
+                            umma_bf16_2sm(tmem_d, a_hi, b_hi, idesc, 1u);
+                        } else {
+                            umma_bf16(tmem_d, a_lo, b_hi, idesc, (kb > 0 || kk > 0) ? 1u : 0u);  // small terms first
+                            umma_bf16(tmem_d, a_hi, b_lo, idesc, 1u);
+                            umma_bf16(tmem_d, a_hi, b_hi, idesc, 1u);
+                        }
                     }
-                    umma_commit(&empty[s]);                                     // stage reusable once these MMAs retire
+                    if (PAIR) umma_commit_2sm(&empty[s]); else umma_commit(&empty[s]);   // stage reusable (in both CTAs) once these MMAs retire
                 }
-                umma_commit(&tmem_full[acc_stage]);
+                if (PAIR) umma_commit_2sm(&tmem_full[acc_stage]); else umma_commit(&tmem_full[acc_stage]);
             }
         }
     } else {
@@ -210,12 +235,13 @@ gemm_bf3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         const int q = warp & 3, half = warp >> 2;
         const int c_begin = half * (g.BN >> 1), c_end = c_begin + (g.BN >> 1);
         const bool h_fast = (g.epi == EPI_SPLIT_DELU) && ((g.ldhs & 7) == 0) && ((g.hs_plane & 7) == 0) && ((reinterpret_cast<uintptr_t>(g.Hs) & 15u) == 0);
-        const bool bias_fast = (g.epi == EPI_F32_BIAS || g.epi == EPI_SPLIT_BIAS_ELU) && ((reinterpret_cast<uintptr_t>(g.bias) & 15u) == 0);
+        const bool bias_fast = (g.epi == EPI_F32_BIAS || g.epi == EPI_SPLIT_BIAS_ELU || g.epi == EPI_DISCARD) && ((reinterpret_cast<uintptr_t>(g.bias) & 15u) == 0);
+        const uint32_t tmem_empty0_leader = PAIR ? mapa_u32(&tmem_empty[0], 0) : 0u;
         int item = 0;
-        for (int w = blockIdx.x; w < total_work; w += gridDim.x, ++item) {
-            const Work wk = decode_work(g, w, tiles_n, tiles_mn, num_kb_total);
+        for (int w = w_begin; w < total_work; w += w_step, ++item) {
+            const Work wk = decode_work(g, w, tiles_n, tiles_mn, num_kb_total, TILE_M);
             const int acc_stage = item & 1;
-            const int row = wk.m0 + q * 32 + lane;
+            const int row = wk.m0 + (int)rank * BM + q * 32 + lane;
             const bool row_ok = row < g.M;
             uint4 hn[8];                                                    // prefetched H (4 x hi, 4 x lo) of the NEXT chunk
             auto prefetch_h = [&](int c0) {
@@ -245,7 +271,7 @@ gemm_bf3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 if (col0 >= g.N) continue;                                  // warp-uniform
                 const int nvalid = min(32, g.N - col0);
                 const bool full_chunk = (nvalid == 32);
-                if (g.epi == EPI_F32_BIAS || g.epi == EPI_SPLIT_BIAS_ELU) {
+                if (g.epi == EPI_F32_BIAS || g.epi == EPI_SPLIT_BIAS_ELU || g.epi == EPI_DISCARD) {
                     if (bias_fast && full_chunk && ((col0 & 3) == 0)) {
 #pragma unroll
                         for (int j = 0; j < 32; j += 4) {
@@ -257,7 +283,7 @@ gemm_bf3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 #pragma unroll
                         for (int j = 0; j < 32; ++j) v[j] += __shfl_sync(0xffffffffu, bl, j);
                     }
-                    if (g.epi == EPI_SPLIT_BIAS_ELU) {
+                    if (g.epi == EPI_SPLIT_BIAS_ELU || g.epi == EPI_DISCARD) {
 #pragma unroll
                         for (int j = 0; j < 32; ++j) v[j] = elu1(v[j]);
                     }
@@ -311,6 +337,16 @@ gemm_bf3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                     }
                     continue;
                 }
+                if (g.epi == EPI_DISCARD) {                                 // keep the math alive, store nothing (almost)
+                    float acc = 0.0f;
+#pragma unroll
+                    for (int j = 0; j < 32; j += 2) {
+                        const uint32_t ph = pack_bf16x2(v[j], v[j + 1]);
+                        acc += bf_lo(pack_bf16x2(v[j] - bf_lo(ph), v[j + 1] - bf_hi(ph)));
+                    }
+                    if (acc == 1.2345e38f && g.Cs) g.Cs[0] = 1;
+                    continue;
+                }
                 // ---- split store (hi / lo bf16 planes) ----
                 if (row_ok) {
                     uint16_t* dp = g.Cs + (int64_t)row * g.ldcs + col0;
@@ -357,14 +393,17 @@ gemm_bf3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&tmem_empty[acc_stage]);                 // accumulator free for item + 2
+            if (lane == 0) {                                                    // accumulator free for item + 2 (the leader's MMA thread waits)
+                if (PAIR) mbar_arrive_remote(tmem_empty0_leader + (uint32_t)(acc_stage * sizeof(uint64_t)));
+                else mbar_arrive(&tmem_empty[acc_stage]);
+            }
         }
     }
     tc_fence_before();
-    __syncthreads();
+    if (PAIR) cluster_sync(); else __syncthreads();             // the peer's shared memory stays alive until the leader's last MMA has read it
     if (warp == EPI_WARPS + 1) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, 512);
+        if (PAIR) tmem_dealloc_2sm(tmem_base, 512); else tmem_dealloc(tmem_base, 512);
     }
 }
 
@@ -466,6 +505,12 @@ int32_t check_split(const HgSplit& s, const char* what) {
 
 }  // namespace
 
+int hg_bf3_pair_enabled() {
+    static int pair_env = -1;
+    if (pair_env < 0) { const char* e = getenv("HG_BF3_PAIR"); pair_env = (e && e[0] == '0') ? 0 : 1; }
+    return pair_env;
+}
+
 extern "C" int32_t hg_split_bf16(const float* src, int64_t ld_src, const HgSplit* dst, int64_t rows, int64_t cols, void* stream) {
     HG_REQUIRE(src); HG_REQUIRE(dst); HG_REQUIRE(dst->p);
     if (rows <= 0 || cols <= 0 || ld_src < cols || dst->ld < cols) return hg_fail(HG_E_SIZE, "hg_split_bf16: bad extents");
@@ -491,13 +536,13 @@ extern "C" int32_t hg_gemm_bf16x3(const HgGemmSplit* d, void* stream) {
     if (int32_t rc = check_split(d->B, "hg_gemm_bf16x3: B is NULL")) return rc;
     if (d->M <= 0 || d->N <= 0 || d->K <= 0) return hg_fail(HG_E_SIZE, "hg_gemm_bf16x3: bad extents");
     const int epi = d->epilogue;
-    if (epi < 0 || epi > EPI_SPLIT) return hg_fail(HG_E_ARG, "hg_gemm_bf16x3: bad epilogue");
-    const bool split_out = (epi == EPI_SPLIT_BIAS_ELU || epi == EPI_SPLIT_DELU || epi == EPI_SPLIT);
+    if (epi < 0 || epi > EPI_DISCARD) return hg_fail(HG_E_ARG, "hg_gemm_bf16x3: bad epilogue");
+    const bool split_out = (epi == EPI_SPLIT_BIAS_ELU || epi == EPI_SPLIT_DELU || epi == EPI_SPLIT || epi == EPI_DISCARD);
     if (split_out) {
         if (!d->Cs.p) return hg_fail(HG_E_NULL, "hg_gemm_bf16x3: Cs is NULL");
         if (d->Cs.ld < d->N) return hg_fail(HG_E_SIZE, "hg_gemm_bf16x3: Cs.ld < N");
     } else if (!d->C) return hg_fail(HG_E_NULL, "hg_gemm_bf16x3: C is NULL");
-    if ((epi == EPI_F32_BIAS || epi == EPI_SPLIT_BIAS_ELU) && !d->bias) return hg_fail(HG_E_NULL, "hg_gemm_bf16x3: bias is NULL");
+    if ((epi == EPI_F32_BIAS || epi == EPI_SPLIT_BIAS_ELU || epi == EPI_DISCARD) && !d->bias) return hg_fail(HG_E_NULL, "hg_gemm_bf16x3: bias is NULL");
     if (epi == EPI_SPLIT_DELU && !d->Hs.p) return hg_fail(HG_E_NULL, "hg_gemm_bf16x3: Hs is NULL");
     if (int32_t rc = load_encode()) return rc;
     cudaStream_t st = (cudaStream_t)stream;
@@ -513,7 +558,11 @@ extern "C" int32_t hg_gemm_bf16x3(const HgGemmSplit* d, void* stream) {
     g.epi = epi;
     int bn = ((d->N + 63) / 64) * 64;                    // multiples of 64: MN-major boxes are 64 wide, column halves 32-aligned
     g.BN = bn > 256 ? 256 : bn;
-    const int stage_bytes = A_BYTES + 2 * g.BN * BK * 2;
+    // CTA pairs (cta_group::2) when the tile is wide enough to halve (each CTA loads BN / 2 rows of B: >= 64 for the MN-major
+    // boxes) and there are at least as many 256-row tiles as clusters worth filling; HG_BF3_PAIR=0 pins the single-CTA form
+    const bool pair = hg_bf3_pair_enabled() && g.BN >= 128 && d->M >= 256;
+    const int bn_cta = pair ? g.BN / 2 : g.BN;
+    const int stage_bytes = A_BYTES + 2 * bn_cta * BK * 2;
     int stages = (SMEM_LIMIT - 1024 - BAR_BYTES) / stage_bytes;
     g.stages = stages > MAX_STAGES ? MAX_STAGES : stages;
     const int smem_bytes = g.stages * stage_bytes + 1024 + BAR_BYTES;
@@ -531,7 +580,7 @@ extern "C" int32_t hg_gemm_bf16x3(const HgGemmSplit* d, void* stream) {
     if (!g.a_mn) rc = get_map(&tmA, d->A.p, d->K, d->M, d->A.ld, d->A.plane, BM);
     else rc = get_map(&tmA, d->A.p, d->M, d->K, d->A.ld, d->A.plane, BK);
     if (rc) return rc;
-    if (!g.b_mn) rc = get_map(&tmB, d->B.p, d->K, d->N, d->B.ld, d->B.plane, g.BN);
+    if (!g.b_mn) rc = get_map(&tmB, d->B.p, d->K, d->N, d->B.ld, d->B.plane, bn_cta);
     else rc = get_map(&tmB, d->B.p, d->N, d->K, d->B.ld, d->B.plane, BK);
     if (rc) return rc;
 
@@ -539,13 +588,27 @@ extern "C" int32_t hg_gemm_bf16x3(const HgGemmSplit* d, void* stream) {
     int dev = 0;
     cudaGetDevice(&dev);
     if (dev >= 0 && dev < 64 && !attr_set[dev]) {
-        cudaError_t e = cudaFuncSetAttribute(gemm_bf3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
+        cudaError_t e = cudaFuncSetAttribute(gemm_bf3_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_bf3_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
         if (e != cudaSuccess) return hg_fail((int32_t)e, cudaGetErrorString(e));
         attr_set[dev] = true;
     }
-    const int total_work = ((d->N + g.BN - 1) / g.BN) * ((d->M + BM - 1) / BM) * splits;
-    const int grid = total_work < HG_NUM_SMS ? total_work : HG_NUM_SMS;       // persistent: one CTA per SM
-    gemm_bf3_kernel<<<grid, THREADS, smem_bytes, st>>>(tmA, tmB, g);
+    const int tile_m = pair ? 2 * BM : BM;
+    const int total_work = ((d->N + g.BN - 1) / g.BN) * ((d->M + tile_m - 1) / tile_m) * splits;
+    if (pair) {
+        const int clusters = total_work < HG_NUM_SMS / 2 ? total_work : HG_NUM_SMS / 2;
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3(2 * clusters); cfg.blockDim = dim3(THREADS); cfg.dynamicSmemBytes = smem_bytes; cfg.stream = st;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_bf3_kernel<true>, tmA, tmB, g);
+        if (e != cudaSuccess) return hg_fail((int32_t)e, cudaGetErrorString(e));
+    } else {
+        const int grid = total_work < HG_NUM_SMS ? total_work : HG_NUM_SMS;   // persistent: one CTA per SM
+        gemm_bf3_kernel<false><<<grid, THREADS, smem_bytes, st>>>(tmA, tmB, g);
+    }
     HG_LAUNCHED(1);
     return hg_cuda_status("hg_gemm_bf16x3");
 }

@@ -322,9 +322,39 @@ class PPO:
         split = self.use_split_path()
         if split:
             self.actor_critic.refresh_split()              # parameters may have been written from outside (load, tests)
-        for _ in range(self.num_learning_epochs):
-            for i in range(self.num_mini_batches):
-                mb = s.gather(indices[i * mini:(i + 1) * mini], split=split)
+        steps = [(ep, i) for ep in range(self.num_learning_epochs) for i in range(self.num_mini_batches)]
+        if split:
+            # software pipeline: minibatch k+1 is gathered (a pure HBM copy, 0.47 GB) on its own stream into the other buffer slot
+            # while minibatch k runs its GEMM chains -- the gather's CTAs are small and share the SMs with the persistent GEMM CTAs
+            cur = torch.cuda.current_stream(self._dev_index)
+            if not hasattr(self, "_gather_stream"):
+                self._gather_stream = torch.cuda.Stream(self._dev_index)
+            gs = self._gather_stream
+            gs.wait_stream(cur)
+            done = [None, None]                                 # event: the minibatch step that last READ slot j has been enqueued
+
+            def issue(k):
+                i = steps[k][1]
+                with torch.cuda.stream(gs):
+                    if done[k % 2] is not None:
+                        gs.wait_event(done[k % 2])
+                    mb = s.gather(indices[i * mini:(i + 1) * mini], split=True, slot=k % 2)
+                    ev = torch.cuda.Event()
+                    ev.record(gs)
+                return mb, ev
+            nxt = issue(0)
+            for k in range(len(steps)):
+                mb, ready = nxt
+                if k + 1 < len(steps):
+                    nxt = issue(k + 1)
+                cur.wait_event(ready)
+                self.minibatch_step(mb, world)
+                done[k % 2] = torch.cuda.Event()
+                done[k % 2].record(cur)
+            cur.wait_stream(gs)
+        else:
+            for _, i in steps:
+                mb = s.gather(indices[i * mini:(i + 1) * mini], split=False)
                 self.minibatch_step(mb, world)
         self.actor_critic.refresh_lo()                       # the next rollout's GEMMs load weight-lo tiles by TMA
         num_updates = self.num_learning_epochs * self.num_mini_batches

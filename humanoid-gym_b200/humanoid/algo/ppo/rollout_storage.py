@@ -139,37 +139,51 @@ class RolloutStorage:
             m.ld_obs = self._mb["obs"].stride(0)
             m.ld_priv = self._mb["priv_obs"].stride(0) if self._mb["priv_obs"] is not None else 0
             self._mbs = m
-            self._mbs_split = None
         return self._mb
 
-    def _split_buffers(self, B):
-        """Split (bf16 hi / lo planes, row pitch % 8) images of the minibatch observations for the bf16x3 update path;
-        the fp32 copies are then not written at all (same bytes, no extra traffic)."""
-        mb = self._minibatch_buffers(B)
-        if self._mbs_split is None:
+    def _split_buffers(self, B, slot=0):
+        """Split (bf16 hi / lo planes, row pitch % 8) minibatch buffers for the bf16x3 update path: the observations are written
+        ONLY in this form (same bytes as fp32, no extra traffic).  Two independent slots, so that PPO.update can gather
+        minibatch i+1 on a side stream while minibatch i is being consumed."""
+        key = (B, slot)
+        if getattr(self, "_split_slots", None) is None:
+            self._split_slots = {}
+        if key not in self._split_slots:
+            z = dict(device=self.device, dtype=torch.float32)
+            A = self.actions_shape[0]
+
             def planes(width):
                 return torch.zeros(2, B, (width + 7) // 8 * 8, dtype=torch.int16, device=self.device)
-            self._split_t = dict(obs_split=planes(self.obs_shape[0]),
-                                 priv_split=planes(self.privileged_obs_shape[0]) if self.privileged_observations is not None else None)
+            t = dict(obs=None, priv_obs=None, obs_split=planes(self.obs_shape[0]),
+                     priv_split=planes(self.privileged_obs_shape[0]) if self.privileged_observations is not None else None,
+                     actions=torch.empty(B, A, **z), values=torch.empty(B, 1, **z), advantages=torch.empty(B, 1, **z),
+                     returns=torch.empty(B, 1, **z), old_log_prob=torch.empty(B, 1, **z), old_mu=torch.empty(B, A, **z),
+                     old_sigma=torch.empty(B, A, **z))
             m = nat.MiniBatch()
             for k in ("actions", "values", "advantages", "returns", "old_log_prob", "old_mu", "old_sigma"):
-                setattr(m, k, mb[k].data_ptr())
+                setattr(m, k, t[k].data_ptr())
             m.obs = None
             m.priv_obs = None
-            m.obs_split = nat.Split.of(self._split_t["obs_split"])
-            if self._split_t["priv_split"] is not None:
-                m.priv_split = nat.Split.of(self._split_t["priv_split"])
-            self._mbs_split = m
-        return dict(mb, obs=None, priv_obs=None, **self._split_t)
+            m.obs_split = nat.Split.of(t["obs_split"])
+            if t["priv_split"] is not None:
+                m.priv_split = nat.Split.of(t["priv_split"])
+            if len(self._split_slots) >= 4:
+                self._split_slots.clear()
+            self._split_slots[key] = (t, m)
+        return self._split_slots[key]
 
-    def gather(self, batch_idx, split=False):
+    def gather(self, batch_idx, split=False, slot=0):
         """Rows `batch_idx` of the flattened (T*N, .) storage -> contiguous minibatch tensors (split=True: the
-        observations come out as split bf16 planes `obs_split` / `priv_split` instead of fp32)."""
+        observations come out as split bf16 planes `obs_split` / `priv_split` instead of fp32), on the current stream."""
         B = batch_idx.numel()
-        mb = self._split_buffers(B) if split else self._minibatch_buffers(B)
-        nat.check(nat.lib.hg_minibatch_gather(self._native(), batch_idx.data_ptr(), self._mbs_split if split else self._mbs, B,
+        if split:
+            mb, desc = self._split_buffers(B, slot)
+        else:
+            mb, desc = self._minibatch_buffers(B), None
+            desc = self._mbs
+        nat.check(nat.lib.hg_minibatch_gather(self._native(), batch_idx.data_ptr(), desc, B,
                                               nat.stream_ptr(self._dev_index)), "hg_minibatch_gather")
-        return mb
+        return dict(mb)
 
     def mini_batch_generator(self, num_mini_batches, num_epochs=8):
         batch_size = self.num_envs * self.num_transitions_per_env
