@@ -41,7 +41,9 @@ constexpr int PRIV_KEEP = PRIV_W - HG_PRIV1;        // 146
 constexpr float kTwoPi = 6.283185307179586f;        // float32(2*np.pi)
 constexpr float kPi = 3.141592653589793f;           // float32(np.pi)
 
-__constant__ HgEnvParams cP;
+// The env constants (HgEnvParams, ~0.8 KB) travel BY VALUE as a __grid_constant__ kernel parameter: same constant-bank operand
+// access as a __constant__ global, but per launch -- nothing process-global that a second env instance (or another device)
+// could overwrite under a captured CUDA graph, and no upload before the launch.
 
 struct V3 { float x, y, z; };
 
@@ -206,7 +208,7 @@ __device__ __forceinline__ float draw_u(const float* inj, int64_t idx, uint64_t 
 }
 
 // legged_robot.py:322-336  (torch_rand_float(lo,hi) = (hi-lo)*u + lo; spans are formed in double on the host)
-__device__ __forceinline__ void resample_commands(float* cmd, float u0, float u1, float u2) {
+__device__ __forceinline__ void resample_commands(const HgEnvParams& cP, float* cmd, float u0, float u1, float u2) {
     cmd[0] = cP.cmd_x_span * u0 + cP.cmd_x_lo;
     cmd[1] = cP.cmd_y_span * u1 + cP.cmd_y_lo;
     cmd[3] = cP.cmd_heading_span * u2 + cP.cmd_heading_lo;
@@ -269,7 +271,8 @@ __device__ __forceinline__ void stream_history(float* __restrict__ out, const fl
 #define ETRACE(slot_) do { if (trace && threadIdx.x == 0) { long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); trace[(size_t)blockIdx.x * 12 + (slot_)] = t_; } } while (0)
 template <int T>
 __global__ void __launch_bounds__(T, (T == 128 ? HIST_CTAS_128 : (T == 256 ? 2 : 1)))
-post_physics_kernel(HgEnvBuffers B, HgEnvNoise Z, uint32_t phases, int64_t common_step, int N, long long* trace) {
+post_physics_kernel(const __grid_constant__ HgEnvParams cP, HgEnvBuffers B, HgEnvNoise Z, uint32_t phases, int64_t common_step, int N,
+                    long long* trace) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     EnvSmem& S = *reinterpret_cast<EnvSmem*>(smem_raw);
     auto& X = S.x;
@@ -433,7 +436,7 @@ post_physics_kernel(HgEnvBuffers B, HgEnvNoise Z, uint32_t phases, int64_t commo
                     float u0 = draw_u(Z.u_cmd_cb, (int64_t)e * 3 + 0, Z.seed, Z.step, e, HG_RNG_CMD_CB, 0);
                     float u1 = draw_u(Z.u_cmd_cb, (int64_t)e * 3 + 1, Z.seed, Z.step, e, HG_RNG_CMD_CB, 1);
                     float u2 = draw_u(Z.u_cmd_cb, (int64_t)e * 3 + 2, Z.seed, Z.step, e, HG_RNG_CMD_CB, 2);
-                    resample_commands(cmd, u0, u1, u2);
+                    resample_commands(cP, cmd, u0, u1, u2);
                 }
                 if (cP.heading_command) {
                     // forward = quat_apply(q, (1,0,0)) = v + w t + u x t,  t = 2 (u x v)
@@ -679,7 +682,7 @@ post_physics_kernel(HgEnvBuffers B, HgEnvNoise Z, uint32_t phases, int64_t commo
                 float u0 = draw_u(Z.u_cmd_rs, (int64_t)e * 3 + 0, Z.seed, Z.step, e, HG_RNG_CMD_RS, 0);
                 float u1 = draw_u(Z.u_cmd_rs, (int64_t)e * 3 + 1, Z.seed, Z.step, e, HG_RNG_CMD_RS, 1);
                 float u2 = draw_u(Z.u_cmd_rs, (int64_t)e * 3 + 2, Z.seed, Z.step, e, HG_RNG_CMD_RS, 2);
-                resample_commands(cmd, u0, u1, u2);
+                resample_commands(cP, cmd, u0, u1, u2);
                 X.cmd[0][le] = cmd[0]; X.cmd[1][le] = cmd[1]; X.cmd[2][le] = cmd[2]; X.cmd[3][le] = cmd[3];
             }
 #pragma unroll 1
@@ -939,7 +942,7 @@ post_physics_kernel(HgEnvBuffers B, HgEnvNoise Z, uint32_t phases, int64_t commo
 }
 
 // ---------------------------------------------------------------------------------------------------
-__global__ void pre_physics_kernel(HgEnvBuffers B, const float* __restrict__ actions_in, const float* __restrict__ u_delay,
+__global__ void pre_physics_kernel(const __grid_constant__ HgEnvParams cP, HgEnvBuffers B, const float* __restrict__ actions_in, const float* __restrict__ u_delay,
                                    const float* __restrict__ z_act, uint64_t seed, uint64_t step, int N) {
     if (step == ~0ull) step = *reinterpret_cast<const uint64_t*>(B.scratch + 6);   // device-side counter
     int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -961,7 +964,7 @@ __global__ void pre_physics_kernel(HgEnvBuffers B, const float* __restrict__ act
     B.actions[i] = clampf(a, -c, c);                            // legged_robot.py:90-91
 }
 
-__global__ void compute_torques_kernel(HgEnvBuffers B, int N) {
+__global__ void compute_torques_kernel(const __grid_constant__ HgEnvParams cP, HgEnvBuffers B, int N) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= N * 12) return;
     int j = i % 12;
@@ -976,7 +979,7 @@ __global__ void compute_torques_kernel(HgEnvBuffers B, int N) {
 // post_physics_step (:124-126) are ONE launch instead of ~23 graph nodes.  Every sub-step's PD law is still
 // evaluated against the dof state the previous sub-step left (the first one against the live state, which carries the
 // reset rewrites); only the last torque and the last dof frame are observable downstream, exactly as in the loop.
-__global__ void synth_decimation_kernel(HgEnvBuffers B, const float2* __restrict__ dof_frames, int decimation,
+__global__ void synth_decimation_kernel(const __grid_constant__ HgEnvParams cP, HgEnvBuffers B, const float2* __restrict__ dof_frames, int decimation,
                                         const float* __restrict__ root_f, const float* __restrict__ contact_f,
                                         const float* __restrict__ rigid_f, int N, int nb) {
     const int tid = blockIdx.x * blockDim.x + threadIdx.x, nt = gridDim.x * blockDim.x;
@@ -1008,19 +1011,6 @@ __global__ void synth_decimation_kernel(HgEnvBuffers B, const float2* __restrict
     }
 }
 
-// The params live in __constant__ memory; re-upload only when they change.
-HgEnvParams g_params_host;
-bool g_params_valid = false;
-
-int32_t upload_params(const HgEnvParams* P, cudaStream_t st) {
-    if (g_params_valid && memcmp(&g_params_host, P, sizeof(HgEnvParams)) == 0) return 0;
-    cudaError_t e = cudaMemcpyToSymbolAsync(cP, P, sizeof(HgEnvParams), 0, cudaMemcpyHostToDevice, st);
-    if (e != cudaSuccess) return hg_fail((int32_t)e, cudaGetErrorString(e));
-    g_params_host = *P;
-    g_params_valid = true;
-    return 0;
-}
-
 long long* g_env_trace = nullptr;
 
 int32_t check_buffers(const HgEnvBuffers* B) {
@@ -1048,9 +1038,8 @@ extern "C" int32_t hg_env_pre_physics(const HgEnvBuffers* B, const HgEnvParams* 
     HG_REQUIRE(B); HG_REQUIRE(P); HG_REQUIRE(actions_in); HG_REQUIRE(B->actions);
     if (N <= 0 || N > (1 << 26)) return hg_fail(HG_E_SIZE, "hg_env_pre_physics: bad N");
     cudaStream_t st = (cudaStream_t)stream;
-    if (int32_t rc = upload_params(P, st)) return rc;
     int total = (int)N * 12;
-    pre_physics_kernel<<<(total + 255) / 256, 256, 0, st>>>(*B, actions_in, u_delay, z_act, seed, step, (int)N);
+    pre_physics_kernel<<<(total + 255) / 256, 256, 0, st>>>(*P, *B, actions_in, u_delay, z_act, seed, step, (int)N);
     HG_LAUNCHED(1);
     return hg_cuda_status("hg_env_pre_physics");
 }
@@ -1059,9 +1048,8 @@ extern "C" int32_t hg_env_compute_torques(const HgEnvBuffers* B, const HgEnvPara
     HG_REQUIRE(B); HG_REQUIRE(P); HG_REQUIRE(B->actions); HG_REQUIRE(B->dof_state); HG_REQUIRE(B->torques);
     if (N <= 0 || N > (1 << 26)) return hg_fail(HG_E_SIZE, "hg_env_compute_torques: bad N");
     cudaStream_t st = (cudaStream_t)stream;
-    if (int32_t rc = upload_params(P, st)) return rc;
     int total = (int)N * 12;
-    compute_torques_kernel<<<(total + 255) / 256, 256, 0, st>>>(*B, (int)N);
+    compute_torques_kernel<<<(total + 255) / 256, 256, 0, st>>>(*P, *B, (int)N);
     HG_LAUNCHED(1);
     return hg_cuda_status("hg_env_compute_torques");
 }
@@ -1078,12 +1066,11 @@ extern "C" int32_t hg_env_synth_decimation(const HgEnvBuffers* B, const HgEnvPar
     if (N <= 0 || N > (1 << 22) || decimation < 1) return hg_fail(HG_E_SIZE, "hg_env_synth_decimation: bad N / decimation");
     if (!hg_aligned16(B->dof_state) || (reinterpret_cast<uintptr_t>(dof_frames) & 7u)) return hg_fail(HG_E_ALIGN, "hg_env_synth_decimation: dof tensors must be 8-byte aligned");
     cudaStream_t st = (cudaStream_t)stream;
-    if (int32_t rc = upload_params(P, st)) return rc;
     const int64_t work = N * P->num_bodies * 13 / 4;
     int grid = (int)((work + 255) / 256);
     if (grid > 4 * HG_NUM_SMS) grid = 4 * HG_NUM_SMS;
     if (grid < 1) grid = 1;
-    synth_decimation_kernel<<<grid, 256, 0, st>>>(*B, reinterpret_cast<const float2*>(dof_frames), decimation, root_frame, contact_frame,
+    synth_decimation_kernel<<<grid, 256, 0, st>>>(*P, *B, reinterpret_cast<const float2*>(dof_frames), decimation, root_frame, contact_frame,
                                                   rigid_frame, (int)N, P->num_bodies);
     HG_LAUNCHED(1);
     return hg_cuda_status("hg_env_synth_decimation");
@@ -1103,13 +1090,14 @@ extern "C" int32_t hg_env_post_physics(const HgEnvBuffers* B, const HgEnvParams*
         return hg_fail(HG_E_ARG, "hg_env_post_physics: bad body indices");
     if ((phases & ~HG_PHASE_STEP_ALL) || phases == 0) return hg_fail(HG_E_ARG, "hg_env_post_physics: bad phase mask");
     cudaStream_t st = (cudaStream_t)stream;
-    if (int32_t rc = upload_params(P, st)) return rc;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static bool attr_set[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev >= 0 && dev < 64 && !attr_set[dev]) {
         cudaFuncSetAttribute(post_physics_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(EnvSmem));
         cudaFuncSetAttribute(post_physics_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(EnvSmem));
         cudaFuncSetAttribute(post_physics_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(EnvSmem));
-        attr_set = true;
+        attr_set[dev] = true;
     }
     int grid = (int)((N + HG_ENVS_PER_CTA - 1) / HG_ENVS_PER_CTA);
     // one CTA per 32-env tile (the kernel body is a tile loop, so a capped persistent grid also works, but measured no
@@ -1120,9 +1108,9 @@ extern "C" int32_t hg_env_post_physics(const HgEnvBuffers* B, const HgEnvParams*
     // (the 8-warp variant measured no better than either neighbour -- 49 us at N=4096, 84 vs 72 us at N=16384 -- so it
     // is only reachable through HG_ENV_CTA)
     const int width = env_threads ? env_threads : (grid <= HG_NUM_SMS ? 512 : 256);
-    if (width == 512) post_physics_kernel<512><<<grid, 512, sizeof(EnvSmem), st>>>(*B, *Z, phases, common_step_counter, (int)N, g_env_trace);
-    else if (width == 256) post_physics_kernel<256><<<grid, 256, sizeof(EnvSmem), st>>>(*B, *Z, phases, common_step_counter, (int)N, g_env_trace);
-    else post_physics_kernel<128><<<grid, 128, sizeof(EnvSmem), st>>>(*B, *Z, phases, common_step_counter, (int)N, g_env_trace);
+    if (width == 512) post_physics_kernel<512><<<grid, 512, sizeof(EnvSmem), st>>>(*P, *B, *Z, phases, common_step_counter, (int)N, g_env_trace);
+    else if (width == 256) post_physics_kernel<256><<<grid, 256, sizeof(EnvSmem), st>>>(*P, *B, *Z, phases, common_step_counter, (int)N, g_env_trace);
+    else post_physics_kernel<128><<<grid, 128, sizeof(EnvSmem), st>>>(*P, *B, *Z, phases, common_step_counter, (int)N, g_env_trace);
     HG_LAUNCHED(1);
     return hg_cuda_status("hg_env_post_physics");
 }
