@@ -42,6 +42,8 @@ constexpr int A_BYTES = 2 * A_PLANE;                 // hi + lo
 constexpr int SMEM_LIMIT = 227 * 1024;
 constexpr int BAR_BYTES = 256;
 constexpr int MAX_STAGES = 4;
+constexpr int EPI_STAGE_WARP = 2 * 32 * 64;            // per epilogue warp: [2 planes][32 rows][32 bf16], SWIZZLE_64B
+constexpr int EPI_STAGE_BYTES = 8 * EPI_STAGE_WARP;     // 32 KB
 
 enum { EPI_F32 = 0, EPI_F32_BIAS = 1, EPI_SPLIT_BIAS_ELU = 2, EPI_SPLIT_DELU = 3, EPI_ATOMIC = 4, EPI_SPLIT = 5, EPI_DISCARD = 6 /* profiling: bias + ELU + split math, no stores */ };
 
@@ -54,6 +56,10 @@ struct Args {
     int M, N, K;
     int BN, a_mn, b_mn, epi;
     int kb_per_split, splits, stages;
+    int cs_tma;                          // split outputs leave through shared memory + TMA stores (tmC valid)
+    int relay;                           // pair form: 1 = each CTA's TMA signals its OWN barrier and a relay thread of the peer forwards one arrival per stage
+    int dbg;                             // profiling (HG_BF3_DEBUG): 1 = no TMA loads (MMA on whatever is in smem), 2 = no MMAs (loads + commits only)
+    long long* trace;                    // optional (hg_gemm_bf16x3_set_trace): [grid][8] cycle sums, see tools/bf3_trace.py
 };
 
 // shared-memory matrix descriptor (sm_100 UMMA, version 1), 16-bit operands, SWIZZLE_128B:
@@ -81,7 +87,15 @@ __device__ __forceinline__ uint32_t make_idesc(int M, int N, bool a_mn, bool b_m
     return d;
 }
 
+__device__ __forceinline__ unsigned long long hg_globaltimer() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
 struct Work { int m0, n0, kb_begin, num_kb; };
+// profiling: per-CTA event stamps of the first 64 k-blocks, behind the [grid][8] cycle sums: [grid][64][4] globaltimer ns
+// (0 producer saw the stage free, 1 producer issued its loads, 2 peer relay saw its half land, 3 MMA thread saw the stage full)
+#define BF3_STAMP(it_, slot_) do { if (g.trace && (it_) < 64) g.trace[(size_t)gridDim.x * 8 + ((size_t)blockIdx.x * 64 + (it_)) * 4 + (slot_)] = (long long)hg_globaltimer(); } while (0)
 __device__ __forceinline__ Work decode_work(const Args& g, int w, int tiles_n, int tiles_mn, int num_kb_total, int tile_m = BM) {
     Work r;
     const int split = w / tiles_mn, t = w - split * tiles_mn;
@@ -114,14 +128,16 @@ __device__ __forceinline__ float elu1(float x) { return x > 0.0f ? x : __expf(x)
 // (64 KB instead of 96 KB per 64-k stage at BN = 256, so three stages fit instead of two).
 template <bool PAIR>
 __global__ void __launch_bounds__(THREADS, 1)
-gemm_bf3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const Args g) {
+gemm_bf3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmC,
+                const Args g) {
     extern __shared__ unsigned char smem_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     const uint32_t rank = PAIR ? cluster_ctarank() : 0u;        // 0 = leader
     const int bn_cta = PAIR ? (g.BN >> 1) : g.BN;               // B rows this CTA holds
     const int b_plane = bn_cta * BK * 2;                        // bytes of one bf16 plane of this CTA's share of the B tile
     const int stage_bytes = A_BYTES + 2 * b_plane;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + g.stages * stage_bytes);
+    unsigned char* epi_stage = smem + g.stages * stage_bytes;                         // 1024-aligned (stage_bytes is a multiple of 1 KB)
+    uint64_t* bars = reinterpret_cast<uint64_t*>(epi_stage + (g.cs_tma ? EPI_STAGE_BYTES : 0));
     uint64_t* full = bars;                          // [S] TMA -> MMA
     uint64_t* empty = full + MAX_STAGES;            // [S] MMA -> TMA
     uint64_t* tmem_full = empty + MAX_STAGES;       // [2] MMA -> epilogue
@@ -135,11 +151,14 @@ gemm_bf3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     const int tiles_mn = tiles_n * tiles_m;
     const int total_work = tiles_mn * g.splits;
     const int S = g.stages;
+    // work items are dealt round-robin to the CTAs (pair: to the clusters): neighbouring CTAs then hold the n-tiles of one m-tile at
+    // the same time (the second read of those A rows is an L2 hit) and the split-K partials of one C tile are spread in time
     const int w_begin = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x, w_step = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+    const int w_end = total_work;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < S; ++s) {
-            mbar_init(&full[s], PAIR ? 2 : 1);                  // pair: the leader's expect_tx arrival + the peer's remote arrival
+            mbar_init(&full[s], (PAIR && rank == 0) ? 2 : 1);   // pair leader: its own expect_tx arrival + the peer's remote arrival
             mbar_init(&empty[s], 1);
         }
         for (int a = 0; a < 2; ++a) {
@@ -161,30 +180,46 @@ gemm_bf3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         if (lane == 0) {
             asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
             asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
-            const uint32_t tx = (uint32_t)stage_bytes * (PAIR ? 2u : 1u);      // pair: both CTAs' loads are credited to the leader's barrier
+            // pair, direct form: both CTAs' loads are credited to the leader's barrier (cta_group::2 TMA, a remote complete_tx per
+            // arriving packet).  Relay form: every CTA's loads complete on its OWN barrier and the peer forwards ONE remote arrival.
+            const bool direct = PAIR && !g.relay;
+            const uint32_t tx = (uint32_t)(((g.dbg & 4) ? 0 : A_BYTES) + ((g.dbg & 8) ? 0 : 2 * b_plane)) * (direct ? 2u : 1u);
             const uint32_t full0_remote = PAIR ? mapa_u32(&full[0], 0) : 0u;
             auto load = [&](void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
-                if (PAIR) tma_load_3d_2sm(dst, map, bar, c0, c1, 0); else tma_load_3d(dst, map, bar, c0, c1, 0);
+                if (direct) tma_load_3d_2sm(dst, map, bar, c0, c1, 0); else tma_load_3d(dst, map, bar, c0, c1, 0);
             };
             int it = 0;
-            for (int w = w_begin; w < total_work; w += w_step) {
+            long long t_wait = 0;
+            for (int w = w_begin; w < w_end; w += w_step) {
                 const Work wk = decode_work(g, w, tiles_n, tiles_mn, num_kb_total, TILE_M);
                 const int m0 = wk.m0 + (int)rank * BM, n0 = wk.n0 + (int)rank * bn_cta;       // this CTA's rows of A / rows of B
                 for (int kb = 0; kb < wk.num_kb; ++kb, ++it) {
                     const int s = it % S, k0 = (wk.kb_begin + kb) * BK;
+                    const long long tw0 = g.trace ? clock64() : 0;
                     mbar_wait(&empty[s], ((it / S) & 1) ^ 1);
+                    if (g.trace) t_wait += clock64() - tw0;
+                    BF3_STAMP(it, 0);
                     unsigned char* sa = smem + s * stage_bytes;
                     unsigned char* sb = sa + A_BYTES;
-                    if (!PAIR || rank == 0) mbar_expect_tx(&full[s], tx);
+                    if (g.dbg & 1) {                                    // profiling: signal "loaded" without loading
+                        if (!direct || rank == 0) mbar_arrive(&full[s]);
+                        else mbar_arrive_remote(full0_remote + (uint32_t)(s * sizeof(uint64_t)));
+                        continue;
+                    }
+                    if (!direct || rank == 0) mbar_expect_tx(&full[s], tx);
                     else mbar_arrive_remote(full0_remote + (uint32_t)(s * sizeof(uint64_t)));
-                    if (!g.a_mn) load(sa, &tmA, &full[s], k0, m0);                                // [plane][128][64]
+                    if (g.dbg & 4) {}                                                             // profiling: no A loads
+                    else if (!g.a_mn) load(sa, &tmA, &full[s], k0, m0);                           // [plane][128][64]
                     else
                         for (int j = 0; j < BM / 64; ++j) load(sa + j * 16384, &tmA, &full[s], m0 + 64 * j, k0);   // [plane][64 k][64 mn]
-                    if (!g.b_mn) load(sb, &tmB, &full[s], k0, n0);                                // [plane][bn_cta][64]
+                    if (g.dbg & 8) {}                                                             // profiling: no B loads
+                    else if (!g.b_mn) load(sb, &tmB, &full[s], k0, n0);                           // [plane][bn_cta][64]
                     else
                         for (int j = 0; j < bn_cta / 64; ++j) load(sb + j * 16384, &tmB, &full[s], n0 + 64 * j, k0);
+                    BF3_STAMP(it, 1);
                 }
             }
+            if (g.trace) g.trace[(size_t)blockIdx.x * 8 + 3] = t_wait;
         }
     } else if (warp == EPI_WARPS + 1) {
         // ===== MMA issuer =====
@@ -195,17 +230,25 @@ gemm_bf3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             const uint32_t a_kstep = g.a_mn ? 2048u : 32u, b_kstep = g.b_mn ? 2048u : 32u;
             const uint32_t a_lbo = g.a_mn ? 16384u : 16u, b_lbo = g.b_mn ? 16384u : 16u;
             int it = 0, item = 0;
-            for (int w = w_begin; w < total_work; w += w_step, ++item) {
+            long long t_full = 0, t_acc = 0;
+            const long long t_begin = g.trace ? clock64() : 0;
+            for (int w = w_begin; w < w_end; w += w_step, ++item) {
                 const Work wk = decode_work(g, w, tiles_n, tiles_mn, num_kb_total, TILE_M);
                 const int acc_stage = item & 1;
+                const long long ta0 = g.trace ? clock64() : 0;
                 mbar_wait(&tmem_empty[acc_stage], ((item >> 1) & 1) ^ 1);       // epilogue(s) have drained this accumulator
+                if (g.trace) t_acc += clock64() - ta0;
                 tc_fence_after();
                 const uint32_t tmem_d = tmem_base + (uint32_t)(acc_stage * 256);
                 for (int kb = 0; kb < wk.num_kb; ++kb, ++it) {
                     const int s = it % S;
+                    const long long tf0 = g.trace ? clock64() : 0;
                     mbar_wait(&full[s], (it / S) & 1);
+                    if (g.trace) t_full += clock64() - tf0;
+                    BF3_STAMP(it, 3);
                     tc_fence_after();
                     const uint32_t a0 = smem_u32(smem + s * stage_bytes), b0 = a0 + A_BYTES;
+                    if (!(g.dbg & 2))
 #pragma unroll
                     for (int kk = 0; kk < BK / 16; ++kk) {
                         const uint64_t a_hi = make_desc(a0 + kk * a_kstep, a_lbo);
@@ -226,6 +269,23 @@ gemm_bf3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 }
                 if (PAIR) umma_commit_2sm(&tmem_full[acc_stage]); else umma_commit(&tmem_full[acc_stage]);
             }
+            if (g.trace) {
+                long long* tr = g.trace + (size_t)blockIdx.x * 8;
+                tr[0] = clock64() - t_begin; tr[1] = t_full; tr[2] = t_acc; tr[6] = item; tr[7] = it;
+            }
+        } else if (PAIR && lane == 0 && rank == 1 && g.relay) {
+            // ===== relay (peer CTA): "my half of stage s has landed" -> one arrival on the leader's full[s] =====
+            const uint32_t full0_leader = mapa_u32(&full[0], 0);
+            int it = 0;
+            for (int w = w_begin; w < w_end; w += w_step) {
+                const Work wk = decode_work(g, w, tiles_n, tiles_mn, num_kb_total, TILE_M);
+                for (int kb = 0; kb < wk.num_kb; ++kb, ++it) {
+                    const int s = it % S;
+                    mbar_wait(&full[s], (it / S) & 1);
+                    mbar_arrive_remote(full0_leader + (uint32_t)(s * sizeof(uint64_t)));
+                    BF3_STAMP(it, 2);
+                }
+            }
         }
     } else {
         // ===== epilogue: warp w <-> TMEM lanes 32*(w%4) .. +31, columns [(w/4) * BN/2, +BN/2) =====
@@ -238,9 +298,11 @@ gemm_bf3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         const bool bias_fast = (g.epi == EPI_F32_BIAS || g.epi == EPI_SPLIT_BIAS_ELU || g.epi == EPI_DISCARD) && ((reinterpret_cast<uintptr_t>(g.bias) & 15u) == 0);
         const uint32_t tmem_empty0_leader = PAIR ? mapa_u32(&tmem_empty[0], 0) : 0u;
         int item = 0;
-        for (int w = w_begin; w < total_work; w += w_step, ++item) {
+        long long t_wfull = 0, t_busy = 0;
+        for (int w = w_begin; w < w_end; w += w_step, ++item) {
             const Work wk = decode_work(g, w, tiles_n, tiles_mn, num_kb_total, TILE_M);
             const int acc_stage = item & 1;
+            const long long te0 = g.trace ? clock64() : 0;
             const int row = wk.m0 + (int)rank * BM + q * 32 + lane;
             const bool row_ok = row < g.M;
             uint4 hn[8];                                                    // prefetched H (4 x hi, 4 x lo) of the NEXT chunk
@@ -257,6 +319,7 @@ gemm_bf3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             };
             if (g.epi == EPI_SPLIT_DELU) prefetch_h(c_begin);
             mbar_wait(&tmem_full[acc_stage], (item >> 1) & 1);
+            const long long te1 = g.trace ? clock64() : 0;
             tc_fence_after();
             for (int c0 = c_begin; c0 < c_end; c0 += 32) {
                 float v[32];
@@ -348,7 +411,35 @@ gemm_bf3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                     continue;
                 }
                 // ---- split store (hi / lo bf16 planes) ----
-                if (row_ok) {
+                if (g.cs_tma) {
+                    // The 32 x 32 block leaves as ONE TMA store per warp (hi and lo planes): a lane's direct 16-byte stores touch 32
+                    // different 128-byte lines per instruction, which crawls on an LSU/L1 path the tensor cores already saturate.
+                    // Lane = row; 16-byte chunk c of a row sits at chunk c ^ ((row >> 1) & 3) (SWIZZLE_64B), so each 8-lane phase
+                    // of a shared-memory store covers all 32 banks.
+                    unsigned char* stg = epi_stage + warp * EPI_STAGE_WARP;
+                    if (lane == 0) tma_store_wait_read();                       // the previous block's store has read the buffer
+                    __syncwarp();
+                    const int sw = (lane >> 1) & 3;
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        uint32_t ph[4], pl[4];
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            const float x0 = v[8 * c + 2 * u], x1 = v[8 * c + 2 * u + 1];
+                            ph[u] = pack_bf16x2(x0, x1);
+                            pl[u] = pack_bf16x2(x0 - bf_lo(ph[u]), x1 - bf_hi(ph[u]));
+                        }
+                        unsigned char* d = stg + lane * 64 + ((c ^ sw) << 4);
+                        *reinterpret_cast<uint4*>(d) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
+                        *reinterpret_cast<uint4*>(d + 32 * 64) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
+                    }
+                    fence_proxy_async();                                        // generic-proxy writes -> the TMA's reads
+                    __syncwarp();
+                    if (lane == 0) {                                            // rows >= M and columns >= N are clipped by the map
+                        tma_store_3d(&tmC, stg, col0, wk.m0 + (int)rank * BM + q * 32, 0);
+                        tma_store_commit();
+                    }
+                } else if (row_ok) {
                     uint16_t* dp = g.Cs + (int64_t)row * g.ldcs + col0;
                     uint32_t ph[16], pl[16];
 #pragma unroll
@@ -397,7 +488,10 @@ gemm_bf3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 if (PAIR) mbar_arrive_remote(tmem_empty0_leader + (uint32_t)(acc_stage * sizeof(uint64_t)));
                 else mbar_arrive(&tmem_empty[acc_stage]);
             }
+            if (g.trace) { t_wfull += te1 - te0; t_busy += clock64() - te1; }
         }
+        if (g.cs_tma && lane == 0) tma_store_wait_all();
+        if (g.trace && threadIdx.x == 0) { g.trace[(size_t)blockIdx.x * 8 + 4] = t_wfull; g.trace[(size_t)blockIdx.x * 8 + 5] = t_busy; }
     }
     tc_fence_before();
     if (PAIR) cluster_sync(); else __syncthreads();             // the peer's shared memory stays alive until the leader's last MMA has read it
@@ -455,15 +549,15 @@ int32_t load_encode() {
 // every minibatch, so each distinct map is encoded once per process and then found in this cache (~176
 // host-side cuTensorMapEncodeTiled calls per update otherwise).
 struct MapKey {
-    const void* base; uint64_t inner, outer, ld, plane; uint32_t box_outer;
+    const void* base; uint64_t inner, outer, ld, plane; uint32_t box_outer, box_inner;
     bool operator==(const MapKey& o) const {
-        return base == o.base && inner == o.inner && outer == o.outer && ld == o.ld && plane == o.plane && box_outer == o.box_outer;
+        return base == o.base && inner == o.inner && outer == o.outer && ld == o.ld && plane == o.plane && box_outer == o.box_outer && box_inner == o.box_inner;
     }
 };
 struct MapKeyHash {
     size_t operator()(const MapKey& k) const {
         uint64_t h = 1469598103934665603ull;
-        const uint64_t v[6] = {(uint64_t)(uintptr_t)k.base, k.inner, k.outer, k.ld, k.plane, k.box_outer};
+        const uint64_t v[6] = {(uint64_t)(uintptr_t)k.base, k.inner, k.outer, k.ld, k.plane, ((uint64_t)k.box_inner << 32) | k.box_outer};
         for (uint64_t x : v) { h ^= x; h *= 1099511628211ull; }
         return (size_t)h;
     }
@@ -471,9 +565,11 @@ struct MapKeyHash {
 std::unordered_map<MapKey, CUtensorMap, MapKeyHash> g_maps;
 std::mutex g_maps_mu;
 
-// 3-D bf16 map over a split tensor: {inner (contiguous), outer (rows of pitch ld), 2 planes}; box {64, box_outer, 2}
-int32_t get_map(CUtensorMap* out, const uint16_t* base, uint64_t inner, uint64_t outer, uint64_t ld, uint64_t plane, uint32_t box_outer) {
-    MapKey key{base, inner, outer, ld, plane, box_outer};
+// 3-D bf16 map over a split tensor: {inner (contiguous), outer (rows of pitch ld), 2 planes}; box {64, box_outer, 2} with
+// SWIZZLE_128B (operand loads) or {32, box_outer, 2} with SWIZZLE_64B (the epilogue's stores)
+int32_t get_map(CUtensorMap* out, const uint16_t* base, uint64_t inner, uint64_t outer, uint64_t ld, uint64_t plane, uint32_t box_outer,
+                uint32_t box_inner = 64) {
+    MapKey key{base, inner, outer, ld, plane, box_outer, box_inner};
     {
         std::lock_guard<std::mutex> lk(g_maps_mu);
         auto it = g_maps.find(key);
@@ -481,10 +577,11 @@ int32_t get_map(CUtensorMap* out, const uint16_t* base, uint64_t inner, uint64_t
     }
     cuuint64_t dims[3] = {inner, outer, 2};
     cuuint64_t strides[2] = {ld * sizeof(uint16_t), plane * sizeof(uint16_t)};
-    cuuint32_t box[3] = {64, box_outer, 2};
+    cuuint32_t box[3] = {box_inner, box_outer, 2};
     cuuint32_t estr[3] = {1, 1, 1};
     CUresult r = g_encode(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<uint16_t*>(base), dims, strides, box, estr,
-                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, box_inner == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                          CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
         snprintf(g_hg_err, sizeof(g_hg_err), "cuTensorMapEncodeTiled (bf16 3-D) failed (%d): inner=%llu outer=%llu ld=%llu plane=%llu box=%u",
@@ -505,11 +602,16 @@ int32_t check_split(const HgSplit& s, const char* what) {
 
 }  // namespace
 
-int hg_bf3_pair_enabled() {
+long long* g_bf3_trace = nullptr;
+extern "C" void hg_gemm_bf16x3_set_trace(long long* buf) { g_bf3_trace = buf; }
+
+// HG_BF3_PAIR: 0 = single-CTA form, 1 (default) = CTA pairs with the relay signalling, 2 = CTA pairs with cta_group::2 TMA signalling
+static int bf3_pair_mode() {
     static int pair_env = -1;
-    if (pair_env < 0) { const char* e = getenv("HG_BF3_PAIR"); pair_env = (e && e[0] == '0') ? 0 : 1; }
+    if (pair_env < 0) { const char* e = getenv("HG_BF3_PAIR"); pair_env = e ? atoi(e) : 1; }
     return pair_env;
 }
+int hg_bf3_pair_enabled() { return bf3_pair_mode() != 0; }
 
 extern "C" int32_t hg_split_bf16(const float* src, int64_t ld_src, const HgSplit* dst, int64_t rows, int64_t cols, void* stream) {
     HG_REQUIRE(src); HG_REQUIRE(dst); HG_REQUIRE(dst->p);
@@ -563,9 +665,23 @@ extern "C" int32_t hg_gemm_bf16x3(const HgGemmSplit* d, void* stream) {
     const bool pair = hg_bf3_pair_enabled() && g.BN >= 128 && d->M >= 256;
     const int bn_cta = pair ? g.BN / 2 : g.BN;
     const int stage_bytes = A_BYTES + 2 * bn_cta * BK * 2;
-    int stages = (SMEM_LIMIT - 1024 - BAR_BYTES) / stage_bytes;
+    // split outputs go out through shared memory and TMA when the output planes qualify for a tensor map (HG_BF3_TMA_STORE=0: direct stores)
+    static int tma_store_env = -1;
+    if (tma_store_env < 0) { const char* e = getenv("HG_BF3_TMA_STORE"); tma_store_env = (e && e[0] == '0') ? 0 : 1; }
+    g.cs_tma = (tma_store_env && (epi == EPI_SPLIT_BIAS_ELU || epi == EPI_SPLIT_DELU || epi == EPI_SPLIT) && hg_aligned16(d->Cs.p) &&
+                (d->Cs.ld & 7) == 0 && (d->Cs.plane & 7) == 0) ? 1 : 0;
+    const int epi_bytes = g.cs_tma ? EPI_STAGE_BYTES : 0;
+    int stages = (SMEM_LIMIT - 1024 - BAR_BYTES - epi_bytes) / stage_bytes;
     g.stages = stages > MAX_STAGES ? MAX_STAGES : stages;
-    const int smem_bytes = g.stages * stage_bytes + 1024 + BAR_BYTES;
+    {   // profiling knob: HG_BF3_STAGES=n caps the ring depth (tools/bf3_trace.py measures the latency it has to cover)
+        static int cap = -1;
+        if (cap < 0) { const char* e = getenv("HG_BF3_STAGES"); cap = e ? atoi(e) : 0; }
+        if (cap > 0 && cap < g.stages) g.stages = cap;
+    }
+    g.trace = g_bf3_trace;
+    g.relay = bf3_pair_mode() == 1;
+    { static int dbg = -1; if (dbg < 0) { const char* e = getenv("HG_BF3_DEBUG"); dbg = e ? atoi(e) : 0; } g.dbg = dbg; }
+    const int smem_bytes = g.stages * stage_bytes + epi_bytes + 1024 + BAR_BYTES;
     const int num_kb = (d->K + BK - 1) / BK;
     int splits = d->split_k > 0 ? d->split_k : 1;
     if (splits > num_kb) splits = num_kb;
@@ -575,8 +691,13 @@ extern "C" int32_t hg_gemm_bf16x3(const HgGemmSplit* d, void* stream) {
     g.splits = splits;
 
     // K-major operand: map {K, rows, 2}, box {64, tile rows, 2}.  MN-major: map {rows, K, 2}, box {64, 64, 2}.
-    CUtensorMap tmA, tmB;
+    CUtensorMap tmA, tmB, tmC;
+    memset(&tmC, 0, sizeof(tmC));
     int32_t rc;
+    if (g.cs_tma) {
+        rc = get_map(&tmC, d->Cs.p, d->N, d->M, d->Cs.ld, d->Cs.plane, 32, 32);
+        if (rc) return rc;
+    }
     if (!g.a_mn) rc = get_map(&tmA, d->A.p, d->K, d->M, d->A.ld, d->A.plane, BM);
     else rc = get_map(&tmA, d->A.p, d->M, d->K, d->A.ld, d->A.plane, BK);
     if (rc) return rc;
@@ -603,11 +724,20 @@ extern "C" int32_t hg_gemm_bf16x3(const HgGemmSplit* d, void* stream) {
         at[0].id = cudaLaunchAttributeClusterDimension;
         at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
         cfg.attrs = at; cfg.numAttrs = 1;
-        cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_bf3_kernel<true>, tmA, tmB, g);
+        cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_bf3_kernel<true>, tmA, tmB, tmC, g);
         if (e != cudaSuccess) return hg_fail((int32_t)e, cudaGetErrorString(e));
     } else {
         const int grid = total_work < HG_NUM_SMS ? total_work : HG_NUM_SMS;   // persistent: one CTA per SM
-        gemm_bf3_kernel<false><<<grid, THREADS, smem_bytes, st>>>(tmA, tmB, g);
+        if (getenv("HG_BF3_XCLUSTER")) {                                      // profiling experiment: the single-CTA kernel under a cluster launch
+            cudaLaunchConfig_t cfg{};
+            cfg.gridDim = dim3(grid & ~1); cfg.blockDim = dim3(THREADS); cfg.dynamicSmemBytes = smem_bytes; cfg.stream = st;
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeClusterDimension;
+            at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+            cfg.attrs = at; cfg.numAttrs = 1;
+            cudaLaunchKernelEx(&cfg, gemm_bf3_kernel<false>, tmA, tmB, tmC, g);
+        } else
+        gemm_bf3_kernel<false><<<grid, THREADS, smem_bytes, st>>>(tmA, tmB, tmC, g);
     }
     HG_LAUNCHED(1);
     return hg_cuda_status("hg_gemm_bf16x3");

@@ -160,6 +160,7 @@ def _load():
         "hg_tf32_residual": (i32, [PF, PF, i64, PF]),
         "hg_actor_critic_counters_size": (i64, [i64]),
         "hg_actor_critic_set_trace": (None, [PF]),
+        "hg_gemm_bf16x3_set_trace": (None, [PF]),
         "hg_actor_critic_forward": (i32, [P(MlpDesc), P(MlpDesc), PF, PF, PF, i64, PF, i64, PF, PF, PF, PF, PF, PF, P(MlpFwdOpts), PF, i64, PF]),
         "hg_mlp_backward": (i32, [P(MlpDesc), PF, PF, i64, PF, PF, PF, PF, i64, PF]),
         "hg_gemm_tf32": (i32, [P(Gemm), PF]),

@@ -270,6 +270,10 @@ int32_t hg_mlp_forward_ex(const HgMlpDesc* net, const float* params, const float
 int64_t hg_actor_critic_counters_size(int64_t M);
 /* debug aid: per-item %globaltimer stamps of the following launches go to buf ([148][16][16] int64, device); NULL = off */
 void hg_actor_critic_set_trace(long long* buf);
+/* profiling only: [grid][8] int64 cycle sums per CTA of the next hg_gemm_bf16x3 launches (NULL = off), tools/bf3_trace.py:
+ * 0 MMA-thread loop cycles, 1 of which waiting for operands (full), 2 waiting for a drained accumulator, 3 TMA thread waiting
+ * for a free stage, 4 epilogue warp 0 waiting for an accumulator, 5 epilogue warp 0 busy, 6 items, 7 k-blocks */
+void hg_gemm_bf16x3_set_trace(long long* buf);
 int32_t hg_actor_critic_forward(const HgMlpDesc* actor, const HgMlpDesc* critic, const float* params, const float* params_lo,
                                 const float* obs, int64_t ld_obs, const float* cobs, int64_t ld_cobs, float* hidden_a,
                                 float* hidden_c, float* hidden_lo_a, float* hidden_lo_c, float* mu, float* value,
