@@ -119,14 +119,16 @@ __device__ __forceinline__ float bf_hi(uint32_t p) { return __uint_as_float(p & 
 // nn.ELU(alpha=1) as exp(x) - 1 for x <= 0: ABSOLUTE error ~1e-7 (same form as torch's CUDA kernel).  The consumers are
 // matrix products and ELU' = h + 1, for which only the absolute error matters; the epilogue is issue-bound, so the
 // series that would restore relative accuracy near 0 is not spent here (the 3xTF32 rollout path keeps expm1).
-__device__ __forceinline__ float elu1(float x) { return x > 0.0f ? x : __expf(x) - 1.0f; }
+__device__ __forceinline__ float elu1(float x) { return x > 0.0f ? x : exp_neg_fast(x) - 1.0f; }
 
 // PAIR = true: the CTA-pair form (cluster of 2 on one TPC, tcgen05 cta_group::2).  The pair owns a 256 x BN tile: each CTA loads
 // its own 128 rows of A and HALF of the B tile, the leader's single MMA thread issues M = 256 instructions that read B from
 // both CTAs' shared memory, each CTA's TMEM receives its 128 rows and each CTA's epilogue warps drain them.  Per SM that halves
 // the B bytes fetched over L2 -> SM and read from shared memory per MMA -- the two feeds that bound the single-CTA form
 // (64 KB instead of 96 KB per 64-k stage at BN = 256, so three stages fit instead of two).
-template <bool PAIR>
+// EPI is a template parameter: one tight epilogue loop per instantiation (the all-in-one kernel was > 64 KB of SASS, most of it the
+// other epilogues' branches, on a path where the 8 epilogue warps are the bottleneck of every short-K launch)
+template <bool PAIR, int EPI>
 __global__ void __launch_bounds__(THREADS, 1)
 gemm_bf3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmC,
                 const Args g) {
@@ -294,8 +296,8 @@ gemm_bf3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         // 128-bit loads (one L1 broadcast each) instead of 32 shuffles.
         const int q = warp & 3, half = warp >> 2;
         const int c_begin = half * (g.BN >> 1), c_end = c_begin + (g.BN >> 1);
-        const bool h_fast = (g.epi == EPI_SPLIT_DELU) && ((g.ldhs & 7) == 0) && ((g.hs_plane & 7) == 0) && ((reinterpret_cast<uintptr_t>(g.Hs) & 15u) == 0);
-        const bool bias_fast = (g.epi == EPI_F32_BIAS || g.epi == EPI_SPLIT_BIAS_ELU || g.epi == EPI_DISCARD) && ((reinterpret_cast<uintptr_t>(g.bias) & 15u) == 0);
+        const bool h_fast = (EPI == EPI_SPLIT_DELU) && ((g.ldhs & 7) == 0) && ((g.hs_plane & 7) == 0) && ((reinterpret_cast<uintptr_t>(g.Hs) & 15u) == 0);
+        const bool bias_fast = (EPI == EPI_F32_BIAS || EPI == EPI_SPLIT_BIAS_ELU || EPI == EPI_DISCARD) && ((reinterpret_cast<uintptr_t>(g.bias) & 15u) == 0);
         const uint32_t tmem_empty0_leader = PAIR ? mapa_u32(&tmem_empty[0], 0) : 0u;
         int item = 0;
         long long t_wfull = 0, t_busy = 0;
@@ -317,7 +319,7 @@ gemm_bf3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                     }
                 }
             };
-            if (g.epi == EPI_SPLIT_DELU) prefetch_h(c_begin);
+            if (EPI == EPI_SPLIT_DELU) prefetch_h(c_begin);
             mbar_wait(&tmem_full[acc_stage], (item >> 1) & 1);
             const long long te1 = g.trace ? clock64() : 0;
             tc_fence_after();
@@ -326,7 +328,7 @@ gemm_bf3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc_stage * 256 + c0), v);
                 const int col0 = wk.n0 + c0;
                 uint4 hc[8];
-                if (g.epi == EPI_SPLIT_DELU) {
+                if (EPI == EPI_SPLIT_DELU) {
 #pragma unroll
                     for (int t = 0; t < 8; ++t) hc[t] = hn[t];
                     if (c0 + 32 < c_end) prefetch_h(c0 + 32);
@@ -334,7 +336,7 @@ gemm_bf3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 if (col0 >= g.N) continue;                                  // warp-uniform
                 const int nvalid = min(32, g.N - col0);
                 const bool full_chunk = (nvalid == 32);
-                if (g.epi == EPI_F32_BIAS || g.epi == EPI_SPLIT_BIAS_ELU || g.epi == EPI_DISCARD) {
+                if (EPI == EPI_F32_BIAS || EPI == EPI_SPLIT_BIAS_ELU || EPI == EPI_DISCARD) {
                     if (bias_fast && full_chunk && ((col0 & 3) == 0)) {
 #pragma unroll
                         for (int j = 0; j < 32; j += 4) {
@@ -346,11 +348,11 @@ gemm_bf3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 #pragma unroll
                         for (int j = 0; j < 32; ++j) v[j] += __shfl_sync(0xffffffffu, bl, j);
                     }
-                    if (g.epi == EPI_SPLIT_BIAS_ELU || g.epi == EPI_DISCARD) {
+                    if (EPI == EPI_SPLIT_BIAS_ELU || EPI == EPI_DISCARD) {
 #pragma unroll
                         for (int j = 0; j < 32; ++j) v[j] = elu1(v[j]);
                     }
-                } else if (g.epi == EPI_SPLIT_DELU) {
+                } else if (EPI == EPI_SPLIT_DELU) {
                     // ELU'(z) recovered from h = ELU(z) ~= h_hi + h_lo:  1 for h > 0, h + 1 otherwise
                     if (h_fast && full_chunk) {
                         if (row_ok) {
@@ -376,11 +378,11 @@ gemm_bf3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                             }
                     }
                 }
-                if (g.epi == EPI_F32 || g.epi == EPI_F32_BIAS || g.epi == EPI_ATOMIC) {
+                if (EPI == EPI_F32 || EPI == EPI_F32_BIAS || EPI == EPI_ATOMIC) {
                     if (!row_ok) continue;
                     float* dst = g.C + (int64_t)row * g.ldc + col0;
                     const bool vec = full_chunk && ((reinterpret_cast<uintptr_t>(dst) & 15u) == 0);
-                    if (g.epi == EPI_ATOMIC) {
+                    if (EPI == EPI_ATOMIC) {
                         if (vec) {
 #pragma unroll
                             for (int j = 0; j < 32; j += 4)
@@ -400,7 +402,7 @@ gemm_bf3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                     }
                     continue;
                 }
-                if (g.epi == EPI_DISCARD) {                                 // keep the math alive, store nothing (almost)
+                if (EPI == EPI_DISCARD) {                                 // keep the math alive, store nothing (almost)
                     float acc = 0.0f;
 #pragma unroll
                     for (int j = 0; j < 32; j += 2) {
@@ -462,7 +464,7 @@ gemm_bf3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                             }
                     }
                 }
-                if (g.epi == EPI_SPLIT_DELU && g.colsum != nullptr) {
+                if (EPI == EPI_SPLIT_DELU && g.colsum != nullptr) {
                     // bias gradient: column sums of this 32 x 32 block by a butterfly transpose-reduce (31 shuffles),
                     // lane j ends up with the sum of column j; one atomic per column per warp
                     if (!row_ok) {
@@ -602,16 +604,31 @@ int32_t check_split(const HgSplit& s, const char* what) {
 
 }  // namespace
 
+template <bool PAIR>
+static const void* kernel_for_pair(int epi) {
+    switch (epi) {
+        case EPI_F32: return (const void*)gemm_bf3_kernel<PAIR, EPI_F32>;
+        case EPI_F32_BIAS: return (const void*)gemm_bf3_kernel<PAIR, EPI_F32_BIAS>;
+        case EPI_SPLIT_BIAS_ELU: return (const void*)gemm_bf3_kernel<PAIR, EPI_SPLIT_BIAS_ELU>;
+        case EPI_SPLIT_DELU: return (const void*)gemm_bf3_kernel<PAIR, EPI_SPLIT_DELU>;
+        case EPI_ATOMIC: return (const void*)gemm_bf3_kernel<PAIR, EPI_ATOMIC>;
+        case EPI_SPLIT: return (const void*)gemm_bf3_kernel<PAIR, EPI_SPLIT>;
+        case EPI_DISCARD: return (const void*)gemm_bf3_kernel<PAIR, EPI_DISCARD>;
+    }
+    return nullptr;
+}
+static const void* kernel_for(bool pair, int epi) { return pair ? kernel_for_pair<true>(epi) : kernel_for_pair<false>(epi); }
+
 long long* g_bf3_trace = nullptr;
 extern "C" void hg_gemm_bf16x3_set_trace(long long* buf) { g_bf3_trace = buf; }
 
-// HG_BF3_PAIR: 0 = single-CTA form, 1 (default) = CTA pairs with the relay signalling, 2 = CTA pairs with cta_group::2 TMA signalling
+// HG_BF3_PAIR: 0 = single-CTA form only, 1 (default) = CTA pairs (relay signalling) where they pay, 2 = same with cta_group::2 TMA
+// signalling, 3 = CTA pairs (relay) wherever legal
 static int bf3_pair_mode() {
     static int pair_env = -1;
     if (pair_env < 0) { const char* e = getenv("HG_BF3_PAIR"); pair_env = e ? atoi(e) : 1; }
     return pair_env;
 }
-int hg_bf3_pair_enabled() { return bf3_pair_mode() != 0; }
 
 extern "C" int32_t hg_split_bf16(const float* src, int64_t ld_src, const HgSplit* dst, int64_t rows, int64_t cols, void* stream) {
     HG_REQUIRE(src); HG_REQUIRE(dst); HG_REQUIRE(dst->p);
@@ -660,9 +677,13 @@ extern "C" int32_t hg_gemm_bf16x3(const HgGemmSplit* d, void* stream) {
     g.epi = epi;
     int bn = ((d->N + 63) / 64) * 64;                    // multiples of 64: MN-major boxes are 64 wide, column halves 32-aligned
     g.BN = bn > 256 ? 256 : bn;
-    // CTA pairs (cta_group::2) when the tile is wide enough to halve (each CTA loads BN / 2 rows of B: >= 64 for the MN-major
-    // boxes) and there are at least as many 256-row tiles as clusters worth filling; HG_BF3_PAIR=0 pins the single-CTA form
-    const bool pair = hg_bf3_pair_enabled() && g.BN >= 128 && d->M >= 256;
+    // CTA pairs (cta_group::2) where they measure faster (tools/bf3_trace.py): long-K launches without split-K, whose time is the
+    // L2 -> SM operand feed that the pair halves for B.  Short-K launches are epilogue-bound and the pair's lock-step loads cost a
+    // little, split-K launches measure equal.  The tile must be wide enough to halve (each CTA loads BN / 2 rows of B: >= 64 for
+    // the MN-major boxes).  HG_BF3_PAIR=0 pins the single-CTA form, HG_BF3_PAIR=3 forces pairs wherever they are legal.
+    const int pm = bf3_pair_mode();
+    const bool pair_legal = g.BN >= 128 && d->M >= 256;
+    const bool pair = pm != 0 && pair_legal && (pm == 3 || (d->split_k <= 1 && (d->K + BK - 1) / BK >= 8));
     const int bn_cta = pair ? g.BN / 2 : g.BN;
     const int stage_bytes = A_BYTES + 2 * bn_cta * BK * 2;
     // split outputs go out through shared memory and TMA when the output planes qualify for a tensor map (HG_BF3_TMA_STORE=0: direct stores)
@@ -679,7 +700,7 @@ extern "C" int32_t hg_gemm_bf16x3(const HgGemmSplit* d, void* stream) {
         if (cap > 0 && cap < g.stages) g.stages = cap;
     }
     g.trace = g_bf3_trace;
-    g.relay = bf3_pair_mode() == 1;
+    g.relay = bf3_pair_mode() != 2;
     { static int dbg = -1; if (dbg < 0) { const char* e = getenv("HG_BF3_DEBUG"); dbg = e ? atoi(e) : 0; } g.dbg = dbg; }
     const int smem_bytes = g.stages * stage_bytes + epi_bytes + 1024 + BAR_BYTES;
     const int num_kb = (d->K + BK - 1) / BK;
@@ -705,40 +726,31 @@ extern "C" int32_t hg_gemm_bf16x3(const HgGemmSplit* d, void* stream) {
     else rc = get_map(&tmB, d->B.p, d->N, d->K, d->B.ld, d->B.plane, BK);
     if (rc) return rc;
 
-    static bool attr_set[64] = {};
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (dev >= 0 && dev < 64 && !attr_set[dev]) {
-        cudaError_t e = cudaFuncSetAttribute(gemm_bf3_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_bf3_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
-        if (e != cudaSuccess) return hg_fail((int32_t)e, cudaGetErrorString(e));
-        attr_set[dev] = true;
-    }
     const int tile_m = pair ? 2 * BM : BM;
     const int total_work = ((d->N + g.BN - 1) / g.BN) * ((d->M + tile_m - 1) / tile_m) * splits;
-    if (pair) {
-        const int clusters = total_work < HG_NUM_SMS / 2 ? total_work : HG_NUM_SMS / 2;
-        cudaLaunchConfig_t cfg{};
-        cfg.gridDim = dim3(2 * clusters); cfg.blockDim = dim3(THREADS); cfg.dynamicSmemBytes = smem_bytes; cfg.stream = st;
-        cudaLaunchAttribute at[1];
-        at[0].id = cudaLaunchAttributeClusterDimension;
-        at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-        cfg.attrs = at; cfg.numAttrs = 1;
-        cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_bf3_kernel<true>, tmA, tmB, tmC, g);
-        if (e != cudaSuccess) return hg_fail((int32_t)e, cudaGetErrorString(e));
-    } else {
-        const int grid = total_work < HG_NUM_SMS ? total_work : HG_NUM_SMS;   // persistent: one CTA per SM
-        if (getenv("HG_BF3_XCLUSTER")) {                                      // profiling experiment: the single-CTA kernel under a cluster launch
-            cudaLaunchConfig_t cfg{};
-            cfg.gridDim = dim3(grid & ~1); cfg.blockDim = dim3(THREADS); cfg.dynamicSmemBytes = smem_bytes; cfg.stream = st;
-            cudaLaunchAttribute at[1];
-            at[0].id = cudaLaunchAttributeClusterDimension;
-            at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-            cfg.attrs = at; cfg.numAttrs = 1;
-            cudaLaunchKernelEx(&cfg, gemm_bf3_kernel<false>, tmA, tmB, tmC, g);
-        } else
-        gemm_bf3_kernel<false><<<grid, THREADS, smem_bytes, st>>>(tmA, tmB, tmC, g);
+    const int workers = pair ? HG_NUM_SMS / 2 : HG_NUM_SMS;
+    const int grid = (total_work < workers ? total_work : workers) * (pair ? 2 : 1);          // persistent: one CTA (pair: one cluster) per SM (pair)
+    const void* fn = kernel_for(pair, epi);
+    if (!fn) return hg_fail(HG_E_ARG, "hg_gemm_bf16x3: bad epilogue");
+    {
+        static bool attr_set[64][2][EPI_DISCARD + 1] = {};
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (dev >= 0 && dev < 64 && !attr_set[dev][pair ? 1 : 0][epi]) {
+            cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
+            if (e != cudaSuccess) return hg_fail((int32_t)e, cudaGetErrorString(e));
+            attr_set[dev][pair ? 1 : 0][epi] = true;
+        }
     }
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(THREADS); cfg.dynamicSmemBytes = smem_bytes; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = pair ? 1 : 0;
+    void* kargs[4] = {&tmA, &tmB, &tmC, &g};
+    cudaError_t e = cudaLaunchKernelExC(&cfg, fn, kargs);
+    if (e != cudaSuccess) return hg_fail((int32_t)e, cudaGetErrorString(e));
     HG_LAUNCHED(1);
     return hg_cuda_status("hg_gemm_bf16x3");
 }

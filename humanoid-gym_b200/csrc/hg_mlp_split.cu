@@ -10,7 +10,6 @@
 //                           bias gradient -- ONE pass over h instead of four.
 #include "hg_common.cuh"
 
-int hg_bf3_pair_enabled();          // hg_gemm_bf3.cu
 
 namespace {
 
@@ -241,12 +240,10 @@ extern "C" int32_t hg_mlp_backward_split(const HgMlpDesc* net, const float* para
             d.C = grads + net->w_off[l]; d.ldc = net->ldw[l];
             d.M = N; d.N = K; d.K = (int32_t)M;
             d.a_mn_major = 1; d.b_mn_major = 1; d.epilogue = 4;
-            // one wave of work items: 128 x bn tiles on 148 CTAs, or 256 x bn tiles on 74 CTA pairs (same rule as hg_gemm_bf16x3)
+            // one wave of work items: 128 x bn tiles on 148 CTAs (split-K launches use the single-CTA form, see hg_gemm_bf16x3)
             const int bn = K >= 256 ? 256 : (K + 63) / 64 * 64;
-            const bool pair = hg_bf3_pair_enabled() && bn >= 128 && N >= 256;
-            const int tile_m = pair ? 256 : 128, slots = pair ? HG_NUM_SMS / 2 : HG_NUM_SMS;
-            const int tiles = ((N + tile_m - 1) / tile_m) * ((K + bn - 1) / bn);
-            int splits = slots / tiles;
+            const int tiles = ((N + 127) / 128) * ((K + bn - 1) / bn);
+            int splits = HG_NUM_SMS / tiles;
             const int64_t cap = (M / 64) / 4;                      // at least 4 k-blocks per work item
             if (splits > cap) splits = (int)cap;
             d.split_k = splits < 1 ? 1 : splits;

@@ -159,11 +159,20 @@ __device__ __forceinline__ void umma_commit_2sm(uint64_t* bar) {
                  : "memory");
 }
 
-// nn.ELU(alpha=1) with fp32-class RELATIVE accuracy at ~11 instructions (expm1f costs ~30, a quarter of the rollout kernel's
+// exp(x) for x <= 0 as ONE multiply and one MUFU.EX2 (ex2.approx.ftz, relative error 2^-22).  __expf adds a range fix-up around the
+// MUFU (scale by 0.5, square) under per-element predicates; with 32 independent elements in flight the compiler runs out of predicate
+// registers and the epilogue serialises on P2R/PLOP3 traffic (measured: ~12 issue slots per element, 5 clk each).  The fix-up only
+// matters for results below 2^-126, which "- 1" rounds away anyway.
+__device__ __forceinline__ float exp_neg_fast(float x) {
+    float e;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * 1.4426950408889634f));
+    return e;
+}
+// nn.ELU(alpha=1) with fp32-class RELATIVE accuracy at ~10 instructions (expm1f costs ~30, a quarter of the rollout kernel's
 // instruction count): exp(x) - 1 loses relative accuracy only near 0, where a 6-term series is exact to < 5e-8
 __device__ __forceinline__ float elu_fp32(float x) {
     const float p = x * (1.0f + x * (0.5f + x * (0.16666667f + x * (0.041666668f + x * (0.008333334f + x * 0.0013888889f)))));
-    const float e = __expf(x) - 1.0f;
+    const float e = exp_neg_fast(x) - 1.0f;
     return x > 0.0f ? x : (x > -0.25f ? p : e);
 }
 

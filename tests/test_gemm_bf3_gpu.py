@@ -131,3 +131,19 @@ def test_argument_errors():
     Xs = torch.zeros(2, 64, 712, dtype=torch.int16, device="cuda")
     with pytest.raises(nat.NativeError, match="split_k"):
         _gemm(Xs, Ws, 64, 32, 705, 0, 0, 0, split_k=2)
+
+
+@pytest.mark.parametrize("env", [{"HG_BF3_PAIR": "3"}, {"HG_BF3_PAIR": "2"}, {"HG_BF3_PAIR": "0"}, {"HG_BF3_PAIR": "3", "HG_BF3_TMA_STORE": "0"}],
+                         ids=["pairs-everywhere", "pairs-cta_group2-tma", "single-cta-only", "direct-stores"])
+def test_kernel_variants(env):
+    """The library picks the CTA-pair (cta_group::2) or single-CTA kernel per launch and reads its knobs once per process:
+    rerun this module's layout tests in a child process with each form pinned, so every variant sees every layout."""
+    import os
+    import subprocess
+    import sys
+    if os.environ.get("HG_BF3_VARIANT_CHILD"):
+        pytest.skip("child run")
+    child_env = dict(os.environ, HG_BF3_VARIANT_CHILD="1", **env)
+    r = subprocess.run([sys.executable, "-m", "pytest", __file__, "-x", "-q", "-m", "gpu", "-k", "layout or roundtrip", "-p", "no:cacheprovider"],
+                       env=child_env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
