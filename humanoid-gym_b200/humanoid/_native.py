@@ -162,6 +162,10 @@ def _load():
         "hg_actor_critic_set_trace": (None, [PF]),
         "hg_gemm_bf16x3_set_trace": (None, [PF]),
         "hg_actor_critic_forward": (i32, [P(MlpDesc), P(MlpDesc), PF, PF, PF, i64, PF, i64, PF, PF, PF, PF, PF, PF, P(MlpFwdOpts), PF, i64, PF]),
+        "hg_f16_weight_scale": (C.c_float, []),
+        "hg_split_f16": (i32, [PF, i64, P(Split), i64, i64, C.c_float, PF]),
+        "hg_actor_critic_f16_scratch_elems": (i64, [P(MlpDesc), P(MlpDesc), i64]),
+        "hg_actor_critic_forward_f16": (i32, [P(MlpDesc), P(MlpDesc), PF, PF, i64, PF, i64, PF, i64, PF, PF, PF, P(MlpFwdOpts), PF, i64, PF]),
         "hg_mlp_backward": (i32, [P(MlpDesc), PF, PF, i64, PF, PF, PF, PF, i64, PF]),
         "hg_gemm_tf32": (i32, [P(Gemm), PF]),
         "hg_set_gemm_mode": (i32, [i32]),

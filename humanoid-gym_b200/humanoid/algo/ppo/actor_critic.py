@@ -81,6 +81,8 @@ class ActorCritic(nn.Module):
         self._wsplit_dirty = True
         self._wlo = torch.zeros(n, dtype=torch.float32, device=dev)            # tf32 residuals of the flat buffer (3xTF32 "lo" operand)
         self._wlo_dirty = True
+        self._w16 = torch.zeros(2, 1, n, dtype=torch.int16, device=dev)        # fp16 hi / lo planes of flat * 2^10 (fp16x3 rollout chain)
+        self._w16_dirty = True
         self.num_params = n                       # allocated floats (incl. pads) == length of every flat buffer
         self.num_real_params = sum(p.numel() for p in params)
         self._desc = {}
@@ -163,6 +165,7 @@ class ActorCritic(nn.Module):
         split images of the weights (bf16 hi / lo planes, tf32 residuals) are recomputed on next use."""
         self._wsplit_dirty = True
         self._wlo_dirty = True
+        self._w16_dirty = True
 
     def load_state_dict(self, *a, **k):
         r = super().load_state_dict(*a, **k)
@@ -176,6 +179,26 @@ class ActorCritic(nn.Module):
         nat.check(nat.lib.hg_tf32_residual(flat.data_ptr(), self._wlo.data_ptr(), flat.numel(), nat.stream_ptr(flat.device.index)),
                   "hg_tf32_residual")
         self._wlo_dirty = False
+
+    def refresh_w16(self):
+        """fp16 hi / lo planes of the flat buffer scaled by hg_f16_weight_scale() (one launch): operand B of the fp16x3 rollout
+        chain (hg_actor_critic_forward_f16)."""
+        flat = self.flat_params()
+        nat.check(nat.lib.hg_split_f16(flat.data_ptr(), flat.numel(), nat.Split.of(self._w16), 1, flat.numel(),
+                                       nat.lib.hg_f16_weight_scale(), nat.stream_ptr(flat.device.index)), "hg_split_f16(params)")
+        self._w16_dirty = False
+
+    def refresh_rollout_weights(self):
+        """Derived weight images the rollout reads (after an optimizer step / checkpoint load)."""
+        if self.chain_f16:
+            self.refresh_w16()
+        else:
+            self.refresh_lo()
+
+    @property
+    def chain_f16(self):
+        """fp16x3 operands for the one-launch PPO.act chain (default); HG_CHAIN_F16=0 selects the 3xTF32 chain on fp32 tiles."""
+        return os.environ.get("HG_CHAIN_F16", "1") != "0"
 
     def native_forward(self, which, x, out, hidden=None, sample=None):
         """out (M, dims[-1]) <- MLP_which(x); returns the hidden-activation scratch.
@@ -208,7 +231,12 @@ class ActorCritic(nn.Module):
                 return False
         if len(self._actor_dims) + len(self._critic_dims) - 2 > 8 or self.num_actions > 32:
             return False
-        if self._wlo_dirty:
+        if self.chain_f16:
+            if self._w16_dirty:
+                if torch.cuda.is_current_stream_capturing():
+                    return False
+                self.refresh_w16()
+        elif self._wlo_dirty:
             if torch.cuda.is_current_stream_capturing():
                 return False
             self.refresh_lo()
@@ -231,11 +259,23 @@ class ActorCritic(nn.Module):
             o.actions, o.log_prob, o.sigma = sample["actions"].data_ptr(), sample["log_prob"].data_ptr(), sample["sigma"].data_ptr()
             o.seed, o.step, o.step_dev = sample["seed"], sample["step"], sample.get("step_dev")
         a_on, c_on = obs is not None, cobs is not None
+        P = nat.ptr
+        if self.chain_f16:
+            da, dc = (self._desc["actor"] if a_on else None), (self._desc["critic"] if c_on else None)
+            skey = ("chain16_scratch", which, M)
+            if skey not in self._scratch:
+                self._scratch[skey] = torch.zeros(int(nat.lib.hg_actor_critic_f16_scratch_elems(da, dc, M)), dtype=torch.int16, device=flat.device)
+            nat.check(nat.lib.hg_actor_critic_forward_f16(da, dc, flat.data_ptr(), self._w16.data_ptr(), self._w16.stride(0),
+                                                          obs.data_ptr() if a_on else None, obs.stride(0) if a_on else 0,
+                                                          cobs.data_ptr() if c_on else None, cobs.stride(0) if c_on else 0,
+                                                          self._scratch[skey].data_ptr(), mu.data_ptr() if a_on else None,
+                                                          value.data_ptr() if c_on else None, o, self._scratch[key].data_ptr(), M,
+                                                          nat.stream_ptr(flat.device.index)), "hg_actor_critic_forward_f16")
+            return
         ha = self._hidden_scratch("actor", M) if a_on else None
         la = self._hidden_scratch("actor_lo", M) if a_on else None
         hc = self._hidden_scratch("critic", M) if c_on else None
         lc = self._hidden_scratch("critic_lo", M) if c_on else None
-        P = nat.ptr
         nat.check(nat.lib.hg_actor_critic_forward(self._desc["actor"] if a_on else None, self._desc["critic"] if c_on else None,
                                                   flat.data_ptr(), self._wlo.data_ptr(),
                                                   obs.data_ptr() if a_on else None, obs.stride(0) if a_on else 0,

@@ -356,7 +356,9 @@ class PPO:
             for _, i in steps:
                 mb = s.gather(indices[i * mini:(i + 1) * mini], split=False)
                 self.minibatch_step(mb, world)
-        self.actor_critic.refresh_lo()                       # the next rollout's GEMMs load weight-lo tiles by TMA
+        self.actor_critic.refresh_lo()                       # stand-alone 3xTF32 forwards (compute_returns) load weight-lo tiles by TMA
+        if self.actor_critic.chain_f16:
+            self.actor_critic.refresh_w16()                  # the next rollout's PPO.act chain reads the fp16x3 weight image
         num_updates = self.num_learning_epochs * self.num_mini_batches
         sums = self._loss_sums.tolist()                          # the only device->host read of the update
         s.clear()

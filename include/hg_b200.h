@@ -424,6 +424,24 @@ int32_t hg_adapt_lr(const float* kl_mean_dev, double desired_kl, double* lr_dev,
 /* misc                                                                     */
 /* ------------------------------------------------------------------------ */
 int32_t hg_version(void);
+/* fp16x3 form of hg_actor_critic_forward (the rollout default): same persistent multi-layer kernel and dependency scheme,
+ * operands as two fp16 planes x ~= hi + lo (22 significant bits, like the hi / lo pair of 3xTF32) multiplied as three
+ * tcgen05 kind::f16 MMAs -- half the operand bytes per k and twice the MMA rate of 3xTF32 on fp32 tiles, same ~1e-7
+ * network-level error.  fp16's narrow exponent is handled by storing the WEIGHTS scaled by hg_f16_weight_scale() (2^10;
+ * the epilogue scales back exactly); activations must stay below 65504 in magnitude (they saturate there).
+ *   w16 / w16_plane : hg_split_f16(params, scale = hg_f16_weight_scale()) image of the whole flat parameter buffer
+ *                     (plane k at w16 + k * w16_plane), refreshed by the caller after every optimizer step;
+ *   scratch16       : hg_actor_critic_f16_scratch_elems(actor, critic, M) uint16 of staging (input + hidden planes);
+ *   obs / cobs      : fp32 network inputs (split into planes by a first small launch of this call).
+ * Everything else as hg_actor_critic_forward (counters, sample, either net may be NULL). */
+float hg_f16_weight_scale(void);
+int32_t hg_split_f16(const float* src, int64_t ld_src, const HgSplit* dst, int64_t rows, int64_t cols, float scale, void* stream);
+int64_t hg_actor_critic_f16_scratch_elems(const HgMlpDesc* actor, const HgMlpDesc* critic, int64_t M);
+int32_t hg_actor_critic_forward_f16(const HgMlpDesc* actor, const HgMlpDesc* critic, const float* params, const uint16_t* w16,
+                                    int64_t w16_plane, const float* obs, int64_t ld_obs, const float* cobs, int64_t ld_cobs,
+                                    uint16_t* scratch16, float* mu, float* value, const HgMlpFwdOpts* sample, int32_t* counters,
+                                    int64_t M, void* stream);
+
 /* sizeof() of the ABI structs, for binding self-checks: 0 HgEnvParams, 1 HgEnvBuffers,
  * 2 HgEnvNoise, 3 HgMlpDesc, 4 HgTransition, 5 HgStorage, 6 HgMiniBatch, 7 HgPpoLossArgs, 8 HgGemm, 9 HgSplit,
  * 10 HgGemmSplit, 11 HgMlpFwdOpts */
