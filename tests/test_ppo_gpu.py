@@ -149,7 +149,9 @@ def test_fused_act_matches_separate_chains(N, gemm_engine, chain, monkeypatch):
     over several calls (the tile counters must come back to zero) and with a ragged last row tile.
     3xtf32 chain (hg_actor_critic_forward): same tile shapes and MMA order as the per-layer kernel -> bit-identical mean / value /
     actions / log-prob.  f16x3 chain (hg_actor_critic_forward_f16, the default): a different operand format -> mean / value within
-    2e-6 of the per-layer 3xTF32 results and 1e-5 of the oracle; sigma bit-identical; actions = mean + sigma z on the same z."""
+    1e-5 of the oracle (measured 3.8e-6 against fp64, the 3xTF32 engines 8e-6: tools/act_accuracy.py -- the error of both is the
+    truncating fp32 accumulation of the tensor core, proportional to the number of MMAs per accumulator, and fp16x3 issues half as
+    many) and so within 1.5e-5 of the per-layer 3xTF32 results; sigma bit-identical; actions = mean + sigma z on the same z."""
     import os
     from humanoid.algo import PPO
     if gemm_engine == "simt_fp32":
@@ -185,9 +187,9 @@ def test_fused_act_matches_separate_chains(N, gemm_engine, chain, monkeypatch):
             if chain == "3xtf32" or k == "sigma":
                 assert torch.equal(a, b), (t, k, float((a - b).abs().max()))
             elif k in ("mu", "values"):
-                assert _rel(a, b) < 2e-6, (t, k, _rel(a, b))
+                assert _rel(a, b) < 1.5e-5, (t, k, _rel(a, b))
             elif k == "actions":                          # same noise: the action differs by exactly the difference of the means
-                assert float(((a - s.mu[t]) - (b - s.mu[t + 3])).abs().max()) < 1e-6, (t, k)
+                assert float(((a - s.mu[t]) - (b - s.mu[t + 3])).abs().max()) < 2e-6, (t, k)
             else:
                 assert float((a - b).abs().max()) < 1e-4, (t, k, float((a - b).abs().max()))
     p = {k: v.detach().cpu() for k, v in ac.state_dict().items()}
