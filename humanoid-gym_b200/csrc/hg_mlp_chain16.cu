@@ -132,6 +132,15 @@ __global__ void __launch_bounds__(THREADS, 1) mlp_chain16_kernel(const __grid_co
                 const uint32_t tx = (uint32_t)A_BYTES + 2u * (uint32_t)Ly.BN * BK * 2u;
                 for (int w = (blockIdx.x + Ly.rot) % G; w < items; w += G) {
                     const int tm = w / Ly.tiles_n, tn = w - tm * Ly.tiles_n;
+                    // The WEIGHT tiles of the item's first stages depend on nothing: they are requested before the wait for the
+                    // producing layer, so only the activation tiles pay their L2 latency after the dependency resolves.
+                    const int pre = (Ly.dep >= 0) ? min(num_kb, STAGES) : 0;
+                    for (int kb = 0; kb < pre; ++kb) {
+                        const int s = (it + kb) % STAGES;
+                        mbar_wait(&empty[s], (((it + kb) / STAGES) & 1) ^ 1);
+                        mbar_expect_tx(&full[s], tx);
+                        tma_load_3d(smem + s * STAGE_BYTES + A_BYTES, &maps.b[l], &full[s], kb * BK, tn * Ly.BN, 0);      // [plane][BN][64]
+                    }
                     if (Ly.dep >= 0) {                   // wait until every column tile of the producing layer has published row tile tm
                         const int need = g.L[Ly.dep].tiles_n;
                         const int* c = g.counters + Ly.dep * g.tiles_m + tm;
@@ -140,11 +149,13 @@ __global__ void __launch_bounds__(THREADS, 1) mlp_chain16_kernel(const __grid_co
                     }
                     for (int kb = 0; kb < num_kb; ++kb, ++it) {
                         const int s = it % STAGES, k0 = kb * BK;
-                        mbar_wait(&empty[s], ((it / STAGES) & 1) ^ 1);
                         unsigned char* st = smem + s * STAGE_BYTES;
-                        mbar_expect_tx(&full[s], tx);
+                        if (kb >= pre) {
+                            mbar_wait(&empty[s], ((it / STAGES) & 1) ^ 1);
+                            mbar_expect_tx(&full[s], tx);
+                            tma_load_3d(st + A_BYTES, &maps.b[l], &full[s], k0, tn * Ly.BN, 0);
+                        }
                         tma_load_3d(st, &maps.a[l], &full[s], k0, tm * BM, 0);                   // [plane][128][64]
-                        tma_load_3d(st + A_BYTES, &maps.b[l], &full[s], k0, tn * Ly.BN, 0);      // [plane][BN][64]
                     }
                 }
             }
@@ -311,21 +322,35 @@ __global__ void __launch_bounds__(THREADS, 1) mlp_chain16_kernel(const __grid_co
     }
 }
 
-// fp32 -> fp16 hi / lo planes of (x * scale); up to two tensors per launch (obs and critic obs)
+// fp32 -> fp16 hi / lo planes of (x * scale); up to two tensors per launch (obs and critic obs).  One thread = 8 consecutive
+// columns of a row: two 16-byte loads when the source row allows it, one 16-byte store per plane; pad columns get zeros.
 struct SplitJob { const float* src; int64_t ld_src; uint16_t* dst; int64_t ld_dst, plane, rows, cols; };
 __global__ void split_f16_kernel(SplitJob j0, SplitJob j1, float scale) {
     const SplitJob& j = blockIdx.y == 0 ? j0 : j1;
-    const int64_t pairs_per_row = j.ld_dst >> 1;            // pad columns (cols <= c < ld_dst) get zeros
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= j.rows * pairs_per_row) return;
-    const int64_t r = i / pairs_per_row, c = (i - r * pairs_per_row) * 2;
-    const float x0 = (c < j.cols) ? j.src[r * j.ld_src + c] * scale : 0.0f, x1 = (c + 1 < j.cols) ? j.src[r * j.ld_src + c + 1] * scale : 0.0f;
-    const uint32_t h = pack_f16x2(x0, x1);
-    const float2 hf = unpack_f16x2(h);
-    const uint32_t l = pack_f16x2(x0 - hf.x, x1 - hf.y);
-    uint16_t* d = j.dst + r * j.ld_dst + c;
-    *reinterpret_cast<uint32_t*>(d) = h;
-    *reinterpret_cast<uint32_t*>(d + j.plane) = l;
+    const uint32_t groups = (uint32_t)(j.ld_dst >> 3);      // ld_dst % 8 == 0
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (uint64_t)j.rows * groups) return;
+    const uint32_t r = (uint32_t)(i / groups), c = (uint32_t)(i - (uint64_t)r * groups) * 8u;
+    const float* s = j.src + (int64_t)r * j.ld_src + c;
+    float x[8];
+    if (c + 8 <= (uint32_t)j.cols && ((reinterpret_cast<uintptr_t>(s) & 15u) == 0)) {
+        const float4 a = __ldg(reinterpret_cast<const float4*>(s)), b = __ldg(reinterpret_cast<const float4*>(s) + 1);
+        x[0] = a.x; x[1] = a.y; x[2] = a.z; x[3] = a.w; x[4] = b.x; x[5] = b.y; x[6] = b.z; x[7] = b.w;
+    } else {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) x[k] = (c + k < (uint32_t)j.cols) ? __ldg(s + k) : 0.0f;
+    }
+    uint32_t h[4], l[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const float x0 = x[2 * k] * scale, x1 = x[2 * k + 1] * scale;
+        h[k] = pack_f16x2(x0, x1);
+        const float2 hf = unpack_f16x2(h[k]);
+        l[k] = pack_f16x2(x0 - hf.x, x1 - hf.y);
+    }
+    uint16_t* d = j.dst + (int64_t)r * j.ld_dst + c;
+    *reinterpret_cast<uint4*>(d) = make_uint4(h[0], h[1], h[2], h[3]);
+    *reinterpret_cast<uint4*>(d + j.plane) = make_uint4(l[0], l[1], l[2], l[3]);
 }
 
 // ---- host ----------------------------------------------------------------------------------------------------------
@@ -389,10 +414,10 @@ extern "C" float hg_f16_weight_scale(void) { return kWScale; }
 
 extern "C" int32_t hg_split_f16(const float* src, int64_t ld_src, const HgSplit* dst, int64_t rows, int64_t cols, float scale, void* stream) {
     HG_REQUIRE(src); HG_REQUIRE(dst); HG_REQUIRE(dst->p);
-    if (rows <= 0 || cols <= 0 || ld_src < cols || dst->ld < cols || (dst->ld & 1) || (dst->plane & 1) || (reinterpret_cast<uintptr_t>(dst->p) & 3u))
-        return hg_fail(HG_E_SIZE, "hg_split_f16: bad extents (ld >= cols, even ld / plane, 4-byte aligned planes)");
+    if (rows <= 0 || cols <= 0 || ld_src < cols || dst->ld < cols || (dst->ld & 7) || (dst->plane & 7) || !hg_aligned16(dst->p))
+        return hg_fail(HG_E_SIZE, "hg_split_f16: bad extents (ld >= cols, ld % 8 == 0, plane % 8 == 0, 16-byte aligned planes)");
     SplitJob j{src, ld_src, dst->p, dst->ld, dst->plane, rows, cols};
-    const int64_t n = rows * (dst->ld >> 1);
+    const int64_t n = rows * (dst->ld >> 3);
     split_f16_kernel<<<dim3((unsigned)((n + 255) / 256), 1), 256, 0, (cudaStream_t)stream>>>(j, j, scale);
     HG_LAUNCHED(1);
     return hg_cuda_status("hg_split_f16");
@@ -513,7 +538,7 @@ extern "C" int32_t hg_actor_critic_forward_f16(const HgMlpDesc* actor, const HgM
     }
     {   // network inputs -> fp16 planes (both nets in one launch)
         int64_t nmax = 0;
-        for (int i = 0; i < plan.n_in; ++i) { const int64_t n = plan.in[i].rows * (plan.in[i].ld_dst >> 1); if (n > nmax) nmax = n; }
+        for (int i = 0; i < plan.n_in; ++i) { const int64_t n = plan.in[i].rows * (plan.in[i].ld_dst >> 3); if (n > nmax) nmax = n; }
         split_f16_kernel<<<dim3((unsigned)((nmax + 255) / 256), plan.n_in), 256, 0, st>>>(plan.in[0], plan.in[plan.n_in - 1], 1.0f);
     }
     mlp_chain16_kernel<<<plan.grid, THREADS, SMEM_BYTES, st>>>(plan.maps, g);
