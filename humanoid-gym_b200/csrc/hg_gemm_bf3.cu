@@ -45,7 +45,8 @@ constexpr int MAX_STAGES = 4;
 constexpr int EPI_STAGE_WARP = 2 * 32 * 64;            // per epilogue warp: [2 planes][32 rows][32 bf16], SWIZZLE_64B
 constexpr int EPI_STAGE_BYTES = 8 * EPI_STAGE_WARP;     // 32 KB
 
-enum { EPI_F32 = 0, EPI_F32_BIAS = 1, EPI_SPLIT_BIAS_ELU = 2, EPI_SPLIT_DELU = 3, EPI_ATOMIC = 4, EPI_SPLIT = 5, EPI_DISCARD = 6 /* profiling: bias + ELU + split math, no stores */ };
+enum { EPI_F32 = 0, EPI_F32_BIAS = 1, EPI_SPLIT_BIAS_ELU = 2, EPI_SPLIT_DELU = 3, EPI_ATOMIC = 4, EPI_SPLIT = 5, EPI_DISCARD = 6 /* profiling: bias + ELU + split math, no stores */,
+       EPI_SPLIT_DELU_TMA = 7 /* kernel-internal: EPI_SPLIT_DELU with the H blocks fetched by TMA (Args::h_tma) */ };
 
 struct Args {
     float* C; int64_t ldc;
@@ -56,6 +57,7 @@ struct Args {
     int M, N, K;
     int BN, a_mn, b_mn, epi;
     int kb_per_split, splits, stages;
+    int h_tma;                           // dgrad: the H block of every 32 x 32 chunk arrives by TMA in a per-warp buffer (tmH valid)
     int cs_tma;                          // split outputs leave through shared memory + TMA stores (tmC valid)
     int relay;                           // pair form: 1 = each CTA's TMA signals its OWN barrier and a relay thread of the peer forwards one arrival per stage
     int dbg;                             // profiling (HG_BF3_DEBUG): 1 = no TMA loads (MMA on whatever is in smem), 2 = no MMAs (loads + commits only)
@@ -131,7 +133,8 @@ __device__ __forceinline__ float elu1(float x) { return x > 0.0f ? x : exp_neg_f
 template <bool PAIR, int EPI>
 __global__ void __launch_bounds__(THREADS, 1)
 gemm_bf3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmC,
-                const Args g) {
+                const __grid_constant__ CUtensorMap tmH, const Args g) {
+    constexpr bool DELU = (EPI == EPI_SPLIT_DELU || EPI == EPI_SPLIT_DELU_TMA), HTMA = (EPI == EPI_SPLIT_DELU_TMA);
     extern __shared__ unsigned char smem_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     const uint32_t rank = PAIR ? cluster_ctarank() : 0u;        // 0 = leader
@@ -139,12 +142,14 @@ gemm_bf3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     const int b_plane = bn_cta * BK * 2;                        // bytes of one bf16 plane of this CTA's share of the B tile
     const int stage_bytes = A_BYTES + 2 * b_plane;
     unsigned char* epi_stage = smem + g.stages * stage_bytes;                         // 1024-aligned (stage_bytes is a multiple of 1 KB)
-    uint64_t* bars = reinterpret_cast<uint64_t*>(epi_stage + (g.cs_tma ? EPI_STAGE_BYTES : 0));
+    unsigned char* h_stage = epi_stage + (g.cs_tma ? EPI_STAGE_BYTES : 0);            // [8 warps][2 planes][32 rows][32 bf16], dgrad only
+    uint64_t* bars = reinterpret_cast<uint64_t*>(h_stage + (HTMA ? EPI_STAGE_BYTES : 0));
     uint64_t* full = bars;                          // [S] TMA -> MMA
     uint64_t* empty = full + MAX_STAGES;            // [S] MMA -> TMA
     uint64_t* tmem_full = empty + MAX_STAGES;       // [2] MMA -> epilogue
     uint64_t* tmem_empty = tmem_full + 2;           // [2] epilogue -> MMA
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+    uint64_t* h_full = tmem_empty + 4;              // [8] TMA -> epilogue warp w: its H block has landed
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int num_kb_total = (g.K + BK - 1) / BK;
@@ -167,6 +172,8 @@ gemm_bf3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             mbar_init(&tmem_full[a], 1);
             mbar_init(&tmem_empty[a], PAIR ? 2 * EPI_WARPS : EPI_WARPS);
         }
+        if (DELU)
+            for (int e = 0; e < EPI_WARPS; ++e) mbar_init(&h_full[e], 1);
         fence_barrier_init();
     }
     if (warp == EPI_WARPS + 1) {
@@ -296,11 +303,27 @@ gemm_bf3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         // 128-bit loads (one L1 broadcast each) instead of 32 shuffles.
         const int q = warp & 3, half = warp >> 2;
         const int c_begin = half * (g.BN >> 1), c_end = c_begin + (g.BN >> 1);
-        const bool h_fast = (EPI == EPI_SPLIT_DELU) && ((g.ldhs & 7) == 0) && ((g.hs_plane & 7) == 0) && ((reinterpret_cast<uintptr_t>(g.Hs) & 15u) == 0);
+        const bool h_fast = (DELU) && ((g.ldhs & 7) == 0) && ((g.hs_plane & 7) == 0) && ((reinterpret_cast<uintptr_t>(g.Hs) & 15u) == 0);
         const bool bias_fast = (EPI == EPI_F32_BIAS || EPI == EPI_SPLIT_BIAS_ELU || EPI == EPI_DISCARD) && ((reinterpret_cast<uintptr_t>(g.bias) & 15u) == 0);
         const uint32_t tmem_empty0_leader = PAIR ? mapa_u32(&tmem_empty[0], 0) : 0u;
         int item = 0;
         long long t_wfull = 0, t_busy = 0;
+        // dgrad, TMA form: the 32 x 32 x {hi, lo} block of H a chunk needs is fetched into this warp's 4 KB buffer (same SWIZZLE_64B
+        // geometry as the output staging) while the previous chunk is processed -- 8 conflict-free LDS.128 per lane instead of 8
+        // LDG.128 that each touch 32 different lines (256 sector requests per chunk through the L1 the tensor core saturates).
+        constexpr bool h_tma = HTMA;
+        unsigned char* hb = h_stage + warp * EPI_STAGE_WARP;
+        uint32_t h_phase = 0;
+        auto h_request = [&](int row0, int col0) {
+            if (lane == 0) {
+                mbar_expect_tx(&h_full[warp], (uint32_t)EPI_STAGE_WARP);
+                tma_load_3d(hb, &tmH, &h_full[warp], col0, row0, 0);                   // out-of-range rows / columns arrive as zeros
+            }
+        };
+        if (h_tma && w_begin < w_end) {
+            const Work w0 = decode_work(g, w_begin, tiles_n, tiles_mn, num_kb_total, TILE_M);
+            h_request(w0.m0 + (int)rank * BM + q * 32, w0.n0 + c_begin);
+        }
         for (int w = w_begin; w < w_end; w += w_step, ++item) {
             const Work wk = decode_work(g, w, tiles_n, tiles_mn, num_kb_total, TILE_M);
             const int acc_stage = item & 1;
@@ -319,7 +342,7 @@ gemm_bf3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                     }
                 }
             };
-            if (EPI == EPI_SPLIT_DELU) prefetch_h(c_begin);
+            if (DELU && !h_tma) prefetch_h(c_begin);
             mbar_wait(&tmem_full[acc_stage], (item >> 1) & 1);
             const long long te1 = g.trace ? clock64() : 0;
             tc_fence_after();
@@ -328,7 +351,23 @@ gemm_bf3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc_stage * 256 + c0), v);
                 const int col0 = wk.n0 + c0;
                 uint4 hc[8];
-                if (EPI == EPI_SPLIT_DELU) {
+                if (h_tma) {
+                    mbar_wait(&h_full[warp], h_phase);
+                    h_phase ^= 1u;
+                    const int sw = (lane >> 1) & 3;
+#pragma unroll
+                    for (int t = 0; t < 4; ++t) {
+                        const unsigned char* src = hb + lane * 64 + ((t ^ sw) << 4);
+                        hc[t] = *reinterpret_cast<const uint4*>(src);
+                        hc[4 + t] = *reinterpret_cast<const uint4*>(src + 32 * 64);
+                    }
+                    __syncwarp();                                               // every lane has read the buffer: request the next block
+                    if (c0 + 32 < c_end) h_request(wk.m0 + (int)rank * BM + q * 32, wk.n0 + c0 + 32);
+                    else if (w + w_step < w_end) {
+                        const Work nx = decode_work(g, w + w_step, tiles_n, tiles_mn, num_kb_total, TILE_M);
+                        h_request(nx.m0 + (int)rank * BM + q * 32, nx.n0 + c_begin);
+                    }
+                } else if (DELU) {
 #pragma unroll
                     for (int t = 0; t < 8; ++t) hc[t] = hn[t];
                     if (c0 + 32 < c_end) prefetch_h(c0 + 32);
@@ -352,10 +391,10 @@ gemm_bf3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 #pragma unroll
                         for (int j = 0; j < 32; ++j) v[j] = elu1(v[j]);
                     }
-                } else if (EPI == EPI_SPLIT_DELU) {
+                } else if (DELU) {
                     // ELU'(z) recovered from h = ELU(z) ~= h_hi + h_lo:  1 for h > 0, h + 1 otherwise
-                    if (h_fast && full_chunk) {
-                        if (row_ok) {
+                    if (h_tma || (h_fast && full_chunk)) {
+                        if (h_tma || row_ok) {
 #pragma unroll
                             for (int t = 0; t < 4; ++t) {
                                 const uint32_t ah[4] = {hc[t].x, hc[t].y, hc[t].z, hc[t].w};
@@ -464,7 +503,7 @@ gemm_bf3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                             }
                     }
                 }
-                if (EPI == EPI_SPLIT_DELU && g.colsum != nullptr) {
+                if (DELU && g.colsum != nullptr) {
                     // bias gradient: column sums of this 32 x 32 block by a butterfly transpose-reduce (31 shuffles),
                     // lane j ends up with the sum of column j; one atomic per column per warp
                     if (!row_ok) {
@@ -614,6 +653,7 @@ static const void* kernel_for_pair(int epi) {
         case EPI_ATOMIC: return (const void*)gemm_bf3_kernel<PAIR, EPI_ATOMIC>;
         case EPI_SPLIT: return (const void*)gemm_bf3_kernel<PAIR, EPI_SPLIT>;
         case EPI_DISCARD: return (const void*)gemm_bf3_kernel<PAIR, EPI_DISCARD>;
+        case EPI_SPLIT_DELU_TMA: return (const void*)gemm_bf3_kernel<PAIR, EPI_SPLIT_DELU_TMA>;
     }
     return nullptr;
 }
@@ -684,14 +724,24 @@ extern "C" int32_t hg_gemm_bf16x3(const HgGemmSplit* d, void* stream) {
     const int pm = bf3_pair_mode();
     const bool pair_legal = g.BN >= 128 && d->M >= 256;
     const bool pair = pm != 0 && pair_legal && (pm == 3 || (d->split_k <= 1 && (d->K + BK - 1) / BK >= 8));
-    const int bn_cta = pair ? g.BN / 2 : g.BN;
-    const int stage_bytes = A_BYTES + 2 * bn_cta * BK * 2;
     // split outputs go out through shared memory and TMA when the output planes qualify for a tensor map (HG_BF3_TMA_STORE=0: direct stores)
-    static int tma_store_env = -1;
+    static int tma_store_env = -1, tma_h_env = -1;
     if (tma_store_env < 0) { const char* e = getenv("HG_BF3_TMA_STORE"); tma_store_env = (e && e[0] == '0') ? 0 : 1; }
+    if (tma_h_env < 0) { const char* e = getenv("HG_BF3_TMA_H"); tma_h_env = (e && e[0] == '0') ? 0 : 1; }
     g.cs_tma = (tma_store_env && (epi == EPI_SPLIT_BIAS_ELU || epi == EPI_SPLIT_DELU || epi == EPI_SPLIT) && hg_aligned16(d->Cs.p) &&
                 (d->Cs.ld & 7) == 0 && (d->Cs.plane & 7) == 0) ? 1 : 0;
-    const int epi_bytes = g.cs_tma ? EPI_STAGE_BYTES : 0;
+    // dgrad (single-CTA form): H blocks by TMA too (HG_BF3_TMA_H=0: per-lane loads).  Their 32 KB of buffers come out of the
+    // operand ring, so the tile narrows to 192 or 128 columns (whichever pads N less): these short-K launches are bound by
+    // their epilogue, not by the A-tile reuse a 256-wide tile buys.
+    g.h_tma = (tma_h_env && epi == EPI_SPLIT_DELU && !pair && g.cs_tma && hg_aligned16(d->Hs.p) && (d->Hs.ld & 7) == 0 && (d->Hs.plane & 7) == 0 &&
+               d->Hs.ld >= d->N) ? 1 : 0;
+    if (g.h_tma && d->N > 128) {
+        const int w192 = (d->N + 191) / 192 * 192 - d->N, w128 = (d->N + 127) / 128 * 128 - d->N;
+        g.BN = (w192 <= w128) ? 192 : 128;
+    }
+    const int bn_cta = pair ? g.BN / 2 : g.BN;
+    const int stage_bytes = A_BYTES + 2 * bn_cta * BK * 2;
+    const int epi_bytes = (g.cs_tma ? EPI_STAGE_BYTES : 0) + (g.h_tma ? EPI_STAGE_BYTES : 0);
     int stages = (SMEM_LIMIT - 1024 - BAR_BYTES - epi_bytes) / stage_bytes;
     g.stages = stages > MAX_STAGES ? MAX_STAGES : stages;
     {   // profiling knob: HG_BF3_STAGES=n caps the ring depth (tools/bf3_trace.py measures the latency it has to cover)
@@ -712,9 +762,14 @@ extern "C" int32_t hg_gemm_bf16x3(const HgGemmSplit* d, void* stream) {
     g.splits = splits;
 
     // K-major operand: map {K, rows, 2}, box {64, tile rows, 2}.  MN-major: map {rows, K, 2}, box {64, 64, 2}.
-    CUtensorMap tmA, tmB, tmC;
+    CUtensorMap tmA, tmB, tmC, tmH;
     memset(&tmC, 0, sizeof(tmC));
+    memset(&tmH, 0, sizeof(tmH));
     int32_t rc;
+    if (g.h_tma) {
+        rc = get_map(&tmH, d->Hs.p, d->N, d->M, d->Hs.ld, d->Hs.plane, 32, 32);
+        if (rc) return rc;
+    }
     if (g.cs_tma) {
         rc = get_map(&tmC, d->Cs.p, d->N, d->M, d->Cs.ld, d->Cs.plane, 32, 32);
         if (rc) return rc;
@@ -730,16 +785,17 @@ extern "C" int32_t hg_gemm_bf16x3(const HgGemmSplit* d, void* stream) {
     const int total_work = ((d->N + g.BN - 1) / g.BN) * ((d->M + tile_m - 1) / tile_m) * splits;
     const int workers = pair ? HG_NUM_SMS / 2 : HG_NUM_SMS;
     const int grid = (total_work < workers ? total_work : workers) * (pair ? 2 : 1);          // persistent: one CTA (pair: one cluster) per SM (pair)
-    const void* fn = kernel_for(pair, epi);
+    const int kepi = g.h_tma ? (int)EPI_SPLIT_DELU_TMA : epi;
+    const void* fn = kernel_for(pair, kepi);
     if (!fn) return hg_fail(HG_E_ARG, "hg_gemm_bf16x3: bad epilogue");
     {
-        static bool attr_set[64][2][EPI_DISCARD + 1] = {};
+        static bool attr_set[64][2][EPI_SPLIT_DELU_TMA + 1] = {};
         int dev = 0;
         cudaGetDevice(&dev);
-        if (dev >= 0 && dev < 64 && !attr_set[dev][pair ? 1 : 0][epi]) {
+        if (dev >= 0 && dev < 64 && !attr_set[dev][pair ? 1 : 0][kepi]) {
             cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
             if (e != cudaSuccess) return hg_fail((int32_t)e, cudaGetErrorString(e));
-            attr_set[dev][pair ? 1 : 0][epi] = true;
+            attr_set[dev][pair ? 1 : 0][kepi] = true;
         }
     }
     cudaLaunchConfig_t cfg{};
@@ -748,7 +804,7 @@ extern "C" int32_t hg_gemm_bf16x3(const HgGemmSplit* d, void* stream) {
     at[0].id = cudaLaunchAttributeClusterDimension;
     at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     cfg.attrs = at; cfg.numAttrs = pair ? 1 : 0;
-    void* kargs[4] = {&tmA, &tmB, &tmC, &g};
+    void* kargs[5] = {&tmA, &tmB, &tmC, &tmH, &g};
     cudaError_t e = cudaLaunchKernelExC(&cfg, fn, kargs);
     if (e != cudaSuccess) return hg_fail((int32_t)e, cudaGetErrorString(e));
     HG_LAUNCHED(1);

@@ -67,7 +67,7 @@ __global__ void __launch_bounds__(128) head_forward_kernel(const uint16_t* __res
 //   db[n]     += sum_m dY[m][n]                               (head bias gradient; blockIdx.x == 0 only)
 //   dZ[m][k]   = (sum_n dY[m][n] W[n][k]) * ELU'(h[m][k])     -> split store
 //   dbp[k]    += sum_m dZ[m][k]                               (bias gradient of the layer that produced h)
-constexpr int HB_ROWS = 64, HB_THREADS = 256;
+constexpr int HB_ROWS = 192, HB_THREADS = 256;    // 192 rows: a third of the atomics of 64-row blocks on the same ~1.7 k addresses; static smem 47 KB at NO = 16
 template <int NO>
 __global__ void __launch_bounds__(HB_THREADS) head_backward_kernel(const float* __restrict__ dY, const uint16_t* __restrict__ hs, int64_t ldh,
                                                                    int64_t hplane, const float* __restrict__ W, int64_t ldw,

@@ -133,8 +133,9 @@ def test_argument_errors():
         _gemm(Xs, Ws, 64, 32, 705, 0, 0, 0, split_k=2)
 
 
-@pytest.mark.parametrize("env", [{"HG_BF3_PAIR": "3"}, {"HG_BF3_PAIR": "2"}, {"HG_BF3_PAIR": "0"}, {"HG_BF3_PAIR": "3", "HG_BF3_TMA_STORE": "0"}],
-                         ids=["pairs-everywhere", "pairs-cta_group2-tma", "single-cta-only", "direct-stores"])
+@pytest.mark.parametrize("env", [{"HG_BF3_PAIR": "3"}, {"HG_BF3_PAIR": "2"}, {"HG_BF3_PAIR": "0"}, {"HG_BF3_PAIR": "3", "HG_BF3_TMA_STORE": "0"},
+                                 {"HG_BF3_TMA_H": "0"}],
+                         ids=["pairs-everywhere", "pairs-cta_group2-tma", "single-cta-only", "direct-stores", "dgrad-h-by-lane-loads"])
 def test_kernel_variants(env):
     """The library picks the CTA-pair (cta_group::2) or single-CTA kernel per launch and reads its knobs once per process:
     rerun this module's layout tests in a child process with each form pinned, so every variant sees every layout."""
