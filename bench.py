@@ -183,10 +183,10 @@ def _time_iterations(runner, state, steps, device, world, e2e=False, book=None):
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum of post_physics_kernel from the committed `ncu --set full` captures
-# (profiles/r01_env_v5_n*_ncu_full.md).  At N=4096 the 16.8 MB the kernel writes are still in the 126 MB L2 when it
+# (profiles/r02c_env_n*_ncu_full.md, the round-2 kernel).  At N=4096 the 16.8 MB the kernel writes are still in the 126 MB L2 when it
 # ends, so only the reads reach DRAM inside the launch.
-NCU_TRAFFIC_SOURCE = "profiles/r01_env_v5_n4096_ncu_full.md, profiles/r01_env_v5_n65536_ncu_full.md (ncu --set full, one launch)"
-_NCU_ENV_TRAFFIC = {4096: 19808512 + 2560, 65536: 321089792 + 215574784}
+NCU_TRAFFIC_SOURCE = "profiles/r02c_env_n4096_ncu_full.md, profiles/r02c_env_n65536_ncu_full.md (ncu --set full, one launch)"
+_NCU_ENV_TRAFFIC = {4096: 19809792 + 1536, 65536: 319186688 + 215517696}
 
 
 def _ncu_traffic(num_envs):
