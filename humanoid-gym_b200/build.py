@@ -12,7 +12,7 @@ LIB = os.path.join(LIB_DIR, "libhg_b200.so")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC", "-I", os.path.join(ROOT, "include"), "-I", CSRC]
 # per-file extra flags; hg_env.cu mirrors a chain of separately-rounded fp32 torch ops -> no FMA contraction
-EXTRA = {"hg_env.cu": ["-fmad=false"]}
+EXTRA = {"hg_env.cu": ["-fmad=false"], "hg_terrain.cu": ["-fmad=false"]}
 
 
 def _nvcc():

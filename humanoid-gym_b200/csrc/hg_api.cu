@@ -21,6 +21,7 @@ extern "C" int64_t hg_struct_size(int32_t which) {
         case 9: return sizeof(HgSplit);
         case 10: return sizeof(HgGemmSplit);
         case 11: return sizeof(HgMlpFwdOpts);
+        case 12: return sizeof(HgTerrain);
         default: return -1;
     }
 }

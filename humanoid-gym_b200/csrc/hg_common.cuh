@@ -67,5 +67,5 @@ __device__ __forceinline__ float hg_normal(uint32_t a, uint32_t b) {
 // stream ids for the env-side draws (c2 of the Philox counter)
 enum : uint32_t {
     HG_RNG_CMD_CB = 1, HG_RNG_CMD_RS = 2, HG_RNG_DOF = 3, HG_RNG_PUSH = 4, HG_RNG_OBS = 5,
-    HG_RNG_DELAY = 6, HG_RNG_ACT = 7, HG_RNG_SAMPLE = 8
+    HG_RNG_DELAY = 6, HG_RNG_ACT = 7, HG_RNG_SAMPLE = 8, HG_RNG_LEVEL = 9, HG_RNG_ROOT = 10
 };

@@ -131,7 +131,15 @@ class GemmSplit(C.Structure):
                 ("epilogue", i32), ("split_k", i32)]
 
 
-_STRUCTS = (EnvParams, EnvBuffers, EnvNoise, MlpDesc, Transition, Storage, MiniBatch, PpoLossArgs, Gemm, Split, GemmSplit, MlpFwdOpts)
+class Terrain(C.Structure):
+    """HgTerrain: the rough-terrain height field and curriculum constants (include/hg_b200.h)."""
+    _fields_ = [("height_samples", PF), ("rows", i32), ("cols", i32), ("border_size", f32), ("horizontal_scale", f32),
+                ("vertical_scale", f32), ("terrain_origins", PF), ("num_levels", i32), ("num_types", i32),
+                ("half_env_length", f32), ("max_episode_length_s", f32), ("curriculum", i32), ("_pad", i32)]
+
+
+_STRUCTS = (EnvParams, EnvBuffers, EnvNoise, MlpDesc, Transition, Storage, MiniBatch, PpoLossArgs, Gemm, Split, GemmSplit, MlpFwdOpts,
+            Terrain)
 
 
 class NativeError(RuntimeError):
@@ -155,6 +163,9 @@ def _load():
         "hg_env_set_trace": (None, [PF]),
         "hg_env_synth_decimation": (i32, [P(EnvBuffers), P(EnvParams), PF, i32, PF, PF, PF, i64, PF]),
         "hg_env_post_physics": (i32, [P(EnvBuffers), P(EnvParams), P(EnvNoise), C.c_uint32, i64, i64, PF]),
+        "hg_terrain_get_heights": (i32, [P(Terrain), PF, PF, i32, PF, i64, PF]),
+        "hg_terrain_reset_prepare": (i32, [P(Terrain), PF, PF, PF, PF, PF, PF, PF, PF, PF, u64, u64, PF, i64, PF]),
+        "hg_terrain_priv_frames": (i32, [PF, i64, i32, PF, PF, i32, f32, f32, PF, PF, PF, i64, i32, i64, PF]),
         "hg_mlp_forward": (i32, [P(MlpDesc), PF, PF, i64, PF, PF, i64, PF]),
         "hg_mlp_forward_ex": (i32, [P(MlpDesc), PF, PF, i64, PF, PF, i64, P(MlpFwdOpts), PF]),
         "hg_tf32_residual": (i32, [PF, PF, i64, PF]),

@@ -4,8 +4,13 @@ Same public surface as reference envs/base/legged_robot.py (ctor, step, reset, p
 check_termination, compute_reward, reset_idx, _compute_torques, the live state tensors), but every
 tensor op between the physics refresh and the return of step() is ONE launch of the fused
 sm_100a kernel `hg_env_post_physics`; this class only owns the buffers, the physics seam and the
-argument marshalling.  Rough terrain, curricula and the viewer are out of scope (XBotLCfg disables
-them: humanoid_config.py:72-76).
+argument marshalling.
+
+Rough terrain (cfg.terrain.mesh_type 'heightfield' / 'trimesh'; XBotLCfg ships 'plane', humanoid_config.py:72-76):
+the height field is built on the host by utils/terrain.py; per step the env samples it around every robot
+(`_get_heights`), moves terminated envs through the terrain curriculum (`_update_terrain_curriculum`) and spawns
+them within 1 m of their terrain origin -- three small kernels of csrc/hg_terrain.cu around the fused kernel, which
+then runs as two launches (see post_physics_step).  The viewer is out of scope.
 """
 import os
 
@@ -15,10 +20,17 @@ import torch
 from humanoid import _native as nat
 from humanoid.envs.base.base_task import BaseTask
 from humanoid.utils.helpers import class_to_dict
+from humanoid.utils.terrain import Terrain
 from humanoid import physics as phys
+
+# the two halves of a rough-terrain step: the curriculum sits between termination and reset (reference :175-186)
+_PHASES_BEFORE_RESET = nat.PHASE_COUNTERS | nat.PHASE_CALLBACK | nat.PHASE_TERMINATE | nat.PHASE_REWARD
+_PHASES_FROM_RESET = nat.PHASE_RESET | nat.PHASE_OBS | nat.PHASE_LAST
 
 
 class LeggedRobot(BaseTask):
+    terrain_class = Terrain                                      # XBotLFreeEnv: HumanoidTerrain (humanoid_env.py:153)
+
     def __init__(self, cfg, sim_params, physics_engine, sim_device, headless):
         self.cfg = cfg
         self.sim_params = sim_params
@@ -42,10 +54,6 @@ class LeggedRobot(BaseTask):
         self.command_ranges = class_to_dict(self.cfg.commands.ranges)
         if self.cfg.terrain.mesh_type not in ("heightfield", "trimesh"):
             self.cfg.terrain.curriculum = False
-        else:
-            raise NotImplementedError("rough terrain is outside the humanoid_ppo hot path (plane only)")
-        if self.cfg.terrain.measure_heights:
-            raise NotImplementedError("measure_heights is outside the humanoid_ppo hot path")
         self.max_episode_length_s = self.cfg.env.episode_length_s
         self.max_episode_length = np.ceil(self.max_episode_length_s / self.dt)
         self.cfg.domain_rand.push_interval = np.ceil(self.cfg.domain_rand.push_interval_s / self.dt)
@@ -53,12 +61,21 @@ class LeggedRobot(BaseTask):
     def create_sim(self):
         """Physics seam (reference humanoid_env.py:145-163 + legged_robot.py:588-681)."""
         self.up_axis_idx = 2
+        mesh_type = self.cfg.terrain.mesh_type                    # humanoid_env.py:151-162
+        if mesh_type not in (None, "plane", "heightfield", "trimesh"):
+            raise ValueError("Terrain mesh type not recognised. Allowed types are [None, plane, heightfield, trimesh]")
+        self.terrain = self.terrain_class(self.cfg.terrain, self.num_envs) if mesh_type in ("heightfield", "trimesh") else None
+        if self.terrain is not None:                              # _create_heightfield / _create_trimesh :570,586
+            self.height_samples = torch.tensor(self.terrain.heightsamples).view(
+                self.terrain.tot_rows, self.terrain.tot_cols).to(self.device).contiguous()
         self._get_env_origins()
         kind = os.environ.get("HG_PHYSICS", getattr(self.cfg, "physics_backend", "auto"))
         seed = getattr(self.cfg, "seed", 0)
         rank = int(os.environ.get("RANK", "0"))
         self.gym = phys.make_physics(kind, self.num_envs, self.device, self.cfg, self.env_origins, seed=seed, rank=rank)
         self.sim = self.gym
+        if self.terrain is not None:
+            self.gym.add_terrain(self.terrain, mesh_type)
         self.num_dof = self.num_dofs = self.gym.num_dof
         self.num_bodies = self.gym.num_bodies
         self.dof_names = list(self.gym.dof_names)
@@ -101,9 +118,19 @@ class LeggedRobot(BaseTask):
             lo, hi = dr.added_mass_range
             self.body_mass += torch.from_numpy(np.random.uniform(lo, hi, size=(N, 1)).astype(np.float32)).to(dev)
 
-    def _get_env_origins(self):                                  # :683-708 (flat-ground grid)
-        self.custom_origins = False
+    def _get_env_origins(self):                                  # :683-708
         N = self.num_envs
+        if self.terrain is not None:                              # origins are the terrain platforms :687-697
+            tc = self.cfg.terrain
+            self.custom_origins = True
+            max_init_level = tc.max_init_terrain_level if tc.curriculum else tc.num_rows - 1
+            self.terrain_levels = torch.randint(0, max_init_level + 1, (N,)).to(self.device)
+            self.terrain_types = torch.div(torch.arange(N), (N / tc.num_cols), rounding_mode="floor").to(torch.long).to(self.device)
+            self.max_terrain_level = tc.num_rows
+            self.terrain_origins = torch.from_numpy(self.terrain.env_origins).to(self.device).to(torch.float).contiguous()
+            self.env_origins = self.terrain_origins[self.terrain_levels, self.terrain_types].contiguous()
+            return
+        self.custom_origins = False                               # flat ground: a grid :698-708
         cols = np.floor(np.sqrt(N))
         rows = np.ceil(N / cols)
         xx, yy = torch.meshgrid(torch.arange(rows), torch.arange(cols), indexing="ij")
@@ -154,6 +181,8 @@ class LeggedRobot(BaseTask):
         self.projected_gravity = zeros(N, 3)
         self.projected_gravity[:, 2] = -1.0
         self.base_euler_xyz = zeros(N, 3)
+        if self.cfg.terrain.measure_heights:                      # :481-483
+            self.height_points = self._init_height_points()
         self.measured_heights = 0
         self.feet_height = zeros(N, 2)
         self.last_feet_z = torch.full((N, 2), 0.05, device=dev)
@@ -176,6 +205,19 @@ class LeggedRobot(BaseTask):
 
     def _get_noise_scale_vec(self, cfg):
         raise NotImplementedError
+
+    def _init_height_points(self):                               # :743-757
+        """Base-frame grid (num_envs, num_height_points, 3) around every robot at which the terrain is sampled."""
+        tc = self.cfg.terrain
+        y = torch.tensor(tc.measured_points_y, device=self.device)
+        x = torch.tensor(tc.measured_points_x, device=self.device)
+        grid_x, grid_y = torch.meshgrid(x, y, indexing="ij")
+        self.num_height_points = grid_x.numel()
+        self._height_points_xy = torch.stack((grid_x.flatten(), grid_y.flatten()), dim=1).contiguous()   # the kernel's (P, 2) view
+        points = torch.zeros(self.num_envs, self.num_height_points, 3, device=self.device)
+        points[:, :, 0] = grid_x.flatten()
+        points[:, :, 1] = grid_y.flatten()
+        return points
 
     def _prepare_reward_function(self):                          # :518-541
         for key in list(self.reward_scales.keys()):
@@ -220,19 +262,58 @@ class LeggedRobot(BaseTask):
         def twin(v):        # same pitch, fresh storage
             return torch.zeros(v.shape[0], v.stride(0), dtype=v.dtype, device=v.device)[:, :v.shape[1]]
         self._obs_pp = [self.obs_buf, twin(self.obs_buf)]
-        self._priv_pp = [self.privileged_obs_buf, twin(self.privileged_obs_buf)]
+        if self.cfg.terrain.measure_heights:
+            # critic frames carry the terrain heights (humanoid_env.py:246-248): env.privileged_obs_buf is the
+            # c_frame_stack x (num_obs + num_height_points) history written by hg_terrain_priv_frames; the fused kernel keeps
+            # its 3 x 73 frames in a private pair
+            self._privh_pp = [self.privileged_obs_buf, twin(self.privileged_obs_buf)]
+            w = nat.PRIV1 * nat.PRIV_FRAMES
+            first = torch.zeros(self.num_envs, (w + 31) // 32 * 32, device=self.device)[:, :w]
+            self._priv_pp = [first, twin(first)]
+        else:
+            self._privh_pp = None
+            self._priv_pp = [self.privileged_obs_buf, twin(self.privileged_obs_buf)]
         for k, t in tensors.items():
             setattr(B, k, nat.ptr(t))
         B.obs_buf, B.obs_out = self._obs_pp[0].data_ptr(), self._obs_pp[1].data_ptr()
         B.privileged_obs_buf, B.priv_out = self._priv_pp[0].data_ptr(), self._priv_pp[1].data_ptr()
-        B.obs_pitch, B.priv_pitch = self.obs_buf.stride(0), self.privileged_obs_buf.stride(0)
+        B.obs_pitch, B.priv_pitch = self.obs_buf.stride(0), self._priv_pp[0].stride(0)
         self._B = B
         self._keepalive = tensors
+        self._bind_terrain()
         self._Z = nat.EnvNoise()
         self._Z.seed = int(getattr(self.cfg, "seed", 0)) * 0x9E3779B97F4A7C15 % (1 << 64) + int(os.environ.get("RANK", "0"))
         self._noise_step = 0
         self._injected = {}
         self._dev_index = torch.device(self.device).index
+
+    def _bind_terrain(self):
+        """Rough terrain: HgTerrain descriptor, the spawn-origin buffer the fused kernel's reset reads instead of
+        env_origins (origin + the +-1 m jitter of :381-384), the heights buffer."""
+        self._T = None
+        self._launches_per_step = 1
+        if self.terrain is None:
+            if self.cfg.terrain.measure_heights:                  # plane: _get_heights returns zeros (:772-773)
+                self._heights = torch.zeros(self.num_envs, self.num_height_points, device=self.device)
+            return
+        if float(self.base_init_state[0]) != 0.0 or float(self.base_init_state[1]) != 0.0:
+            # spawn = (init + origin) + jitter in the reference; the kernels form init + (origin + jitter): equal iff init_xy = 0
+            raise NotImplementedError("rough terrain needs init_state.pos[0:2] == 0 (XBotLCfg: [0, 0, 0.95])")
+        tc, T = self.cfg.terrain, nat.Terrain()
+        T.height_samples = self.height_samples.data_ptr()
+        T.rows, T.cols = self.height_samples.shape
+        T.border_size, T.horizontal_scale, T.vertical_scale = tc.border_size, tc.horizontal_scale, tc.vertical_scale
+        T.terrain_origins = self.terrain_origins.data_ptr()
+        T.num_levels, T.num_types = self.terrain_origins.shape[0], self.terrain_origins.shape[1]
+        T.half_env_length = self.terrain.env_length / 2
+        T.max_episode_length_s = self.max_episode_length_s
+        T.curriculum = int(bool(tc.curriculum))
+        self._T = T
+        self._spawn = self.env_origins.clone()
+        self._B.env_origins = self._spawn.data_ptr()
+        self._launches_per_step = 2
+        if tc.measure_heights:
+            self._heights = torch.zeros(self.num_envs, self.num_height_points, device=self.device)
 
     # ---- CUDA-graph support: per-step counters move to device memory -----------------------------------
     def use_device_counters(self, on=True):
@@ -254,7 +335,7 @@ class LeggedRobot(BaseTask):
     def advance_host_counters(self, steps):
         """After replaying a captured rollout of `steps` env steps: keep the host mirrors in sync."""
         self.common_step_counter += steps
-        self._noise_step += steps
+        self._noise_step += steps * self._launches_per_step
         if hasattr(self.gym, "substep"):
             self.gym.substep += steps * self.cfg.control.decimation
 
@@ -267,9 +348,10 @@ class LeggedRobot(BaseTask):
         return steps is None or steps % self.gym.ring == 0
 
     def inject_noise(self, **tensors):
-        """Parity hook: dense per-env draws (u_cmd_cb, u_cmd_rs, u_dof, u_push, z_obs, u_delay, z_act)
-        used instead of in-kernel Philox for the NEXT kernel call(s) of this step."""
-        self._injected = {k: v.to(self.device, torch.float32).contiguous() for k, v in tensors.items()}
+        """Parity hook: dense per-env draws (u_cmd_cb, u_cmd_rs, u_dof, u_push, z_obs, u_delay, z_act; rough terrain:
+        u_root (N,2), r_level (N) int64) used instead of in-kernel Philox for the NEXT kernel call(s) of this step."""
+        self._injected = {k: v.to(self.device, torch.int64 if k == "r_level" else torch.float32).contiguous()
+                          for k, v in tensors.items()}
 
     def _launch_post_physics(self, phases):
         Z = self._Z
@@ -285,16 +367,28 @@ class LeggedRobot(BaseTask):
             src, dst = 1, 0
         else:       # user code rebound env.obs_buf: adopt its contents
             self._obs_pp[0].copy_(self.obs_buf)
-            self._priv_pp[0].copy_(self.privileged_obs_buf)
+            (self._privh_pp or self._priv_pp)[0].copy_(self.privileged_obs_buf)
             src, dst = 0, 1
         B.obs_buf, B.privileged_obs_buf = self._obs_pp[src].data_ptr(), self._priv_pp[src].data_ptr()
         B.obs_out, B.priv_out = self._obs_pp[dst].data_ptr(), self._priv_pp[dst].data_ptr()
         nat.check(nat.lib.hg_env_post_physics(B, self._P, Z, phases, int(self.common_step_counter),
                                               self.num_envs, nat.stream_ptr(self._dev_index)), "hg_env_post_physics")
-        if phases & nat.PHASE_OBS:
-            self.obs_buf, self.privileged_obs_buf = self._obs_pp[dst], self._priv_pp[dst]
+        now = dst if phases & nat.PHASE_OBS else src
+        self.obs_buf = self._obs_pp[now]
+        if self._privh_pp is None:
+            self.privileged_obs_buf = self._priv_pp[now]
+        elif phases & nat.PHASE_OBS:
+            # humanoid_env.py:246-248: the critic frame is [the obs_buf this step STARTED with | scaled heights]
+            cfg = self.cfg
+            nat.check(nat.lib.hg_terrain_priv_frames(
+                self._obs_pp[src].data_ptr(), self.obs_buf.stride(0), self.num_obs, nat.ptr(self.root_states),
+                nat.ptr(self._heights), self.num_height_points, self.obs_scales.height_measurements,
+                cfg.normalization.clip_observations, nat.ptr(self.reset_buf) if phases & nat.PHASE_RESET else None,
+                self._privh_pp[src].data_ptr(), self._privh_pp[dst].data_ptr(), self._privh_pp[0].stride(0),
+                cfg.env.c_frame_stack, self.num_envs, nat.stream_ptr(self._dev_index)), "hg_terrain_priv_frames")
+            self.privileged_obs_buf = self._privh_pp[dst]
         else:
-            self.obs_buf, self.privileged_obs_buf = self._obs_pp[src], self._priv_pp[src]
+            self.privileged_obs_buf = self._privh_pp[src]
 
     # ------------------------------------------------------------------------------------------
     # stepping
@@ -332,15 +426,66 @@ class LeggedRobot(BaseTask):
             g.refresh_rigid_body_state_tensor()
         self._refreshed = False
         self.common_step_counter += 1
-        self._launch_post_physics(nat.PHASE_STEP_ALL)
+        if self.cfg.terrain.measure_heights:                      # _post_physics_step_callback :316-317
+            self.measured_heights = self._get_heights()
+        if self._T is None:
+            self._launch_post_physics(nat.PHASE_STEP_ALL)
+        else:
+            # rough terrain: termination + rewards, then the curriculum / spawn origins of the envs that terminated
+            # (reset_idx :175-177, _reset_root_states :381-384), then reset + observations + last_* copies
+            self._launch_post_physics(_PHASES_BEFORE_RESET)
+            self._terrain_reset_prepare(curriculum=True)
+            self._launch_post_physics(_PHASES_FROM_RESET)
         self._injected = {}
         pushed = self.cfg.domain_rand.push_robots and (self.common_step_counter % self.cfg.domain_rand.push_interval == 0)
         g.apply_env_writes(self.reset_ids, self._scratch, pushed)
         self._publish_extras()
 
+    # ---- rough terrain -------------------------------------------------------------------------------------
+    def _get_heights(self, env_ids=None):                         # :759-795
+        """Terrain heights (num_envs, num_height_points) at the grid points around each robot: one launch of
+        hg_terrain_get_heights; zeros on a plane.  `env_ids` selects rows of the result."""
+        if self.cfg.terrain.mesh_type == "plane":
+            h = self._heights
+        elif self.cfg.terrain.mesh_type == "none":
+            raise NameError("Can't measure height with terrain mesh type 'none'")
+        else:
+            nat.check(nat.lib.hg_terrain_get_heights(self._T, nat.ptr(self.root_states), nat.ptr(self._height_points_xy),
+                                                     self.num_height_points, nat.ptr(self._heights), self.num_envs,
+                                                     nat.stream_ptr(self._dev_index)), "hg_terrain_get_heights")
+            h = self._heights
+        return h if env_ids is None else h[env_ids]
+
+    def _terrain_reset_prepare(self, curriculum):
+        """For the envs flagged in reset_buf: terrain curriculum (if enabled) and the spawn origins of the reset."""
+        T = self._T
+        saved = T.curriculum
+        T.curriculum = int(bool(curriculum and saved))
+        inj, Z = self._injected, self._Z
+        dev_ctr = Z.use_device_counters
+        nat.check(nat.lib.hg_terrain_reset_prepare(
+            T, nat.ptr(self.reset_buf), nat.ptr(self.root_states), nat.ptr(self.commands), nat.ptr(self.terrain_levels),
+            nat.ptr(self.terrain_types), nat.ptr(self.env_origins), nat.ptr(self._spawn), nat.ptr(inj.get("r_level")),
+            nat.ptr(inj.get("u_root")), Z.seed, self._noise_step, self.noise_step_dev_ptr if dev_ctr else None,
+            self.num_envs, nat.stream_ptr(self._dev_index)), "hg_terrain_reset_prepare")
+        T.curriculum = saved
+
+    def _update_terrain_curriculum(self, env_ids):                # :400-420
+        """Game-inspired curriculum for the envs being reset (stand-alone entry point; a step runs it between its two
+        fused launches)."""
+        if not self.init_done or self._T is None or not self.cfg.terrain.curriculum:
+            return
+        previous = self.reset_buf.clone()
+        self.reset_buf.zero_()
+        self.reset_buf[env_ids] = True
+        self._terrain_reset_prepare(curriculum=True)
+        self.reset_buf.copy_(previous)
+
     def _publish_extras(self):
         if "episode" not in self.extras:
             self.extras["episode"] = {"rew_" + n: self._episode_means[k] for k, n in enumerate(self.reward_names)}
+        if self.cfg.terrain.mesh_type == "trimesh":                # :204-205 (the reference refreshes it on steps with a reset;
+            self.extras["episode"]["terrain_level"] = torch.mean(self.terrain_levels.float())   # levels only change on those)
         if self.cfg.env.send_timeouts:
             self.extras["time_outs"] = self.extras_time_outs
 
@@ -360,6 +505,8 @@ class LeggedRobot(BaseTask):
         previous = self.reset_buf.clone()
         self.reset_buf.zero_()
         self.reset_buf[env_ids] = True                            # the kernel resets the masked envs
+        if self._T is not None:
+            self._terrain_reset_prepare(curriculum=self.init_done)     # "don't change on initial reset" :407-409
         self._launch_post_physics(nat.PHASE_RESET)
         self.reset_buf |= previous                                # reference only sets [env_ids] = 1 (:196)
         self._injected = {}

@@ -8,9 +8,12 @@ import torch
 
 from humanoid import _native as nat
 from humanoid.envs.base.legged_robot import LeggedRobot
+from humanoid.utils.terrain import HumanoidTerrain
 
 
 class XBotLFreeEnv(LeggedRobot):
+    terrain_class = HumanoidTerrain                               # humanoid_env.py:153
+
     def __init__(self, cfg, sim_params, physics_engine, sim_device, headless):
         super().__init__(cfg, sim_params, physics_engine, sim_device, headless)
         self.reset_idx(torch.arange(self.num_envs, device=self.device))     # humanoid_env.py:80-81
@@ -29,8 +32,17 @@ class XBotLFreeEnv(LeggedRobot):
     def _native_params(self):
         cfg, P = self.cfg, nat.EnvParams()
         e = cfg.env
+        priv1 = nat.PRIV1
+        if cfg.terrain.measure_heights:
+            # humanoid_env.py:246-248 replaces the 73-wide critic frame by [obs_buf | heights]: the cfg has to size the critic
+            # for it (the reference otherwise fails in the critic's first matmul)
+            priv1 = e.num_observations + self.num_height_points
+            if e.num_privileged_obs != e.c_frame_stack * priv1:
+                raise nat.NativeError(
+                    f"measure_heights: the critic frame is num_observations + {self.num_height_points} height points = {priv1} "
+                    f"wide; set env.single_num_privileged_obs = {priv1} and env.num_privileged_obs = {e.c_frame_stack * priv1}")
         if (e.num_single_obs, e.frame_stack, e.single_num_privileged_obs, e.c_frame_stack, e.num_actions) != \
-                (nat.OBS1, nat.OBS_FRAMES, nat.PRIV1, nat.PRIV_FRAMES, nat.NUM_DOF):
+                (nat.OBS1, nat.OBS_FRAMES, priv1, nat.PRIV_FRAMES, nat.NUM_DOF):
             raise nat.NativeError("the fused env kernel is specialised to 15x47 / 3x73 observations and 12 actions")
         if e.use_ref_actions:
             raise NotImplementedError("use_ref_actions is not part of the humanoid_ppo hot path")
@@ -92,6 +104,11 @@ class XBotLFreeEnv(LeggedRobot):
             self._Z.seed, nat.STEP_FROM_DEVICE if self._Z.use_device_counters else self._noise_step, self.num_envs,
             nat.stream_ptr(self._dev_index)), "hg_env_pre_physics")
         return super().step(self.actions)
+
+    def reset_idx(self, env_ids):                                 # humanoid_env.py:264-269
+        super().reset_idx(env_ids)
+        if self._privh_pp is not None and len(env_ids):           # the height-augmented critic history is zeroed as well
+            self.privileged_obs_buf[env_ids] = 0.0
 
     # conveniences kept from the reference API ------------------------------------------------
     def _get_phase(self):                                         # :100-103

@@ -38,6 +38,12 @@ class PhysicsBackend:
         return dict(lower=list(robot.DOF_LOWER), upper=list(robot.DOF_UPPER),
                     velocity=list(robot.DOF_VELOCITY), effort=list(robot.DOF_EFFORT))
 
+    def add_terrain(self, terrain, mesh_type):
+        """gym.add_heightfield / gym.add_triangle_mesh (reference legged_robot.py:553-586): `terrain` is the
+        utils.terrain.Terrain whose heightsamples / vertices / triangles a simulator collides the robots with.
+        Sources that do not simulate contact ignore it."""
+        pass
+
     # -- stepping ---------------------------------------------------------------------------
     def set_dof_actuation_force_tensor(self, torques):
         pass

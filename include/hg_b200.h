@@ -185,6 +185,55 @@ int32_t hg_env_synth_decimation(const HgEnvBuffers* B, const HgEnvParams* P, con
 int32_t hg_env_post_physics(const HgEnvBuffers* B, const HgEnvParams* P, const HgEnvNoise* Z,
                             uint32_t phases, int64_t common_step_counter, int64_t N, void* stream);
 
+/* ---- rough terrain: mesh_type 'heightfield' / 'trimesh' -------------------------------
+ * The height field is the int16 grid HumanoidTerrain builds on the host (utils/terrain.py:38-63); everything
+ * the env does with it per step runs here.  In this mode LeggedRobot splits hg_env_post_physics into
+ * {COUNTERS|CALLBACK|TERMINATE|REWARD} and {RESET|OBS|LAST} with hg_terrain_reset_prepare in between, because
+ * the curriculum moves env_origins of the envs that terminated BEFORE their root state is re-initialised
+ * (legged_robot.py:175-186). */
+typedef struct HgTerrain {
+    const int16_t* height_samples;  /* (rows, cols) row-major = Terrain.heightsamples (legged_robot.py:570,586)   */
+    int32_t rows, cols;             /* tot_rows, tot_cols                                                         */
+    float border_size;              /* [m]                                                                        */
+    float horizontal_scale;         /* [m per cell]                                                               */
+    float vertical_scale;           /* [m per int16 unit]                                                         */
+    const float* terrain_origins;   /* (num_levels, num_types, 3) = Terrain.env_origins as fp32 (:696)            */
+    int32_t num_levels, num_types;  /* cfg.terrain.num_rows (= max_terrain_level), num_cols                       */
+    float half_env_length;          /* terrain.env_length / 2: walking further moves an env up one level (:412)   */
+    float max_episode_length_s;
+    int32_t curriculum;             /* cfg.terrain.curriculum                                                      */
+    int32_t _pad;
+} HgTerrain;
+
+/* LeggedRobot._get_heights (legged_robot.py:759-795): for every env the P base-frame grid points
+ * `points_xy` (P,2) are rotated by the base yaw (quat_apply_yaw, utils/math.py:38-43), moved to the root
+ * position, shifted by the border, divided by the horizontal scale and truncated (.long()); the height is the
+ * minimum of the three samples (px,py), (px+1,py), (px,py+1) with px / py clipped to [0, rows-2] / [0, cols-2],
+ * times the vertical scale.  heights: (N,P). */
+int32_t hg_terrain_get_heights(const HgTerrain* T, const float* root_states, const float* points_xy, int32_t P,
+                               float* heights, int64_t N, void* stream);
+
+/* For the envs with reset_buf set: LeggedRobot._update_terrain_curriculum (legged_robot.py:400-420, skipped when
+ * T->curriculum == 0) on terrain_levels / env_origins, then the spawn position _reset_root_states adds to
+ * base_init_state under custom origins (:381-384): spawn = env_origins + (U(-1,1), U(-1,1), 0).  `spawn` (N,3)
+ * is what the following hg_env_post_physics(RESET|...) launch must see as B->env_origins.
+ * r_level (N) int64: the torch.randint_like draw of an env that solved the last level; u_root (N,2) U[0,1).
+ * Either may be NULL: Philox4x32-10 keyed by (seed, step, env). */
+int32_t hg_terrain_reset_prepare(const HgTerrain* T, const uint8_t* reset_buf, const float* root_states,
+                                 const float* commands, int64_t* terrain_levels, const int64_t* terrain_types,
+                                 float* env_origins, float* spawn, const int64_t* r_level, const float* u_root,
+                                 uint64_t seed, uint64_t step, const uint64_t* step_dev, int64_t N, void* stream);
+
+/* XBotLFreeEnv.compute_observations with measure_heights (humanoid_env.py:246-248,253-258,264-269): the critic
+ * frame becomes [obs_buf of the PREVIOUS step (num_obs wide, already clipped) | clip(root_z - 0.5 - heights, -1, 1)
+ * * height_scale], W = num_obs + P wide; priv_out = the `frames`-deep history (oldest first) with that frame
+ * appended, rows of reset envs zeroed before the append (reset_buf may be NULL: a stand-alone compute_observations),
+ * everything clipped to +-clip_obs.  Pitches in elements. */
+int32_t hg_terrain_priv_frames(const float* obs_prev, int64_t obs_pitch, int32_t num_obs, const float* root_states,
+                               const float* heights, int32_t P, float height_scale, float clip_obs,
+                               const uint8_t* reset_buf, const float* priv_in, float* priv_out, int64_t priv_pitch,
+                               int32_t frames, int64_t N, void* stream);
+
 /* ------------------------------------------------------------------------ */
 /* Learning side                                                            */
 /* ------------------------------------------------------------------------ */

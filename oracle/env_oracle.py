@@ -123,6 +123,60 @@ def _uniform(lo, hi, u):                                    # isaacgym torch_ran
     return (hi - lo) * u + lo
 
 
+def quat_apply_yaw(q, v):                                   # utils/math.py:38-43 (isaacgym normalize: x / |x|.clamp(min=1e-9))
+    qy = q.clone().view(-1, 4)
+    qy[:, :2] = 0.
+    qy = qy / qy.norm(p=2, dim=-1).clamp(min=1e-9).unsqueeze(-1)
+    return quat_apply(qy, v.reshape(-1, 3)).view(v.shape)       # isaacgym quat_apply flattens to (-1, 4) / (-1, 3)
+
+
+# ----------------------------------------------------------------------------
+# rough terrain: P["terrain"] is None on a plane, else a dict
+# ----------------------------------------------------------------------------
+def make_terrain_params(height_samples, terrain_origins, border_size, horizontal_scale, vertical_scale, env_length,
+                        curriculum, measure_heights, points_x=None, points_y=None, height_scale=5.0):
+    """height_samples: int16 (rows, cols) = Terrain.heightsamples; terrain_origins: (levels, types, 3) fp32
+    (legged_robot.py:570,586,695-696); height points as _init_height_points builds them (:743-757)."""
+    T = dict(height_samples=torch.as_tensor(height_samples), terrain_origins=torch.as_tensor(terrain_origins).float(),
+             border_size=border_size, horizontal_scale=horizontal_scale, vertical_scale=vertical_scale,
+             env_length=env_length, max_terrain_level=int(terrain_origins.shape[0]), curriculum=bool(curriculum),
+             measure_heights=bool(measure_heights), height_scale=height_scale)
+    if measure_heights:
+        gx, gy = torch.meshgrid(torch.tensor(points_x), torch.tensor(points_y), indexing="ij")
+        pts = torch.zeros(gx.numel(), 3)
+        pts[:, 0], pts[:, 1] = gx.flatten(), gy.flatten()
+        T["height_points"] = pts
+    return T
+
+
+def get_heights(S, P):                                      # legged_robot.py:759-795
+    T = P["terrain"]
+    N = S["root_states"].shape[0]
+    pts = T["height_points"].unsqueeze(0).repeat(N, 1, 1)
+    npts = pts.shape[1]
+    q = S["root_states"][:, 3:7]
+    points = quat_apply_yaw(q.repeat(1, npts), pts) + (S["root_states"][:, :3]).unsqueeze(1)
+    points += T["border_size"]
+    points = (points / T["horizontal_scale"]).long()
+    hs = T["height_samples"]
+    px = torch.clip(points[:, :, 0].view(-1), 0, hs.shape[0] - 2)
+    py = torch.clip(points[:, :, 1].view(-1), 0, hs.shape[1] - 2)
+    h = torch.min(torch.min(hs[px, py], hs[px + 1, py]), hs[px, py + 1])
+    return h.view(N, -1) * T["vertical_scale"]
+
+
+def update_terrain_curriculum(S, P, ids, r_level):          # legged_robot.py:400-420
+    """r_level (N,) int64: the torch.randint_like draw, densified per env."""
+    T = P["terrain"]
+    distance = torch.norm(S["root_states"][ids, :2] - S["env_origins"][ids, :2], dim=1)
+    move_up = distance > T["env_length"] / 2
+    move_down = (distance < torch.norm(S["commands"][ids, :2], dim=1) * P["max_episode_length_s"] * 0.5) * ~move_up
+    S["terrain_levels"][ids] += 1 * move_up - 1 * move_down
+    S["terrain_levels"][ids] = torch.where(S["terrain_levels"][ids] >= T["max_terrain_level"], r_level[ids],
+                                           torch.clip(S["terrain_levels"][ids], 0))
+    S["env_origins"][ids] = T["terrain_origins"][S["terrain_levels"][ids], S["terrain_types"][ids]]
+
+
 # ----------------------------------------------------------------------------
 # state
 # ----------------------------------------------------------------------------
@@ -375,6 +429,9 @@ def step_callback(S, P, noise):
     fwd = quat_apply(q, torch.tensor([1., 0., 0.]).repeat(q.shape[0], 1))
     heading = torch.atan2(fwd[:, 1], fwd[:, 0])
     S["commands"][:, 2] = torch.clip(0.5 * wrap_to_pi(S["commands"][:, 3] - heading), -1., 1.)
+    T = P.get("terrain")
+    if T is not None and T["measure_heights"]:                  # :316-317
+        S["measured_heights"] = get_heights(S, P)
     if S["common_step_counter"] % P["push_interval"] == 0:
         u = noise["u_push"]
         mv, ma = P["max_push_vel_xy"], P["max_push_ang_vel"]
@@ -407,10 +464,15 @@ def reset_idx(S, P, ids, noise):
     """legged_robot.py:163-215 + :359-397 + humanoid_env.py:264-269."""
     if len(ids) == 0:
         return
+    T = P.get("terrain")
+    if T is not None and T["curriculum"] and S.get("init_done", True):       # :175-177, :407-409
+        update_terrain_curriculum(S, P, ids, noise["r_level"])
     S["dof_pos"][ids] = P["default_dof_pos"] + _uniform(-0.1, 0.1, noise["u_dof"][ids])
     S["dof_vel"][ids] = 0.
     S["root_states"][ids] = torch.tensor(P["base_init_state"])
     S["root_states"][ids, :3] += S["env_origins"][ids]
+    if T is not None:                                                         # custom origins :381-384
+        S["root_states"][ids, :2] += _uniform(-1., 1., noise["u_root"][ids])
     resample_commands(S, P, ids, noise["u_cmd_rs"])
     for k in ("last_last_actions", "actions", "last_actions", "last_dof_vel", "feet_air_time"):
         S[k][ids] = 0.
@@ -458,6 +520,10 @@ def compute_observations(S, P, z_obs):
         S["env_frictions"], S["body_mass"] / 30., stance, contact), dim=-1)
     obs = torch.cat((cmd_in, q, dq, S["actions"], S["base_ang_vel"] * P["obs_scale_ang_vel"],
                      S["base_euler_xyz"] * P["obs_scale_quat"]), dim=-1)
+    T = P.get("terrain")
+    if T is not None and T["measure_heights"]:                  # humanoid_env.py:246-248: [STACKED obs of the last step | heights]
+        heights = torch.clip(S["root_states"][:, 2].unsqueeze(1) - 0.5 - S["measured_heights"], -1, 1.) * T["height_scale"]
+        priv = torch.cat((S["obs_buf"], heights), dim=-1)
     if P["add_noise"]:
         obs = obs + z_obs * P["noise_scale_vec"] * P["noise_level"]
     S["obs_hist"] = torch.cat((S["obs_hist"][:, 1:], obs.unsqueeze(1)), dim=1)

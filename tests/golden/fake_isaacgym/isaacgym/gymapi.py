@@ -49,6 +49,16 @@ class AssetOptions:
     pass
 
 
+class HeightFieldParams:
+    def __init__(self):
+        self.transform = Transform()
+
+
+class TriangleMeshParams:
+    def __init__(self):
+        self.transform = Transform()
+
+
 class CameraProperties:
     pass
 
@@ -156,6 +166,13 @@ class Gym:
 
     def add_ground(self, sim, plane_params):
         pass
+
+    def add_heightfield(self, sim, samples, params):
+        sim.terrain = ("heightfield", samples.shape, params)
+
+    def add_triangle_mesh(self, sim, vertices, triangles, params):
+        assert vertices.size == 3 * params.nb_vertices and triangles.size == 3 * params.nb_triangles
+        sim.terrain = ("trimesh", vertices.shape, params)
 
     def load_asset(self, sim, root, file, options):
         path = os.path.join(root, file)

@@ -1,1 +1,20 @@
-"""Empty: XBotLCfg uses mesh_type='plane' (reference humanoid_config.py:72)."""
+"""TEST-ONLY stand-in for isaacgym.terrain_utils: the product's restatement of the Isaac Gym primitives
+(humanoid-gym_b200/humanoid/utils/terrain.py, loaded by file path -- the product package is not imported).  The
+reference's Terrain / HumanoidTerrain classes (utils/terrain.py) run UNMODIFIED on top of it, which is what
+tests/golden/terrain.npz pins; the primitives themselves are third-party and parity-unpinned."""
+import importlib.util
+import os
+
+_REPO = os.path.dirname(os.path.dirname(os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))))
+_spec = importlib.util.spec_from_file_location(
+    "_hg_terrain_primitives", os.path.join(_REPO, "humanoid-gym_b200", "humanoid", "utils", "terrain.py"))
+_m = importlib.util.module_from_spec(_spec)
+_spec.loader.exec_module(_m)
+
+SubTerrain = _m.SubTerrain
+random_uniform_terrain = _m.random_uniform_terrain
+pyramid_sloped_terrain = _m.pyramid_sloped_terrain
+pyramid_stairs_terrain = _m.pyramid_stairs_terrain
+discrete_obstacles_terrain = _m.discrete_obstacles_terrain
+stepping_stones_terrain = _m.stepping_stones_terrain
+convert_heightfield_to_trimesh = _m.convert_heightfield_to_trimesh

@@ -15,6 +15,8 @@ Outputs
   ppo_learning.npz       : ActorCritic fwd, GAE, one PPO.update() incl. gradients
   policy_example_kat.npz : weights + known answers of the reference's only
                            shipped fixture (logs/XBot_ppo/exported/policies/policy_example.pt)
+  env_terrain.npz        : the same env on rough terrain (mesh_type 'trimesh', terrain curriculum, measured heights
+                           in the critic frames): HumanoidTerrain's height field + chained env.step() calls
 """
 import argparse
 import os
@@ -26,6 +28,7 @@ import torch
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 REF = os.environ.get("HG_REFERENCE_ROOT", "/root/reference")
+_REAL = dict(rand=torch.rand, randn_like=torch.randn_like, randint_like=torch.randint_like)   # instrument_env patches these
 
 
 def _install_shims():
@@ -85,11 +88,13 @@ class DrawRecorder:
         self.z_obs = np.zeros((n, 47), np.float32)
         self.u_delay = np.zeros((n, 1), np.float32)
         self.z_act = np.zeros((n, 12), np.float32)
+        self.u_root = np.zeros((n, 2), np.float32)       # rough terrain: spawn jitter (legged_robot.py:384)
+        self.r_level = np.zeros((n,), np.int64)          # rough terrain: random level after the last one (:418)
         self._cmd_call = 0
 
-    def noise(self):
-        return {k: getattr(self, k).copy() for k in
-                ("u_cmd_cb", "u_cmd_rs", "u_dof", "u_push", "z_obs", "u_delay", "z_act")}
+    def noise(self, terrain=False):
+        keys = ("u_cmd_cb", "u_cmd_rs", "u_dof", "u_push", "z_obs", "u_delay", "z_act") + (("u_root", "r_level") if terrain else ())
+        return {k: getattr(self, k).copy() for k in keys}
 
     # replacement for isaacgym.torch_utils.torch_rand_float inside the reference modules
     def torch_rand_float(self, lower, upper, shape, device):
@@ -107,9 +112,20 @@ class DrawRecorder:
                 self.u_push[:, 0:2] = u.numpy()
             else:
                 self.u_push[:, 2:5] = u.numpy()
+        elif kind == "root":
+            self.u_root[ids.numpy()] = u.numpy()
         else:
             raise RuntimeError(f"unexpected draw in ctx {self.ctx}")
         return (upper - lower) * u + lower
+
+
+def uninstrument():
+    """Undo instrument_env's module-level patches (a second env built in the same process must draw un-recorded)."""
+    import humanoid.envs.base.legged_robot as lr
+    import humanoid.envs.custom.humanoid_env as he
+    from isaacgym.torch_utils import torch_rand_float
+    lr.torch_rand_float = he.torch_rand_float = torch_rand_float
+    torch.rand, torch.randn_like, torch.randint_like = _REAL["rand"], _REAL["randn_like"], _REAL["randint_like"]
 
 
 def instrument_env(env, rec):
@@ -149,7 +165,29 @@ def instrument_env(env, rec):
     env._push_robots = push
     env.reset_idx = reset_idx
 
-    real_rand, real_randn_like = torch.rand, torch.randn_like
+    if env.custom_origins:                               # rough terrain: two more draws inside reset_idx
+        orig_root, orig_curr = env._reset_root_states, env._update_terrain_curriculum
+
+        def reset_root_states(env_ids):
+            rec.ctx = ("root", env_ids.clone())
+            orig_root(env_ids)
+            rec.ctx = None
+
+        def update_terrain_curriculum(env_ids):
+            def randint_like(t, high, **k):
+                r = _REAL["randint_like"](t, high, **k)
+                rec.r_level[env_ids.numpy()] = r.numpy()
+                return r
+            torch.randint_like = randint_like
+            try:
+                orig_curr(env_ids)
+            finally:
+                torch.randint_like = _REAL["randint_like"]
+
+        env._reset_root_states = reset_root_states
+        env._update_terrain_curriculum = update_terrain_curriculum
+
+    real_rand, real_randn_like = _REAL["rand"], _REAL["randn_like"]
 
     def rand(*a, **k):
         u = real_rand(*a, **k)
@@ -268,6 +306,160 @@ def make_env_golden(out_path, n_envs=24, n_steps=56):
     np.savez_compressed(out_path, **data)
     print(f"wrote {out_path}: {n_steps} steps x {n_envs} envs, {n_reset} resets,"
           f" {os.path.getsize(out_path) / 1e6:.2f} MB")
+
+
+def make_terrain_golden(out_path, n_envs=20, n_steps=24):
+    """XBotLFreeEnv on rough terrain: HumanoidTerrain (reference utils/terrain.py, UNMODIFIED) over the restated Isaac Gym
+    primitives, `_get_heights`, `_update_terrain_curriculum`, the custom-origin spawn and the height-augmented critic frames
+    (humanoid_env.py:246-248; the cfg sizes the critic for them, otherwise the reference fails in its first matmul)."""
+    from humanoid.envs import XBotLCfg, XBotLFreeEnv  # noqa: F401
+    from humanoid.utils import task_registry
+    uninstrument()
+
+    class TerrainCfg(XBotLCfg):
+        class env(XBotLCfg.env):
+            single_num_privileged_obs = XBotLCfg.env.num_observations + 17 * 11
+            num_privileged_obs = int(XBotLCfg.env.c_frame_stack * single_num_privileged_obs)
+
+        class terrain(XBotLCfg.terrain):
+            mesh_type, curriculum, measure_heights = "trimesh", True, True
+            num_rows, num_cols, border_size, max_init_terrain_level = 4, 5, 5, 3
+            terrain_proportions = [0.1, 0.25, 0.25, 0.1, 0.1, 0.1, 0.1]
+
+    args = argparse.Namespace(
+        task="humanoid_ppo", resume=False, experiment_name=None, run_name=None, load_run=None,
+        checkpoint=None, headless=True, horovod=False, rl_device="cpu", num_envs=n_envs, seed=5,
+        max_iterations=None, physics_engine=1, use_gpu=False, use_gpu_pipeline=False, subscenes=0,
+        num_threads=0, sim_device="cpu", sim_device_type="cpu", compute_device_id=0, sim_device_id=0,
+        device="cpu")
+    env_cfg = TerrainCfg()
+    env_cfg.seed = 5                                 # task_registry.get_cfgs copies the runner's seed (task_registry.py:74-76)
+    env, cfg = task_registry.make_env(name="humanoid_ppo", args=args, env_cfg=env_cfg)
+    tc = env.cfg.terrain
+    data = {
+        "meta.height_samples": env.height_samples.numpy().copy(), "meta.terrain_origins": env.terrain_origins.numpy().copy(),
+        "meta.terrain_env_origins_f64": env.terrain.env_origins.copy(),
+        "meta.vertices_head": env.terrain.vertices[:4096].copy(), "meta.triangles_head": env.terrain.triangles[:4096].copy(),
+        "meta.n_vertices": np.int64(env.terrain.vertices.shape[0]), "meta.n_triangles": np.int64(env.terrain.triangles.shape[0]),
+        "meta.vertices_sum": np.float64(env.terrain.vertices.astype(np.float64).sum()),
+        "meta.terrain_types": env.terrain_types.numpy().copy(), "meta.init_terrain_levels": env.terrain_levels.numpy().copy(),
+        "meta.border_size": np.float64(tc.border_size), "meta.horizontal_scale": np.float64(tc.horizontal_scale),
+        "meta.vertical_scale": np.float64(tc.vertical_scale), "meta.env_length": np.float64(env.terrain.env_length),
+        "meta.num_rows": np.int64(tc.num_rows), "meta.num_cols": np.int64(tc.num_cols),
+        "meta.max_init_terrain_level": np.int64(tc.max_init_terrain_level),
+        "meta.terrain_proportions": np.array(tc.terrain_proportions, np.float64),
+        "meta.measured_points_x": np.array(tc.measured_points_x, np.float64),
+        "meta.measured_points_y": np.array(tc.measured_points_y, np.float64),
+        "meta.height_scale": np.float64(env.obs_scales.height_measurements),
+        "meta.np_seed": np.int64(cfg.seed), "meta.n_steps": np.int64(n_steps), "meta.n_envs": np.int64(n_envs),
+    }
+    rec = DrawRecorder(n_envs)
+    instrument_env(env, rec)
+
+    def tsnap():
+        out = snap_terrain(env)
+        return out
+
+    def snap_terrain(env):
+        out = {}
+        for k in STATE_KEYS:
+            v = getattr(env, k)
+            out[k] = v.detach().clone().numpy() if isinstance(v, torch.Tensor) else np.asarray(v)
+        lf = env.last_feet_z
+        out["last_feet_z"] = lf.clone().numpy() if isinstance(lf, torch.Tensor) else np.full((n_envs, 2), lf, np.float32)
+        out["episode_sums"] = np.stack([env.episode_sums[k].numpy().copy() for k in env.reward_names])
+        out["obs_hist"] = torch.stack(list(env.obs_history), dim=1).numpy().copy()
+        out["critic_hist"] = torch.stack(list(env.critic_history), dim=1).numpy().copy()
+        out["obs_buf"] = env.obs_buf.numpy().copy()
+        out["privileged_obs_buf"] = env.privileged_obs_buf.numpy().copy()
+        out["common_step_counter"] = np.int64(env.common_step_counter)
+        out["terrain_levels"] = env.terrain_levels.numpy().copy()
+        mh = env.measured_heights
+        out["measured_heights"] = mh.numpy().copy() if isinstance(mh, torch.Tensor) else np.zeros((n_envs, 187), np.float32)
+        return out
+
+    g = torch.Generator().manual_seed(78)
+    ep = torch.randint(0, 2300, (n_envs,), generator=g)
+    env.episode_length_buf[:] = ep
+    # The reference's FIRST critic frame is malformed in this mode: __init__ calls compute_observations() while
+    # measured_heights is still the scalar 0 (legged_robot.py:483), so the frame is 705 + 1 wide and privileged_obs_buf only
+    # reaches its nominal 3 x 892 columns once c_frame_stack steps have pushed it out.  The fixture starts from there.
+    for _ in range(env.cfg.env.c_frame_stack):
+        env.step(torch.zeros(n_envs, 12))
+    assert env.privileged_obs_buf.shape == (n_envs, 3 * 892)
+    env.common_step_counter = 395                    # a push inside the rollout
+    for k, v in tsnap().items():
+        data[f"init.{k}"] = v
+
+    last_torque_in = {}
+    orig_ct = env._compute_torques
+
+    def compute_torques(actions):
+        last_torque_in["dof_pos"] = env.dof_pos.clone().numpy()
+        last_torque_in["dof_vel"] = env.dof_vel.clone().numpy()
+        return orig_ct(actions)
+
+    env._compute_torques = compute_torques
+    orig_pps = env.post_physics_step
+    pre_post = {}
+    plan = {}                                        # step -> what the stand-in physics did to a few robots
+
+    def post_physics_step():
+        t = plan["t"]
+        r = env.root_states
+        # walk robots around so that the height samples change and the curriculum sees every case:
+        #  far from the origin (> env_length / 2) -> level up (wraps to a random level from the last one);
+        #  close to it with a non-zero command -> level down (floor 0); zero command -> unchanged
+        r[:, 0:2] += 0.35 * torch.randn(n_envs, 2, generator=g)
+        if t % 4 == 1:
+            far = torch.tensor([(3 * t) % n_envs, (3 * t + 7) % n_envs])
+            r[far, 0] += 4.6
+            env.episode_length_buf[far] = 2400       # they time out this step -> reset -> curriculum
+            near = torch.tensor([(3 * t + 11) % n_envs])
+            env.episode_length_buf[near] = 2400
+        if t == 9:
+            env.terrain_levels[:] = tc.num_rows - 1   # next promotions wrap around
+        pre_post["pre"] = tsnap()
+        orig_pps()
+
+    env.post_physics_step = post_physics_step
+
+    ag = torch.Generator().manual_seed(98)
+    n_reset = 0
+    for t in range(n_steps):
+        rec.new_step()
+        plan["t"] = t
+        act_in = 2.0 * torch.randn(n_envs, 12, generator=ag)
+        obs, priv, rew, reset, extras = env.step(act_in.clone())
+        noise = rec.noise(terrain=True)
+        pre, post = pre_post["pre"], tsnap()
+        p = f"step{t:03d}."
+        data[p + "actions_in"] = act_in.numpy()
+        for k, v in noise.items():
+            data[p + "noise." + k] = v
+        data[p + "torque_in.dof_pos"] = last_torque_in["dof_pos"]
+        data[p + "torque_in.dof_vel"] = last_torque_in["dof_vel"]
+        for k in ("root_states", "dof_pos", "dof_vel", "contact_forces", "rigid_state", "actions", "torques",
+                  "episode_length_buf", "terrain_levels"):
+            data[p + "pre." + k] = pre[k]
+        for k in STATE_KEYS + ("last_feet_z", "episode_sums", "terrain_levels", "measured_heights"):
+            if k in ("contact_forces", "rigid_state", "env_frictions", "body_mass"):
+                continue
+            data[p + "post." + k] = post[k]
+        W = 705 + 187
+        data[p + "post.obs_frame"] = obs[:, -47:].numpy().copy()
+        data[p + "post.priv_frame"] = priv[:, -W:].numpy().copy()
+        if t % 8 == 7 or t == n_steps - 1:
+            data[p + "post.obs_buf"] = obs.numpy().copy()
+            data[p + "post.privileged_obs_buf"] = priv.numpy().copy()
+        data[p + "post.extras_time_outs"] = extras["time_outs"].numpy().copy()
+        data[p + "post.episode_means"] = np.array(
+            [float(extras["episode"]["rew_" + k]) for k in env.reward_names], np.float32)
+        data[p + "post.extras_terrain_level"] = np.float32(float(extras["episode"]["terrain_level"]))
+        n_reset += int(reset.sum())
+    np.savez_compressed(out_path, **data)
+    print(f"wrote {out_path}: {n_steps} steps x {n_envs} envs, {n_reset} resets,"
+          f" height field {env.height_samples.shape}, {os.path.getsize(out_path) / 1e6:.2f} MB")
 
 
 # --------------------------------------------------------------------------
@@ -400,7 +592,7 @@ def make_cfg_golden(out_path):
 if __name__ == "__main__":
     _install_shims()
     torch.set_num_threads(1)
-    which = sys.argv[1:] or ["env", "ppo", "kat", "cfg"]
+    which = sys.argv[1:] or ["env", "ppo", "kat", "cfg", "terrain"]
     if "env" in which:
         make_env_golden(os.path.join(HERE, "env_rollout.npz"))
     if "ppo" in which:
@@ -409,3 +601,5 @@ if __name__ == "__main__":
         make_cfg_golden(os.path.join(HERE, "cfg_dump.json"))
     if "kat" in which:
         make_policy_kat(os.path.join(HERE, "policy_example_kat.npz"))
+    if "terrain" in which:
+        make_terrain_golden(os.path.join(HERE, "env_terrain.npz"))

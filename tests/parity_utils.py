@@ -29,16 +29,46 @@ def make_args(num_envs, device="cuda:0"):
         sim_device_type="cuda", compute_device_id=0, sim_device_id=0)
 
 
-def make_env(num_envs, physics="external", device="cuda:0"):
+def make_env(num_envs, physics="external", device="cuda:0", cfg=None):
     from humanoid.envs import XBotLCfg, XBotLFreeEnv
     from humanoid.utils.helpers import class_to_dict, parse_sim_params
-    cfg = XBotLCfg()
+    cfg = XBotLCfg() if cfg is None else cfg
     cfg.env.num_envs = num_envs
     cfg.seed = 5
     cfg.physics_backend = physics
     args = make_args(num_envs, device)
     sim_params = parse_sim_params(args, {"sim": class_to_dict(cfg.sim)})
     return XBotLFreeEnv(cfg, sim_params, args.physics_engine, device, True)
+
+
+def terrain_cfg_from_golden(g, num_envs=None):
+    """XBotLCfg as tests/golden/make_golden.py::make_terrain_golden configured the reference (rough terrain, curriculum,
+    measured heights in the critic frames)."""
+    from humanoid.envs import XBotLCfg
+
+    class TerrainCfg(XBotLCfg):
+        class env(XBotLCfg.env):
+            single_num_privileged_obs = XBotLCfg.env.num_observations + 17 * 11
+            num_privileged_obs = int(XBotLCfg.env.c_frame_stack * single_num_privileged_obs)
+
+        class terrain(XBotLCfg.terrain):
+            mesh_type, curriculum, measure_heights = "trimesh", True, True
+            num_rows, num_cols = int(g["meta.num_rows"]), int(g["meta.num_cols"])
+            border_size, max_init_terrain_level = int(g["meta.border_size"]), int(g["meta.max_init_terrain_level"])
+            terrain_proportions = [float(x) for x in g["meta.terrain_proportions"]]
+    cfg = TerrainCfg()
+    cfg.seed = 5
+    if num_envs is not None:
+        cfg.env.num_envs = num_envs
+    return cfg
+
+
+def terrain_params_from_golden(g):
+    return eo.make_terrain_params(
+        g["meta.height_samples"], g["meta.terrain_origins"], float(g["meta.border_size"]), float(g["meta.horizontal_scale"]),
+        float(g["meta.vertical_scale"]), float(g["meta.env_length"]), curriculum=True, measure_heights=True,
+        points_x=[float(x) for x in g["meta.measured_points_x"]], points_y=[float(x) for x in g["meta.measured_points_y"]],
+        height_scale=float(g["meta.height_scale"]))
 
 
 def random_state(N, g, p_base_contact=0.03, ep_max=2400):
@@ -131,6 +161,8 @@ def load_state(env, S):
         env._episode_means.copy_(S["episode_means"].to(dev))
     if "extras_time_outs" in S:
         env.extras_time_outs.copy_(S["extras_time_outs"].to(dev))
+    if "terrain_levels" in S and getattr(env, "terrain", None) is not None:
+        env.terrain_levels.copy_(S["terrain_levels"].to(dev))
 
 
 def oracle_step(S, noise, actions, physics_after=None):
