@@ -75,7 +75,10 @@ def test_two_launch_step_equals_fused_launch():
         outs[-1]["reset_count"] = torch.tensor(env.last_reset_count)
     assert int(outs[0]["reset_buf"].sum()) > 10
     for k in outs[0]:
-        assert torch.equal(outs[0][k], outs[1][k]), k
+        if k == "episode_means":          # float atomics across CTAs: the summation order differs from launch to launch
+            assert torch.allclose(outs[0][k], outs[1][k], rtol=1e-5, atol=0), k
+        else:
+            assert torch.equal(outs[0][k], outs[1][k]), k
 
 
 def test_golden_terrain_rollout_step_by_step():
@@ -91,6 +94,10 @@ def test_golden_terrain_rollout_step_by_step():
     assert int(env.terrain_levels.max()) <= int(g["meta.max_init_terrain_level"])
 
     S = oracle_state_from_golden(g)
+    if not g.t("step000.post.reset_buf").any():
+        # extras["episode"] is only refreshed on steps with a reset: until the first one the reference still reports the
+        # means of its warm-up steps, which the init snapshot does not carry
+        S["episode_means"] = g.t("step000.post.episode_means")
     hist_o, hist_p = S["obs_hist"].clone(), S["critic_hist"].clone()
     problems = []
     for t in range(steps):
@@ -215,8 +222,7 @@ def test_random_state_vs_oracle_on_terrain(N, seed):
     flips = ~torch.isclose(env.measured_heights.cpu(), R["measured_heights"], rtol=RTOL, atol=ATOL)
     # curriculum: a level may differ only where the walked distance sits on one of its two thresholds
     dist = torch.norm(S["root_states"][:, :2] - S["env_origins"][:, :2], dim=1)
-    need = torch.norm(R["commands"][:, :2], dim=1)           # (commands are resampled AFTER the curriculum; use the pre-step ones)
-    need = torch.norm(S["commands"][:, :2], dim=1) * 24.0 * 0.5
+    need = torch.norm(S["commands"][:, :2], dim=1) * 24.0 * 0.5      # pre-step commands: resampled only after the curriculum
     edge = ((dist - env.terrain.env_length / 2).abs() < 1e-5) | ((dist - need).abs() < 1e-5)
     lv_bad = (env.terrain_levels.cpu() != R["terrain_levels"]) & ~edge
     assert not lv_bad.any(), int(lv_bad.sum())
