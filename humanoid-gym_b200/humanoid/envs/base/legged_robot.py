@@ -72,10 +72,16 @@ class LeggedRobot(BaseTask):
         kind = os.environ.get("HG_PHYSICS", getattr(self.cfg, "physics_backend", "auto"))
         seed = getattr(self.cfg, "seed", 0)
         rank = int(os.environ.get("RANK", "0"))
-        self.gym = phys.make_physics(kind, self.num_envs, self.device, self.cfg, self.env_origins, seed=seed, rank=rank)
+        self.gym = phys.make_physics(kind, self.num_envs, self.device, self.cfg, self.env_origins, seed=seed, rank=rank,
+                                     sim_params=self.sim_params, physics_engine=self.physics_engine,
+                                     sim_device_id=self.sim_device_id, custom_origins=self.custom_origins)
         self.sim = self.gym
         if self.terrain is not None:
             self.gym.add_terrain(self.terrain, mesh_type)
+        real_sim = hasattr(self.gym, "create_actors")             # a simulator: actors carry the randomised properties
+        if real_sim:
+            sim_frictions, sim_masses = self.gym.create_actors()  # _create_envs :638-665
+            self.gym.prepare()                                    # base_task.py:96 + tensor acquisition :438-457
         self.num_dof = self.num_dofs = self.gym.num_dof
         self.num_bodies = self.gym.num_bodies
         self.dof_names = list(self.gym.dof_names)
@@ -86,7 +92,8 @@ class LeggedRobot(BaseTask):
             names = []
             for pat in pattern_list:
                 names.extend(s for s in body_names if pat in s)
-            return torch.tensor([body_names.index(n) for n in names], dtype=torch.long, device=dev)
+            find = self.gym.body_index if real_sim else body_names.index       # find_actor_rigid_body_handle :667-681
+            return torch.tensor([find(n) for n in names], dtype=torch.long, device=dev)
 
         self.feet_indices = indices([self.cfg.asset.foot_name])
         self.knee_indices = indices([self.cfg.asset.knee_name])
@@ -102,9 +109,15 @@ class LeggedRobot(BaseTask):
         init = self.cfg.init_state
         self.base_init_state = torch.tensor(init.pos + init.rot + init.lin_vel + init.ang_vel, dtype=torch.float, device=dev)
 
-        # one-time domain randomisation, drawn on the CPU like the reference (:257-270, :296-302)
         N = self.num_envs
         dr = self.cfg.domain_rand
+        if real_sim:                                              # drawn by the actor loop, per env
+            self.env_frictions = sim_frictions.to(dev)
+            self.body_mass = sim_masses.to(dev)
+            if self.gym.friction_coeffs is not None:
+                self.friction_coeffs = self.gym.friction_coeffs
+            return
+        # one-time domain randomisation, drawn on the CPU like the reference (:257-270, :296-302)
         self.env_frictions = torch.zeros(N, 1, dtype=torch.float32, device=dev)
         if dr.randomize_friction:
             buckets = 256

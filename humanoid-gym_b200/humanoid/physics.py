@@ -6,7 +6,8 @@ The reference talks to Isaac Gym through its tensor API: four state tensors
 legged_robot.py:96-101,124-126,371-373,395-397,438-457; humanoid_env.py:97-98).
 `PhysicsBackend` keeps exactly that surface so `LeggedRobot` reads like the reference:
 
-* `IsaacGymPhysics`   -- thin adapter, used when `isaacgym` is importable (not in this image).
+* `IsaacGymPhysics`   -- the adapter over the real simulator (humanoid/isaacgym_physics.py), used when `isaacgym` is
+  importable (not in this image: the tests run it over the functional fake in tests/golden/fake_isaacgym).
 * `SyntheticPhysics`  -- seeded synthetic tensor source: a ring of
   pre-generated frames, either resident in HBM or in pinned host memory (`host_resident=True`,
   the end-to-end bench arm: every refresh is then a host->device copy inside the step).
@@ -273,7 +274,8 @@ def isaacgym_available():
         return False
 
 
-def make_physics(kind, num_envs, device, cfg, env_origins, seed=5, rank=0):
+def make_physics(kind, num_envs, device, cfg, env_origins, seed=5, rank=0, sim_params=None, physics_engine=None,
+                 sim_device_id=0, custom_origins=False):
     """kind: 'auto' | 'synthetic' | 'synthetic_host' | 'external' | 'isaacgym'."""
     if kind == "auto":
         kind = "isaacgym" if isaacgym_available() else "synthetic"
@@ -284,7 +286,11 @@ def make_physics(kind, num_envs, device, cfg, env_origins, seed=5, rank=0):
     if kind == "external":
         return ExternalPhysics(num_envs, device)
     if kind == "isaacgym":
-        raise NotImplementedError(
-            "Isaac Gym Preview 4 ships no sm_100 build; the adapter seam is PhysicsBackend "
-            "(see INTEGRATION.md) -- select HG_PHYSICS=synthetic on this image")
+        if not isaacgym_available():
+            raise RuntimeError(
+                "HG_PHYSICS=isaacgym: `import isaacgym` failed (Isaac Gym Preview 4 ships no sm_100 build and is not in this "
+                "image) -- select HG_PHYSICS=synthetic, or put a Blackwell-capable build on PYTHONPATH (INTEGRATION.md)")
+        from humanoid.isaacgym_physics import IsaacGymPhysics
+        return IsaacGymPhysics(num_envs, device, cfg, env_origins, sim_params, physics_engine=physics_engine,
+                               sim_device_id=sim_device_id, custom_origins=custom_origins)
     raise ValueError(f"unknown physics backend {kind!r}")

@@ -251,3 +251,94 @@ def test_fused_decimation_matches_the_loop():
             assert torch.equal(getattr(a, k), getattr(b, k)), (t, k)
         assert torch.equal(oa, ob) and torch.equal(pa, pb) and torch.equal(ra, rb) and torch.equal(da, db), t
     assert a.gym.substep == b.gym.substep == steps * 10
+
+
+def test_env_over_isaacgym_adapter(monkeypatch):
+    """the env over IsaacGymPhysics (real gym API; here the functional fake of tests/golden/fake_isaacgym
+    in ring mode on cuda:0, because Isaac Gym has no sm_100 build) steps exactly like the env over ExternalPhysics fed with
+    the same frames, and drives the simulator with the reference's call sequence (legged_robot.py:94-101,124-126,371-397)."""
+    import os
+    import sys
+    from humanoid import physics
+    here = os.path.dirname(os.path.abspath(__file__))
+    monkeypatch.syspath_prepend(os.path.join(here, "golden", "fake_isaacgym"))
+    monkeypatch.setenv("HG_FAKE_GYM", "ring")
+    for m in [k for k in sys.modules if k == "isaacgym" or k.startswith("isaacgym.")] + ["humanoid.isaacgym_physics"]:
+        monkeypatch.delitem(sys.modules, m, raising=False)
+    assert physics.isaacgym_available()
+    N = 512
+    torch.manual_seed(3)
+    np.random.seed(3)
+    env_a = make_env(N, physics="isaacgym")
+    env_e = make_env(N, physics="external")
+    from humanoid.isaacgym_physics import IsaacGymPhysics
+    assert isinstance(env_a.gym, IsaacGymPhysics) and env_a.root_states.is_cuda and len(env_a.gym.envs) == N
+    assert env_a.feet_indices.tolist() == [6, 12] and env_a.knee_indices.tolist() == [4, 10]
+    assert 0.1 <= float(env_a.env_frictions.min()) and float(env_a.env_frictions.max()) <= 2.0
+    sim, gym = env_a.gym.sim, env_a.gym.gym
+    log = []
+    for name in ("set_dof_actuation_force_tensor", "simulate", "refresh_dof_state_tensor", "refresh_actor_root_state_tensor",
+                 "refresh_net_contact_force_tensor", "refresh_rigid_body_state_tensor", "set_dof_state_tensor_indexed",
+                 "set_actor_root_state_tensor", "set_actor_root_state_tensor_indexed"):
+        real = getattr(gym, name)
+
+        def wrapped(*a, _real=real, _name=name):
+            log.append((_name, a[1:]))
+            return _real(*a)
+        setattr(gym, name, wrapped)
+    env_a.common_step_counter = 395                               # a push at the 5th step
+    env_a.episode_length_buf = torch.randint(0, 2400, (N,), device="cuda")
+    env_a.episode_length_buf[::40] = 2399                         # time-outs -> resets
+    g = torch.Generator().manual_seed(5)
+    dec, K = sim.decimation, sim.ring
+    total_resets = 0
+    for t in range(8):
+        # mirror every buffer of the adapter-driven env into the externally-driven one
+        for k, v in env_a._keepalive.items():
+            if v is not None:
+                env_e._keepalive[k].copy_(v)
+        env_e.obs_buf.copy_(env_a.obs_buf)
+        env_e.privileged_obs_buf.copy_(env_a.privileged_obs_buf)
+        env_e.common_step_counter, env_e._noise_step = env_a.common_step_counter, env_a._noise_step
+        s0 = sim.substep
+        calls = {"n": 0}
+
+        def on_simulate(ph, s0=s0, calls=calls):
+            calls["n"] += 1
+            s = s0 + calls["n"]
+            ph.dof_state.copy_(sim.frames["dof"][(s - 1) % (K * dec)])
+            if calls["n"] == dec:
+                k = ((s - 1) // dec) % K
+                ph.root_states.copy_(sim.frames["root"][k])
+                ph.contact_forces.copy_(sim.frames["contact"][k])
+                ph.rigid_state.copy_(sim.frames["rigid"][k])
+        env_e.gym.on_simulate = on_simulate
+        actions = (2.0 * torch.randn(N, 12, generator=g)).cuda()
+        log.clear()
+        oa = env_a.step(actions.clone())
+        oe = env_e.step(actions.clone())
+        torch.cuda.synchronize()
+        for a, e, what in zip(oa[:4], oe[:4], ("obs", "priv", "rew", "reset")):
+            assert torch.equal(a, e), (t, what)
+        assert torch.equal(oa[4]["time_outs"], oe[4]["time_outs"])
+        for k, v in env_a._keepalive.items():
+            if v is None or k in ("scratch", "reset_ids"):
+                continue
+            if k == "episode_means":
+                assert torch.allclose(v, env_e._keepalive[k], rtol=1e-5, atol=0), (t, k)
+            else:
+                assert torch.equal(v, env_e._keepalive[k]), (t, k)
+        kinds = [c[0] for c in log]
+        assert kinds[:3 * dec] == ["set_dof_actuation_force_tensor", "simulate", "refresh_dof_state_tensor"] * dec
+        assert kinds[3 * dec:3 * dec + 3] == ["refresh_actor_root_state_tensor", "refresh_net_contact_force_tensor",
+                                              "refresh_rigid_body_state_tensor"]
+        tail = kinds[3 * dec + 3:]
+        n_reset = int(oa[3].sum())
+        total_resets += n_reset
+        want = (["set_actor_root_state_tensor"] if env_a.common_step_counter % 400 == 0 else []) + \
+            (["set_dof_state_tensor_indexed", "set_actor_root_state_tensor_indexed"] if n_reset else [])
+        assert tail == want, (t, tail, want)
+        if n_reset:
+            ids = [c for c in log if c[0] == "set_dof_state_tensor_indexed"][0][1]
+            assert ids[2] == n_reset and sorted(ids[1].tolist()) == oa[3].nonzero().flatten().tolist()
+    assert total_resets >= N // 40 and env_a.common_step_counter == 403
