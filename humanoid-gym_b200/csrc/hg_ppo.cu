@@ -345,7 +345,44 @@ __global__ void clip_adam_kernel(AdamArgs a) {
         a.m[i] = m; a.v[i] = v;
     }
 }
-__global__ void adam_finish_kernel(int32_t* step, double* sqnorm) { *step += 1; *sqnorm = 0.0; }
+// one thread after the update: Adam step count, sqnorm re-zeroed, and (optionally) this minibatch's loss statistics added to
+// the running sums PPO.update reports (ppo.py:175-176: mean_value_loss += ..., mean_surrogate_loss += ...)
+__global__ void adam_finish_kernel(int32_t* step, double* sqnorm, const float* stats, float* stats_sum, int n_stats) {
+    *step += 1;
+    *sqnorm = 0.0;
+    if (stats_sum)
+        for (int k = 0; k < n_stats; ++k) stats_sum[k] += stats[k];
+}
+
+// ---------------------------------------------------------------------------------------------
+// minibatch permutation (rollout_storage.py:155: torch.randperm) without a sort: a keyed bijection of [0, 2^b) --
+// an alternating unbalanced Feistel network, 8 half-rounds with a murmur3-finalizer round function -- walked along
+// its cycle until it lands inside [0, n) ("cycle walking"); 2^b < 2n, so fewer than 2 evaluations on average.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t fmix32(uint32_t h) {
+    h ^= h >> 16; h *= 0x85EBCA6Bu; h ^= h >> 13; h *= 0xC2B2AE35u; h ^= h >> 16;
+    return h;
+}
+__global__ void randperm_kernel(int64_t n, int bits_lo, int bits_hi, uint64_t seed, uint64_t counter, int64_t* __restrict__ out) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t mlo = (bits_lo >= 32) ? 0xFFFFFFFFu : ((1u << bits_lo) - 1u);
+    const uint32_t mhi = (bits_hi >= 32) ? 0xFFFFFFFFu : ((1u << bits_hi) - 1u);
+    const HgPhilox kx = hg_philox(seed, (uint32_t)counter, (uint32_t)(counter >> 32), 0x50455246u, 0);   // round keys
+    const HgPhilox ky = hg_philox(seed, (uint32_t)counter, (uint32_t)(counter >> 32), 0x50455246u, 1);
+    const uint32_t key[8] = {kx.c[0], kx.c[1], kx.c[2], kx.c[3], ky.c[0], ky.c[1], ky.c[2], ky.c[3]};
+    uint64_t x = (uint64_t)i;
+    do {
+        uint32_t lo = (uint32_t)x & mlo, hi = (uint32_t)(x >> bits_lo) & mhi;
+#pragma unroll
+        for (int r = 0; r < 8; r += 2) {
+            hi ^= fmix32(lo ^ key[r]) & mhi;
+            lo ^= fmix32(hi ^ key[r + 1]) & mlo;
+        }
+        x = ((uint64_t)hi << bits_lo) | lo;
+    } while (x >= (uint64_t)n);
+    out[i] = (int64_t)x;
+}
 
 // OnPolicyRunner.learn's per-step bookkeeping (on_policy_runner.py:140-154) for one env step: running reward / length of the
 // current episode per env; where the env finished, the totals go to row t of (T, N) result slabs (NaN elsewhere) and the
@@ -463,9 +500,11 @@ extern "C" int32_t hg_grad_sqnorm(const float* grads, int64_t n, double* sqnorm_
     return hg_cuda_status("hg_grad_sqnorm");
 }
 
-extern "C" int32_t hg_clip_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq,
-                                     double* sqnorm, float max_grad_norm, const double* lr_dev, int32_t* step_dev,
-                                     float beta1, float beta2, float eps, float grad_scale, int64_t n, void* stream) {
+extern "C" int32_t hg_clip_adam_step_stats(float* params, const float* grads, float* exp_avg, float* exp_avg_sq,
+                                           double* sqnorm, float max_grad_norm, const double* lr_dev, int32_t* step_dev,
+                                           float beta1, float beta2, float eps, float grad_scale, int64_t n,
+                                           const float* stats, float* stats_sum, int32_t n_stats, void* stream) {
+    if (stats_sum && (!stats || n_stats <= 0 || n_stats > 64)) return hg_fail(HG_E_ARG, "hg_clip_adam_step_stats: stats_sum without stats");
     HG_REQUIRE(params); HG_REQUIRE(grads); HG_REQUIRE(exp_avg); HG_REQUIRE(exp_avg_sq); HG_REQUIRE(sqnorm);
     HG_REQUIRE(lr_dev); HG_REQUIRE(step_dev);
     if (n <= 0) return hg_fail(HG_E_SIZE, "hg_clip_adam_step: bad n");
@@ -474,9 +513,28 @@ extern "C" int32_t hg_clip_adam_step(float* params, const float* grads, float* e
     unsigned grid = (unsigned)((n + 255) / 256);
     if (grid > 8 * HG_NUM_SMS) grid = 8 * HG_NUM_SMS;
     clip_adam_kernel<<<grid, 256, 0, st>>>(a);
-    adam_finish_kernel<<<1, 1, 0, st>>>(step_dev, sqnorm);
+    adam_finish_kernel<<<1, 1, 0, st>>>(step_dev, sqnorm, stats, stats_sum, n_stats);
     HG_LAUNCHED(2);
     return hg_cuda_status("hg_clip_adam_step");
+}
+
+extern "C" int32_t hg_clip_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq,
+                                     double* sqnorm, float max_grad_norm, const double* lr_dev, int32_t* step_dev,
+                                     float beta1, float beta2, float eps, float grad_scale, int64_t n, void* stream) {
+    return hg_clip_adam_step_stats(params, grads, exp_avg, exp_avg_sq, sqnorm, max_grad_norm, lr_dev, step_dev, beta1, beta2, eps,
+                                   grad_scale, n, nullptr, nullptr, 0, stream);
+}
+
+extern "C" int32_t hg_randperm(int64_t n, uint64_t seed, uint64_t counter, int64_t* out, void* stream) {
+    HG_REQUIRE(out);
+    if (n <= 0 || n > ((int64_t)1 << 40)) return hg_fail(HG_E_SIZE, "hg_randperm: bad n");
+    int bits = 1;
+    while (((int64_t)1 << bits) < n) ++bits;
+    if (bits < 2) bits = 2;
+    const int bits_lo = bits / 2, bits_hi = bits - bits_lo;
+    randperm_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(n, bits_lo, bits_hi, seed, counter, out);
+    HG_LAUNCHED(1);
+    return hg_cuda_status("hg_randperm");
 }
 
 extern "C" int32_t hg_episode_book_step(const float* rewards, const uint8_t* dones, float* cur_reward_sum, float* cur_episode_length,

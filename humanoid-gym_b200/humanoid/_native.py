@@ -193,6 +193,8 @@ def _load():
         "hg_ppo_loss_fwd_bwd": (i32, [P(PpoLossArgs), i64, PF]),
         "hg_grad_sqnorm": (i32, [PF, i64, PF, PF]),
         "hg_clip_adam_step": (i32, [PF, PF, PF, PF, PF, f32, PF, PF, f32, f32, f32, f32, i64, PF]),
+        "hg_clip_adam_step_stats": (i32, [PF, PF, PF, PF, PF, f32, PF, PF, f32, f32, f32, f32, i64, PF, PF, i32, PF]),
+        "hg_randperm": (i32, [i64, u64, u64, PF, PF]),
         "hg_adapt_lr": (i32, [PF, C.c_double, PF, PF]),
         "hg_episode_book_step": (i32, [PF, PF, PF, PF, PF, PF, PF, PF, i32, i64, PF]),
     }

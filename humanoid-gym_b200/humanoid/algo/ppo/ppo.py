@@ -303,13 +303,28 @@ class PPO:
             nat.check(nat.lib.hg_adapt_lr(self._scalars.data_ptr() + 12, float(self.desired_kl), self._lr.data_ptr(), st), "hg_adapt_lr")
         n = ac.num_params
         nat.check(nat.lib.hg_grad_sqnorm(g, n, self._sqnorm.data_ptr(), st), "hg_grad_sqnorm")
-        nat.check(nat.lib.hg_clip_adam_step(flat.data_ptr(), g, self._exp_avg.data_ptr(), self._exp_avg_sq.data_ptr(),
-                                            self._sqnorm.data_ptr(), float(self.max_grad_norm), self._lr.data_ptr(),
-                                            self._adam_step.data_ptr(), 0.9, 0.999, 1e-8, 1.0, n, st), "hg_clip_adam_step")
+        # the update's one-thread tail kernel also adds this step's 8 loss statistics to the sums update() reports
+        nat.check(nat.lib.hg_clip_adam_step_stats(flat.data_ptr(), g, self._exp_avg.data_ptr(), self._exp_avg_sq.data_ptr(),
+                                                  self._sqnorm.data_ptr(), float(self.max_grad_norm), self._lr.data_ptr(),
+                                                  self._adam_step.data_ptr(), 0.9, 0.999, 1e-8, 1.0, n,
+                                                  self._scalars.data_ptr(), self._loss_sums.data_ptr(), _TAIL, st),
+                  "hg_clip_adam_step_stats")
         ac.invalidate_derived()
         if split:
             ac.refresh_split()                             # the next minibatch's GEMMs read the split image of the new weights
-        self._loss_sums.add_(self._scalars)
+
+    def _permutation(self, n):
+        """rollout_storage.py:155 `torch.randperm(n)`: one native launch (hg_randperm: keyed bijection + cycle walking, no
+        sort), keyed by the rank-dependent seed and the number of updates so far.  HG_TORCH_RANDPERM=1 keeps torch's."""
+        if os.environ.get("HG_TORCH_RANDPERM", "0") == "1":
+            return torch.randperm(n, requires_grad=False, device=self.device)
+        if getattr(self, "_perm", None) is None or self._perm.numel() != n:
+            self._perm = torch.empty(n, dtype=torch.int64, device=self.device)
+            self._perm_count = 0
+        nat.check(nat.lib.hg_randperm(n, self._seed ^ 0x5045524D55544531, self._perm_count, self._perm.data_ptr(),
+                                      nat.stream_ptr(self._dev_index)), "hg_randperm")
+        self._perm_count += 1
+        return self._perm
 
     def update(self):
         """ppo.py:119-184."""
@@ -317,7 +332,7 @@ class PPO:
         world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
         batch_size = s.num_envs * s.num_transitions_per_env
         mini = batch_size // self.num_mini_batches
-        indices = torch.randperm(self.num_mini_batches * mini, requires_grad=False, device=self.device)
+        indices = self._permutation(self.num_mini_batches * mini)
         self._loss_sums.zero_()
         split = self.use_split_path()
         if split:

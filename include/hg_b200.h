@@ -455,6 +455,19 @@ int32_t hg_grad_sqnorm(const float* grads, int64_t n, double* sqnorm_out, void* 
 int32_t hg_clip_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq,
                           double* sqnorm, float max_grad_norm, const double* lr_dev, int32_t* step_dev,
                           float beta1, float beta2, float eps, float grad_scale, int64_t n, void* stream);
+/* Same, and the one-thread tail kernel also adds this minibatch's n_stats loss statistics `stats` to the running sums
+ * `stats_sum` that PPO.update averages at its end (ppo.py:175-184): no separate accumulation op per optimizer step. */
+int32_t hg_clip_adam_step_stats(float* params, const float* grads, float* exp_avg, float* exp_avg_sq,
+                                double* sqnorm, float max_grad_norm, const double* lr_dev, int32_t* step_dev,
+                                float beta1, float beta2, float eps, float grad_scale, int64_t n,
+                                const float* stats, float* stats_sum, int32_t n_stats, void* stream);
+
+/* Minibatch permutation of PPO.update (rollout_storage.py:155 `torch.randperm`): out[0..n) = a pseudo-random permutation
+ * of 0..n-1 determined by (seed, counter), in ONE launch and without a sort (keyed Feistel bijection of the enclosing
+ * power-of-two range + cycle walking).  It is a different generator than torch's, so the minibatch COMPOSITION differs
+ * from a torch run with the same seed -- as it does between any two torch seeds; every sample is still used exactly once
+ * per epoch. */
+int32_t hg_randperm(int64_t n, uint64_t seed, uint64_t counter, int64_t* out, void* stream);
 
 /* OnPolicyRunner.learn's per-step episode bookkeeping (on_policy_runner.py:140-154), one launch, no host sync:
  * cur_reward_sum += rewards; cur_episode_length += 1; for finished envs (dones != 0) the totals are written to

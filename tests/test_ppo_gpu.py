@@ -517,3 +517,43 @@ def test_export_policy_as_jit_roundtrip(tmp_path):
     y_native = ac.act_inference(x.cuda()).cpu()
     assert _rel(y_native, y) < 1e-5
     assert ac.actor[0].weight.is_cuda                      # exporting must not move the live module off the GPU
+
+
+@pytest.mark.parametrize("n", [1, 2, 7, 1000, 4096, 245760, 1 << 20, (1 << 20) + 1])
+def test_native_randperm_is_a_permutation(n):
+    """hg_randperm (the minibatch permutation of PPO.update, rollout_storage.py:155): every index exactly once, a pure
+    function of (seed, counter), different for different counters / seeds."""
+    from humanoid import _native as nat
+    out = torch.empty(3, n, dtype=torch.int64, device="cuda")
+    for k, (seed, ctr) in enumerate(((11, 0), (11, 1), (12, 0))):
+        nat.check(nat.lib.hg_randperm(n, seed, ctr, out[k].data_ptr(), nat.stream_ptr(0)), "hg_randperm")
+    again = torch.empty(n, dtype=torch.int64, device="cuda")
+    nat.check(nat.lib.hg_randperm(n, 11, 0, again.data_ptr(), nat.stream_ptr(0)), "hg_randperm")
+    torch.cuda.synchronize()
+    ar = torch.arange(n, device="cuda")
+    for k in range(3):
+        assert torch.equal(torch.sort(out[k]).values, ar)
+    assert torch.equal(out[0], again)
+    if n >= 1000:
+        assert not torch.equal(out[0], out[1]) and not torch.equal(out[0], out[2])
+        # no visible structure: fixed points are rare, neighbours are not kept together, the first half is a fair sample
+        assert int((out[0] == ar).sum()) < 12
+        assert int(((out[0][1:] - out[0][:-1]).abs() == 1).sum()) < 24
+        assert abs(float((out[0][: n // 2] < n // 2).double().mean()) - 0.5) < 5.0 / np.sqrt(n)
+
+
+def test_native_randperm_uniform_positions():
+    """Over many keys each position receives each value about equally often (chi-square on a 64-element permutation)."""
+    from humanoid import _native as nat
+    n, trials = 64, 8192
+    out = torch.empty(trials, n, dtype=torch.int64, device="cuda")
+    for t in range(trials):
+        nat.check(nat.lib.hg_randperm(n, 99, t, out[t].data_ptr(), nat.stream_ptr(0)), "hg_randperm")
+    torch.cuda.synchronize()
+    counts = torch.zeros(n, n, device="cuda")
+    counts.index_put_((torch.arange(n, device="cuda").repeat(trials), out.flatten()), torch.ones(trials * n, device="cuda"),
+                      accumulate=True)
+    expected = trials / n
+    chi2 = float(((counts - expected) ** 2 / expected).sum())
+    dof = (n - 1) ** 2
+    assert abs(chi2 - dof) < 6 * np.sqrt(2 * dof), (chi2, dof)
