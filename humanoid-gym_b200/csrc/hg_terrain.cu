@@ -9,30 +9,38 @@ namespace {
 
 // LeggedRobot._get_heights, legged_robot.py:759-795; quat_apply_yaw utils/math.py:38-43 with Isaac Gym's
 // normalize (x / |x|.clamp(min=1e-9)) and quat_apply (b + w t + xyz x t, t = 2 xyz x b), xyzw quaternions.
-__global__ void get_heights_kernel(HgTerrain T, const float* __restrict__ root, const float* __restrict__ pts, int P,
-                                   float* __restrict__ heights, int64_t total) {
-    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= total) return;
-    const int64_t e = i / P;
-    const int p = (int)(i - e * P);
+// One CTA per env: thread 0 normalises the yaw quaternion once (sqrt + 2 divisions), the others wait for it; every
+// thread then owns points p, p + blockDim, ...: ~10 flops, two IEEE divisions, three int16 gathers that stay in L1 (the
+// 187 points of a robot cover a 17 x 11-cell patch), one coalesced store.
+__global__ void __launch_bounds__(192) get_heights_kernel(HgTerrain T, const float* __restrict__ root, const float* __restrict__ pts, int P,
+                                                          float* __restrict__ heights) {
+    __shared__ float sh[4];
+    const int64_t e = blockIdx.x;
     const float* r = root + e * 13;
-    float qz = r[5], qw = r[6];
-    float n = sqrtf(qz * qz + qw * qw);          // quat_yaw = (0, 0, z, w): the two zeroed components add nothing
-    n = fmaxf(n, 1e-9f);
-    qz = qz / n; qw = qw / n;
-    const float bx = pts[2 * p], by = pts[2 * p + 1];                 // height_points[..., 2] = 0
-    const float tx = (0.0f - qz * by) * 2.0f, ty = (qz * bx) * 2.0f;   // t = cross((0,0,z), b) * 2
-    const float cx = 0.0f - qz * ty, cy = qz * tx;                     // cross((0,0,z), t)
-    float x = (bx + qw * tx) + cx, y = (by + qw * ty) + cy;
-    x = x + r[0]; y = y + r[1];                                       // + root_states[:, :3]
-    x = x + T.border_size; y = y + T.border_size;                     // points += border_size
-    long long px = (long long)(x / T.horizontal_scale);               // (points / horizontal_scale).long(): truncation
-    long long py = (long long)(y / T.horizontal_scale);
-    px = px < 0 ? 0 : (px > T.rows - 2 ? T.rows - 2 : px);            // clip to [0, shape-2]
-    py = py < 0 ? 0 : (py > T.cols - 2 ? T.cols - 2 : py);
-    const int16_t* hs = T.height_samples + px * T.cols + py;
-    int h = min(min((int)hs[0], (int)hs[T.cols]), (int)hs[1]);         // (px,py), (px+1,py), (px,py+1)
-    heights[i] = (float)h * T.vertical_scale;
+    if (threadIdx.x == 0) {
+        float qz = r[5], qw = r[6];
+        float n = sqrtf(qz * qz + qw * qw);          // quat_yaw = (0, 0, z, w): the two zeroed components add nothing
+        n = fmaxf(n, 1e-9f);
+        sh[0] = qz / n; sh[1] = qw / n; sh[2] = r[0]; sh[3] = r[1];
+    }
+    __syncthreads();
+    const float qz = sh[0], qw = sh[1], rx = sh[2], ry = sh[3];
+    for (int p = threadIdx.x; p < P; p += blockDim.x) {
+        const float bx = pts[2 * p], by = pts[2 * p + 1];                 // height_points[..., 2] = 0
+        const float tx = (0.0f - qz * by) * 2.0f, ty = (qz * bx) * 2.0f;   // t = cross((0,0,z), b) * 2
+        const float cx = 0.0f - qz * ty, cy = qz * tx;                     // cross((0,0,z), t)
+        float x = (bx + qw * tx) + cx, y = (by + qw * ty) + cy;
+        x = x + rx; y = y + ry;                                           // + root_states[:, :3]
+        x = x + T.border_size; y = y + T.border_size;                     // points += border_size
+        // (points / horizontal_scale).long(): truncation; clamping the float first keeps the conversion defined off the map
+        const float fx = fminf(fmaxf(x / T.horizontal_scale, -1.0f), 2147483520.0f), fy = fminf(fmaxf(y / T.horizontal_scale, -1.0f), 2147483520.0f);
+        int px = (int)fx, py = (int)fy;
+        px = px < 0 ? 0 : (px > T.rows - 2 ? T.rows - 2 : px);            // clip to [0, shape-2]
+        py = py < 0 ? 0 : (py > T.cols - 2 ? T.cols - 2 : py);
+        const int16_t* hs = T.height_samples + (size_t)px * T.cols + py;
+        const int h = min(min((int)hs[0], (int)hs[T.cols]), (int)hs[1]);   // (px,py), (px+1,py), (px,py+1)
+        heights[e * P + p] = (float)h * T.vertical_scale;
+    }
 }
 
 // _update_terrain_curriculum legged_robot.py:400-420 followed by the custom-origin spawn of _reset_root_states :381-384
@@ -77,29 +85,35 @@ __global__ void reset_prepare_kernel(HgTerrain T, const uint8_t* __restrict__ re
     spawn[(size_t)e * 3 + 2] = org[2];
 }
 
-// humanoid_env.py:246-248 (frame), :253-258 (append), :264-269 (reset zeroing), legged_robot.py:104-108 (clip)
-__global__ void priv_frames_kernel(const float* __restrict__ obs_prev, int64_t obs_pitch, int num_obs,
-                                   const float* __restrict__ root, const float* __restrict__ heights, int P, float height_scale,
-                                   float clip_obs, const uint8_t* __restrict__ reset_buf, const float* __restrict__ priv_in,
-                                   float* __restrict__ priv_out, int64_t priv_pitch, int frames, int64_t total) {
-    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= total) return;
-    const int W = num_obs + P, row = frames * W;
-    const int64_t e = i / row;
-    const int c = (int)(i - e * row);
-    float v;
-    if (c < row - W) {
-        v = (reset_buf && reset_buf[e]) ? 0.0f : priv_in[e * priv_pitch + c + W];
+// humanoid_env.py:246-248 (frame), :253-258 (append), :264-269 (reset zeroing), legged_robot.py:104-108 (clip).
+// grid = (envs, column chunks): no per-element index division; the history shift out[0 : (F-1) W] = in[W : F W] moves as
+// 16-byte vectors when W and the pitch are multiples of 4 floats (892 and 2688 are); the new frame is assembled scalar.
+template <bool VEC>
+__global__ void __launch_bounds__(256) priv_frames_kernel(const float* __restrict__ obs_prev, int64_t obs_pitch, int num_obs,
+                                                          const float* __restrict__ root, const float* __restrict__ heights, int P,
+                                                          float height_scale, float clip_obs, const uint8_t* __restrict__ reset_buf,
+                                                          const float* __restrict__ priv_in, float* __restrict__ priv_out,
+                                                          int64_t priv_pitch, int frames) {
+    const int64_t e = blockIdx.x;
+    const int W = num_obs + P, keep = (frames - 1) * W;
+    const bool rz = reset_buf && reset_buf[e];
+    const float* in = priv_in + e * priv_pitch + W;
+    float* out = priv_out + e * priv_pitch;
+    const int t0 = blockIdx.y * blockDim.x + threadIdx.x, stride = gridDim.y * blockDim.x;
+    if (VEC) {
+        const float4 z4 = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        for (int c = t0; c < keep / 4; c += stride)
+            reinterpret_cast<float4*>(out)[c] = rz ? z4 : reinterpret_cast<const float4*>(in)[c];
     } else {
-        const int k = c - (row - W);
-        if (k < num_obs) v = obs_prev[e * obs_pitch + k];
-        else {
-            float h = (root[e * 13 + 2] - 0.5f) - heights[e * P + (k - num_obs)];
-            v = fminf(fmaxf(h, -1.0f), 1.0f) * height_scale;
-        }
-        v = fminf(fmaxf(v, -clip_obs), clip_obs);
+        for (int c = t0; c < keep; c += stride) out[c] = rz ? 0.0f : in[c];
     }
-    priv_out[e * priv_pitch + c] = v;
+    const float rz_m = root[e * 13 + 2] - 0.5f;
+    for (int k = t0; k < W; k += stride) {
+        float v;
+        if (k < num_obs) v = obs_prev[e * obs_pitch + k];
+        else v = fminf(fmaxf(rz_m - heights[e * P + (k - num_obs)], -1.0f), 1.0f) * height_scale;
+        out[keep + k] = fminf(fmaxf(v, -clip_obs), clip_obs);
+    }
 }
 
 int32_t check_terrain(const HgTerrain* T, bool need_origins) {
@@ -121,8 +135,7 @@ extern "C" int32_t hg_terrain_get_heights(const HgTerrain* T, const float* root_
     if (int32_t rc = check_terrain(T, false)) return rc;
     HG_REQUIRE(root_states); HG_REQUIRE(points_xy); HG_REQUIRE(heights);
     if (N <= 0 || N > (1 << 26) || P <= 0 || P > 4096) return hg_fail(HG_E_SIZE, "hg_terrain_get_heights: bad N or P");
-    const int64_t total = N * P;
-    get_heights_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(*T, root_states, points_xy, P, heights, total);
+    get_heights_kernel<<<(unsigned)N, P <= 64 ? 64 : (P <= 128 ? 128 : 192), 0, (cudaStream_t)stream>>>(*T, root_states, points_xy, P, heights);
     HG_LAUNCHED(1);
     return hg_cuda_status("hg_terrain_get_heights");
 }
@@ -151,10 +164,15 @@ extern "C" int32_t hg_terrain_priv_frames(const float* obs_prev, int64_t obs_pit
     if (priv_in == priv_out) return hg_fail(HG_E_ARG, "hg_terrain_priv_frames: priv_out must not alias priv_in (ping-pong pair)");
     if (N <= 0 || N > (1 << 26) || P <= 0 || num_obs <= 0 || frames <= 0) return hg_fail(HG_E_SIZE, "hg_terrain_priv_frames: bad sizes");
     if (obs_pitch < num_obs || priv_pitch < (int64_t)frames * (num_obs + P)) return hg_fail(HG_E_SIZE, "hg_terrain_priv_frames: pitch smaller than the row");
-    const int64_t total = N * frames * (int64_t)(num_obs + P);
-    priv_frames_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
-        obs_prev, obs_pitch, num_obs, root_states, heights, P, height_scale, clip_obs, reset_buf, priv_in, priv_out, priv_pitch,
-        frames, total);
+    const int W = num_obs + P;
+    const bool vec = (W % 4 == 0) && (priv_pitch % 4 == 0) && hg_aligned16(priv_in) && hg_aligned16(priv_out);
+    const dim3 grid((unsigned)N, 2);
+    if (vec)
+        priv_frames_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(obs_prev, obs_pitch, num_obs, root_states, heights, P, height_scale,
+                                                                         clip_obs, reset_buf, priv_in, priv_out, priv_pitch, frames);
+    else
+        priv_frames_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(obs_prev, obs_pitch, num_obs, root_states, heights, P, height_scale,
+                                                                          clip_obs, reset_buf, priv_in, priv_out, priv_pitch, frames);
     HG_LAUNCHED(1);
     return hg_cuda_status("hg_terrain_priv_frames");
 }

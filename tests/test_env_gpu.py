@@ -253,18 +253,12 @@ def test_fused_decimation_matches_the_loop():
     assert a.gym.substep == b.gym.substep == steps * 10
 
 
-def test_env_over_isaacgym_adapter(monkeypatch):
+def test_env_over_isaacgym_adapter(fake_isaacgym):
     """the env over IsaacGymPhysics (real gym API; here the functional fake of tests/golden/fake_isaacgym
     in ring mode on cuda:0, because Isaac Gym has no sm_100 build) steps exactly like the env over ExternalPhysics fed with
     the same frames, and drives the simulator with the reference's call sequence (legged_robot.py:94-101,124-126,371-397)."""
-    import os
-    import sys
     from humanoid import physics
-    here = os.path.dirname(os.path.abspath(__file__))
-    monkeypatch.syspath_prepend(os.path.join(here, "golden", "fake_isaacgym"))
-    monkeypatch.setenv("HG_FAKE_GYM", "ring")
-    for m in [k for k in sys.modules if k == "isaacgym" or k.startswith("isaacgym.")] + ["humanoid.isaacgym_physics"]:
-        monkeypatch.delitem(sys.modules, m, raising=False)
+    fake_isaacgym.setenv("HG_FAKE_GYM", "ring")
     assert physics.isaacgym_available()
     N = 512
     torch.manual_seed(3)

@@ -2,25 +2,14 @@
 functional fake `isaacgym` of tests/golden/fake_isaacgym -- Isaac Gym itself ships no sm_100 build and is not in the
 image.  CPU only: the adapter is plain gym-API plumbing; the env on top of it is covered by
 tests/test_env_gpu.py::test_env_over_isaacgym_adapter."""
-import os
-import sys
-
 import numpy as np
 import pytest
 import torch
 
-HERE = os.path.dirname(os.path.abspath(__file__))
-
-
 @pytest.fixture()
-def fake_gym(monkeypatch):
-    monkeypatch.syspath_prepend(os.path.join(HERE, "golden", "fake_isaacgym"))
-    monkeypatch.setenv("HG_FAKE_GYM", "golden")
-    for m in [k for k in sys.modules if k == "isaacgym" or k.startswith("isaacgym.")] + ["humanoid.isaacgym_physics"]:
-        monkeypatch.delitem(sys.modules, m, raising=False)
+def fake_gym(fake_isaacgym):
+    fake_isaacgym.setenv("HG_FAKE_GYM", "golden")
     yield
-    for m in [k for k in sys.modules if k == "isaacgym" or k.startswith("isaacgym.")] + ["humanoid.isaacgym_physics"]:
-        sys.modules.pop(m, None)
 
 
 def _log_calls(gym, log):
