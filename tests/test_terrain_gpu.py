@@ -258,3 +258,54 @@ def test_heights_properties_large():
     h = env._get_heights()
     assert torch.equal(h, torch.full_like(h, 37 * np.float32(env.cfg.terrain.vertical_scale)))
     assert env._get_heights(torch.tensor([3, 5], device=r.device)).shape == (2, 187)
+
+
+def test_runner_on_rough_terrain_graph_matches_eager():
+    """task_registry -> OnPolicyRunner on rough terrain with the critic sized for the 3 x 892 frames: the CUDA-graph rollout
+    (two fused launches + curriculum + heights + critic frames per step, per-step counters on the device) reproduces the
+    eager rollout bit for bit over three collection phases, and a learning iteration runs on top of it."""
+    import os
+    from parity_utils import make_args
+    from humanoid.utils import task_registry
+
+    def build():
+        torch.manual_seed(0)
+        np.random.seed(0)
+        args = make_args(256)
+        env, _ = task_registry.make_env("humanoid_ppo", args=args, env_cfg=_big_terrain_cfg(256))
+        runner, _ = task_registry.make_alg_runner(env, name="humanoid_ppo", args=args, log_root=None)
+        return env, runner
+
+    def run(runner, env, phases):
+        obs, cobs = env.get_observations(), env.get_privileged_observations()
+        out = []
+        with torch.inference_mode():
+            for _ in range(phases):
+                obs, cobs = runner.collect(obs, cobs)
+                torch.cuda.synchronize()
+                s = runner.alg.storage
+                out.append({k: getattr(s, k).clone() for k in ("observations", "privileged_observations", "actions", "rewards",
+                                                               "dones", "values", "actions_log_prob")})
+                out[-1]["obs"], out[-1]["cobs"], out[-1]["rew"] = obs.clone(), cobs.clone(), env.rew_buf.clone()
+                out[-1]["levels"], out[-1]["origins"] = env.terrain_levels.clone(), env.env_origins.clone()
+                out[-1]["heights"] = env.measured_heights.clone()
+                s.clear()
+        return out
+
+    os.environ["HG_CUDA_GRAPH"] = "0"
+    try:
+        env_e, run_e = build()
+        eager = run(run_e, env_e, 3)
+    finally:
+        os.environ["HG_CUDA_GRAPH"] = "1"
+    env_g, run_g = build()
+    assert env_g.privileged_obs_buf.shape == (256, 3 * 892) and run_g.alg.actor_critic.critic[0].in_features == 3 * 892
+    graph = run(run_g, env_g, 3)
+    assert getattr(run_g, "_graph", None) is not None, "the graph path did not engage"
+    for ph, (a, b) in enumerate(zip(eager, graph)):
+        for k in a:
+            assert torch.equal(a[k], b[k]), (ph, k, float((a[k].float() - b[k].float()).abs().max()))
+    assert float(eager[-1]["heights"].abs().max()) > 0 and int(eager[-1]["dones"].sum()) > 0
+    w0 = run_g.alg.actor_critic.flat_params().clone()
+    run_g.learn(2, init_at_random_ep_len=True)
+    assert torch.isfinite(run_g.alg.actor_critic.flat_params()).all() and not torch.equal(w0, run_g.alg.actor_critic.flat_params())
