@@ -272,7 +272,7 @@ __device__ __forceinline__ void stream_history(float* __restrict__ out, const fl
 template <int T>
 __global__ void __launch_bounds__(T, (T == 128 ? HIST_CTAS_128 : (T == 256 ? 2 : 1)))
 post_physics_kernel(const __grid_constant__ HgEnvParams cP, HgEnvBuffers B, HgEnvNoise Z, uint32_t phases, int64_t common_step, int N,
-                    long long* trace) {
+                    long long* trace, int l2_prefetch) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     EnvSmem& S = *reinterpret_cast<EnvSmem*>(smem_raw);
     auto& X = S.x;
@@ -304,6 +304,18 @@ post_physics_kernel(const __grid_constant__ HgEnvParams cP, HgEnvBuffers B, HgEn
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, tile_parity ^= 1u) {
     const int e0 = tile * E;
     const int nE = min(E, N - e0);
+    if (l2_prefetch && do_obs && tid == 0) {
+        // The tile's history rows are one contiguous run of nE * pitch floats per buffer: ask L2 for all of it now (two bulk
+        // prefetches, no registers, no shared memory), so that the register-staged shift below finds the rows on chip
+        // instead of paying a DRAM round trip per batch of 21 requests.
+        const uint32_t ob = (uint32_t)(nE * opitch * 4), pb = (uint32_t)(nE * ppitch * 4);
+        const float* op = B.obs_buf + (size_t)e0 * opitch;
+        const float* pp = B.privileged_obs_buf + (size_t)e0 * ppitch;
+        if (((reinterpret_cast<uintptr_t>(op) | ob) & 15u) == 0)
+            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(op), "r"(ob) : "memory");
+        if (((reinterpret_cast<uintptr_t>(pp) | pb) & 15u) == 0)
+            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(pp), "r"(pb) : "memory");
+    }
     if (tid < E) { S.reset[tid] = 0; S.root_dirty[tid] = 0; }
     if (tid == 0) { S.next_row[0] = 0; S.next_row[1] = 0; S.next_noise = 0; }
     __syncthreads();
@@ -1108,9 +1120,14 @@ extern "C" int32_t hg_env_post_physics(const HgEnvBuffers* B, const HgEnvParams*
     // (the 8-warp variant measured no better than either neighbour -- 49 us at N=4096, 84 vs 72 us at N=16384 -- so it
     // is only reachable through HG_ENV_CTA)
     const int width = env_threads ? env_threads : (grid <= HG_NUM_SMS ? 512 : 256);
-    if (width == 512) post_physics_kernel<512><<<grid, 512, sizeof(EnvSmem), st>>>(*P, *B, *Z, phases, common_step_counter, (int)N, g_env_trace);
-    else if (width == 256) post_physics_kernel<256><<<grid, 256, sizeof(EnvSmem), st>>>(*P, *B, *Z, phases, common_step_counter, (int)N, g_env_trace);
-    else post_physics_kernel<128><<<grid, 128, sizeof(EnvSmem), st>>>(*P, *B, *Z, phases, common_step_counter, (int)N, g_env_trace);
+    // HG_ENV_L2_PREFETCH=0|1|2: bulk L2 prefetch of each tile's history rows at tile start (1: grids deeper than one tile per
+    // SM only, 2: always)
+    static int l2pf_mode = -1;
+    if (l2pf_mode < 0) { const char* v = getenv("HG_ENV_L2_PREFETCH"); l2pf_mode = v ? atoi(v) : 0; }
+    const int l2pf = l2pf_mode == 2 || (l2pf_mode == 1 && grid > HG_NUM_SMS);
+    if (width == 512) post_physics_kernel<512><<<grid, 512, sizeof(EnvSmem), st>>>(*P, *B, *Z, phases, common_step_counter, (int)N, g_env_trace, l2pf);
+    else if (width == 256) post_physics_kernel<256><<<grid, 256, sizeof(EnvSmem), st>>>(*P, *B, *Z, phases, common_step_counter, (int)N, g_env_trace, l2pf);
+    else post_physics_kernel<128><<<grid, 128, sizeof(EnvSmem), st>>>(*P, *B, *Z, phases, common_step_counter, (int)N, g_env_trace, l2pf);
     HG_LAUNCHED(1);
     return hg_cuda_status("hg_env_post_physics");
 }

@@ -209,9 +209,11 @@ typedef struct HgTerrain {
  * `points_xy` (P,2) are rotated by the base yaw (quat_apply_yaw, utils/math.py:38-43), moved to the root
  * position, shifted by the border, divided by the horizontal scale and truncated (.long()); the height is the
  * minimum of the three samples (px,py), (px+1,py), (px,py+1) with px / py clipped to [0, rows-2] / [0, cols-2],
- * times the vertical scale.  heights: (N,P). */
+ * times the vertical scale.  heights: (N,P).  reach_m = max |point| (the radius of the grid around the root, 0.943 m
+ * for the 1.6 m x 1 m default): a performance hint only -- the kernel stages the 32 x 32-cell window that covers it in
+ * shared memory and reads the samples of points outside the window from global memory. */
 int32_t hg_terrain_get_heights(const HgTerrain* T, const float* root_states, const float* points_xy, int32_t P,
-                               float* heights, int64_t N, void* stream);
+                               float reach_m, float* heights, int64_t N, void* stream);
 
 /* For the envs with reset_buf set: LeggedRobot._update_terrain_curriculum (legged_robot.py:400-420, skipped when
  * T->curriculum == 0) on terrain_levels / env_origins, then the spawn position _reset_root_states adds to
