@@ -9,41 +9,25 @@ namespace {
 
 // LeggedRobot._get_heights, legged_robot.py:759-795; quat_apply_yaw utils/math.py:38-43 with Isaac Gym's
 // normalize (x / |x|.clamp(min=1e-9)) and quat_apply (b + w t + xyz x t, t = 2 xyz x b), xyzw quaternions.
-// One CTA per env.  Thread 0 normalises the yaw quaternion once (sqrt + 2 divisions).  The 187 points of a robot lie
-// within `reach` metres of its root, i.e. inside a PATCH x PATCH-cell window of the height field: the CTA copies that
-// window into shared memory with row-contiguous loads (~2 sectors per row instead of one scattered 2-byte gather per
-// sample: the scattered form was LSU-bound at 0.5 points / clk / SM) and the three samples of a point come from there;
-// a point whose (clipped) cell falls outside the window -- robots off the map, unusually wide point grids -- reads global
-// memory like before.
-constexpr int HG_PATCH = 32;
-__global__ void __launch_bounds__(192) get_heights_kernel(HgTerrain T, const float* __restrict__ root, const float* __restrict__ pts, int P,
-                                                          float reach, float* __restrict__ heights) {
-    __shared__ float sh[4];
-    __shared__ int org[2];
-    __shared__ int16_t patch[HG_PATCH][HG_PATCH + 2];
-    const int64_t e = blockIdx.x;
+// One WARP per env, 8 envs per CTA, no block-level synchronisation: every lane reads the root row (a broadcast), normalises
+// the yaw quaternion itself (1 sqrt + 2 divisions per lane, not per point) and owns points lane, lane + 32, ...; per point
+// ~10 flops, two IEEE divisions, three int16 gathers, one coalesced store.  What bounds it is the L1 line rate of those
+// gathers (a warp's 32 points touch ~16 different 128-byte lines of the height field per load; measured variants: one
+// thread per point 80 us, one CTA per env 76 us, a shared-memory copy of the 32 x 32-cell window around the robot 141 us
+// at N = 65536 -- the extra barriers cost more than the gathers they saved).
+constexpr int HG_HEIGHT_WARPS = 8;
+__global__ void __launch_bounds__(HG_HEIGHT_WARPS * 32) get_heights_kernel(HgTerrain T, const float* __restrict__ root, const float* __restrict__ pts,
+                                                                          int P, float* __restrict__ heights, int64_t N) {
+    const int64_t e = (int64_t)blockIdx.x * HG_HEIGHT_WARPS + (threadIdx.x >> 5);
+    if (e >= N) return;
+    const int lane = threadIdx.x & 31;
     const float* r = root + e * 13;
-    if (threadIdx.x == 0) {
-        float qz = r[5], qw = r[6];
-        float n = sqrtf(qz * qz + qw * qw);          // quat_yaw = (0, 0, z, w): the two zeroed components add nothing
-        n = fmaxf(n, 1e-9f);
-        sh[0] = qz / n; sh[1] = qw / n; sh[2] = r[0]; sh[3] = r[1];
-        // window origin: the cell of (root - reach), kept inside the field
-        const float cx = fminf(fmaxf((r[0] - reach + T.border_size) / T.horizontal_scale - 1.0f, 0.0f), 2147483520.0f);
-        const float cy = fminf(fmaxf((r[1] - reach + T.border_size) / T.horizontal_scale - 1.0f, 0.0f), 2147483520.0f);
-        org[0] = max(0, min((int)cx, T.rows - HG_PATCH));
-        org[1] = max(0, min((int)cy, T.cols - HG_PATCH));
-    }
-    __syncthreads();
-    const int ox = org[0], oy = org[1];
-    for (int i = threadIdx.x; i < HG_PATCH * HG_PATCH; i += blockDim.x) {
-        const int pr = i / HG_PATCH, pc = i - pr * HG_PATCH;
-        const int gx = ox + pr, gy = oy + pc;
-        patch[pr][pc] = (gx < T.rows && gy < T.cols) ? T.height_samples[(size_t)gx * T.cols + gy] : (int16_t)0;
-    }
-    __syncthreads();
-    const float qz = sh[0], qw = sh[1], rx = sh[2], ry = sh[3];
-    for (int p = threadIdx.x; p < P; p += blockDim.x) {
+    float qz = r[5], qw = r[6];
+    float n = sqrtf(qz * qz + qw * qw);              // quat_yaw = (0, 0, z, w): the two zeroed components add nothing
+    n = fmaxf(n, 1e-9f);
+    qz = qz / n; qw = qw / n;
+    const float rx = r[0], ry = r[1];
+    for (int p = lane; p < P; p += 32) {
         const float bx = pts[2 * p], by = pts[2 * p + 1];                 // height_points[..., 2] = 0
         const float tx = (0.0f - qz * by) * 2.0f, ty = (qz * bx) * 2.0f;   // t = cross((0,0,z), b) * 2
         const float cx = 0.0f - qz * ty, cy = qz * tx;                     // cross((0,0,z), t)
@@ -55,14 +39,8 @@ __global__ void __launch_bounds__(192) get_heights_kernel(HgTerrain T, const flo
         int px = (int)fx, py = (int)fy;
         px = px < 0 ? 0 : (px > T.rows - 2 ? T.rows - 2 : px);            // clip to [0, shape-2]
         py = py < 0 ? 0 : (py > T.cols - 2 ? T.cols - 2 : py);
-        const int lx = px - ox, ly = py - oy;
-        int h;
-        if (lx >= 0 && ly >= 0 && lx < HG_PATCH - 1 && ly < HG_PATCH - 1) {
-            h = min(min((int)patch[lx][ly], (int)patch[lx + 1][ly]), (int)patch[lx][ly + 1]);
-        } else {
-            const int16_t* hs = T.height_samples + (size_t)px * T.cols + py;
-            h = min(min((int)hs[0], (int)hs[T.cols]), (int)hs[1]);         // (px,py), (px+1,py), (px,py+1)
-        }
+        const int16_t* hs = T.height_samples + (size_t)px * T.cols + py;
+        const int h = min(min((int)hs[0], (int)hs[T.cols]), (int)hs[1]);   // (px,py), (px+1,py), (px,py+1)
         heights[e * P + p] = (float)h * T.vertical_scale;
     }
 }
@@ -155,13 +133,12 @@ int32_t check_terrain(const HgTerrain* T, bool need_origins) {
 }  // namespace
 
 extern "C" int32_t hg_terrain_get_heights(const HgTerrain* T, const float* root_states, const float* points_xy, int32_t P,
-                                          float reach_m, float* heights, int64_t N, void* stream) {
+                                          float* heights, int64_t N, void* stream) {
     if (int32_t rc = check_terrain(T, false)) return rc;
     HG_REQUIRE(root_states); HG_REQUIRE(points_xy); HG_REQUIRE(heights);
     if (N <= 0 || N > (1 << 26) || P <= 0 || P > 4096) return hg_fail(HG_E_SIZE, "hg_terrain_get_heights: bad N or P");
-    if (reach_m < 0.0f) return hg_fail(HG_E_ARG, "hg_terrain_get_heights: reach_m must be >= 0");
-    get_heights_kernel<<<(unsigned)N, P <= 64 ? 64 : (P <= 128 ? 128 : 192), 0, (cudaStream_t)stream>>>(*T, root_states, points_xy, P, reach_m,
-                                                                                                     heights);
+    get_heights_kernel<<<(unsigned)((N + HG_HEIGHT_WARPS - 1) / HG_HEIGHT_WARPS), HG_HEIGHT_WARPS * 32, 0, (cudaStream_t)stream>>>(
+        *T, root_states, points_xy, P, heights, N);
     HG_LAUNCHED(1);
     return hg_cuda_status("hg_terrain_get_heights");
 }

@@ -163,7 +163,7 @@ def _load():
         "hg_env_set_trace": (None, [PF]),
         "hg_env_synth_decimation": (i32, [P(EnvBuffers), P(EnvParams), PF, i32, PF, PF, PF, i64, PF]),
         "hg_env_post_physics": (i32, [P(EnvBuffers), P(EnvParams), P(EnvNoise), C.c_uint32, i64, i64, PF]),
-        "hg_terrain_get_heights": (i32, [P(Terrain), PF, PF, i32, f32, PF, i64, PF]),
+        "hg_terrain_get_heights": (i32, [P(Terrain), PF, PF, i32, PF, i64, PF]),
         "hg_terrain_reset_prepare": (i32, [P(Terrain), PF, PF, PF, PF, PF, PF, PF, PF, PF, u64, u64, PF, i64, PF]),
         "hg_terrain_priv_frames": (i32, [PF, i64, i32, PF, PF, i32, f32, f32, PF, PF, PF, i64, i32, i64, PF]),
         "hg_mlp_forward": (i32, [P(MlpDesc), PF, PF, i64, PF, PF, i64, PF]),
@@ -187,6 +187,7 @@ def _load():
         "hg_mlp_backward_split": (i32, [P(MlpDesc), PF, PF, i64, P(Split), PF, PF, PF, PF, i64, PF]),
         "hg_policy_sample": (i32, [PF, PF, PF, u64, u64, PF, PF, PF, PF, i64, i32, PF]),
         "hg_storage_add": (i32, [P(Storage), P(Transition), i32, f32, i64, PF]),
+        "hg_set_gae_mode": (i32, [i32]),
         "hg_gae": (i32, [P(Storage), PF, f32, f32, PF, i32, i64, PF]),
         "hg_adv_normalise": (i32, [P(Storage), PF, i64, PF]),
         "hg_minibatch_gather": (i32, [P(Storage), PF, P(MiniBatch), i64, PF]),

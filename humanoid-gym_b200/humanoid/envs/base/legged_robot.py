@@ -227,7 +227,6 @@ class LeggedRobot(BaseTask):
         grid_x, grid_y = torch.meshgrid(x, y, indexing="ij")
         self.num_height_points = grid_x.numel()
         self._height_points_xy = torch.stack((grid_x.flatten(), grid_y.flatten()), dim=1).contiguous()   # the kernel's (P, 2) view
-        self._height_reach = float(self._height_points_xy.norm(dim=1).max())                             # radius of the grid around the root
         points = torch.zeros(self.num_envs, self.num_height_points, 3, device=self.device)
         points[:, :, 0] = grid_x.flatten()
         points[:, :, 1] = grid_y.flatten()
@@ -465,7 +464,7 @@ class LeggedRobot(BaseTask):
             raise NameError("Can't measure height with terrain mesh type 'none'")
         else:
             nat.check(nat.lib.hg_terrain_get_heights(self._T, nat.ptr(self.root_states), nat.ptr(self._height_points_xy),
-                                                     self.num_height_points, self._height_reach, nat.ptr(self._heights), self.num_envs,
+                                                     self.num_height_points, nat.ptr(self._heights), self.num_envs,
                                                      nat.stream_ptr(self._dev_index)), "hg_terrain_get_heights")
             h = self._heights
         return h if env_ids is None else h[env_ids]

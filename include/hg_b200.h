@@ -209,11 +209,9 @@ typedef struct HgTerrain {
  * `points_xy` (P,2) are rotated by the base yaw (quat_apply_yaw, utils/math.py:38-43), moved to the root
  * position, shifted by the border, divided by the horizontal scale and truncated (.long()); the height is the
  * minimum of the three samples (px,py), (px+1,py), (px,py+1) with px / py clipped to [0, rows-2] / [0, cols-2],
- * times the vertical scale.  heights: (N,P).  reach_m = max |point| (the radius of the grid around the root, 0.943 m
- * for the 1.6 m x 1 m default): a performance hint only -- the kernel stages the 32 x 32-cell window that covers it in
- * shared memory and reads the samples of points outside the window from global memory. */
+ * times the vertical scale.  heights: (N,P). */
 int32_t hg_terrain_get_heights(const HgTerrain* T, const float* root_states, const float* points_xy, int32_t P,
-                               float reach_m, float* heights, int64_t N, void* stream);
+                               float* heights, int64_t N, void* stream);
 
 /* For the envs with reset_buf set: LeggedRobot._update_terrain_curriculum (legged_robot.py:400-420, skipped when
  * T->curriculum == 0) on terrain_levels / env_origins, then the spawn position _reset_root_states adds to
@@ -414,6 +412,12 @@ int32_t hg_storage_add(const HgStorage* S, const HgTransition* tr, int32_t t, fl
  * then call hg_adv_normalise). */
 int32_t hg_gae(const HgStorage* S, const float* last_values, float gamma, float lam, double* stats,
                int32_t normalise, int64_t N, void* stream);
+/* The reverse scan runs as a WARP SCAN OVER TIME (default): the recurrence adv_t = d_t + c_t adv_{t+1} is a chain of
+ * affine maps, composed associatively with shuffles (one warp per env, 32 envs per CTA staged through shared memory,
+ * each lane replays its own steps with the reference's serial formula from the scanned carry-in).
+ * hg_set_gae_mode(0) selects the one-thread-per-env serial walk, 1 the warp scan, -1 re-reads HG_GAE=scan|serial
+ * from the environment; returns the previous setting. */
+int32_t hg_set_gae_mode(int32_t scan);
 int32_t hg_adv_normalise(const HgStorage* S, const double* stats, int64_t N, void* stream);
 
 /* mini_batch_generator gather (rollout_storage.py:146-182): rows idx[0..B) of

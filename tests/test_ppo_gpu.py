@@ -197,7 +197,32 @@ def test_fused_act_matches_separate_chains(N, gemm_engine, chain, monkeypatch):
     assert _rel(s.values[0].cpu(), po.mlp(cobs[0].cpu(), p, "critic")) < 1e-5
 
 
-def test_gae_vs_golden_and_large():
+@pytest.fixture(params=["warp_scan", "serial"])
+def gae_mode(request):
+    from humanoid import _native as nat
+    prev = nat.lib.hg_set_gae_mode(1 if request.param == "warp_scan" else 0)
+    yield request.param
+    nat.lib.hg_set_gae_mode(prev)
+
+
+@pytest.mark.parametrize("T,N", [(1, 33), (31, 64), (32, 1), (33, 100), (60, 1000), (200, 96)])
+def test_gae_shapes_vs_oracle(gae_mode, T, N):
+    """Ragged env counts and rollout lengths on both sides of the 32-lane width (chunks of 1, 2, 7 steps per lane)."""
+    from humanoid.algo import RolloutStorage
+    gen = torch.Generator().manual_seed(T * 1000 + N)
+    st = RolloutStorage(N, T, [4], [4], [12], "cuda:0")
+    r, v = torch.rand(T, N, 1, generator=gen), torch.randn(T, N, 1, generator=gen)
+    d = (torch.rand(T, N, 1, generator=gen) < 0.1).byte()
+    lv = torch.randn(N, 1, generator=gen)
+    st.rewards.copy_(r), st.values.copy_(v), st.dones.copy_(d)
+    st.compute_returns(lv.cuda(), 0.994, 0.9)
+    ret, adv = po.gae(r, v, d, lv, 0.994, 0.9)
+    np.testing.assert_allclose(st.returns.cpu().numpy(), ret.numpy(), rtol=1e-5, atol=1e-5)
+    if T * N > 1:
+        np.testing.assert_allclose(st.advantages.cpu().numpy(), adv.numpy(), rtol=1e-5, atol=2e-5)
+
+
+def test_gae_vs_golden_and_large(gae_mode):
     from humanoid.algo import RolloutStorage
     g = Golden("ppo_learning.npz")
     T, N = g["gae.rewards"].shape[:2]
