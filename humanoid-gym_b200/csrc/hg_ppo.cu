@@ -158,7 +158,7 @@ __global__ void gae_kernel(HgStorage S, const float* __restrict__ last_values, f
 // lanes (shuffles) gives every lane the advantage entering its chunk from the future, and the lane replays its own steps
 // with the reference's serial formula.  The 60 dependent steps of the per-env loop become 2 CH + 5.  Rounding differs from
 // the serial order only through the scanned carry-in (|c| < 0.9: ~1e-7 relative; the parity bar on returns is 1e-5).
-constexpr int GAE_ENVS = 32, GAE_WARPS = 8, GAE_SCAN_MAX_ENVS = 8192;
+constexpr int GAE_ENVS = 32, GAE_WARPS = 8, GAE_SCAN_MAX_ENVS = 32768;
 __global__ void __launch_bounds__(GAE_WARPS * 32) gae_scan_kernel(HgStorage S, const float* __restrict__ last_values, float gamma, float lam,
                                                                   double* __restrict__ stats, int N) {
     // shared tiles [3][32 envs][RS]: rewards -> returns, values, not-terminal -> advantages.  Within an env's row step t sits at
@@ -552,9 +552,9 @@ extern "C" int32_t hg_gae(const HgStorage* S, const float* last_values, float ga
     if (N <= 0 || S->T <= 0) return hg_fail(HG_E_SIZE, "hg_gae: bad N/T");
     cudaStream_t st = (cudaStream_t)stream;
     cudaMemsetAsync(stats, 0, 4 * sizeof(double), st);
-    // HG_GAE=scan | serial | auto (default).  auto: the warp scan over time for N <= GAE_SCAN_MAX_ENVS (where a thread-per-env walk
-    // leaves most SMs idle behind 60 dependent steps: 26.6 vs 45.1 us at N = 4096), the serial walk above that (enough envs to fill
-    // the machine and no shared-memory transposition: 63 vs 168 us at N = 65536 before the conflict-free tile layout).
+    // HG_GAE=scan | serial | auto (default).  auto: the warp scan over time for N <= GAE_SCAN_MAX_ENVS, where a thread-per-env walk
+    // leaves SMs idle behind 60 dependent steps (compute_returns at T = 60, scan vs serial: 20.5 vs 45.0 us at N = 4096, 28.5 vs
+    // 49.1 us at 16384), the serial walk above that (65.4 vs 62.1 us at 65536: enough envs to fill the machine, no transposition).
     if (g_gae_scan == -1) {
         const char* v = getenv("HG_GAE");
         g_gae_scan = (v && !strcmp(v, "serial")) ? 0 : ((v && !strcmp(v, "scan")) ? 1 : 2);

@@ -415,8 +415,8 @@ int32_t hg_gae(const HgStorage* S, const float* last_values, float gamma, float 
 /* The reverse scan runs as a WARP SCAN OVER TIME (default): the recurrence adv_t = d_t + c_t adv_{t+1} is a chain of
  * affine maps, composed associatively with shuffles (one warp per env, 32 envs per CTA staged through shared memory,
  * each lane replays its own steps with the reference's serial formula from the scanned carry-in).
- * hg_set_gae_mode(0) selects the one-thread-per-env serial walk, 1 the warp scan, 2 picks by N (scan up to 8192 envs: a
- * thread-per-env walk leaves most SMs idle behind T dependent steps there), -1 re-reads HG_GAE=scan|serial|auto (default
+ * hg_set_gae_mode(0) selects the one-thread-per-env serial walk, 1 the warp scan, 2 picks by N (scan up to 32768 envs: a
+ * thread-per-env walk leaves SMs idle behind T dependent steps there), -1 re-reads HG_GAE=scan|serial|auto (default
  * auto) from the environment; returns the previous setting. */
 int32_t hg_set_gae_mode(int32_t scan);
 int32_t hg_adv_normalise(const HgStorage* S, const double* stats, int64_t N, void* stream);
