@@ -66,3 +66,19 @@ def test_full_update(g):
     assert L.lr == float(g["upd.final_lr"])
     for k, v in g.group("w1.").items():
         np.testing.assert_allclose(L.p[k].detach().numpy(), v.numpy(), rtol=1e-5, atol=1e-7, err_msg=k)
+
+
+def test_perm_oracle_known_answers():
+    """oracle/perm_oracle.py: Philox4x32-10 against the Random123 known-answer vectors; the restated hg_randperm is a
+    permutation for every size, a pure function of (seed, counter)."""
+    import numpy as np
+    from oracle.perm_oracle import philox4x32_10, randperm
+    assert philox4x32_10(0, 0, 0, 0, 0) == (0x6627E8D5, 0xE169C58D, 0xBC57AC4C, 0x9B00DBD8)
+    assert philox4x32_10(0xFFFFFFFFFFFFFFFF, 0xFFFFFFFF, 0xFFFFFFFF, 0xFFFFFFFF, 0xFFFFFFFF) == \
+        (0x408F276D, 0x41C83B0E, 0xA20BC7C6, 0x6D5451FD)
+    for n in (1, 2, 3, 31, 32, 33, 1000, 4097):
+        p = randperm(n, 5, 0)
+        assert np.array_equal(np.sort(p), np.arange(n))
+        assert np.array_equal(p, randperm(n, 5, 0))
+        if n >= 31:
+            assert not np.array_equal(p, randperm(n, 5, 1)) and not np.array_equal(p, randperm(n, 6, 0))

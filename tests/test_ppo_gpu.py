@@ -582,3 +582,14 @@ def test_native_randperm_uniform_positions():
     chi2 = float(((counts - expected) ** 2 / expected).sum())
     dof = (n - 1) ** 2
     assert abs(chi2 - dof) < 6 * np.sqrt(2 * dof), (chi2, dof)
+
+
+@pytest.mark.parametrize("n,seed,ctr", [(1, 3, 0), (5, 3, 1), (64, 99, 7), (1000, 2 ** 63 + 5, 2 ** 33 + 1), (245760, 11, 3)])
+def test_native_randperm_bit_exact_vs_oracle(n, seed, ctr):
+    """Integer work: the kernel's permutation equals the numpy restatement (oracle/perm_oracle.py) element for element."""
+    from humanoid import _native as nat
+    from oracle.perm_oracle import randperm
+    out = torch.empty(n, dtype=torch.int64, device="cuda")
+    nat.check(nat.lib.hg_randperm(n, seed, ctr, out.data_ptr(), nat.stream_ptr(0)), "hg_randperm")
+    torch.cuda.synchronize()
+    np.testing.assert_array_equal(out.cpu().numpy(), randperm(n, seed, ctr))
