@@ -51,7 +51,8 @@ class LeggedRobot(BaseTask):
         self.dt = self.cfg.control.decimation * self.sim_params.dt
         self.obs_scales = self.cfg.normalization.obs_scales
         self.reward_scales = class_to_dict(self.cfg.rewards.scales)
-        self.command_ranges = class_to_dict(self.cfg.commands.ranges)
+        self.command_ranges = {k: (list(v) if isinstance(v, (list, tuple)) else v)          # own lists: the command curriculum
+                               for k, v in class_to_dict(self.cfg.commands.ranges).items()}   # widens them in place
         if self.cfg.terrain.mesh_type not in ("heightfield", "trimesh"):
             self.cfg.terrain.curriculum = False
         self.max_episode_length_s = self.cfg.env.episode_length_s
@@ -358,6 +359,8 @@ class LeggedRobot(BaseTask):
         copies become memcpy nodes of the graph)."""
         if not isinstance(self.gym, phys.SyntheticPhysics):
             return False
+        if self.cfg.commands.curriculum:          # a host-side decision inside some steps (update_command_curriculum)
+            return False
         return steps is None or steps % self.gym.ring == 0
 
     def inject_noise(self, **tensors):
@@ -441,13 +444,21 @@ class LeggedRobot(BaseTask):
         self.common_step_counter += 1
         if self.cfg.terrain.measure_heights:                      # _post_physics_step_callback :316-317
             self.measured_heights = self._get_heights()
-        if self._T is None:
+        # avoid updating the command curriculum at each step: the maximum command is common to all envs (:178-180)
+        cmd_cur = bool(self.cfg.commands.curriculum) and self.common_step_counter % self.max_episode_length == 0
+        if self._T is None and not cmd_cur:
             self._launch_post_physics(nat.PHASE_STEP_ALL)
         else:
-            # rough terrain: termination + rewards, then the curriculum / spawn origins of the envs that terminated
-            # (reset_idx :175-177, _reset_root_states :381-384), then reset + observations + last_* copies
+            # rough terrain / command-curriculum steps: termination + rewards, then what reset_idx does BEFORE it re-initialises
+            # the envs that terminated -- terrain curriculum and spawn origins (:175-177, :381-384), command curriculum
+            # (:178-180; a host decision, hence a sync on those rare steps) --, then reset + observations + last_* copies
             self._launch_post_physics(_PHASES_BEFORE_RESET)
-            self._terrain_reset_prepare(curriculum=True)
+            if self._T is not None:
+                self._terrain_reset_prepare(curriculum=True)
+            if cmd_cur:
+                env_ids = self.reset_buf.nonzero(as_tuple=False).flatten()
+                if len(env_ids):
+                    self.update_command_curriculum(env_ids)
             self._launch_post_physics(_PHASES_FROM_RESET)
         self._injected = {}
         pushed = self.cfg.domain_rand.push_robots and (self.common_step_counter % self.cfg.domain_rand.push_interval == 0)
@@ -494,9 +505,23 @@ class LeggedRobot(BaseTask):
         self._terrain_reset_prepare(curriculum=True)
         self.reset_buf.copy_(previous)
 
+    def update_command_curriculum(self, env_ids):                 # :422-431
+        """Curriculum of increasing commands: when the envs being reset tracked their velocity command well (mean episode
+        sum above 80 % of the maximum), widen the lin_vel_x range by 0.5 m/s on both sides up to commands.max_curriculum.
+        The comparison is the reference's (fp32 mean / max_episode_length against a Python float) and, like there, a
+        device->host read; the widened range reaches the kernels through the HgEnvParams block of the next launch."""
+        k = self.reward_names.index("tracking_lin_vel")
+        if torch.mean(self._episode_sums[k][env_ids]) / self.max_episode_length > 0.8 * self.reward_scales["tracking_lin_vel"]:
+            r, m = self.command_ranges["lin_vel_x"], self.cfg.commands.max_curriculum
+            r[0] = np.clip(r[0] - 0.5, -m, 0.0)
+            r[1] = np.clip(r[1] + 0.5, 0.0, m)
+            self._P.cmd_x_lo, self._P.cmd_x_span = r[0], r[1] - r[0]      # span formed in double, like torch_rand_float's
+
     def _publish_extras(self):
         if "episode" not in self.extras:
             self.extras["episode"] = {"rew_" + n: self._episode_means[k] for k, n in enumerate(self.reward_names)}
+        if self.cfg.commands.curriculum:                           # :206-207
+            self.extras["episode"]["max_command_x"] = self.command_ranges["lin_vel_x"][1]
         if self.cfg.terrain.mesh_type == "trimesh":                # :204-205 (the reference refreshes it on steps with a reset;
             self.extras["episode"]["terrain_level"] = torch.mean(self.terrain_levels.float())   # levels only change on those)
         if self.cfg.env.send_timeouts:
@@ -520,6 +545,8 @@ class LeggedRobot(BaseTask):
         self.reset_buf[env_ids] = True                            # the kernel resets the masked envs
         if self._T is not None:
             self._terrain_reset_prepare(curriculum=self.init_done)     # "don't change on initial reset" :407-409
+        if self.cfg.commands.curriculum and self.common_step_counter % self.max_episode_length == 0:
+            self.update_command_curriculum(env_ids)
         self._launch_post_physics(nat.PHASE_RESET)
         self.reset_buf |= previous                                # reference only sets [env_ids] = 1 (:196)
         self._injected = {}

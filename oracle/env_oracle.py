@@ -460,6 +460,15 @@ def compute_reward(S, P):                                         # legged_robot
         S["rew_buf"] = torch.clip(S["rew_buf"], min=0.)
 
 
+def update_command_curriculum(S, P, ids):                       # legged_robot.py:422-431
+    """Widens P["cmd_x"] in place (the reference mutates self.command_ranges)."""
+    k = REWARD_NAMES.index("tracking_lin_vel")
+    if torch.mean(S["episode_sums"][k][ids]) / P["max_episode_length"] > 0.8 * P["reward_scales"][k]:
+        lo, hi = P["cmd_x"]
+        m = P["max_curriculum"]
+        P["cmd_x"] = (np.clip(lo - 0.5, -m, 0.), np.clip(hi + 0.5, 0., m))
+
+
 def reset_idx(S, P, ids, noise):
     """legged_robot.py:163-215 + :359-397 + humanoid_env.py:264-269."""
     if len(ids) == 0:
@@ -467,6 +476,8 @@ def reset_idx(S, P, ids, noise):
     T = P.get("terrain")
     if T is not None and T["curriculum"] and S.get("init_done", True):       # :175-177, :407-409
         update_terrain_curriculum(S, P, ids, noise["r_level"])
+    if P.get("cmd_curriculum") and S["common_step_counter"] % P["max_episode_length"] == 0:      # :178-180
+        update_command_curriculum(S, P, ids)
     S["dof_pos"][ids] = P["default_dof_pos"] + _uniform(-0.1, 0.1, noise["u_dof"][ids])
     S["dof_vel"][ids] = 0.
     S["root_states"][ids] = torch.tensor(P["base_init_state"])

@@ -15,6 +15,9 @@ Outputs
   ppo_learning.npz       : ActorCritic fwd, GAE, one PPO.update() incl. gradients
   policy_example_kat.npz : weights + known answers of the reference's only
                            shipped fixture (logs/XBot_ppo/exported/policies/policy_example.pt)
+  env_cmd_curriculum.npz : the same env with commands.curriculum on: steps on which common_step_counter hits a multiple of
+                           max_episode_length with envs resetting (range widened twice, clipped at max_curriculum, then a
+                           step whose resetting envs tracked badly -> unchanged)
   env_terrain.npz        : the same env on rough terrain (mesh_type 'trimesh', terrain curriculum, measured heights
                            in the critic frames): HumanoidTerrain's height field + chained env.step() calls
 """
@@ -462,6 +465,96 @@ def make_terrain_golden(out_path, n_envs=20, n_steps=24):
           f" height field {env.height_samples.shape}, {os.path.getsize(out_path) / 1e6:.2f} MB")
 
 
+def make_cmd_curriculum_golden(out_path, n_envs=12, n_steps=8):
+    """update_command_curriculum (legged_robot.py:178-180,422-431) inside chained env.step() calls."""
+    from humanoid.envs import XBotLCfg, XBotLFreeEnv  # noqa: F401
+    from humanoid.utils import task_registry
+    uninstrument()
+
+    class CurCfg(XBotLCfg):
+        class commands(XBotLCfg.commands):
+            curriculum, max_curriculum = True, 1.5
+
+            class ranges(XBotLCfg.commands.ranges):
+                lin_vel_x = [-0.3, 0.6]            # own list: the reference widens it in place
+
+    args = argparse.Namespace(
+        task="humanoid_ppo", resume=False, experiment_name=None, run_name=None, load_run=None,
+        checkpoint=None, headless=True, horovod=False, rl_device="cpu", num_envs=n_envs, seed=5,
+        max_iterations=None, physics_engine=1, use_gpu=False, use_gpu_pipeline=False, subscenes=0,
+        num_threads=0, sim_device="cpu", sim_device_type="cpu", compute_device_id=0, sim_device_id=0,
+        device="cpu")
+    env_cfg = CurCfg()
+    env_cfg.seed = 5
+    env, cfg = task_registry.make_env(name="humanoid_ppo", args=args, env_cfg=env_cfg)
+    rec = DrawRecorder(n_envs)
+    instrument_env(env, rec)
+    data = {"meta.n_envs": np.int64(n_envs), "meta.n_steps": np.int64(n_steps),
+            "meta.max_curriculum": np.float64(env.cfg.commands.max_curriculum),
+            "meta.init_range_x": np.array(env.command_ranges["lin_vel_x"], np.float64)}
+    g = torch.Generator().manual_seed(79)
+    env.episode_length_buf[:] = torch.randint(0, 2300, (n_envs,), generator=g)
+    env.common_step_counter = 2398                   # step 1 lands on 2400
+    k_track = env.reward_names.index("tracking_lin_vel")
+    for k, v in snap(env).items():
+        data[f"init.{k}"] = v
+
+    last_torque_in, pre_post, plan = {}, {}, {}
+    orig_ct, orig_pps = env._compute_torques, env.post_physics_step
+
+    def compute_torques(actions):
+        last_torque_in["dof_pos"] = env.dof_pos.clone().numpy()
+        last_torque_in["dof_vel"] = env.dof_vel.clone().numpy()
+        return orig_ct(actions)
+
+    def post_physics_step():
+        t = plan["t"]
+        # t = 1, 3: counter -> 2400, 4800 with well-tracking envs timing out (range widens, the second time into the clip);
+        # t = 5: counter -> 7200, the resetting envs tracked badly (unchanged); t = 6: a reset off the multiple (no check)
+        if t in (1, 3, 5, 6):
+            ids = torch.tensor([(2 * t) % n_envs, (2 * t + 5) % n_envs])
+            env.episode_length_buf[ids] = 2400
+            env.episode_sums["tracking_lin_vel"][:] = 3.0 if t == 5 else 40.0 + t
+        if t == 3:
+            env.common_step_counter = 4799
+        if t == 5:
+            env.common_step_counter = 7199
+        pre_post["pre"] = snap(env)
+        orig_pps()
+
+    env._compute_torques = compute_torques
+    env.post_physics_step = post_physics_step
+    ag = torch.Generator().manual_seed(97)
+    for t in range(n_steps):
+        rec.new_step()
+        plan["t"] = t
+        act_in = 2.0 * torch.randn(n_envs, 12, generator=ag)
+        obs, priv, rew, reset, extras = env.step(act_in.clone())
+        noise, pre, post = rec.noise(), pre_post["pre"], snap(env)
+        p = f"step{t:03d}."
+        data[p + "actions_in"] = act_in.numpy()
+        for k, v in noise.items():
+            data[p + "noise." + k] = v
+        data[p + "torque_in.dof_pos"], data[p + "torque_in.dof_vel"] = last_torque_in["dof_pos"], last_torque_in["dof_vel"]
+        for k in ("root_states", "dof_pos", "dof_vel", "contact_forces", "rigid_state", "actions", "torques", "episode_length_buf",
+                  "episode_sums", "common_step_counter"):
+            data[p + "pre." + k] = pre[k]
+        for k in STATE_KEYS + ("last_feet_z", "episode_sums"):
+            if k in ("contact_forces", "rigid_state", "env_frictions", "body_mass", "env_origins"):
+                continue
+            data[p + "post." + k] = post[k]
+        data[p + "post.obs_frame"] = obs[:, -47:].numpy().copy()
+        data[p + "post.priv_frame"] = priv[:, -73:].numpy().copy()
+        data[p + "post.extras_time_outs"] = extras["time_outs"].numpy().copy()
+        data[p + "post.episode_means"] = np.array([float(extras["episode"]["rew_" + k]) for k in env.reward_names], np.float32)
+        data[p + "post.range_x"] = np.array(env.command_ranges["lin_vel_x"], np.float64)
+        data[p + "post.max_command_x"] = np.float64(extras["episode"]["max_command_x"])
+        data[p + "post.common_step_counter"] = np.int64(env.common_step_counter)
+    np.savez_compressed(out_path, **data)
+    print(f"wrote {out_path}: {n_steps} steps x {n_envs} envs, ranges {[tuple(data[f'step{t:03d}.post.range_x']) for t in range(n_steps)]},"
+          f" {os.path.getsize(out_path) / 1e6:.2f} MB")
+
+
 # --------------------------------------------------------------------------
 # learning-side goldens
 # --------------------------------------------------------------------------
@@ -592,7 +685,7 @@ def make_cfg_golden(out_path):
 if __name__ == "__main__":
     _install_shims()
     torch.set_num_threads(1)
-    which = sys.argv[1:] or ["env", "ppo", "kat", "cfg", "terrain"]
+    which = sys.argv[1:] or ["env", "ppo", "kat", "cfg", "terrain", "cmdcur"]
     if "env" in which:
         make_env_golden(os.path.join(HERE, "env_rollout.npz"))
     if "ppo" in which:
@@ -603,3 +696,5 @@ if __name__ == "__main__":
         make_policy_kat(os.path.join(HERE, "policy_example_kat.npz"))
     if "terrain" in which:
         make_terrain_golden(os.path.join(HERE, "env_terrain.npz"))
+    if "cmdcur" in which:
+        make_cmd_curriculum_golden(os.path.join(HERE, "env_cmd_curriculum.npz"))

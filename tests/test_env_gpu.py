@@ -336,3 +336,78 @@ def test_env_over_isaacgym_adapter(fake_isaacgym):
             ids = [c for c in log if c[0] == "set_dof_state_tensor_indexed"][0][1]
             assert ids[2] == n_reset and sorted(ids[1].tolist()) == oa[3].nonzero().flatten().tolist()
     assert total_resets >= N // 40 and env_a.common_step_counter == 403
+
+
+def test_command_curriculum_golden_step_by_step():
+    """commands.curriculum (legged_robot.py:178-180,422-431) in the product: on steps whose counter hits a multiple of
+    max_episode_length the env splits the fused launch, reads the mean tracking reward of the envs about to reset and widens
+    the lin_vel_x range BEFORE they resample their commands -- against tests/golden/env_cmd_curriculum.npz (unmodified reference)."""
+    from humanoid.envs import XBotLCfg
+    g = Golden("env_cmd_curriculum.npz")
+    n, steps = int(g["meta.n_envs"]), int(g["meta.n_steps"])
+
+    class CurCfg(XBotLCfg):
+        class commands(XBotLCfg.commands):
+            curriculum, max_curriculum = True, float(g["meta.max_curriculum"])
+
+            class ranges(XBotLCfg.commands.ranges):
+                lin_vel_x = [float(x) for x in g["meta.init_range_x"]]
+    cfg = CurCfg()
+    cfg.seed = 5
+    env = make_env(n, physics="external", cfg=cfg)
+    assert not env.graph_safe()                       # a host decision inside some steps: no graph capture
+    S = oracle_state_from_golden(g)
+    hist_o, hist_p = S["obs_hist"].clone(), S["critic_hist"].clone()
+    problems, widened = [], 0
+    for t in range(steps):
+        p = f"step{t:03d}."
+        noise = g.group(p + "noise.")
+        S["obs_hist"], S["critic_hist"] = hist_o, hist_p
+        for k in ("episode_length_buf", "episode_sums"):
+            S[k] = g.t(p + "pre." + k).clone()
+        S["common_step_counter"] = int(g[p + "pre.common_step_counter"])
+        load_state(env, S)
+        frames = {k: g.t(p + "pre." + k) for k in ("root_states", "contact_forces", "rigid_state")}
+        dof_seq = [(g.t(p + "torque_in.dof_pos"), g.t(p + "torque_in.dof_vel")), (g.t(p + "pre.dof_pos"), g.t(p + "pre.dof_vel"))]
+        calls = {"n": 0}
+
+        def on_simulate(ph, frames=frames, dof_seq=dof_seq, calls=calls):
+            calls["n"] += 1
+            if calls["n"] in (9, 10):
+                ds = ph.dof_state.view(n, 12, 2)
+                ds[..., 0], ds[..., 1] = dof_seq[calls["n"] - 9][0].cuda(), dof_seq[calls["n"] - 9][1].cuda()
+            if calls["n"] == 10:
+                ph.root_states.copy_(frames["root_states"].cuda())
+                ph.contact_forces.copy_(frames["contact_forces"].reshape(-1, 3).cuda())
+                ph.rigid_state.copy_(frames["rigid_state"].reshape(-1, 13).cuda())
+        env.gym.on_simulate = on_simulate
+        env.inject_noise(**noise)
+        before = tuple(env.command_ranges["lin_vel_x"])
+        obs, priv, rew, reset, extras = env.step(g.t(p + "actions_in").cuda())
+        torch.cuda.synchronize()
+        got = tuple(float(x) for x in env.command_ranges["lin_vel_x"])
+        want = tuple(float(x) for x in g[p + "post.range_x"])
+        widened += got != tuple(float(x) for x in before)
+        bad = []
+        if got != want:
+            bad.append(f"lin_vel_x range {got} != {want}")
+        if float(extras["episode"]["max_command_x"]) != float(g[p + "post.max_command_x"]):
+            bad.append("extras max_command_x")
+        if (float(env._P.cmd_x_lo), float(env._P.cmd_x_span)) != (np.float32(want[0]), np.float32(want[1] - want[0])):
+            bad.append("kernel parameter block not refreshed")
+        ref = {k: v for k, v in g.group(p + "post.").items()}
+        keys = [k for k in ref if k in CHECK_KEYS_SMALL]
+        bad += compare_step(env, ref, RTOL, ATOL, max_outlier_frac=0.0, keys=keys)
+        if not torch.allclose(obs[:, -47:].cpu(), ref["obs_frame"], rtol=RTOL, atol=ATOL):
+            bad.append("obs_frame")
+        if bad:
+            problems.append((t, bad))
+        hist_o = obs.detach().cpu().view(n, 15, 47).clone()
+        hist_p = priv.detach().cpu().view(n, 3, 73).clone()
+        S = _golden_state_after(g, S, t)
+    assert not problems, problems[:3]
+    assert widened == 2 and env.command_ranges["lin_vel_x"][1] == 1.5
+
+
+CHECK_KEYS_SMALL = ("commands", "root_states", "reset_buf", "time_out_buf", "episode_sums", "rew_buf", "episode_length_buf",
+                    "dof_pos", "dof_vel", "actions", "last_actions", "feet_air_time", "episode_means", "extras_time_outs")

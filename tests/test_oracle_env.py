@@ -86,3 +86,35 @@ def test_rollout_replay_matches_reference(g):
         n_push += int(S["common_step_counter"] % 400 == 0)
     # the fixture must actually exercise the rare branches
     assert n_resets > 10 and n_timeouts >= 3 and n_push == 1
+
+
+def test_command_curriculum_replay_matches_reference():
+    """update_command_curriculum (legged_robot.py:178-180,422-431) inside chained steps: tests/golden/env_cmd_curriculum.npz
+    (unmodified reference with commands.curriculum on; the range widens twice -- the second time into the max_curriculum clip
+    -- and stays put when the resetting envs tracked badly or the counter is off the multiple of max_episode_length)."""
+    g = Golden("env_cmd_curriculum.npz")
+    P = eo.make_params()
+    P["cmd_curriculum"], P["max_curriculum"] = True, float(g["meta.max_curriculum"])
+    P["cmd_x"] = tuple(g["meta.init_range_x"])
+    S = oracle_state_from_golden(g)
+    widened = 0
+    for t in range(int(g["meta.n_steps"])):
+        p = f"step{t:03d}."
+        noise = g.group(p + "noise.")
+        eo.pre_physics(S, P, g.t(p + "actions_in"), noise["u_delay"], noise["z_act"])
+        S["dof_pos"], S["dof_vel"] = g.t(p + "torque_in.dof_pos"), g.t(p + "torque_in.dof_vel")
+        eo.compute_torques(S, P)
+        for k in ("root_states", "dof_pos", "dof_vel", "contact_forces", "rigid_state", "episode_length_buf", "episode_sums"):
+            S[k] = g.t(p + "pre." + k).clone()
+        S["common_step_counter"] = int(g[p + "pre.common_step_counter"])
+        before = P["cmd_x"]
+        obs, priv, rew, reset = eo.post_physics(S, P, noise)
+        post = g.group(p + "post.")
+        assert tuple(float(x) for x in P["cmd_x"]) == tuple(float(x) for x in g[p + "post.range_x"]), t
+        widened += P["cmd_x"] != before
+        for k in ("commands", "root_states", "reset_buf", "episode_sums", "rew_buf", "episode_length_buf"):
+            _cmp(k, S[k], post[k], t)
+        _cmp("obs_frame", obs[:, -47:], post["obs_frame"], t)
+        _cmp("episode_means", S["episode_means"], post["episode_means"], t)
+        assert S["common_step_counter"] == int(g[p + "post.common_step_counter"])
+    assert widened == 2 and float(P["cmd_x"][1]) == 1.5
