@@ -5,9 +5,11 @@ tests/golden/terrain.npz pins; the primitives themselves are third-party and par
 import importlib.util
 import os
 
-_REPO = os.path.dirname(os.path.dirname(os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))))
-_spec = importlib.util.spec_from_file_location(
-    "_hg_terrain_primitives", os.path.join(_REPO, "humanoid-gym_b200", "humanoid", "utils", "terrain.py"))
+_REL = os.path.join("humanoid-gym_b200", "humanoid", "utils", "terrain.py")
+_HERE5 = os.path.dirname(os.path.dirname(os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))))
+# the repo root: HG_REPO_ROOT, else five levels up (in-tree), else /root/repo (this file copied elsewhere, e.g. to /tmp)
+_REPO = next((r for r in (os.environ.get("HG_REPO_ROOT"), _HERE5, "/root/repo") if r and os.path.exists(os.path.join(r, _REL))), _HERE5)
+_spec = importlib.util.spec_from_file_location("_hg_terrain_primitives", os.path.join(_REPO, _REL))
 _m = importlib.util.module_from_spec(_spec)
 _spec.loader.exec_module(_m)
 
